@@ -1,0 +1,1036 @@
+// C-ABI implementation of include/ebpmf_b200.h: context, device buffers, pass orchestration
+// of the global-stop Newton solve, reductions and the NCCL combine.  No PyTorch, no CPU
+// fallback: every entry point fails with EBPMF_ERR_CUDA when no sm_100 GPU is usable.
+#include "../../include/ebpmf_b200.h"
+#include "vga_kernels.cuh"
+#include "simgen.cuh"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>      // types only; the library is dlopen'ed (nccl_dyn below)
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+using namespace ebpmf;
+
+// -----------------------------------------------------------------------------------------
+// NCCL through dlopen: single-GPU users need no NCCL at all
+// -----------------------------------------------------------------------------------------
+namespace {
+struct NcclDyn {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string &err) {
+        if (handle) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) { err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+#define EBPMF_SYM(field, name)                                                         \
+        *(void **)(&field) = dlsym(handle, name);                                      \
+        if (!field) { err = std::string("NCCL symbol missing: ") + name; handle = nullptr; return false; }
+        EBPMF_SYM(GetUniqueId, "ncclGetUniqueId");
+        EBPMF_SYM(CommInitRank, "ncclCommInitRank");
+        EBPMF_SYM(CommDestroy, "ncclCommDestroy");
+        EBPMF_SYM(AllReduce, "ncclAllReduce");
+        EBPMF_SYM(GetErrorString, "ncclGetErrorString");
+#undef EBPMF_SYM
+        return true;
+    }
+};
+NcclDyn g_nccl;
+thread_local std::string g_last_error;
+
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t cap = 0;
+};
+}  // namespace
+
+struct ebpmf_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
+    std::string err;
+
+    // shapes
+    long long n = 0, p = 0, nnz = 0;
+    long long nRB = 0, nRW = 0;
+    int K = 0, KTP = 0;
+    int var_type = -1;
+    bool can_rewind = false;
+    bool have_y = false, have_m = false, have_f = false, have_s2 = false, have_v = false, have_vsum = false;
+
+    // resident buffers
+    DevBuf colptr, rowidx, yx, rbptr;
+    DevBuf Mcur, Malt, V;
+    DevBuf EL, EF, EFt, sigma2, l0, f0;
+    DevBuf kunit, colpart, rowpart;
+    DevBuf red;        // [4 scalars: sym, ssexp, slogv, sumV][v_sum ...]
+    DevBuf colsums;    // p x 3
+    DevBuf status;     // Status
+    DevBuf misc;       // small scratch (R2, fitmax, obj terms, lfactorial partials)
+    DevBuf scratch[6]; // dense-signature operands
+
+    Status *h_status = nullptr;   // pinned
+    double *h_small = nullptr;    // pinned, 64 doubles
+
+    // NCCL
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+namespace {
+
+int fail(ebpmf_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_last_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(ctx, EBPMF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+#define NC(call)                                                                                   \
+    do {                                                                                           \
+        ncclResult_t r__ = (call);                                                                 \
+        if (r__ != ncclSuccess)                                                                    \
+            return fail(ctx, EBPMF_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r__));  \
+    } while (0)
+
+#define CHECK(expr)                         \
+    do {                                    \
+        int rc__ = (expr);                  \
+        if (rc__ != EBPMF_OK) return rc__;  \
+    } while (0)
+
+int reserve(ebpmf_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return EBPMF_OK;
+    if (b.ptr) { cudaFree(b.ptr); b.ptr = nullptr; b.cap = 0; }
+    cudaError_t e = cudaMalloc(&b.ptr, bytes);
+    if (e != cudaSuccess) {
+        b.ptr = nullptr;
+        (void)cudaGetLastError();
+        return fail(ctx, e == cudaErrorMemoryAllocation ? EBPMF_ERR_NOMEM : EBPMF_ERR_CUDA,
+                    "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    b.cap = bytes;
+    return EBPMF_OK;
+}
+
+void release(DevBuf &b) {
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = nullptr;
+    b.cap = 0;
+}
+
+template <typename T> T *as(DevBuf &b) { return reinterpret_cast<T *>(b.ptr); }
+
+int ktp_for(int K) {
+    if (K <= 8) return 8;
+    if (K <= 16) return 16;
+    if (K <= 24) return 24;
+    if (K <= 32) return 32;
+    return -1;
+}
+
+constexpr int kE = 2;   // columns per unit in the fused / dense kernels
+
+int cols_per_cta_for(long long p, long long nRB) {
+    // enough CTAs for ~16 waves of 148 SMs x 2 resident CTAs, spans of 16..256 columns
+    const long long want = 148LL * 2 * 16;
+    long long spans = std::max(1LL, (want + nRB - 1) / nRB);
+    long long c = (p + spans - 1) / spans;
+    c = ((c + kTileCols - 1) / kTileCols) * kTileCols;
+    c = std::min(256LL, std::max((long long)kTileCols, c));
+    return (int)c;
+}
+
+template <int FORMULA, int MODE>
+int launch_fused(ebpmf_ctx *ctx, const FusedArgs &a) {
+    const long long ncols = a.col1 - a.col0;
+    if (ncols <= 0) return EBPMF_OK;
+    dim3 grid((unsigned)((ncols + a.cols_per_cta - 1) / a.cols_per_cta), (unsigned)ctx->nRB);
+    dim3 block(kThreads);
+    switch (ctx->KTP) {
+        case 8: vga_fused_kernel<8, kE, FORMULA, MODE><<<grid, block, 0, ctx->stream>>>(a); break;
+        case 16: vga_fused_kernel<16, kE, FORMULA, MODE><<<grid, block, 0, ctx->stream>>>(a); break;
+        case 24: vga_fused_kernel<24, kE, FORMULA, MODE><<<grid, block, 0, ctx->stream>>>(a); break;
+        case 32: vga_fused_kernel<32, kE, FORMULA, MODE><<<grid, block, 0, ctx->stream>>>(a); break;
+        default: return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported (max 32)", ctx->K);
+    }
+    CU(cudaGetLastError());
+    return EBPMF_OK;
+}
+
+int stride_for(int kind, long long n, long long *rs, long long *cs) {
+    switch (kind) {
+        case EBPMF_OP_SCALAR: *rs = 0; *cs = 0; return EBPMF_OK;
+        case EBPMF_OP_ROWVEC: *rs = 1; *cs = 0; return EBPMF_OK;
+        case EBPMF_OP_COLVEC: *rs = 0; *cs = 1; return EBPMF_OK;
+        case EBPMF_OP_MATRIX: *rs = 1; *cs = n; return EBPMF_OK;
+    }
+    return EBPMF_ERR_ARG;
+}
+
+size_t operand_len(int kind, long long n, long long p) {
+    switch (kind) {
+        case EBPMF_OP_SCALAR: return 1;
+        case EBPMF_OP_ROWVEC: return (size_t)n;
+        case EBPMF_OP_COLVEC: return (size_t)p;
+        default: return (size_t)n * (size_t)p;
+    }
+}
+
+// Combine the Status words over ranks (MAX) -- no-op without a communicator.
+int allreduce_status(ebpmf_ctx *ctx) {
+    if (!ctx->comm) return EBPMF_OK;
+    NC(g_nccl.AllReduce(ctx->status.ptr, ctx->status.ptr, 4, ncclInt32, ncclMax, ctx->comm, ctx->stream));
+    return EBPMF_OK;
+}
+
+// Pull the Status words to the host (synchronises the compute stream).
+int fetch_status(ebpmf_ctx *ctx) {
+    CU(cudaMemcpyAsync(ctx->h_status, ctx->status.ptr, sizeof(Status), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return EBPMF_OK;
+}
+
+int set_target(ebpmf_ctx *ctx, int target) {
+    Status s;
+    s.kstar = target; s.nan = 0; s.verify_fail = 0; s.exhausted = 0;
+    *ctx->h_status = s;
+    CU(cudaMemcpyAsync(ctx->status.ptr, ctx->h_status, sizeof(Status), cudaMemcpyHostToDevice, ctx->stream));
+    return EBPMF_OK;
+}
+
+int ensure_common(ebpmf_ctx *ctx) {
+    CU(cudaSetDevice(ctx->device));
+    return EBPMF_OK;
+}
+
+int alloc_solver_state(ebpmf_ctx *ctx, long long n, long long p) {
+    ctx->nRB = (n + kRowsPerCta - 1) / kRowsPerCta;
+    ctx->nRW = (n + 31) / 32;
+    const long long nJG = (p + kE - 1) / kE;
+    CHECK(reserve(ctx, ctx->kunit, sizeof(unsigned short) * (size_t)nJG * (size_t)ctx->nRW));
+    CHECK(reserve(ctx, ctx->status, sizeof(Status)));
+    return EBPMF_OK;
+}
+
+// reductions of the per-unit partials into red = [sym, ssexp, slogv, sumV][v_sum...]
+int run_reductions(ebpmf_ctx *ctx) {
+    const long long n = ctx->n, p = ctx->p;
+    double *red = as<double>(ctx->red);
+    double *colv = (ctx->var_type == EBPMF_VAR_BY_COL) ? red + 4 : as<double>(ctx->colsums) + 3 * p;
+    reduce_cols_kernel<<<(unsigned)((p + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(
+        as<double>(ctx->colpart), ctx->nRW, p, colv, as<double>(ctx->colsums));
+    CU(cudaGetLastError());
+    reduce_scalars_kernel<<<1, 1024, 0, ctx->stream>>>(colv, as<double>(ctx->colsums), p, red);
+    CU(cudaGetLastError());
+    if (ctx->var_type == EBPMF_VAR_BY_ROW) {
+        const long long nJG = (p + kE - 1) / kE;
+        reduce_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(as<double>(ctx->rowpart), n, nJG,
+                                                                                 red + 4);
+        CU(cudaGetLastError());
+    }
+    if (ctx->comm) {
+        const size_t count = 4 + (ctx->var_type == EBPMF_VAR_BY_COL ? (size_t)p : 0);
+        NC(g_nccl.AllReduce(red, red, count, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
+    }
+    return EBPMF_OK;
+}
+
+// The pass orchestration shared by the fused step (A1) and low_memory (A10).
+// first / topup are callables that enqueue one pass on ctx->stream.
+template <typename First, typename Topup, typename After>
+int run_global_stop(ebpmf_ctx *ctx, int maxiter, First first, Topup topup, After after, ebpmf_solve_info *info) {
+    CU(cudaMemsetAsync(ctx->status.ptr, 0, sizeof(Status), ctx->stream));
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    CHECK(first());
+    CHECK(allreduce_status(ctx));
+    CHECK(topup());
+    int passes = 2;
+    for (;;) {
+        CHECK(allreduce_status(ctx));
+        CHECK(after());                      // reductions (speculative: redone if the verify failed)
+        CU(cudaEventRecord(ctx->ev1, ctx->stream));
+        CHECK(fetch_status(ctx));
+        const Status s = *ctx->h_status;
+        if (s.nan)
+            return fail(ctx, EBPMF_ERR_NAN, "missing value where TRUE/FALSE needed (NaN in f at the stop test)");
+        if (s.verify_fail && s.kstar < maxiter) {
+            CHECK(set_target(ctx, s.kstar + 1));
+            CHECK(topup());
+            ++passes;
+            continue;
+        }
+        if (info) {
+            info->n_updates = s.kstar;
+            info->converged = (s.kstar < maxiter) ? 1 : 0;
+            info->passes = passes;
+            info->reserved = 0;
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            info->kernel_ms = ms;
+        }
+        return EBPMF_OK;
+    }
+}
+
+FusedArgs fused_args(ebpmf_ctx *ctx, int maxiter, double tol, bool want_v) {
+    FusedArgs a;
+    memset(&a, 0, sizeof a);
+    a.n = ctx->n; a.p = ctx->p; a.K = ctx->K; a.var_type = ctx->var_type;
+    a.M_in = as<double>(ctx->Mcur); a.M_out = as<double>(ctx->Malt);
+    a.V_out = want_v ? as<double>(ctx->V) : nullptr;
+    a.EL = as<double>(ctx->EL); a.EFt = as<double>(ctx->EFt); a.sigma2 = as<double>(ctx->sigma2);
+    a.l0 = as<double>(ctx->l0); a.f0 = as<double>(ctx->f0);
+    a.rowidx = as<int>(ctx->rowidx); a.yx = as<double>(ctx->yx); a.rbptr = as<int>(ctx->rbptr);
+    a.kunit = as<unsigned short>(ctx->kunit); a.nRW = ctx->nRW;
+    a.colpart = as<double>(ctx->colpart);
+    a.rowpart = (ctx->var_type == EBPMF_VAR_BY_ROW) ? as<double>(ctx->rowpart) : nullptr;
+    a.status = as<Status>(ctx->status);
+    a.maxiter = maxiter; a.tol = tol;
+    a.col0 = 0; a.col1 = ctx->p;
+    a.cols_per_cta = cols_per_cta_for(ctx->p, ctx->nRB);
+    return a;
+}
+
+int upload_csc(ebpmf_ctx *ctx, long long n, long long p, const int32_t *colptr, const int32_t *rowidx,
+               const double *x) {
+    const long long nnz = colptr[p];
+    if (nnz < 0 || colptr[0] != 0) return fail(ctx, EBPMF_ERR_ARG, "bad dgCMatrix @p slot");
+    CHECK(reserve(ctx, ctx->colptr, sizeof(int) * (size_t)(p + 1)));
+    CHECK(reserve(ctx, ctx->rowidx, sizeof(int) * (size_t)std::max(1LL, nnz)));
+    CHECK(reserve(ctx, ctx->yx, sizeof(double) * (size_t)std::max(1LL, nnz)));
+    CU(cudaMemcpyAsync(ctx->colptr.ptr, colptr, sizeof(int) * (size_t)(p + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (nnz > 0) {
+        CU(cudaMemcpyAsync(ctx->rowidx.ptr, rowidx, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->yx.ptr, x, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->nnz = nnz;
+    (void)n;
+    return EBPMF_OK;
+}
+
+// after colptr/rowidx/yx are resident: shapes, row-block offset table, partial buffers
+int finish_set_y(ebpmf_ctx *ctx, long long n, long long p) {
+    ctx->n = n; ctx->p = p;
+    CHECK(alloc_solver_state(ctx, n, p));
+    const long long cells = (ctx->nRB + 1) * p;
+    CHECK(reserve(ctx, ctx->rbptr, sizeof(int) * (size_t)cells));
+    build_rbptr_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(
+        as<int>(ctx->colptr), as<int>(ctx->rowidx), p, ctx->nRB, as<int>(ctx->rbptr));
+    CU(cudaGetLastError());
+    CHECK(reserve(ctx, ctx->colpart, sizeof(double) * 4 * (size_t)ctx->nRW * (size_t)p));
+    CHECK(reserve(ctx, ctx->colsums, sizeof(double) * 4 * (size_t)p));
+    CHECK(reserve(ctx, ctx->red, sizeof(double) * (4 + (size_t)std::max(n, p))));
+    CHECK(reserve(ctx, ctx->misc, sizeof(double) * (size_t)(3 * std::max(n, p) + 4096)));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->have_y = true;
+    ctx->have_m = ctx->have_f = ctx->have_s2 = ctx->have_v = ctx->have_vsum = false;
+    return EBPMF_OK;
+}
+
+int dense_to_csc(ebpmf_ctx *ctx, long long n, long long p, const double *dY /* device */) {
+    // counts -> colptr -> fill; nnz must fit the int32 @p slot of a dgCMatrix
+    CHECK(reserve(ctx, ctx->colptr, sizeof(int) * (size_t)(p + 1)));
+    CHECK(reserve(ctx, ctx->misc, sizeof(double) * (size_t)(3 * std::max(n, p) + 4096)));
+    int *counts = as<int>(ctx->misc);
+    const unsigned blocks = (unsigned)((p * 32 + 255) / 256);
+    count_nnz_kernel<<<blocks, 256, 0, ctx->stream>>>(dY, n, p, counts);
+    CU(cudaGetLastError());
+    scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>(counts, p, as<int>(ctx->colptr));
+    CU(cudaGetLastError());
+    int nnz = 0;
+    CU(cudaMemcpyAsync(&nnz, as<int>(ctx->colptr) + p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (nnz < 0) return fail(ctx, EBPMF_ERR_ARG, "more than 2^31-1 non-zeros in one shard");
+    CHECK(reserve(ctx, ctx->rowidx, sizeof(int) * (size_t)std::max(1, nnz)));
+    CHECK(reserve(ctx, ctx->yx, sizeof(double) * (size_t)std::max(1, nnz)));
+    fill_csc_kernel<<<blocks, 256, 0, ctx->stream>>>(dY, n, p, as<int>(ctx->colptr), as<int>(ctx->rowidx),
+                                                     as<double>(ctx->yx));
+    CU(cudaGetLastError());
+    ctx->nnz = nnz;
+    return EBPMF_OK;
+}
+
+int sum_lfactorial_dev(ebpmf_ctx *ctx, const double *dx, long long len, double *out) {
+    const int blocks = (int)std::min<long long>(2048, std::max<long long>(1, (len + 255) / 256));
+    CHECK(reserve(ctx, ctx->misc, sizeof(double) * 4096));
+    double *partials = as<double>(ctx->misc);
+    lfactorial_partial_kernel<<<blocks, 256, 0, ctx->stream>>>(dx, len, partials);
+    CU(cudaGetLastError());
+    sum_partials_kernel<<<1, 1024, 0, ctx->stream>>>(partials, blocks, partials + 2048);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ctx->h_small, partials + 2048, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out = ctx->h_small[0];
+    return EBPMF_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+// exported C ABI
+// =========================================================================================
+extern "C" {
+
+const char *ebpmf_version(void) { return "ebpmf_b200 0.1.0 (sm_100a)"; }
+
+int ebpmf_device_count(int *count) {
+    ebpmf_ctx *ctx = nullptr;
+    if (!count) return fail(ctx, EBPMF_ERR_ARG, "count is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *count = 0; (void)cudaGetLastError(); return fail(ctx, EBPMF_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *count = c;
+    return EBPMF_OK;
+}
+
+const char *ebpmf_last_error(const ebpmf_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int ebpmf_ctx_create(int device, ebpmf_ctx **out) {
+    ebpmf_ctx *ctx = nullptr;
+    if (!out) return fail(ctx, EBPMF_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        (void)cudaGetLastError();
+        return fail(ctx, EBPMF_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= count) return fail(ctx, EBPMF_ERR_ARG, "device %d out of range [0,%d)", device, count);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(ctx, EBPMF_ERR_CUDA, "device %d is sm_%d%d; the kernels are built for sm_100a only", device,
+                    prop.major, prop.minor);
+    ctx = new (std::nothrow) ebpmf_ctx();
+    if (!ctx) return fail(nullptr, EBPMF_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    cudaError_t ce;
+#define CREATE_STEP(call)                                                                                        \
+    ce = (call);                                                                                                 \
+    if (ce != cudaSuccess) {                                                                                     \
+        fail(nullptr, EBPMF_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(ce));                           \
+        delete ctx;                                                                                              \
+        return EBPMF_ERR_CUDA;                                                                                   \
+    }
+    CREATE_STEP(cudaSetDevice(device));
+    CREATE_STEP(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CREATE_STEP(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CREATE_STEP(cudaEventCreate(&ctx->ev0));
+    CREATE_STEP(cudaEventCreate(&ctx->ev1));
+    CREATE_STEP(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+    CREATE_STEP(cudaMallocHost((void **)&ctx->h_status, sizeof(Status)));
+    CREATE_STEP(cudaMallocHost((void **)&ctx->h_small, sizeof(double) * 64));
+#undef CREATE_STEP
+    *out = ctx;
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_destroy(ebpmf_ctx *ctx) {
+    if (!ctx) return EBPMF_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    DevBuf *bufs[] = {&ctx->colptr, &ctx->rowidx, &ctx->yx, &ctx->rbptr, &ctx->Mcur, &ctx->Malt, &ctx->V,
+                      &ctx->EL, &ctx->EF, &ctx->EFt, &ctx->sigma2, &ctx->l0, &ctx->f0, &ctx->kunit,
+                      &ctx->colpart, &ctx->rowpart, &ctx->red, &ctx->colsums, &ctx->status, &ctx->misc};
+    for (DevBuf *b : bufs) release(*b);
+    for (DevBuf &b : ctx->scratch) release(b);
+    if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    if (ctx->h_small) cudaFreeHost(ctx->h_small);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+    return EBPMF_OK;
+}
+
+int ebpmf_nccl_unique_id(void *id128) {
+    ebpmf_ctx *ctx = nullptr;
+    if (!id128) return fail(ctx, EBPMF_ERR_ARG, "id128 is NULL");
+    std::string err;
+    if (!g_nccl.load(err)) return fail(ctx, EBPMF_ERR_NCCL, "%s", err.c_str());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof id);
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_comm_init(ebpmf_ctx *ctx, int rank, int world, const void *id128) {
+    if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return fail(ctx, EBPMF_ERR_ARG, "bad comm arguments");
+    CHECK(ensure_common(ctx));
+    std::string err;
+    if (!g_nccl.load(err)) return fail(ctx, EBPMF_ERR_NCCL, "%s", err.c_str());
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    NC(g_nccl.CommInitRank(&ctx->comm, world, id, rank));
+    ctx->rank = rank; ctx->world = world;
+    CHECK(reserve(ctx, ctx->status, sizeof(Status)));
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_set_y_csc(ebpmf_ctx *ctx, int64_t n, int64_t p, const int32_t *colptr, const int32_t *rowidx,
+                        const double *x) {
+    if (!ctx || n < 1 || p < 1 || !colptr) return fail(ctx, EBPMF_ERR_ARG, "set_y_csc: bad arguments");
+    if (colptr[p] > 0 && (!rowidx || !x)) return fail(ctx, EBPMF_ERR_ARG, "set_y_csc: @i / @x missing");
+    CHECK(ensure_common(ctx));
+    CHECK(upload_csc(ctx, n, p, colptr, rowidx, x));
+    return finish_set_y(ctx, n, p);
+}
+
+int ebpmf_ctx_set_y_dense(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *Y) {
+    if (!ctx || n < 1 || p < 1 || !Y) return fail(ctx, EBPMF_ERR_ARG, "set_y_dense: bad arguments");
+    CHECK(ensure_common(ctx));
+    const size_t bytes = sizeof(double) * (size_t)n * (size_t)p;
+    CHECK(reserve(ctx, ctx->Malt, bytes));
+    CU(cudaMemcpyAsync(ctx->Malt.ptr, Y, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CHECK(dense_to_csc(ctx, n, p, as<double>(ctx->Malt)));
+    return finish_set_y(ctx, n, p);
+}
+
+int ebpmf_ctx_sum_lfactorial(ebpmf_ctx *ctx, double *out) {
+    if (!ctx || !out) return fail(ctx, EBPMF_ERR_ARG, "sum_lfactorial: bad arguments");
+    if (!ctx->have_y) return fail(ctx, EBPMF_ERR_STATE, "sum_lfactorial: Y not set");
+    CHECK(ensure_common(ctx));
+    return sum_lfactorial_dev(ctx, as<double>(ctx->yx), ctx->nnz, out);
+}
+
+int ebpmf_sum_lfactorial(ebpmf_ctx *ctx, int64_t len, const double *x, double *out) {
+    if (!ctx || len < 0 || !out || (len > 0 && !x)) return fail(ctx, EBPMF_ERR_ARG, "sum_lfactorial: bad arguments");
+    CHECK(ensure_common(ctx));
+    if (len == 0) { *out = 0.0; return EBPMF_OK; }
+    CHECK(reserve(ctx, ctx->scratch[0], sizeof(double) * (size_t)len));
+    CU(cudaMemcpyAsync(ctx->scratch[0].ptr, x, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
+    return sum_lfactorial_dev(ctx, as<double>(ctx->scratch[0]), len, out);
+}
+
+int ebpmf_ctx_set_m(ebpmf_ctx *ctx, const double *M) {
+    if (!ctx || !M) return fail(ctx, EBPMF_ERR_ARG, "set_m: bad arguments");
+    if (!ctx->have_y) return fail(ctx, EBPMF_ERR_STATE, "set_m: Y not set");
+    CHECK(ensure_common(ctx));
+    const size_t bytes = sizeof(double) * (size_t)ctx->n * (size_t)ctx->p;
+    CHECK(reserve(ctx, ctx->Mcur, bytes));
+    CHECK(reserve(ctx, ctx->Malt, bytes));
+    CU(cudaMemcpyAsync(ctx->Mcur.ptr, M, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->have_m = true; ctx->can_rewind = false;
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_set_factors(ebpmf_ctx *ctx, int64_t K, const double *EL, const double *EF) {
+    if (!ctx || !EL || !EF || K < 1) return fail(ctx, EBPMF_ERR_ARG, "set_factors: bad arguments");
+    if (!ctx->have_y) return fail(ctx, EBPMF_ERR_STATE, "set_factors: Y not set");
+    const int ktp = ktp_for((int)K);
+    if (ktp < 0) return fail(ctx, EBPMF_ERR_ARG, "K = %lld factor columns not supported (max 32)", (long long)K);
+    CHECK(ensure_common(ctx));
+    const long long n = ctx->n, p = ctx->p;
+    CHECK(reserve(ctx, ctx->EL, sizeof(double) * (size_t)n * (size_t)K));
+    CHECK(reserve(ctx, ctx->EF, sizeof(double) * (size_t)p * (size_t)K));
+    CHECK(reserve(ctx, ctx->EFt, sizeof(double) * (size_t)p * (size_t)ktp));
+    CU(cudaMemcpyAsync(ctx->EL.ptr, EL, sizeof(double) * (size_t)n * (size_t)K, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->EF.ptr, EF, sizeof(double) * (size_t)p * (size_t)K, cudaMemcpyHostToDevice, ctx->stream));
+    transpose_ef_kernel<<<(unsigned)((p * ktp + 255) / 256), 256, 0, ctx->stream>>>(as<double>(ctx->EF), p, (int)K, ktp,
+                                                                                   as<double>(ctx->EFt));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->K = (int)K; ctx->KTP = ktp; ctx->have_f = true;
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_set_sigma2(ebpmf_ctx *ctx, int var_type, const double *sigma2) {
+    if (!ctx || !sigma2) return fail(ctx, EBPMF_ERR_ARG, "set_sigma2: bad arguments");
+    if (var_type < 0 || var_type > 2) return fail(ctx, EBPMF_ERR_VAR_TYPE, "Non-supported var type");
+    if (!ctx->have_y) return fail(ctx, EBPMF_ERR_STATE, "set_sigma2: Y not set");
+    CHECK(ensure_common(ctx));
+    const size_t len = var_type == EBPMF_VAR_BY_COL ? (size_t)ctx->p : var_type == EBPMF_VAR_BY_ROW ? (size_t)ctx->n : 1;
+    CHECK(reserve(ctx, ctx->sigma2, sizeof(double) * std::max((size_t)ctx->p, (size_t)ctx->n)));
+    CU(cudaMemcpyAsync(ctx->sigma2.ptr, sigma2, sizeof(double) * len, cudaMemcpyHostToDevice, ctx->stream));
+    if (var_type == EBPMF_VAR_BY_ROW) {
+        const long long nJG = (ctx->p + kE - 1) / kE;
+        CHECK(reserve(ctx, ctx->rowpart, sizeof(double) * (size_t)nJG * (size_t)ctx->n));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->var_type = var_type; ctx->have_s2 = true;
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_vga_step(ebpmf_ctx *ctx, int maxiter, double tol, int want_v, ebpmf_solve_info *info) {
+    if (!ctx) return fail(ctx, EBPMF_ERR_ARG, "vga_step: ctx is NULL");
+    if (maxiter < 1 || maxiter > 65535) return fail(ctx, EBPMF_ERR_ARG, "vga_step: maxiter must be in [1, 65535]");
+    if (!ctx->have_y || !ctx->have_m || !ctx->have_f || !ctx->have_s2)
+        return fail(ctx, EBPMF_ERR_STATE, "vga_step: Y, M, factors and sigma2 must be set first");
+    CHECK(ensure_common(ctx));
+    if (want_v) CHECK(reserve(ctx, ctx->V, sizeof(double) * (size_t)ctx->n * (size_t)ctx->p));
+    const FusedArgs a = fused_args(ctx, maxiter, tol, want_v != 0);
+    ctx->have_v = false; ctx->have_vsum = false;
+    int rc = run_global_stop(
+        ctx, maxiter, [&] { return launch_fused<FORMULA_A1, MODE_FIRST>(ctx, a); },
+        [&] { return launch_fused<FORMULA_A1, MODE_TOPUP>(ctx, a); }, [&] { return run_reductions(ctx); }, info);
+    if (rc != EBPMF_OK) return rc;
+    CU(cudaMemcpyAsync(ctx->h_small, ctx->red.ptr, sizeof(double) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (info) { info->sym = ctx->h_small[0]; info->ssexp = ctx->h_small[1]; info->slogv = ctx->h_small[2]; }
+    std::swap(ctx->Mcur, ctx->Malt);      // the resident M is now res$M
+    ctx->have_v = want_v != 0; ctx->have_vsum = true; ctx->can_rewind = true;
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_rewind_m(ebpmf_ctx *ctx) {
+    if (!ctx) return fail(ctx, EBPMF_ERR_ARG, "rewind_m: ctx is NULL");
+    if (!ctx->can_rewind) return fail(ctx, EBPMF_ERR_STATE, "rewind_m: no step to undo");
+    std::swap(ctx->Mcur, ctx->Malt);
+    ctx->can_rewind = false;
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_get_m(ebpmf_ctx *ctx, double *M) {
+    if (!ctx || !M) return fail(ctx, EBPMF_ERR_ARG, "get_m: bad arguments");
+    if (!ctx->have_m) return fail(ctx, EBPMF_ERR_STATE, "get_m: M not set");
+    CHECK(ensure_common(ctx));
+    CU(cudaMemcpyAsync(M, ctx->Mcur.ptr, sizeof(double) * (size_t)ctx->n * (size_t)ctx->p, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_get_v(ebpmf_ctx *ctx, double *V) {
+    if (!ctx || !V) return fail(ctx, EBPMF_ERR_ARG, "get_v: bad arguments");
+    if (!ctx->have_v) return fail(ctx, EBPMF_ERR_STATE, "get_v: the last step did not materialise V (want_v = 0)");
+    CHECK(ensure_common(ctx));
+    CU(cudaMemcpyAsync(V, ctx->V.ptr, sizeof(double) * (size_t)ctx->n * (size_t)ctx->p, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_get_v_sum(ebpmf_ctx *ctx, double *v_sum) {
+    if (!ctx || !v_sum) return fail(ctx, EBPMF_ERR_ARG, "get_v_sum: bad arguments");
+    if (!ctx->have_vsum) return fail(ctx, EBPMF_ERR_STATE, "get_v_sum: no VGA step has run");
+    CHECK(ensure_common(ctx));
+    const double *red = as<double>(ctx->red);
+    if (ctx->var_type == EBPMF_VAR_CONSTANT) {
+        CU(cudaMemcpyAsync(v_sum, red + 3, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        const size_t len = ctx->var_type == EBPMF_VAR_BY_COL ? (size_t)ctx->p : (size_t)ctx->n;
+        CU(cudaMemcpyAsync(v_sum, red + 4, sizeof(double) * len, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_update_sigma2(ebpmf_ctx *ctx, const double *R2, double a0, double b0, double cap_var_mean_ratio,
+                            int64_t n_total, int64_t p_total, double *sigma2_out) {
+    if (!ctx || !R2 || !sigma2_out) return fail(ctx, EBPMF_ERR_ARG, "update_sigma2: bad arguments");
+    if (!ctx->have_vsum || !ctx->have_s2) return fail(ctx, EBPMF_ERR_STATE, "update_sigma2: no VGA step has run");
+    CHECK(ensure_common(ctx));
+    const int vt = ctx->var_type;
+    const long long len = vt == EBPMF_VAR_BY_COL ? ctx->p : vt == EBPMF_VAR_BY_ROW ? ctx->n : 1;
+    const double half_m = vt == EBPMF_VAR_BY_COL ? (double)n_total / 2
+                        : vt == EBPMF_VAR_BY_ROW ? (double)p_total / 2
+                                                 : (double)n_total * (double)p_total / 2;       // :417,:428,:438
+    double *dR2 = as<double>(ctx->misc);
+    double *fitmax = dR2 + std::max(ctx->n, ctx->p);
+    CU(cudaMemcpyAsync(dR2, R2, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
+    if (cap_var_mean_ratio > 0) {
+        if (!ctx->have_f) return fail(ctx, EBPMF_ERR_STATE, "update_sigma2: cap gate needs the factors");
+        if (vt == EBPMF_VAR_BY_ROW) {
+            fitted_rowmax_kernel<<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(
+                as<double>(ctx->EL), as<double>(ctx->EF), ctx->n, ctx->p, ctx->K, fitmax);
+            CU(cudaGetLastError());
+        } else {
+            double *colmax = (vt == EBPMF_VAR_BY_COL) ? fitmax : fitmax + 1;
+            fitted_colmax_kernel<<<(unsigned)ctx->p, 256, 0, ctx->stream>>>(as<double>(ctx->EL), as<double>(ctx->EF),
+                                                                           ctx->n, ctx->p, ctx->K, colmax);
+            CU(cudaGetLastError());
+            if (vt == EBPMF_VAR_CONSTANT) {
+                max_reduce_kernel<<<1, 1024, 0, ctx->stream>>>(colmax, ctx->p, fitmax);
+                CU(cudaGetLastError());
+            }
+            if (ctx->comm) {   // rows are sharded: the column / global max spans all ranks
+                NC(g_nccl.AllReduce(fitmax, fitmax, (size_t)len, ncclFloat64, ncclMax, ctx->comm, ctx->stream));
+            }
+        }
+    }
+    const double *vsum = as<double>(ctx->red) + (vt == EBPMF_VAR_CONSTANT ? 3 : 4);
+    update_sigma2_kernel<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(
+        vsum, dR2, len, half_m, a0, b0, cap_var_mean_ratio, fitmax, as<double>(ctx->sigma2));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(sigma2_out, ctx->sigma2.ptr, sizeof(double) * (size_t)len, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return EBPMF_OK;
+}
+
+int ebpmf_update_sigma2(ebpmf_ctx *ctx, int var_type, int64_t n, int64_t p, const double *sigma2, const double *v_sum,
+                        const double *R2, double a0, double b0, double cap_var_mean_ratio, int64_t K,
+                        const double *EL, const double *EF, double *sigma2_out) {
+    if (!ctx || !sigma2 || !v_sum || !R2 || !sigma2_out || n < 1 || p < 1)
+        return fail(ctx, EBPMF_ERR_ARG, "update_sigma2: bad arguments");
+    if (var_type < 0 || var_type > 2) return fail(ctx, EBPMF_ERR_VAR_TYPE, "Non-supported var type");
+    if (cap_var_mean_ratio > 0 && (!EL || !EF || K < 1))
+        return fail(ctx, EBPMF_ERR_ARG, "update_sigma2: the cap gate needs EL and EF");
+    CHECK(ensure_common(ctx));
+    const long long len = var_type == EBPMF_VAR_BY_COL ? p : var_type == EBPMF_VAR_BY_ROW ? n : 1;
+    const double half_m = var_type == EBPMF_VAR_BY_COL ? (double)n / 2
+                        : var_type == EBPMF_VAR_BY_ROW ? (double)p / 2 : (double)n * (double)p / 2;
+    const size_t big = (size_t)std::max(n, p);
+    CHECK(reserve(ctx, ctx->scratch[0], sizeof(double) * (4 * big + 8)));
+    double *dS = as<double>(ctx->scratch[0]), *dV = dS + big, *dR = dV + big, *fitmax = dR + big;
+    CU(cudaMemcpyAsync(dS, sigma2, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dV, v_sum, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dR, R2, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
+    if (cap_var_mean_ratio > 0) {
+        CHECK(reserve(ctx, ctx->scratch[1], sizeof(double) * ((size_t)n + (size_t)p) * (size_t)K));
+        double *dEL = as<double>(ctx->scratch[1]), *dEF = dEL + (size_t)n * K;
+        CU(cudaMemcpyAsync(dEL, EL, sizeof(double) * (size_t)n * K, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(dEF, EF, sizeof(double) * (size_t)p * K, cudaMemcpyHostToDevice, ctx->stream));
+        if (var_type == EBPMF_VAR_BY_ROW) {
+            fitted_rowmax_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dEL, dEF, n, p, (int)K, fitmax);
+        } else {
+            double *colmax = (var_type == EBPMF_VAR_BY_COL) ? fitmax : fitmax + 1;
+            fitted_colmax_kernel<<<(unsigned)p, 256, 0, ctx->stream>>>(dEL, dEF, n, p, (int)K, colmax);
+            if (var_type == EBPMF_VAR_CONSTANT) max_reduce_kernel<<<1, 1024, 0, ctx->stream>>>(colmax, p, fitmax);
+        }
+        CU(cudaGetLastError());
+    }
+    update_sigma2_kernel<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(dV, dR, len, half_m, a0, b0,
+                                                                                 cap_var_mean_ratio, fitmax, dS);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(sigma2_out, dS, sizeof(double) * (size_t)len, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return EBPMF_OK;
+}
+
+int ebpmf_calc_obj(ebpmf_ctx *ctx, int64_t n, int64_t p, double sym, double ssexp, double slogv, int64_t len,
+                   const double *sv, const double *sigma2, const double *R2, double KL_LF, double const_, double ss,
+                   double a0, double b0, double *obj) {
+    if (!ctx || !sv || !sigma2 || !R2 || !obj || len < 1) return fail(ctx, EBPMF_ERR_ARG, "calc_obj: bad arguments");
+    CHECK(ensure_common(ctx));
+    CHECK(reserve(ctx, ctx->scratch[0], sizeof(double) * (3 * (size_t)len + 8)));
+    double *d = as<double>(ctx->scratch[0]);
+    CU(cudaMemcpyAsync(d, sv, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d + len, sigma2, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d + 2 * len, R2, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
+    obj_terms_kernel<<<1, 1024, 0, ctx->stream>>>(d, d + len, d + 2 * len, len, ss, a0, b0, d + 3 * len);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ctx->h_small, d + 3 * len, sizeof(double) * 5, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const double *t = ctx->h_small;
+    // R/ebpmf_log.R:407, left to right
+    *obj = sym - ssexp + slogv + 0.5 * (double)n * (double)p - t[0] - t[1] - t[2] + const_ + KL_LF - t[3] - t[4];
+    return EBPMF_OK;
+}
+
+int ebpmf_vga_step_host(ebpmf_ctx *ctx, const double *M_in, int64_t K, const double *EL, const double *EF,
+                        int var_type, const double *sigma2, int maxiter, double tol, double *M_out, double *V_out,
+                        double *v_sum, ebpmf_solve_info *info) {
+    if (!ctx || !M_in || !M_out) return fail(ctx, EBPMF_ERR_ARG, "vga_step_host: bad arguments");
+    CHECK(ebpmf_ctx_set_factors(ctx, K, EL, EF));
+    CHECK(ebpmf_ctx_set_sigma2(ctx, var_type, sigma2));
+    CHECK(ebpmf_ctx_set_m(ctx, M_in));
+    CHECK(ebpmf_ctx_vga_step(ctx, maxiter, tol, V_out != nullptr, info));
+    CHECK(ebpmf_ctx_get_m(ctx, M_out));
+    if (V_out) CHECK(ebpmf_ctx_get_v(ctx, V_out));
+    if (v_sum) CHECK(ebpmf_ctx_get_v_sum(ctx, v_sum));
+    return EBPMF_OK;
+}
+
+// ---- drop-in dense signatures ------------------------------------------------------------
+
+int ebpmf_vga_newton(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *M, const double *X,
+                     const int32_t *X_colptr, const int32_t *X_rowidx, const double *X_x, const double *S, int S_kind,
+                     const double *Beta, int Beta_kind, const double *Sigma2, int Sigma2_kind, int maxiter, double tol,
+                     double *M_out, double *V_out, ebpmf_solve_info *info) {
+    if (!ctx || !M || !S || !Beta || !Sigma2 || !M_out || n < 1 || p < 1)
+        return fail(ctx, EBPMF_ERR_ARG, "vga_newton: bad arguments");
+    if (!X && !(X_colptr && (X_colptr[p] == 0 || (X_rowidx && X_x))))
+        return fail(ctx, EBPMF_ERR_ARG, "vga_newton: X must be dense or dgCMatrix slots");
+    if (maxiter < 1 || maxiter > 65535) return fail(ctx, EBPMF_ERR_ARG, "vga_newton: maxiter must be in [1, 65535]");
+    CHECK(ensure_common(ctx));
+    DenseArgs a;
+    memset(&a, 0, sizeof a);
+    if (stride_for(S_kind, n, &a.S_rs, &a.S_cs) || stride_for(Beta_kind, n, &a.B_rs, &a.B_cs) ||
+        stride_for(Sigma2_kind, n, &a.V_rs, &a.V_cs))
+        return fail(ctx, EBPMF_ERR_ARG, "vga_newton: bad operand kind");
+    const size_t NP = (size_t)n * (size_t)p, bytes = sizeof(double) * NP;
+    // scratch: 0 M_in, 1 M_out, 2 X, 3 V, 4 Beta|Sigma2|S packed
+    CHECK(reserve(ctx, ctx->scratch[0], bytes));
+    CHECK(reserve(ctx, ctx->scratch[1], bytes));
+    CHECK(reserve(ctx, ctx->scratch[2], bytes));
+    if (V_out) CHECK(reserve(ctx, ctx->scratch[3], bytes));
+    const size_t lS = operand_len(S_kind, n, p), lB = operand_len(Beta_kind, n, p), lV = operand_len(Sigma2_kind, n, p);
+    CHECK(reserve(ctx, ctx->scratch[4], sizeof(double) * (lS + lB + lV)));
+    double *dS = as<double>(ctx->scratch[4]), *dB = dS + lS, *dV = dB + lB;
+    CU(cudaMemcpyAsync(ctx->scratch[0].ptr, M, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dS, S, sizeof(double) * lS, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dB, Beta, sizeof(double) * lB, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dV, Sigma2, sizeof(double) * lV, cudaMemcpyHostToDevice, ctx->stream));
+    if (X) {
+        CU(cudaMemcpyAsync(ctx->scratch[2].ptr, X, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        const long long nnz = X_colptr[p];
+        CHECK(reserve(ctx, ctx->scratch[5], (sizeof(int) + sizeof(double)) * (size_t)std::max(1LL, nnz) + sizeof(int) * (size_t)(p + 1) + 16));
+        double *dx = as<double>(ctx->scratch[5]);
+        int *di = reinterpret_cast<int *>(dx + std::max(1LL, nnz));
+        int *dp = di + std::max(1LL, nnz);
+        CU(cudaMemcpyAsync(dp, X_colptr, sizeof(int) * (size_t)(p + 1), cudaMemcpyHostToDevice, ctx->stream));
+        if (nnz > 0) {
+            CU(cudaMemcpyAsync(di, X_rowidx, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(dx, X_x, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        CU(cudaMemsetAsync(ctx->scratch[2].ptr, 0, bytes, ctx->stream));
+        scatter_csc_kernel<<<(unsigned)((p * 32 + 255) / 256), 256, 0, ctx->stream>>>(dp, di, dx, n, p,
+                                                                                      as<double>(ctx->scratch[2]));
+        CU(cudaGetLastError());
+    }
+    const long long nRB = (n + kRowsPerCta - 1) / kRowsPerCta, nRW = (n + 31) / 32, nJG = (p + kE - 1) / kE;
+    CHECK(reserve(ctx, ctx->kunit, sizeof(unsigned short) * (size_t)nJG * (size_t)nRW));
+    CHECK(reserve(ctx, ctx->status, sizeof(Status)));
+    a.n = n; a.p = p;
+    a.M_in = as<double>(ctx->scratch[0]); a.M_out = as<double>(ctx->scratch[1]);
+    a.V_out = V_out ? as<double>(ctx->scratch[3]) : nullptr;
+    a.X = as<double>(ctx->scratch[2]);
+    a.S = dS; a.Beta = dB; a.Sigma2 = dV;
+    a.kunit = as<unsigned short>(ctx->kunit); a.nRW = nRW;
+    a.status = as<Status>(ctx->status);
+    a.maxiter = maxiter; a.tol = tol;
+    a.cols_per_cta = cols_per_cta_for(p, nRB);
+    dim3 grid((unsigned)((p + a.cols_per_cta - 1) / a.cols_per_cta), (unsigned)nRB);
+    int rc = run_global_stop(
+        ctx, maxiter,
+        [&] { vga_dense_kernel<kE, MODE_FIRST><<<grid, kThreads, 0, ctx->stream>>>(a); CU(cudaGetLastError()); return EBPMF_OK; },
+        [&] { vga_dense_kernel<kE, MODE_TOPUP><<<grid, kThreads, 0, ctx->stream>>>(a); CU(cudaGetLastError()); return EBPMF_OK; },
+        [&] { return EBPMF_OK; }, info);
+    if (rc != EBPMF_OK) return rc;
+    if (info) { info->sym = info->ssexp = info->slogv = 0.0; }
+    CU(cudaMemcpyAsync(M_out, ctx->scratch[1].ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (V_out) CU(cudaMemcpyAsync(V_out, ctx->scratch[3].ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return EBPMF_OK;
+}
+
+int ebpmf_vga_fixed_iter(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *M, const double *V, const double *Y,
+                         const double *S, int S_kind, const double *Beta, int Beta_kind, const double *Sigma2,
+                         int Sigma2_kind, int maxiter, double *M_out, double *V_out) {
+    if (!ctx || !M || !Y || !S || !Beta || !Sigma2 || !M_out || !V_out || n < 1 || p < 1)
+        return fail(ctx, EBPMF_ERR_ARG, "vga_fixed_iter: bad arguments");
+    if (maxiter < 1) return fail(ctx, EBPMF_ERR_ARG, "vga_fixed_iter: maxiter must be >= 1");
+    CHECK(ensure_common(ctx));
+    FixedArgs a;
+    memset(&a, 0, sizeof a);
+    if (stride_for(S_kind, n, &a.S_rs, &a.S_cs) || stride_for(Beta_kind, n, &a.B_rs, &a.B_cs) ||
+        stride_for(Sigma2_kind, n, &a.V_rs, &a.V_cs))
+        return fail(ctx, EBPMF_ERR_ARG, "vga_fixed_iter: bad operand kind");
+    const size_t NP = (size_t)n * (size_t)p, bytes = sizeof(double) * NP;
+    for (int b = 0; b < 4; ++b) CHECK(reserve(ctx, ctx->scratch[b], bytes));
+    if (V) CHECK(reserve(ctx, ctx->scratch[5], bytes));
+    const size_t lS = operand_len(S_kind, n, p), lB = operand_len(Beta_kind, n, p), lV = operand_len(Sigma2_kind, n, p);
+    CHECK(reserve(ctx, ctx->scratch[4], sizeof(double) * (lS + lB + lV)));
+    double *dS = as<double>(ctx->scratch[4]), *dB = dS + lS, *dV = dB + lB;
+    CU(cudaMemcpyAsync(ctx->scratch[0].ptr, M, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->scratch[2].ptr, Y, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (V) CU(cudaMemcpyAsync(ctx->scratch[5].ptr, V, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dS, S, sizeof(double) * lS, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dB, Beta, sizeof(double) * lB, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dV, Sigma2, sizeof(double) * lV, cudaMemcpyHostToDevice, ctx->stream));
+    a.n = n; a.p = p;
+    a.M_in = as<double>(ctx->scratch[0]); a.V_in = V ? as<double>(ctx->scratch[5]) : nullptr;
+    a.Y = as<double>(ctx->scratch[2]);
+    a.S = dS; a.Beta = dB; a.Sigma2 = dV;
+    a.M_out = as<double>(ctx->scratch[1]); a.V_out = as<double>(ctx->scratch[3]);
+    a.maxiter = maxiter;
+    const long long nRB = (n + kRowsPerCta - 1) / kRowsPerCta;
+    dim3 grid((unsigned)std::min<long long>(p, 4096), (unsigned)nRB);
+    vga_fixed_iter_kernel<<<grid, kThreads, 0, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(M_out, ctx->scratch[1].ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(V_out, ctx->scratch[3].ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return EBPMF_OK;
+}
+
+int ebpmf_vga_low_memory(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, const double *M, const double *Y,
+                         const int32_t *Y_colptr, const int32_t *Y_rowidx, const double *Y_x, const double *l0,
+                         const double *f0, const double *EL, const double *EF, const double *sigma2, int var_type,
+                         int maxiter, double tol, double *M_out, ebpmf_solve_info *info) {
+    if (!ctx || !M || !l0 || !f0 || !EL || !EF || !sigma2 || !M_out || n < 1 || p < 1 || K < 1)
+        return fail(ctx, EBPMF_ERR_ARG, "vga_low_memory: bad arguments");
+    if (maxiter < 1 || maxiter > 65535) return fail(ctx, EBPMF_ERR_ARG, "vga_low_memory: maxiter must be in [1, 65535]");
+    // R falls through both `if(var_type==...)` blocks for an unknown var_type and returns the
+    // clamped M (:78,:108); the clamp needs the kernels too, so run zero iterations of by_col
+    // semantics is NOT the same thing -- report the unsupported type instead of guessing.
+    if (var_type < 0 || var_type > 2) return fail(ctx, EBPMF_ERR_VAR_TYPE, "Non-supported var type");
+    // this entry point owns the context's resident state for the duration of the call
+    if (Y) CHECK(ebpmf_ctx_set_y_dense(ctx, n, p, Y));
+    else CHECK(ebpmf_ctx_set_y_csc(ctx, n, p, Y_colptr, Y_rowidx, Y_x));
+    CHECK(ebpmf_ctx_set_factors(ctx, K, EL, EF));
+    CHECK(ebpmf_ctx_set_sigma2(ctx, var_type, sigma2));
+    CHECK(ebpmf_ctx_set_m(ctx, M));
+    CHECK(reserve(ctx, ctx->l0, sizeof(double) * (size_t)n));
+    CHECK(reserve(ctx, ctx->f0, sizeof(double) * (size_t)p));
+    CU(cudaMemcpyAsync(ctx->l0.ptr, l0, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->f0.ptr, f0, sizeof(double) * (size_t)p, cudaMemcpyHostToDevice, ctx->stream));
+    const FusedArgs a = fused_args(ctx, maxiter, tol, false);
+    int rc = run_global_stop(
+        ctx, maxiter, [&] { return launch_fused<FORMULA_A10, MODE_FIRST>(ctx, a); },
+        [&] { return launch_fused<FORMULA_A10, MODE_TOPUP>(ctx, a); }, [&] { return EBPMF_OK; }, info);
+    if (rc != EBPMF_OK) return rc;
+    if (info) { info->sym = info->ssexp = info->slogv = 0.0; }
+    std::swap(ctx->Mcur, ctx->Malt);
+    ctx->have_vsum = false; ctx->have_v = false;
+    return ebpmf_ctx_get_m(ctx, M_out);
+}
+
+int ebpmf_ctx_get_shape(ebpmf_ctx *ctx, int64_t *n, int64_t *p, int64_t *K, int64_t *nnz) {
+    if (!ctx) return fail(ctx, EBPMF_ERR_ARG, "get_shape: ctx is NULL");
+    if (!ctx->have_y) return fail(ctx, EBPMF_ERR_STATE, "get_shape: Y not set");
+    if (n) *n = ctx->n;
+    if (p) *p = ctx->p;
+    if (K) *K = ctx->have_f ? ctx->K : 0;
+    if (nnz) *nnz = ctx->nnz;
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_get_y_csc(ebpmf_ctx *ctx, int32_t *colptr, int32_t *rowidx, double *x) {
+    if (!ctx || !colptr) return fail(ctx, EBPMF_ERR_ARG, "get_y_csc: bad arguments");
+    if (!ctx->have_y) return fail(ctx, EBPMF_ERR_STATE, "get_y_csc: Y not set");
+    CHECK(ensure_common(ctx));
+    CU(cudaMemcpyAsync(colptr, ctx->colptr.ptr, sizeof(int) * (size_t)(ctx->p + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->nnz > 0 && rowidx && x) {
+        CU(cudaMemcpyAsync(rowidx, ctx->rowidx.ptr, sizeof(int) * (size_t)ctx->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(x, ctx->yx.ptr, sizeof(double) * (size_t)ctx->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_get_factors(ebpmf_ctx *ctx, double *EL, double *EF) {
+    if (!ctx || !EL || !EF) return fail(ctx, EBPMF_ERR_ARG, "get_factors: bad arguments");
+    if (!ctx->have_f) return fail(ctx, EBPMF_ERR_STATE, "get_factors: factors not set");
+    CHECK(ensure_common(ctx));
+    CU(cudaMemcpyAsync(EL, ctx->EL.ptr, sizeof(double) * (size_t)ctx->n * (size_t)ctx->K, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(EF, ctx->EF.ptr, sizeof(double) * (size_t)ctx->p * (size_t)ctx->K, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_get_sigma2(ebpmf_ctx *ctx, double *sigma2) {
+    if (!ctx || !sigma2) return fail(ctx, EBPMF_ERR_ARG, "get_sigma2: bad arguments");
+    if (!ctx->have_s2) return fail(ctx, EBPMF_ERR_STATE, "get_sigma2: sigma2 not set");
+    CHECK(ensure_common(ctx));
+    const size_t len = ctx->var_type == EBPMF_VAR_BY_COL ? (size_t)ctx->p : ctx->var_type == EBPMF_VAR_BY_ROW ? (size_t)ctx->n : 1;
+    CU(cudaMemcpyAsync(sigma2, ctx->sigma2.ptr, sizeof(double) * len, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_get_rows(ebpmf_ctx *ctx, int which, int64_t row0, int64_t nrows, double *out) {
+    if (!ctx || !out || row0 < 0 || nrows < 1) return fail(ctx, EBPMF_ERR_ARG, "get_rows: bad arguments");
+    if (!ctx->have_m || row0 + nrows > ctx->n) return fail(ctx, EBPMF_ERR_STATE, "get_rows: M not set or rows out of range");
+    if (which != 0 && !ctx->have_v) return fail(ctx, EBPMF_ERR_STATE, "get_rows: V was not materialised");
+    CHECK(ensure_common(ctx));
+    const double *src = (which ? as<double>(ctx->V) : as<double>(ctx->Mcur)) + row0;
+    CU(cudaMemcpy2DAsync(out, sizeof(double) * (size_t)nrows, src, sizeof(double) * (size_t)ctx->n,
+                         sizeof(double) * (size_t)nrows, (size_t)ctx->p, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_sim_data_log(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, int64_t row0, uint64_t seed,
+                           double log_offset, double bg_lo, double bg_hi, double pi0, double noise, int warm_start,
+                           int64_t *nnz_out) {
+    if (!ctx || n < 1 || p < 1 || K < 1 || row0 < 0 || !(bg_lo > 0) || !(bg_hi >= bg_lo))
+        return fail(ctx, EBPMF_ERR_ARG, "sim_data_log: bad arguments");
+    const int KT = (int)K + 2;
+    const int ktp = ktp_for(KT);
+    if (ktp < 0) return fail(ctx, EBPMF_ERR_ARG, "sim_data_log: K + 2 = %d factor columns not supported (max 32)", KT);
+    CHECK(ensure_common(ctx));
+    const size_t NP = (size_t)n * (size_t)p;
+    CHECK(reserve(ctx, ctx->Mcur, sizeof(double) * NP));
+    CHECK(reserve(ctx, ctx->Malt, sizeof(double) * NP));
+    CHECK(reserve(ctx, ctx->EL, sizeof(double) * (size_t)n * KT));
+    CHECK(reserve(ctx, ctx->EF, sizeof(double) * (size_t)p * KT));
+    CHECK(reserve(ctx, ctx->EFt, sizeof(double) * (size_t)p * ktp));
+    CHECK(reserve(ctx, ctx->sigma2, sizeof(double) * (size_t)std::max(n, p)));
+    CHECK(reserve(ctx, ctx->scratch[0], sizeof(double) * ((size_t)n * K + (size_t)p * K + (size_t)n + (size_t)p)));
+    CHECK(reserve(ctx, ctx->colptr, sizeof(int) * (size_t)(p + 1)));
+    CHECK(reserve(ctx, ctx->misc, sizeof(double) * (size_t)(3 * std::max(n, p) + 4096)));
+    sim::GenArgs g;
+    g.n = n; g.p = p; g.row0 = row0; g.K = (int)K; g.seed = seed;
+    g.log_offset = log_offset; g.bg_lo = bg_lo; g.bg_hi = bg_hi; g.pi0 = pi0; g.noise = noise;
+    g.Lt = as<double>(ctx->scratch[0]); g.Ft = g.Lt + (size_t)n * K; g.logl0 = g.Ft + (size_t)p * K; g.logf0 = g.logl0 + n;
+    g.EL = as<double>(ctx->EL); g.EF = as<double>(ctx->EF); g.sigma2 = as<double>(ctx->sigma2);
+    sim::gen_factors_kernel<<<(unsigned)((n + p + 255) / 256), 256, 0, ctx->stream>>>(g);
+    CU(cudaGetLastError());
+    int *counts = as<int>(ctx->misc);
+    const unsigned blocks = (unsigned)((p * 32 + 255) / 256);
+    sim::gen_count_kernel<<<blocks, 256, 0, ctx->stream>>>(g, warm_start, as<double>(ctx->Mcur), counts);
+    CU(cudaGetLastError());
+    scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>(counts, p, as<int>(ctx->colptr));
+    CU(cudaGetLastError());
+    int nnz = 0;
+    CU(cudaMemcpyAsync(&nnz, as<int>(ctx->colptr) + p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (nnz < 0) return fail(ctx, EBPMF_ERR_ARG, "sim_data_log: more than 2^31-1 non-zeros in one shard");
+    CHECK(reserve(ctx, ctx->rowidx, sizeof(int) * (size_t)std::max(1, nnz)));
+    CHECK(reserve(ctx, ctx->yx, sizeof(double) * (size_t)std::max(1, nnz)));
+    sim::gen_fill_kernel<<<blocks, 256, 0, ctx->stream>>>(g, as<int>(ctx->colptr), as<int>(ctx->rowidx), as<double>(ctx->yx));
+    CU(cudaGetLastError());
+    ctx->nnz = nnz;
+    CHECK(finish_set_y(ctx, n, p));
+    transpose_ef_kernel<<<(unsigned)((p * ktp + 255) / 256), 256, 0, ctx->stream>>>(as<double>(ctx->EF), p, KT, ktp,
+                                                                                   as<double>(ctx->EFt));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->K = KT; ctx->KTP = ktp; ctx->var_type = EBPMF_VAR_BY_COL;
+    ctx->have_m = ctx->have_f = ctx->have_s2 = true;
+    if (nnz_out) *nnz_out = nnz;
+    return EBPMF_OK;
+}
+
+int ebpmf_probe_fp64_tflops(ebpmf_ctx *ctx, double *tflops) {
+    if (!ctx || !tflops) return fail(ctx, EBPMF_ERR_ARG, "probe: bad arguments");
+    CHECK(ensure_common(ctx));
+    CHECK(reserve(ctx, ctx->misc, sizeof(double) * 4096));
+    const int iters = 20000, blocks = 148 * 8;
+    fp64_probe_kernel<<<blocks, 256, 0, ctx->stream>>>(as<double>(ctx->misc), 1000, 1.0);   // warm-up
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    fp64_probe_kernel<<<blocks, 256, 0, ctx->stream>>>(as<double>(ctx->misc), iters, 1.0);
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    const double flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    return EBPMF_OK;
+}
+
+}  // extern "C"

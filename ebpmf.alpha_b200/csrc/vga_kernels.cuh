@@ -1,0 +1,731 @@
+// Hand-written sm_100a kernels for the VGA Newton hot path of ebpmf_log.
+//
+// What they replace (paths relative to the reference root):
+//   a1  vga_pois_solver_mat_newton            R/vga_solver_mat.R:6-41
+//   a2  Beta = fitted(fit_flash) = EL EF^T    R/ebpmf_log.R:266,305      (rebuilt in registers)
+//   a3  adjust_var_shape                      R/ebpmf_log.R:475-486      (never materialised)
+//   a4  sym / ssexp / slogv                   R/ebpmf_log.R:316-318
+//   a5  v_sum = col/row/total sums of V       R/ebpmf_log.R:321-327
+//   a10 vga_pois_solver_mat_newton_low_memory R/vga_solver_mat.R:71-109
+//
+// Layout.  M is column-major n x p (R), so consecutive THREADS own consecutive ROWS: a CTA
+// of 256 threads owns a row block of 256 rows and walks a span of columns; every global
+// access to M/V is a 2 KB contiguous segment per column.  Each thread keeps its row of EL
+// (K_tot <= KTP doubles) in registers; the EF rows, sigma2 and the dense image of the sparse
+// Y tile (16 columns x 256 rows, scattered from the CSC arrays through a per-row-block
+// offset table) live in shared memory.  Beta_ij = sum_k EL_ik EF_jk is K_tot FMAs per entry:
+// an outer-product rebuild, not a tensor-core contraction.
+//
+// The GLOBAL stop rule.  R stops when max|f| < tol over ALL entries, so every entry receives
+// the same number u of Newton updates.  The kernels reproduce u exactly with
+// register-resident iterations and no per-iteration grid sync:
+//   unit      = one warp x E columns (32*E entries), iterates in lock step;
+//   pass 1    (MODE_FIRST) each unit iterates until ITS entries all satisfy |f_k| < tol at
+//             some k >= t0, where t0 is the largest such k any finished unit has published
+//             so far (never above u, because at k = u every unit is converged); it
+//             finalises speculatively (M_k, partial sums) and records k_unit; K* = max k_unit;
+//   pass 2    (MODE_TOPUP) units with k_unit < K* continue the SAME iteration sequence up to
+//             K* updates, test |f_K*| < tol and re-finalise.  If every unit passes, u = K*
+//             (it is the first k at which all entries are below tol).  Otherwise the host
+//             repeats pass 2 with K*+1 (rare: needs an entry to bounce back above tol).
+//   exhausted if a unit reaches maxiter updates, u = maxiter and V keeps the reciprocal of the
+//             LAST EVALUATED temp, i.e. it is one iteration stale exactly as in R (F6).
+// A NaN in f at any evaluated k <= u is what makes R's `if()` fail; it raises status.nan.
+#pragma once
+#include "vga_math.cuh"
+
+namespace ebpmf {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = 8;
+constexpr int kRowsPerCta = 256;
+constexpr int kTileCols = 16;
+constexpr double kSlogvConst = 0.9189385;   // literal of R/ebpmf_log.R:276,318
+
+enum { FORMULA_A1 = 0, FORMULA_A10 = 1 };
+enum { MODE_FIRST = 0, MODE_TOPUP = 1 };
+
+struct Status {           // device words shared by the passes of one solve
+    int kstar;            // max over units of k_unit (pass 1), target of pass 2
+    int nan;              // a NaN reached the stop test
+    int verify_fail;      // pass 2: some unit is not below tol at K*
+    int exhausted;        // some unit hit maxiter
+};
+
+struct FusedArgs {
+    long long n, p;                 // rows of this shard, columns
+    int K;                          // K_tot
+    int var_type;                   // 0 constant, 1 by_row, 2 by_col
+    const double *M_in;             // pass 1 source
+    double *M_out;                  // pass 1 destination, pass 2 in place
+    double *V_out;                  // nullable
+    const double *EL;               // n x K column-major
+    const double *EFt;              // p x KTP row-major, zero padded
+    const double *sigma2;
+    const double *l0, *f0;          // A10 only
+    const int *rowidx;              // CSC row indices (0-based within the shard)
+    const double *yx;               // CSC values
+    const int *rbptr;               // (nRB+1) x p: first nnz of column j with row >= rb*256
+    unsigned short *kunit;          // [p/E][nRW]
+    long long nRW;                  // ceil(n/32)
+    double *colpart;                // [nRW][p][4] : sum V, sum Y*M, sum exp(M+V/2), sum(log(V)/2+c)
+    double *rowpart;                // [ceil(p/E)][n] sum V (by_row only), else null
+    Status *status;
+    int maxiter;
+    double tol;
+    long long col0, col1;           // columns of this launch
+    int cols_per_cta;               // multiple of kTileCols
+};
+
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// One unit: E entries per lane, all 32 lanes in lock step.  On return k is the number of
+// updates the unit has received, r[] the reciprocal of the last evaluated temp, sexp[] the last
+// evaluated S*exp(.).  Returns a bit mask: 1 converged at k, 2 exhausted, 4 NaN.
+// ---------------------------------------------------------------------------------------
+template <int E, int FORMULA, int MODE>
+__device__ __forceinline__ int newton_unit(double (&m)[E], const double (&y)[E], const double (&beta)[E],
+                                           const double (&c0)[E], const double (&c1)[E], const double (&c2)[E],
+                                           const double (&sc)[E], const bool (&ok)[E],
+                                           int &k, int target, const volatile int *kstar_live,
+                                           int maxiter, double tol, const double *exptab,
+                                           double (&r)[E], double (&sexp)[E])
+{
+    int flags = 0;
+    for (;;) {
+        bool lane_conv = true, lane_nan = false;
+        double f[E], a[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const double temp = c0[e] - m[e];                                  // :22
+            r[e] = rcp_fast(temp);
+            a[e] = c2[e] * r[e];                                               // const2/temp
+            sexp[e] = sc[e] * exp_fast(m[e] + a[e], exptab);                   // :23
+            if (FORMULA == FORMULA_A1)
+                f[e] = fma(beta[e], c1[e], fma(-m[e], c1[e], y[e] - sexp[e])); // :25  x-sexp-M*const1+const3
+            else
+                f[e] = fma(beta[e] - m[e], c1[e], y[e] - sexp[e]);             // :84,:98
+            const bool cv = fabs(f[e]) < tol;                                  // :26 (strict <)
+            lane_conv = lane_conv && (cv || !ok[e]);
+            lane_nan = lane_nan || (ok[e] && (f[e] != f[e]));
+        }
+        if (__any_sync(0xffffffffu, lane_nan)) { flags |= 4; break; }
+        const bool conv = __all_sync(0xffffffffu, lane_conv);
+        bool stop;
+        if (MODE == MODE_FIRST) stop = conv && (k >= *kstar_live);
+        else stop = (k == target);
+        if (stop) { if (conv) flags |= 1; break; }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const double q = (FORMULA == FORMULA_A1) ? a[e] : 0.5 * r[e];     // const2/temp^2 | 0.5*temp^-2
+            const double g = fma(-sexp[e], fma(q, r[e], 1.0), -c1[e]);        // :31 | :90,:105
+            m[e] = fma(-f[e], rcp_fast(g), m[e]);
+        }
+        ++k;
+        if (k >= maxiter) { flags |= 2; break; }
+    }
+    return flags;
+}
+
+// ---------------------------------------------------------------------------------------
+// K1 / K4: fused VGA step on CSC Y with Beta rebuilt from the flash factors.
+// grid = (column spans, row blocks), block = 256 threads.
+// ---------------------------------------------------------------------------------------
+template <int KTP, int E, int FORMULA, int MODE>
+__global__ void __launch_bounds__(kThreads, 2) vga_fused_kernel(const FusedArgs a)
+{
+    static_assert(kTileCols % E == 0, "E must divide the tile width");
+    __shared__ double ys[kTileCols][kRowsPerCta];
+    __shared__ double efs[kTileCols][KTP];
+    __shared__ double s2s[kTileCols], c1s[kTileCols], c2s[kTileCols], f0s[kTileCols];
+    __shared__ double exptab[EBPMF_EXP_TABLE_SIZE];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long rb = blockIdx.y;
+    const long long r0 = rb * kRowsPerCta;
+    const long long i = r0 + tid;
+    const bool row_ok = i < a.n;
+    const long long rw = rb * kWarps + warp;
+    const bool warp_ok = rw < a.nRW;                 // false: every row of this warp is beyond n
+    const long long jc0 = a.col0 + (long long)blockIdx.x * a.cols_per_cta;
+    const long long jc1 = min(a.col1, jc0 + (long long)a.cols_per_cta);
+
+    exp_table_init(exptab, tid, kThreads);
+
+    double el[KTP];
+#pragma unroll
+    for (int k = 0; k < KTP; ++k) el[k] = (row_ok && k < a.K) ? __ldg(a.EL + i + a.n * k) : 0.0;
+
+    // row-constant pieces (by_row / constant sigma2, A10's l0)
+    double s2_row = 1.0, c1_row = 1.0, c2_row = 0.5, l0_i = 1.0;
+    if (a.var_type != 2) {
+        s2_row = (a.var_type == 1) ? (row_ok ? a.sigma2[i] : 1.0) : a.sigma2[0];
+        c1_row = 1.0 / s2_row;                                                 // :10
+        c2_row = s2_row / 2;                                                   // :11
+    }
+    if (FORMULA == FORMULA_A10) l0_i = row_ok ? a.l0[i] : 1.0;
+
+    const int target = (MODE == MODE_TOPUP) ? a.status->kstar : 0;
+    const volatile int *kstar_live = &a.status->kstar;
+    const double *Msrc = (MODE == MODE_FIRST) ? a.M_in : a.M_out;
+    int any_exhausted = 0;
+
+    for (long long j0 = jc0; j0 < jc1; j0 += kTileCols) {
+        // ---- does this tile need work?  (also the barrier that protects the smem tile) ----
+        bool need = (MODE == MODE_FIRST);
+        if (MODE == MODE_TOPUP && warp_ok) {
+#pragma unroll
+            for (int g = 0; g < kTileCols / E; ++g) {
+                const long long jb = j0 + g * E;
+                if (jb < jc1) need = need || (a.kunit[(jb / E) * a.nRW + rw] != target);
+            }
+        }
+        if (!__syncthreads_or(need)) continue;
+
+        // ---- stage the tile: zero Y image, EF rows, per-column constants --------------------
+#pragma unroll
+        for (int c = 0; c < kTileCols; ++c) ys[c][tid] = 0.0;
+        for (int idx = tid; idx < kTileCols * KTP; idx += kThreads) {
+            const int c = idx / KTP, k = idx - c * KTP;
+            const long long j = j0 + c;
+            efs[c][k] = (j < jc1) ? __ldg(a.EFt + j * KTP + k) : 0.0;
+        }
+        if (tid < kTileCols) {
+            const long long j = j0 + tid;
+            double s2 = 1.0;
+            if (a.var_type == 2 && j < jc1) s2 = a.sigma2[j];
+            s2s[tid] = s2;
+            c1s[tid] = 1.0 / s2;
+            c2s[tid] = s2 / 2;
+            f0s[tid] = (FORMULA == FORMULA_A10 && j < jc1) ? a.f0[j] : 1.0;
+        }
+        __syncthreads();
+        // scatter the CSC non-zeros of rows [r0, r0+256) of each tile column
+        for (int c = warp; c < kTileCols; c += kWarps) {
+            const long long j = j0 + c;
+            if (j < jc1) {
+                const int lo = a.rbptr[rb * a.p + j], hi = a.rbptr[(rb + 1) * a.p + j];
+                for (int q = lo + lane; q < hi; q += 32)
+                    ys[c][a.rowidx[q] - (int)r0] = __ldg(a.yx + q);
+            }
+        }
+        __syncthreads();
+
+        // ---- units -----------------------------------------------------------------------
+#pragma unroll 1
+        for (int g = 0; g < kTileCols / E; ++g) {
+            const long long jb = j0 + g * E;
+            if (jb >= jc1 || !warp_ok) break;
+            const long long jg = jb / E;
+            int k = 0;
+            if (MODE == MODE_TOPUP) {
+                k = a.kunit[jg * a.nRW + rw];
+                if (k == target) continue;
+            }
+            double m[E], y[E], beta[E], c0[E], c1[E], c2[E], sc[E], s2[E], r[E], sexp[E];
+            bool ok[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int c = g * E + e;
+                const long long j = jb + e;
+                ok[e] = row_ok && (j < jc1);
+                m[e] = ok[e] ? ld_stream(Msrc + i + a.n * j) : 0.0;
+                y[e] = ys[c][tid];
+                double b = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < KTP; ++kk) b = fma(el[kk], efs[c][kk], b);   // a2
+                beta[e] = b;
+                if (a.var_type == 2) { s2[e] = s2s[c]; c1[e] = c1s[c]; c2[e] = c2s[c]; }
+                else { s2[e] = s2_row; c1[e] = c1_row; c2[e] = c2_row; }
+                c0[e] = fma(s2[e], y[e], b) + 1.0;                                 // :9 | :81,:95
+                if (FORMULA == FORMULA_A1) sc[e] = 1.0;                            // S = 1 (R/ebpmf_log.R:304)
+                else sc[e] = l0_i * f0s[c];                                        // :83,:97
+                if (MODE == MODE_FIRST) {
+                    const double cap = (FORMULA == FORMULA_A1) ? (c0[e] - 1.0) : b;   // :16 | :78
+                    m[e] = (m[e] < cap) ? m[e] : cap;
+                }
+            }
+            const int flags = newton_unit<E, FORMULA, MODE>(m, y, beta, c0, c1, c2, sc, ok, k, target,
+                                                            kstar_live, a.maxiter, a.tol, exptab, r, sexp);
+            if (flags & 4) { if (lane == 0) a.status->nan = 1; }
+            if (flags & 2) any_exhausted = 1;
+            if (MODE == MODE_TOPUP && !(flags & 3) && !(flags & 4)) { if (lane == 0) a.status->verify_fail = 1; }
+
+            // ---- finalise the unit ---------------------------------------------------------
+            double rowv = 0.0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const long long j = jb + e;
+                if (ok[e]) st_stream(a.M_out + i + a.n * j, m[e]);
+                if (FORMULA == FORMULA_A1) {
+                    const double v = s2[e] * r[e];                                  // :36 Sigma2/temp (stale if exhausted)
+                    if (ok[e] && a.V_out) st_stream(a.V_out + i + a.n * j, v);
+                    double ex = sexp[e];                                            // == exp(M+V/2) when S == 1 and the loop broke
+                    if (flags & 2) ex = exp_fast(fma(0.5, v, m[e]), exptab);        // exhausted: M moved after temp
+                    double sv = ok[e] ? v : 0.0;
+                    double sy = ok[e] ? y[e] * m[e] : 0.0;                          // R/ebpmf_log.R:316
+                    double se = ok[e] ? ex : 0.0;                                   // :317
+                    double sl = ok[e] ? fma(0.5, log_fast(v), kSlogvConst) : 0.0;   // :318
+                    rowv += sv;
+                    sv = warp_sum(sv); sy = warp_sum(sy); se = warp_sum(se); sl = warp_sum(sl);
+                    if (lane == 0 && j < jc1) {
+                        double *dst = a.colpart + (rw * a.p + j) * 4;
+                        reinterpret_cast<double2 *>(dst)[0] = make_double2(sv, sy);
+                        reinterpret_cast<double2 *>(dst)[1] = make_double2(se, sl);
+                    }
+                }
+            }
+            if (FORMULA == FORMULA_A1 && a.rowpart && row_ok) a.rowpart[jg * a.n + i] = rowv;
+            if (lane == 0) {
+                a.kunit[jg * a.nRW + rw] = (unsigned short)k;
+                if (MODE == MODE_FIRST && k > *kstar_live) atomicMax(&a.status->kstar, k);
+            }
+        }
+    }
+    if (any_exhausted && lane == 0) a.status->exhausted = 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// K2: drop-in dense-operand solver  vga_pois_solver_mat_newton(M,X,S,Beta,Sigma2,...)
+// Operands recycle through (row stride, col stride).  Same two-pass global-stop scheme.
+// ---------------------------------------------------------------------------------------
+struct DenseArgs {
+    long long n, p;
+    const double *M_in; double *M_out; double *V_out;
+    const double *X;                       // dense n x p
+    const double *S; long long S_rs, S_cs;
+    const double *Beta; long long B_rs, B_cs;
+    const double *Sigma2; long long V_rs, V_cs;
+    unsigned short *kunit; long long nRW;
+    Status *status;
+    int maxiter; double tol;
+    int cols_per_cta;
+};
+
+template <int E, int MODE>
+__global__ void __launch_bounds__(kThreads, 2) vga_dense_kernel(const DenseArgs a)
+{
+    __shared__ double exptab[EBPMF_EXP_TABLE_SIZE];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long rb = blockIdx.y;
+    const long long i = rb * kRowsPerCta + tid;
+    const bool row_ok = i < a.n;
+    const long long rw = rb * kWarps + warp;
+    if (rw >= a.nRW) return;                         // no block-wide barrier below this point
+    const long long jc0 = (long long)blockIdx.x * a.cols_per_cta;
+    const long long jc1 = min(a.p, jc0 + (long long)a.cols_per_cta);
+    exp_table_init(exptab, tid, kThreads);
+    __syncthreads();
+    const int target = (MODE == MODE_TOPUP) ? a.status->kstar : 0;
+    const volatile int *kstar_live = &a.status->kstar;
+    const double *Msrc = (MODE == MODE_FIRST) ? a.M_in : a.M_out;
+    int any_exhausted = 0;
+    const long long ii = row_ok ? i : 0;
+
+#pragma unroll 1
+    for (long long jb = jc0; jb < jc1; jb += E) {
+        const long long jg = jb / E;
+        int k = 0;
+        if (MODE == MODE_TOPUP) {
+            k = a.kunit[jg * a.nRW + rw];
+            if (k == target) continue;
+        }
+        double m[E], y[E], beta[E], c0[E], c1[E], c2[E], sc[E], s2[E], r[E], sexp[E];
+        bool ok[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const long long j = jb + e;
+            ok[e] = row_ok && (j < jc1);
+            const long long jj = (j < jc1) ? j : jc0;
+            m[e] = ok[e] ? ld_stream(Msrc + i + a.n * j) : 0.0;
+            y[e] = ok[e] ? ld_stream(a.X + i + a.n * j) : 0.0;
+            beta[e] = ok[e] ? a.Beta[ii * a.B_rs + jj * a.B_cs] : 0.0;
+            s2[e] = ok[e] ? a.Sigma2[ii * a.V_rs + jj * a.V_cs] : 1.0;
+            sc[e] = ok[e] ? a.S[ii * a.S_rs + jj * a.S_cs] : 1.0;
+            c1[e] = 1.0 / s2[e];                                                   // :10
+            c2[e] = s2[e] / 2;                                                     // :11
+            c0[e] = fma(s2[e], y[e], beta[e]) + 1.0;                               // :9
+            if (MODE == MODE_FIRST) {
+                const double cap = c0[e] - 1.0;                                    // :16
+                m[e] = (m[e] < cap) ? m[e] : cap;
+            }
+        }
+        const int flags = newton_unit<E, FORMULA_A1, MODE>(m, y, beta, c0, c1, c2, sc, ok, k, target,
+                                                           kstar_live, a.maxiter, a.tol, exptab, r, sexp);
+        if (flags & 4) { if (lane == 0) a.status->nan = 1; }
+        if (flags & 2) any_exhausted = 1;
+        if (MODE == MODE_TOPUP && !(flags & 3) && !(flags & 4)) { if (lane == 0) a.status->verify_fail = 1; }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const long long j = jb + e;
+            if (ok[e]) {
+                st_stream(a.M_out + i + a.n * j, m[e]);
+                if (a.V_out) st_stream(a.V_out + i + a.n * j, s2[e] * r[e]);        // :36
+            }
+        }
+        if (lane == 0) {
+            a.kunit[jg * a.nRW + rw] = (unsigned short)k;
+            if (MODE == MODE_FIRST && k > *kstar_live) atomicMax(&a.status->kstar, k);
+        }
+    }
+    if (any_exhausted && lane == 0) a.status->exhausted = 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: vga_pois_solver_mat_newton_fixed_iter  R/vga_solver_mat.R:44-65  (purely per entry)
+// ---------------------------------------------------------------------------------------
+struct FixedArgs {
+    long long n, p;
+    const double *M_in, *V_in;            // V_in null <=> is.null(V)
+    const double *Y;
+    const double *S; long long S_rs, S_cs;
+    const double *Beta; long long B_rs, B_cs;
+    const double *Sigma2; long long V_rs, V_cs;
+    double *M_out, *V_out;
+    int maxiter;
+};
+
+__global__ void __launch_bounds__(kThreads) vga_fixed_iter_kernel(const FixedArgs a)
+{
+    __shared__ double exptab[EBPMF_EXP_TABLE_SIZE];
+    exp_table_init(exptab, threadIdx.x, kThreads);
+    __syncthreads();
+    const long long i = (long long)blockIdx.y * kRowsPerCta + threadIdx.x;
+    if (i >= a.n) return;
+    for (long long j = blockIdx.x; j < a.p; j += gridDim.x) {
+        const long long e = i + a.n * j;
+        const double s2 = a.Sigma2[i * a.V_rs + j * a.V_cs];
+        const double be = a.Beta[i * a.B_rs + j * a.B_cs];
+        const double s = a.S[i * a.S_rs + j * a.S_cs];
+        const double y = ld_stream(a.Y + e);
+        double m = ld_stream(a.M_in + e);
+        double v = a.V_in ? ld_stream(a.V_in + e) : s2 / 2;                         // :48
+        const double is2 = 1.0 / s2;
+        for (int it = 0; it < a.maxiter; ++it) {                                    // :52
+            double temp = s * exp_fast(fma(0.5, v, m), exptab);                     // :54
+            double rt = rcp_fast(temp);
+            // :56  M - (Y/temp - 1 - (M-Beta)/Sigma2/temp) / (-1 - 1/Sigma2/temp)
+            const double num = fma(-(m - be) * is2, rt, fma(y, rt, -1.0));
+            const double den = fma(-is2, rt, -1.0);
+            m = fma(-num, rcp_fast(den), m);
+            temp = s * exp_fast(fma(0.5, v, m), exptab) * v * 0.5;                  // :58
+            rt = rcp_fast(temp);
+            const double h = 0.5 * v * is2 * rt;                                    // V/2/Sigma2/temp
+            const double numv = fma(0.5, rt, -1.0 - h);                             // :62 numerator
+            const double denv = -(1.0 + 0.5 * v) - h;                               // :62 denominator
+            v = v * exp_fast(-numv * rcp_fast(denv), exptab);                       // V / exp(.)
+        }
+        st_stream(a.M_out + e, m);
+        st_stream(a.V_out + e, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// reductions of the per-unit partials (fixed order => run-to-run reproducible)
+// ---------------------------------------------------------------------------------------
+// block (32, 8): x = column within a group of 32, y = slice of row-warps.
+// out[j] = v_sum[j]; colsums[j*3 + {0,1,2}] = per-column sym, ssexp, slogv.
+__global__ void __launch_bounds__(256) reduce_cols_kernel(const double *colpart, long long nRW, long long p,
+                                                          double *v_sum, double *colsums)
+{
+    __shared__ double sm[8][32][4];
+    const long long j = (long long)blockIdx.x * 32 + threadIdx.x;
+    double acc[4] = {0, 0, 0, 0};
+    if (j < p) {
+        for (long long rw = threadIdx.y; rw < nRW; rw += 8) {
+            const double2 *src = reinterpret_cast<const double2 *>(colpart + (rw * p + j) * 4);
+            const double2 u = src[0], w = src[1];
+            acc[0] += u.x; acc[1] += u.y; acc[2] += w.x; acc[3] += w.y;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sm[threadIdx.y][threadIdx.x][q] = acc[q];
+    __syncthreads();
+    if (threadIdx.y == 0 && j < p) {
+        double t[4] = {0, 0, 0, 0};
+        for (int s = 0; s < 8; ++s)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) t[q] += sm[s][threadIdx.x][q];
+        v_sum[j] = t[0];
+        colsums[j * 3 + 0] = t[1]; colsums[j * 3 + 1] = t[2]; colsums[j * 3 + 2] = t[3];
+    }
+}
+
+// one block: scalars[0..2] = sym, ssexp, slogv ; scalars[3] = sum(V)
+__global__ void __launch_bounds__(1024) reduce_scalars_kernel(const double *v_sum, const double *colsums,
+                                                              long long p, double *scalars)
+{
+    __shared__ double sm[4][1024];
+    double acc[4] = {0, 0, 0, 0};
+    for (long long j = threadIdx.x; j < p; j += 1024) {
+        acc[0] += colsums[j * 3 + 0]; acc[1] += colsums[j * 3 + 1]; acc[2] += colsums[j * 3 + 2];
+        acc[3] += v_sum[j];
+    }
+    for (int q = 0; q < 4; ++q) sm[q][threadIdx.x] = acc[q];
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if (threadIdx.x < s)
+            for (int q = 0; q < 4; ++q) sm[q][threadIdx.x] += sm[q][threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) scalars[threadIdx.x] = sm[threadIdx.x][0];
+}
+
+// by_row: v_sum[i] = sum over column groups of rowpart[jg][i]
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const double *rowpart, long long n, long long nJG,
+                                                          double *v_sum)
+{
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    double acc = 0.0;
+    for (long long jg = 0; jg < nJG; ++jg) acc += rowpart[jg * n + i];
+    v_sum[i] = acc;
+}
+
+// ---------------------------------------------------------------------------------------
+// set-up kernels
+// ---------------------------------------------------------------------------------------
+// rbptr[rb*p + j] = first nnz q of column j with rowidx[q] >= rb*256  (rb = 0..nRB)
+__global__ void build_rbptr_kernel(const int *colptr, const int *rowidx, long long p, long long nRB, int *rbptr)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (nRB + 1) * p) return;
+    const long long rb = t / p, j = t - rb * p;
+    int lo = colptr[j], hi = colptr[j + 1];
+    const long long key = rb * kRowsPerCta;
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if ((long long)rowidx[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    rbptr[t] = lo;
+}
+
+// EFt[j*KTP + k] = EF[j + p*k] (zero padded to KTP)
+__global__ void transpose_ef_kernel(const double *EF, long long p, int K, int KTP, double *EFt)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p * KTP) return;
+    const long long j = t / KTP; const int k = (int)(t - j * KTP);
+    EFt[t] = (k < K) ? EF[j + p * k] : 0.0;
+}
+
+// dense -> CSC: count non-zeros per column (one warp per column)
+__global__ void count_nnz_kernel(const double *Y, long long n, long long p, int *counts)
+{
+    const long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (j >= p) return;
+    int c = 0;
+    for (long long i = lane; i < n; i += 32) c += (Y[i + n * j] != 0.0);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) counts[j] = c;
+}
+
+// single-block exclusive scan of counts[0..p) into colptr[0..p]
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const int *counts, long long p, int *colptr)
+{
+    __shared__ long long sm[1024];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (long long base = 0; base < p; base += 1024) {
+        const long long j = base + threadIdx.x;
+        const long long v = (j < p) ? counts[j] : 0;
+        sm[threadIdx.x] = v;
+        __syncthreads();
+        for (int s = 1; s < 1024; s <<= 1) {
+            long long t = (threadIdx.x >= s) ? sm[threadIdx.x - s] : 0;
+            __syncthreads();
+            sm[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (j < p) colptr[j] = (int)(carry + sm[threadIdx.x] - v);
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += sm[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) colptr[p] = (int)carry;
+}
+
+// dense -> CSC: ordered fill (one warp per column, ballot prefix keeps rows sorted)
+__global__ void fill_csc_kernel(const double *Y, long long n, long long p, const int *colptr, int *rowidx, double *x)
+{
+    const long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (j >= p) return;
+    int pos = colptr[j];
+    for (long long i0 = 0; i0 < n; i0 += 32) {
+        const long long i = i0 + lane;
+        const double v = (i < n) ? Y[i + n * j] : 0.0;
+        const unsigned mask = __ballot_sync(0xffffffffu, v != 0.0);
+        if (v != 0.0) {
+            const int off = __popc(mask & ((1u << lane) - 1u));
+            rowidx[pos + off] = (int)i;
+            x[pos + off] = v;
+        }
+        pos += __popc(mask);
+    }
+}
+
+// CSC -> dense (X of the drop-in solver given as dgCMatrix); dst must be zeroed first
+__global__ void scatter_csc_kernel(const int *colptr, const int *rowidx, const double *x, long long n, long long p,
+                                   double *dst)
+{
+    const long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (j >= p) return;
+    for (int q = colptr[j] + lane; q < colptr[j + 1]; q += 32) dst[rowidx[q] + n * j] = x[q];
+}
+
+// a8  sum(lfactorial(x)) = sum(lgamma(x+1))  R/ebpmf_log.R:470-472: per-block partials, fixed order
+__global__ void __launch_bounds__(256) lfactorial_partial_kernel(const double *x, long long len, double *partials)
+{
+    __shared__ double sm[256];
+    double acc = 0.0;
+    for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < len; q += (long long)gridDim.x * 256)
+        acc += lgamma(x[q] + 1.0);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = sm[0];
+}
+
+__global__ void __launch_bounds__(1024) sum_partials_kernel(const double *partials, int count, double *out)
+{
+    __shared__ double sm[1024];
+    double acc = 0.0;
+    for (int q = threadIdx.x; q < count; q += 1024) acc += partials[q];
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sm[0];
+}
+
+// ---------------------------------------------------------------------------------------
+// K5: ebpmf_log_update_sigma2  R/ebpmf_log.R:413-447
+// new = ((v_sum + R2)/2 + b0) / (m/2 + a0 + 1);  gate (cap > 0): fitmax > log(cap) - log(exp(s2)-1) - s2/2
+// ---------------------------------------------------------------------------------------
+__global__ void update_sigma2_kernel(const double *v_sum, const double *R2, long long len, double half_m,
+                                     double a0, double b0, double cap, const double *fitmax, double *sigma2)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= len) return;
+    const double nw = ((v_sum[t] + R2[t]) / 2 + b0) / (half_m + a0 + 1);
+    if (cap > 0) {
+        const double s2 = sigma2[t];
+        const double thr = log(cap) - log(exp(s2) - 1) - s2 / 2;
+        if (fitmax[t] > thr) sigma2[t] = nw;
+    } else {
+        sigma2[t] = nw;
+    }
+}
+
+// col / row / global max of fitted(fit_flash) = EL EF^T for the cap gate (:416,:425,:435).
+// mode 2: out[j] = max_i ; mode 1: out[i] = max_j ; (mode 0 reduces mode-2 output on the host side kernel)
+__global__ void __launch_bounds__(256) fitted_colmax_kernel(const double *EL, const double *EF, long long n,
+                                                            long long p, int K, double *out)
+{
+    __shared__ double sm[256];
+    const long long j = blockIdx.x;
+    double mx = -INFINITY;
+    for (long long i = threadIdx.x; i < n; i += 256) {
+        double b = 0.0;
+        for (int k = 0; k < K; ++k) b = fma(EL[i + n * k], EF[j + p * k], b);
+        mx = fmax(mx, b);
+    }
+    sm[threadIdx.x] = mx;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[j] = sm[0];
+}
+
+__global__ void __launch_bounds__(256) fitted_rowmax_kernel(const double *EL, const double *EF, long long n,
+                                                            long long p, int K, double *out)
+{
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    double mx = -INFINITY;
+    for (long long j = 0; j < p; ++j) {
+        double b = 0.0;
+        for (int k = 0; k < K; ++k) b = fma(EL[i + n * k], EF[j + p * k], b);
+        mx = fmax(mx, b);
+    }
+    out[i] = mx;
+}
+
+__global__ void __launch_bounds__(1024) max_reduce_kernel(const double *in, long long len, double *out)
+{
+    __shared__ double sm[1024];
+    double mx = -INFINITY;
+    for (long long q = threadIdx.x; q < len; q += 1024) mx = fmax(mx, in[q]);
+    sm[threadIdx.x] = mx;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sm[0];
+}
+
+// ---------------------------------------------------------------------------------------
+// a7: calc_ebpmf_log_obj  R/ebpmf_log.R:406-410 -- the O(len) sums; one block, fixed order.
+// terms[0] = sum(ss*log(2*pi*sigma2)/2), [1] = sum(sv/2/sigma2), [2] = sum(R2/2/sigma2),
+// terms[3] = sum((a0+1)*log(sigma2)),   [4] = sum(b0/sigma2)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) obj_terms_kernel(const double *sv, const double *sigma2, const double *R2,
+                                                         long long len, double ss, double a0, double b0,
+                                                         double *terms)
+{
+    __shared__ double sm[5][1024];
+    double acc[5] = {0, 0, 0, 0, 0};
+    const double two_pi = 6.283185307179586;
+    for (long long q = threadIdx.x; q < len; q += 1024) {
+        const double s2 = sigma2[q];
+        acc[0] += ss * log(two_pi * s2) / 2;
+        acc[1] += sv[q] / 2 / s2;
+        acc[2] += R2[q] / 2 / s2;
+        acc[3] += (a0 + 1) * log(s2);
+        acc[4] += b0 / s2;
+    }
+    for (int q = 0; q < 5; ++q) sm[q][threadIdx.x] = acc[q];
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if (threadIdx.x < s)
+            for (int q = 0; q < 5; ++q) sm[q][threadIdx.x] += sm[q][threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x < 5) terms[threadIdx.x] = sm[threadIdx.x][0];
+}
+
+// FP64 pipe probe: 8 independent DFMA chains per thread
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, int iters, double seed)
+{
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6,
+           a7 = seed + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) out[0] = s;
+}
+
+}  // namespace ebpmf

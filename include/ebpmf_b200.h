@@ -1,0 +1,207 @@
+/*
+ * ebpmf_b200.h -- plain C ABI of the B200-native VGA Newton hot path of ebpmf.alpha.
+ *
+ * The reference (DongyueXie/ebpmf.alpha) is 100 % R with no native code (DESCRIPTION:42,
+ * NAMESPACE has no useDynLib), so there is no existing FFI for this path.  The entry points
+ * below are what a `.Call` shim binds; each cites the R function / lines it replaces
+ * (paths relative to the reference root).  The R-side glue that calls them is
+ * ebpmf.alpha_b200/r/src/r_glue.c, the binding a maintainer adds is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a HOST pointer unless the name says `dev`; matrices are column-major
+ *     (R layout): element (i,j) of an n x p matrix is a[i + n*j]; doubles are IEEE fp64;
+ *   - inputs are never written (R shares its arguments, copy-on-modify);
+ *   - every function returns an int status (EBPMF_OK == 0); the message of the last failure on
+ *     a context is returned by ebpmf_last_error();
+ *   - there is NO CPU fallback: without a usable sm_100 GPU every call fails with
+ *     EBPMF_ERR_CUDA;
+ *   - a context is bound to one GPU and is not thread-safe; use one context per host thread
+ *     (R is single-threaded).  Calls are synchronous: results are valid on return.
+ *
+ * var_type coding (the reference's own `var.type`, R/ebpmf_log.R:178-192):
+ *   0 = 'constant', 1 = 'by_row', 2 = 'by_col'; anything else -> EBPMF_ERR_VAR_TYPE
+ *   ("Non-supported var type", R/ebpmf_log.R:444,483).
+ */
+#ifndef EBPMF_B200_H
+#define EBPMF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EBPMF_OK            0
+#define EBPMF_ERR_ARG       1   /* bad argument (NULL, maxiter < 1, shapes that do not conform) */
+#define EBPMF_ERR_CUDA      2   /* CUDA runtime failure / no usable GPU */
+#define EBPMF_ERR_NAN       3   /* a NaN reached the stop test: R stops with "missing value where
+                                   TRUE/FALSE needed" at R/vga_solver_mat.R:26,85,100 */
+#define EBPMF_ERR_VAR_TYPE  4   /* "Non-supported var type" R/ebpmf_log.R:444,483 */
+#define EBPMF_ERR_STATE     5   /* call order: Y / M / factors / sigma2 not set */
+#define EBPMF_ERR_NCCL      6   /* NCCL missing or a collective failed */
+#define EBPMF_ERR_NOMEM     7   /* host or device allocation failed */
+
+#define EBPMF_VAR_CONSTANT  0
+#define EBPMF_VAR_BY_ROW    1
+#define EBPMF_VAR_BY_COL    2
+
+/* How an operand that R would recycle against an n x p matrix is laid out. */
+#define EBPMF_OP_SCALAR     0   /* one double                                         */
+#define EBPMF_OP_ROWVEC     1   /* length n, element i applies to row i (R recycling) */
+#define EBPMF_OP_COLVEC     2   /* length p, element j applies to column j (byrow=TRUE matrix) */
+#define EBPMF_OP_MATRIX     3   /* n x p column-major                                 */
+
+typedef struct ebpmf_ctx ebpmf_ctx;
+
+/* Outcome of one solver call.  n_updates is the GLOBAL Newton update count u that
+ * R/vga_solver_mat.R:21-33 would have performed (break at iteration u+1, or u == maxiter when
+ * the loop is exhausted, in which case V is one iteration stale exactly as in R, :22,:31,:36). */
+typedef struct ebpmf_solve_info {
+    int32_t n_updates;      /* u */
+    int32_t converged;      /* 1: max(abs(f)) < tol held at iteration u+1 ; 0: maxiter exhausted */
+    int32_t passes;         /* kernel passes over the matrix this call needed (diagnostic) */
+    int32_t reserved;
+    double  sym;            /* sum(Y*M)                      R/ebpmf_log.R:274,316 */
+    double  ssexp;          /* sum(exp(M+V/2))               R/ebpmf_log.R:275,317 */
+    double  slogv;          /* sum(log(V)/2+0.9189385)       R/ebpmf_log.R:276,318 */
+    double  kernel_ms;      /* device time of the kernels of this call (CUDA events) */
+} ebpmf_solve_info;
+
+/* ---- library / context ---------------------------------------------------------------- */
+const char *ebpmf_version(void);
+int  ebpmf_device_count(int *count);
+int  ebpmf_ctx_create(int device, ebpmf_ctx **out);
+int  ebpmf_ctx_destroy(ebpmf_ctx *ctx);
+const char *ebpmf_last_error(const ebpmf_ctx *ctx);       /* ctx may be NULL (creation errors) */
+
+/* ---- multi-GPU: one context per GPU, rows sharded ------------------------
+ * Each rank holds a contiguous ROW shard of Y / M / EL (and of sigma2, v_sum for 'by_row');
+ * EF and the by_col/constant sigma2 are replicated.  After ebpmf_ctx_comm_init every
+ * ebpmf_ctx_vga_step combines, over NCCL (NVLink/NVSwitch): the global update count (MAX),
+ * then v_sum[p] || sym,ssexp,slogv || flags (one fp64 SUM all-reduce).  id128 is a 128-byte
+ * ncclUniqueId produced by rank 0 with ebpmf_nccl_unique_id and shipped to the other ranks by
+ * the caller (any side channel).  NCCL is dlopen'ed on first use; single-GPU use needs none. */
+int  ebpmf_nccl_unique_id(void *id128);
+int  ebpmf_ctx_comm_init(ebpmf_ctx *ctx, int rank, int world, const void *id128);
+
+/* ---- resident state of the fused ebpmf_log VGA step --------------------------------------
+ * Y is constant across outer iterations and is uploaded once (R/ebpmf_log.R:195-203).
+ * set_y_csc takes the dgCMatrix slots @p (int32[p+1]), @i (int32[nnz], 0-based, sorted within
+ * a column), @x (double[nnz]) of this rank's row shard; set_y_dense takes as.matrix(Y). */
+int  ebpmf_ctx_set_y_csc(ebpmf_ctx *ctx, int64_t n, int64_t p,
+                         const int32_t *colptr, const int32_t *rowidx, const double *x);
+int  ebpmf_ctx_set_y_dense(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *Y);
+
+/* sum(lfactorial(Y@x)) over the resident Y -- sum_lfactorial_sparseMat, R/ebpmf_log.R:470-472
+ * (call site :172-176; `const` is its negative).  Rank-local; the caller sums over ranks. */
+int  ebpmf_ctx_sum_lfactorial(ebpmf_ctx *ctx, double *out);
+/* same for an arbitrary host vector x (e.g. a dense Y) */
+int  ebpmf_sum_lfactorial(ebpmf_ctx *ctx, int64_t len, const double *x, double *out);
+
+/* flash_fit$Y (the latent M, n x p), flash_fit$EF[[1]] (EL, n x K), flash_fit$EF[[2]]
+ * (EF, p x K) with K = K_flash + 2 offset columns (R/ebpmf_log_flash_init.R:31-45), sigma2 of
+ * length 1 / n / p per var_type.  Beta = EL %*% t(EF) = fitted(fit_flash) is never formed. */
+int  ebpmf_ctx_set_m(ebpmf_ctx *ctx, const double *M);
+int  ebpmf_ctx_set_factors(ebpmf_ctx *ctx, int64_t K, const double *EL, const double *EF);
+int  ebpmf_ctx_set_sigma2(ebpmf_ctx *ctx, int var_type, const double *sigma2);
+
+/* One VGA step on the resident state, R/ebpmf_log.R:302-327 (un-batched branch):
+ *   res   = vga_pois_solver_mat_newton(M, Y, 1, fitted(fit_flash), adjust_var_shape(sigma2,..),
+ *                                      maxiter, tol, return_V=TRUE)       R/vga_solver_mat.R:6-41
+ *   M    <- res$M ; sym, ssexp, slogv (:316-318) ; v_sum = col/row/total sums of res$V (:321-327)
+ * The resident M is replaced by res$M.  V is materialised on the device only if want_v != 0. */
+int  ebpmf_ctx_vga_step(ebpmf_ctx *ctx, int maxiter, double tol, int want_v, ebpmf_solve_info *info);
+
+int  ebpmf_ctx_get_m(ebpmf_ctx *ctx, double *M);
+/* undo the M <- res$M of the last step: the resident M is again the step's input (the input
+ * buffer is never written by a step).  Lets a benchmark repeat the same step without a copy. */
+int  ebpmf_ctx_rewind_m(ebpmf_ctx *ctx);
+int  ebpmf_ctx_get_v(ebpmf_ctx *ctx, double *V);                  /* needs want_v at the step */
+int  ebpmf_ctx_get_v_sum(ebpmf_ctx *ctx, double *v_sum);          /* length 1 / n / p */
+
+/* read-back of the resident state (used by the parity tests on device-generated inputs) */
+int  ebpmf_ctx_get_shape(ebpmf_ctx *ctx, int64_t *n, int64_t *p, int64_t *K, int64_t *nnz);
+int  ebpmf_ctx_get_y_csc(ebpmf_ctx *ctx, int32_t *colptr, int32_t *rowidx, double *x);
+int  ebpmf_ctx_get_factors(ebpmf_ctx *ctx, double *EL, double *EF);
+int  ebpmf_ctx_get_sigma2(ebpmf_ctx *ctx, double *sigma2);
+/* rows [row0, row0+nrows) of the resident M (or of V when which != 0) as an nrows x p matrix */
+int  ebpmf_ctx_get_rows(ebpmf_ctx *ctx, int which, int64_t row0, int64_t nrows, double *out);
+
+/* ebpmf_log_update_sigma2, R/ebpmf_log.R:413-447, on the device from the v_sum of the last step.
+ * R2 = fit_flash$flash_fit$R2 (length 1|n|p; for 'constant' the caller passes sum(R2)).
+ * n_total / p_total are the FULL matrix dims (n of all ranks).  cap_var_mean_ratio > 0 enables
+ * the gate of :416,:425,:435 (col/row/global max of fitted(fit_flash), recomputed on device from
+ * EL, EF).  The new sigma2 becomes the resident one and is copied to sigma2_out. */
+int  ebpmf_ctx_update_sigma2(ebpmf_ctx *ctx, const double *R2, double a0, double b0,
+                             double cap_var_mean_ratio, int64_t n_total, int64_t p_total,
+                             double *sigma2_out);
+
+/* Stand-alone ebpmf_log_update_sigma2(fit_flash,sigma2,v_sum,var_type,cap_var_mean_ratio,a0,b0,n,p),
+ * R/ebpmf_log.R:413-447, all operands given by the caller (host pointers): sigma2 / v_sum / R2 of
+ * length 1|n|p ('constant': R2 is the vector fit_flash$flash_fit$R2 summed by the caller -> length 1).
+ * EL (n x K), EF (p x K) are only read when cap_var_mean_ratio > 0 (the gate needs fitted(fit_flash)). */
+int  ebpmf_update_sigma2(ebpmf_ctx *ctx, int var_type, int64_t n, int64_t p, const double *sigma2,
+                         const double *v_sum, const double *R2, double a0, double b0,
+                         double cap_var_mean_ratio, int64_t K, const double *EL, const double *EF,
+                         double *sigma2_out);
+
+/* calc_ebpmf_log_obj, R/ebpmf_log.R:406-410.  len = length(sigma2) (= length(sv) = length(R2)). */
+int  ebpmf_calc_obj(ebpmf_ctx *ctx, int64_t n, int64_t p, double sym, double ssexp, double slogv,
+                    int64_t len, const double *sv, const double *sigma2, const double *R2,
+                    double KL_LF, double const_, double ss, double a0, double b0, double *obj);
+
+/* The whole step with HOST buffers in one call (what the .Call shim uses each outer iteration):
+ * set_m + set_factors + set_sigma2 + vga_step + get_m [+ get_v] + get_v_sum, with the H2D / D2H
+ * copies of M pipelined by column chunks against the kernels.  V_out may be NULL. */
+int  ebpmf_vga_step_host(ebpmf_ctx *ctx, const double *M_in, int64_t K, const double *EL,
+                         const double *EF, int var_type, const double *sigma2,
+                         int maxiter, double tol,
+                         double *M_out, double *V_out, double *v_sum, ebpmf_solve_info *info);
+
+/* ---- drop-in solver signatures (dense operands, as R passes them) ------------------------ */
+
+/* vga_pois_solver_mat_newton(M,X,S,Beta,Sigma2,maxiter,tol,return_V)  R/vga_solver_mat.R:6-41
+ * X: dense n x p (X != NULL) or dgCMatrix slots (X == NULL; test_memory.R:24-47 passes sparse
+ * counts).  S / Beta / Sigma2 are described by an EBPMF_OP_* kind.  V_out == NULL <=> return_V=FALSE. */
+int  ebpmf_vga_newton(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *M,
+                      const double *X, const int32_t *X_colptr, const int32_t *X_rowidx, const double *X_x,
+                      const double *S, int S_kind, const double *Beta, int Beta_kind,
+                      const double *Sigma2, int Sigma2_kind, int maxiter, double tol,
+                      double *M_out, double *V_out, ebpmf_solve_info *info);
+
+/* vga_pois_solver_mat_newton_fixed_iter(M,V,Y,S,Beta,Sigma2,maxiter)  R/vga_solver_mat.R:44-65
+ * V == NULL <=> is.null(V) -> V = Sigma2/2 (:47-49). */
+int  ebpmf_vga_fixed_iter(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *M, const double *V,
+                          const double *Y, const double *S, int S_kind, const double *Beta, int Beta_kind,
+                          const double *Sigma2, int Sigma2_kind, int maxiter,
+                          double *M_out, double *V_out);
+
+/* vga_pois_solver_mat_newton_low_memory(M,Y,l0,f0,EL,EF,sigma2,var_type,maxiter,tol)
+ * R/vga_solver_mat.R:71-109.  Y dense (Y != NULL) or dgCMatrix slots.  l0 length n, f0 length p,
+ * EL n x K, EF p x K, sigma2 length p ('by_col'), n ('by_row') or 1 ('constant').  Returns M only
+ * (:108).  The stray debug print(range(f)) of :99 is not reproduced. */
+int  ebpmf_vga_low_memory(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, const double *M,
+                          const double *Y, const int32_t *Y_colptr, const int32_t *Y_rowidx, const double *Y_x,
+                          const double *l0, const double *f0, const double *EL, const double *EF,
+                          const double *sigma2, int var_type, int maxiter, double tol,
+                          double *M_out, ebpmf_solve_info *info);
+
+/* ---- benchmark support: on-device synthetic sim_data_log inputs --------------------------
+ * Restates the DGP of sim_data_log (R/simulate_poisson_matrix.R:9-61) with a counter-based RNG
+ * keyed on (seed, global row, column), directly into the context's resident state for THIS
+ * rank's rows [row0, row0+n): Y (CSC), EL = [log l0 + c, 1, L~], EF = [1, log f0, F~],
+ * sigma2 ~ U(0.05,1) by column, M0 = log(Y+0.5) (cold) or Beta (warm).  Not part of the
+ * reference's API; exists so that 1M x 30k inputs never cross PCIe.  density_out / nnz_out report
+ * what was generated. */
+int  ebpmf_ctx_sim_data_log(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, int64_t row0,
+                            uint64_t seed, double log_offset, double bg_lo, double bg_hi,
+                            double pi0, double noise, int warm_start,
+                            int64_t *nnz_out);
+
+/* device-time micro-probe of the FP64 pipe (DFMA chains), used by bench.py for the FP64 line */
+int  ebpmf_probe_fp64_tflops(ebpmf_ctx *ctx, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EBPMF_B200_H */

@@ -1,0 +1,264 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes), against the CPU
+oracle on the same seeded inputs.  Tolerance: 1e-8 relative for M, V, sigma2, ELBO terms
+(BASELINE.json north_star) and the global update count u EXACTLY equal.
+
+`M` is compared as |dM| / max(|M|, 1): M is a log-scale quantity that crosses zero, and the
+north star's 1e-8 is meant relative to the scale of the iterates."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import c_oracle, simdata, vga_numpy
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-8
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+def relM(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0)))
+
+
+def make_case(n, p, K, density, start="cold", var_type="by_col", seed=12345):
+    c = simdata.offset_for_density(density, K=K)
+    sim = simdata.sim_data_log(n, p, K=K, seed=seed, log_offset=c)
+    st = simdata.solver_state(sim, start=start, var_type=var_type, seed=seed + 1)
+    return sim, st
+
+
+def check_step(res, ref, var_type):
+    assert res["n_updates"] == ref["n_updates"][0]
+    assert res["converged"] == ref["converged"][0]
+    assert relM(res["M"], ref["M"]) < RTOL
+    if res["V"] is not None:
+        assert rel(res["V"], ref["V"]) < RTOL
+    assert rel(res["v_sum"], ref["v_sum"]) < RTOL
+    for k in ("sym", "ssexp", "slogv"):
+        assert abs(res[k] - ref[k]) <= RTOL * max(abs(ref[k]), 1.0), (k, res[k], ref[k])
+
+
+# ---------------------------------------------------------------------------------------
+# fused step (K1): a1 + a2 + a3 + a4 + a5
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("var_type", ["by_col", "by_row", "constant"])
+@pytest.mark.parametrize("maxiter,tol", [(10, 1e-5), (1000, 1e-8), (3, 1e-5)])
+def test_fused_step_vs_oracle(gpu_ctx, var_type, maxiter, tol):
+    sim, st = make_case(1500, 333, 5, 0.10, var_type=var_type)
+    gpu_ctx.set_y(sp.csc_matrix(sim["Y"]))
+    res = gpu_ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], var_type, maxiter, tol, return_V=True)
+    ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], var_type, maxiter, tol)
+    check_step(res, ref, var_type)
+    if maxiter == 3:
+        assert not res["converged"] and res["n_updates"] == 3      # exhaustion: stale V (F6)
+
+
+def test_fused_c1_readme_dense_y(gpu_ctx):
+    """C1: README recipe shapes, dense Y (as.matrix(Y), R/ebpmf_log.R:202), l0 = f0 = 0."""
+    sim = simdata.readme_example()
+    st = simdata.solver_state(sim, start="cold")
+    gpu_ctx.set_y(sim["Y"])
+    res = gpu_ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], "by_col", 10, 1e-5, return_V=True)
+    ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], "by_col", 10, 1e-5)
+    check_step(res, ref, "by_col")
+
+
+def test_fused_c2_full_size(gpu_ctx):
+    """C2: sim_data_log 10k x 2k, K = 5, ~10 % non-zero, package defaults; oracle = C transcription."""
+    sim, st = make_case(10000, 2000, 5, 0.10)
+    gpu_ctx.set_y(sp.csc_matrix(sim["Y"]))
+    res = gpu_ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], "by_col", 10, 1e-5, return_V=True)
+    ref = c_oracle.vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], "by_col", 10, 1e-5)
+    ref = dict(ref, n_updates=[ref["n_updates"]], converged=[ref["converged"]])
+    check_step(res, ref, "by_col")
+
+
+@pytest.mark.parametrize("n,p", [(1, 1), (31, 17), (257, 15), (513, 33), (1000, 100)])
+def test_fused_ragged_shapes(gpu_ctx, n, p):
+    sim, st = make_case(n, p, 3, 0.3, seed=n * 1000 + p)
+    gpu_ctx.set_y(sp.csc_matrix(sim["Y"]))
+    res = gpu_ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], "by_col", 50, 1e-8, return_V=True)
+    ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], "by_col", 50, 1e-8)
+    check_step(res, ref, "by_col")
+
+
+def test_fused_all_zero_y(gpu_ctx):
+    """Empty sparse matrix: no non-zeros at all."""
+    sim, st = make_case(300, 40, 3, 0.1)
+    Y0 = np.zeros_like(sim["Y"])
+    gpu_ctx.set_y(sp.csc_matrix(Y0))
+    M0 = st["EL"] @ st["EF"].T
+    res = gpu_ctx.vga_step_host(M0, st["EL"], st["EF"], st["sigma2"], "by_col", 30, 1e-8, return_V=True)
+    ref = vga_numpy.ebpmf_log_vga_step(M0, Y0, st["EL"], st["EF"], st["sigma2"], "by_col", 30, 1e-8)
+    check_step(res, ref, "by_col")
+
+
+def test_fused_warm_start_many_iterations(gpu_ctx):
+    sim, st = make_case(900, 200, 5, 0.10, start="warm")
+    gpu_ctx.set_y(sp.csc_matrix(sim["Y"]))
+    res = gpu_ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], "by_col", 1000, 1e-8, return_V=True)
+    ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], "by_col", 1000, 1e-8)
+    check_step(res, ref, "by_col")
+    assert res["n_updates"] > 10
+
+
+def test_resident_step_rewind_and_sigma2_update(gpu_ctx, pkg):
+    """Resident-state API: two identical steps after rewind give identical results; K5 + a7."""
+    sim, st = make_case(1200, 256, 4, 0.08)
+    n, p = sim["Y"].shape
+    gpu_ctx.set_y(sp.csc_matrix(sim["Y"]))
+    gpu_ctx.set_m(st["M0"]); gpu_ctx.set_factors(st["EL"], st["EF"]); gpu_ctx.set_sigma2(st["sigma2"], "by_col")
+    i1 = gpu_ctx.vga_step(10, 1e-5)
+    m1 = gpu_ctx.get_m(); v1 = gpu_ctx.get_v_sum()
+    gpu_ctx.rewind_m()
+    i2 = gpu_ctx.vga_step(10, 1e-5)
+    m2 = gpu_ctx.get_m(); v2 = gpu_ctx.get_v_sum()
+    assert i1.n_updates == i2.n_updates and np.array_equal(m1, m2) and np.array_equal(v1, v2)
+    assert (i1.sym, i1.ssexp, i1.slogv) == (i2.sym, i2.ssexp, i2.slogv)      # reductions are deterministic
+    ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], "by_col", 10, 1e-5)
+    fit = dict(R2=st["R2"], EL=st["EL"], EF=st["EF"])
+    for cap in (0.0, 5.0):
+        gpu_ctx.set_sigma2(st["sigma2"], "by_col")
+        s_gpu = gpu_ctx.update_sigma2(st["R2"], 1.0, 1.0, cap)
+        s_ref = vga_numpy.ebpmf_log_update_sigma2(fit, st["sigma2"], ref["v_sum"], "by_col", cap, 1.0, 1.0, n, p)
+        assert rel(s_gpu, s_ref) < RTOL
+    const = -vga_numpy.sum_lfactorial_sparseMat(sp.csc_matrix(sim["Y"]))
+    assert abs(-gpu_ctx.sum_lfactorial() - const) <= RTOL * abs(const)
+    o_ref = vga_numpy.calc_ebpmf_log_obj(n, p, ref["sym"], ref["ssexp"], ref["slogv"], ref["v_sum"], s_ref,
+                                         st["R2"], -123.4, const, n, 1.0, 1.0)
+    o_gpu = pkg.calc_ebpmf_log_obj(n, p, i1.sym, i1.ssexp, i1.slogv, v1, s_gpu, st["R2"], -123.4,
+                                   -gpu_ctx.sum_lfactorial(), n, 1.0, 1.0, ctx=gpu_ctx)
+    assert abs(o_gpu - o_ref) <= RTOL * abs(o_ref)
+
+
+@pytest.mark.parametrize("var_type", ["by_row", "constant"])
+def test_update_sigma2_other_var_types(gpu_ctx, pkg, var_type):
+    sim, st = make_case(400, 90, 3, 0.2, var_type=var_type)
+    n, p = sim["Y"].shape
+    ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], var_type, 10, 1e-5)
+    fit = dict(R2=st["R2"], EL=st["EL"], EF=st["EF"])
+    for cap in (0.0, 3.0):
+        s_ref = vga_numpy.ebpmf_log_update_sigma2(fit, st["sigma2"], ref["v_sum"], var_type, cap, 1.0, 1.0, n, p)
+        s_gpu = pkg.ebpmf_log_update_sigma2(fit, st["sigma2"], ref["v_sum"], var_type, cap, 1.0, 1.0, n, p, ctx=gpu_ctx)
+        assert rel(s_gpu, s_ref) < RTOL
+
+
+def test_nan_raises_like_r(gpu_ctx, pkg):
+    """A NaN at the stop test is an error in R (`if(NA)`), R/vga_solver_mat.R:26."""
+    sim, st = make_case(200, 50, 3, 0.2)
+    M0 = st["M0"].copy(); M0[7, 3] = np.nan
+    EL = st["EL"].copy(); EL[11, 2] = np.nan
+    gpu_ctx.set_y(sp.csc_matrix(sim["Y"]))
+    with pytest.raises(pkg.EbpmfError) as ei:
+        gpu_ctx.vga_step_host(st["M0"], EL, st["EF"], st["sigma2"], "by_col", 10, 1e-5)
+    assert ei.value.code == 3
+    with pytest.raises(vga_numpy.RError):
+        vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], EL, st["EF"], st["sigma2"], "by_col", 10, 1e-5)
+
+
+def test_bad_var_type_and_call_order(pkg):
+    ctx = pkg.VgaContext(0)
+    with pytest.raises(pkg.EbpmfError) as ei:
+        ctx.vga_step(10, 1e-5)
+    assert ei.value.code == 5
+    with pytest.raises(pkg.EbpmfError) as ei:
+        pkg.adjust_var_shape(np.ones(3), "by_banana", 3, 3)
+    assert ei.value.code == 4
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------------------
+# drop-in dense signatures (K2, K3, K4)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sigma_kind", ["matrix", "rowvec", "scalar"])
+@pytest.mark.parametrize("sparse_x", [False, True])
+def test_dense_solver_signature(gpu_ctx, pkg, sigma_kind, sparse_x):
+    sim, st = make_case(700, 150, 4, 0.15)
+    n, p = sim["Y"].shape
+    rng = np.random.default_rng(5)
+    Beta = st["EL"] @ st["EF"].T
+    S = np.exp(rng.normal(0, 0.1, size=(n, p)))                    # matrix S = tcrossprod(l0,f0)-like
+    Sigma2 = {"matrix": vga_numpy.adjust_var_shape(st["sigma2"], "by_col", n, p),
+              "rowvec": rng.uniform(0.1, 1.0, size=n), "scalar": 0.37}[sigma_kind]
+    X = sp.csc_matrix(sim["Y"]) if sparse_x else sim["Y"]
+    gi, oi = {}, {}
+    res = pkg.vga_pois_solver_mat_newton(st["M0"], X, S, Beta, Sigma2, maxiter=1000, tol=1e-8, info=gi, ctx=gpu_ctx)
+    ref = vga_numpy.vga_pois_solver_mat_newton(st["M0"], sim["Y"], S, Beta, Sigma2, maxiter=1000, tol=1e-8, info=oi)
+    assert gi["n_updates"] == oi["n_updates"] and gi["converged"] == oi["converged"]
+    assert relM(res["M"], ref["M"]) < RTOL and rel(res["V"], ref["V"]) < RTOL
+    m_only = pkg.vga_pois_solver_mat_newton(st["M0"], X, 1, Beta, Sigma2, maxiter=4, tol=1e-8, return_V=False,
+                                            ctx=gpu_ctx)
+    ref2 = vga_numpy.vga_pois_solver_mat_newton(st["M0"], sim["Y"], 1, Beta, Sigma2, maxiter=4, tol=1e-8,
+                                                return_V=False)
+    assert isinstance(m_only, np.ndarray) and relM(m_only, ref2) < RTOL
+
+
+@pytest.mark.parametrize("maxiter", [1, 10, 60])
+def test_fixed_iter(gpu_ctx, pkg, maxiter):
+    """a9; maxiter = 1 is its only call site (inst/code/Poisson_MF_splitting.R:212-214)."""
+    sim, st = make_case(600, 120, 3, 0.2)
+    n, p = sim["Y"].shape
+    Beta = st["EL"] @ st["EF"].T
+    Sigma2 = vga_numpy.adjust_var_shape(st["sigma2"], "by_col", n, p)
+    for V0 in (None, np.full((n, p), 0.3)):
+        res = pkg.vga_pois_solver_mat_newton_fixed_iter(st["M0"], V0, sim["Y"], 1, Beta, Sigma2, maxiter, ctx=gpu_ctx)
+        ref = vga_numpy.vga_pois_solver_mat_newton_fixed_iter(st["M0"], V0, sim["Y"], 1, Beta, Sigma2, maxiter)
+        assert relM(res["M"], ref["M"]) < RTOL and rel(res["V"], ref["V"]) < RTOL
+
+
+@pytest.mark.parametrize("var_type", ["by_col", "by_row", "constant"])
+@pytest.mark.parametrize("sparse_y", [False, True])
+def test_low_memory(gpu_ctx, pkg, var_type, sparse_y):
+    """a10 with its quirks (F8): multiplicative l0*f0, clamp to Beta, sigma2-less derivative."""
+    sim, st = make_case(800, 130, 3, 0.15, var_type=var_type)
+    n, p = sim["Y"].shape
+    l0 = sim["L0"]; f0 = sim["F0"]
+    EL = st["EL"][:, 2:]; EF = st["EF"][:, 2:]                      # l0, f0 are multiplicative here
+    M0 = np.log(sim["Y"] + 0.5) - np.log(l0)[:, None] - np.log(f0)[None, :]
+    Y = sp.csc_matrix(sim["Y"]) if sparse_y else sim["Y"]
+    for maxiter, tol in ((1000, 1e-8), (3, 1e-5)):
+        gi, oi = {}, {}
+        res = pkg.vga_pois_solver_mat_newton_low_memory(M0, Y, l0, f0, EL, EF, st["sigma2"], var_type, maxiter, tol,
+                                                        info=gi, ctx=gpu_ctx)
+        ref = vga_numpy.vga_pois_solver_mat_newton_low_memory(M0, sim["Y"], l0, f0, EL, EF, st["sigma2"], var_type,
+                                                              maxiter, tol, info=oi)
+        assert gi["n_updates"] == oi["n_updates"] and gi["converged"] == oi["converged"]
+        assert relM(res, ref) < RTOL
+
+
+def test_sum_lfactorial(gpu_ctx, pkg):
+    rng = np.random.default_rng(3)
+    x = rng.poisson(3.0, size=200001).astype(np.float64)
+    x[:5] = [0, 1, 2, 170, 25000]
+    got = pkg.sum_lfactorial_sparseMat(x, ctx=gpu_ctx)
+    ref = c_oracle.sum_lfactorial(x)
+    assert abs(got - ref) <= RTOL * abs(ref)
+
+
+# ---------------------------------------------------------------------------------------
+# device-generated inputs (bench path) read back and checked against the oracle
+# ---------------------------------------------------------------------------------------
+def test_device_sim_data_matches_oracle(gpu_ctx):
+    n, p, K = 3000, 640, 6
+    nnz = gpu_ctx.sim_data_log(n, p, K, seed=12345, log_offset=-3.2)
+    cp, ri, x = gpu_ctx.get_y_csc()
+    Y = sp.csc_matrix((x, ri, cp), shape=(n, p))
+    assert nnz == Y.nnz and 0.02 < nnz / (n * p) < 0.4
+    assert np.all(x > 0) and np.all(x == np.round(x))
+    EL, EF = gpu_ctx.get_factors()
+    s2 = gpu_ctx.get_sigma2()
+    M0 = gpu_ctx.get_m()
+    info = gpu_ctx.vga_step(10, 1e-5, want_v=True)
+    ref = c_oracle.vga_step(M0, Y.toarray(), EL, EF, s2, "by_col", 10, 1e-5)
+    assert info.n_updates == ref["n_updates"] and bool(info.converged) == ref["converged"]
+    assert relM(gpu_ctx.get_m(), ref["M"]) < RTOL
+    assert rel(gpu_ctx.get_v(), ref["V"]) < RTOL
+    assert rel(gpu_ctx.get_v_sum(), ref["v_sum"]) < RTOL
+    for k in ("sym", "ssexp", "slogv"):
+        assert abs(getattr(info, k) - ref[k]) <= RTOL * max(abs(ref[k]), 1.0)
+    rows = gpu_ctx.get_rows(1000, 257)
+    assert np.array_equal(rows, gpu_ctx.get_m()[1000:1257])
