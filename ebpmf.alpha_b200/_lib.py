@@ -27,7 +27,8 @@ class EbpmfError(RuntimeError):
 class SolveInfo(C.Structure):
     _fields_ = [("n_updates", C.c_int32), ("converged", C.c_int32), ("passes", C.c_int32),
                 ("reserved", C.c_int32), ("sym", C.c_double), ("ssexp", C.c_double),
-                ("slogv", C.c_double), ("kernel_ms", C.c_double)]
+                ("slogv", C.c_double), ("kernel_ms", C.c_double), ("pass1_ms", C.c_double),
+                ("pass2_ms", C.c_double), ("reduce_ms", C.c_double)]
 
 
 _vp, _i64, _i32, _dbl, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int
@@ -71,6 +72,7 @@ SIGNATURES = {
                                     _int, _dbl, _vp, _PI]),
     "ebpmf_ctx_sim_data_log": (_int, [_vp, _i64, _i64, _i64, _i64, C.c_uint64, _dbl, _dbl, _dbl, _dbl, _dbl, _int,
                                       C.POINTER(_i64)]),
+    "ebpmf_ctx_last_diag": (_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ebpmf_probe_fp64_tflops": (_int, [_vp, C.POINTER(_dbl)]),
 }
 

@@ -61,7 +61,7 @@ struct DevBuf {
 struct ebpmf_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr, ev_p1 = nullptr, ev_p2 = nullptr;
     std::string err;
 
     // shapes
@@ -70,6 +70,7 @@ struct ebpmf_ctx {
     int K = 0, KTP = 0;
     int var_type = -1;
     bool can_rewind = false;
+    unsigned long long diag_topups = 0, diag_iters = 0;
     bool have_y = false, have_m = false, have_f = false, have_s2 = false, have_v = false, have_vsum = false;
 
     // resident buffers
@@ -167,21 +168,32 @@ int cols_per_cta_for(long long p, long long nRB) {
     return (int)c;
 }
 
+template <int KTP, int FORMULA, int MODE>
+int launch_fused_ktp(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
+    auto kern = vga_fused_kernel<KTP, kE, FORMULA, MODE>;
+    const int smem = (int)sizeof(FusedSmem<KTP>);
+    static bool configured[8] = {false, false, false, false, false, false, false, false};   // per device
+    if (ctx->device < 8 ? !configured[ctx->device] : true) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (ctx->device < 8) configured[ctx->device] = true;
+    }
+    kern<<<grid, dim3(kThreads), smem, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    return EBPMF_OK;
+}
+
 template <int FORMULA, int MODE>
 int launch_fused(ebpmf_ctx *ctx, const FusedArgs &a) {
     const long long ncols = a.col1 - a.col0;
     if (ncols <= 0) return EBPMF_OK;
     dim3 grid((unsigned)((ncols + a.cols_per_cta - 1) / a.cols_per_cta), (unsigned)ctx->nRB);
-    dim3 block(kThreads);
     switch (ctx->KTP) {
-        case 8: vga_fused_kernel<8, kE, FORMULA, MODE><<<grid, block, 0, ctx->stream>>>(a); break;
-        case 16: vga_fused_kernel<16, kE, FORMULA, MODE><<<grid, block, 0, ctx->stream>>>(a); break;
-        case 24: vga_fused_kernel<24, kE, FORMULA, MODE><<<grid, block, 0, ctx->stream>>>(a); break;
-        case 32: vga_fused_kernel<32, kE, FORMULA, MODE><<<grid, block, 0, ctx->stream>>>(a); break;
-        default: return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported (max 32)", ctx->K);
+        case 8: return launch_fused_ktp<8, FORMULA, MODE>(ctx, a, grid);
+        case 16: return launch_fused_ktp<16, FORMULA, MODE>(ctx, a, grid);
+        case 24: return launch_fused_ktp<24, FORMULA, MODE>(ctx, a, grid);
+        case 32: return launch_fused_ktp<32, FORMULA, MODE>(ctx, a, grid);
     }
-    CU(cudaGetLastError());
-    return EBPMF_OK;
+    return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported (max 32)", ctx->K);
 }
 
 int stride_for(int kind, long long n, long long *rs, long long *cs) {
@@ -219,7 +231,8 @@ int fetch_status(ebpmf_ctx *ctx) {
 
 int set_target(ebpmf_ctx *ctx, int target) {
     Status s;
-    s.kstar = target; s.nan = 0; s.verify_fail = 0; s.exhausted = 0;
+    memset(&s, 0, sizeof s);
+    s.kstar = target;
     *ctx->h_status = s;
     CU(cudaMemcpyAsync(ctx->status.ptr, ctx->h_status, sizeof(Status), cudaMemcpyHostToDevice, ctx->stream));
     return EBPMF_OK;
@@ -269,11 +282,13 @@ int run_global_stop(ebpmf_ctx *ctx, int maxiter, First first, Topup topup, After
     CU(cudaMemsetAsync(ctx->status.ptr, 0, sizeof(Status), ctx->stream));
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     CHECK(first());
+    CU(cudaEventRecord(ctx->ev_p1, ctx->stream));
     CHECK(allreduce_status(ctx));
     CHECK(topup());
     int passes = 2;
     for (;;) {
         CHECK(allreduce_status(ctx));
+        CU(cudaEventRecord(ctx->ev_p2, ctx->stream));
         CHECK(after());                      // reductions (speculative: redone if the verify failed)
         CU(cudaEventRecord(ctx->ev1, ctx->stream));
         CHECK(fetch_status(ctx));
@@ -291,9 +306,17 @@ int run_global_stop(ebpmf_ctx *ctx, int maxiter, First first, Topup topup, After
             info->converged = (s.kstar < maxiter) ? 1 : 0;
             info->passes = passes;
             info->reserved = 0;
+            ctx->diag_topups = s.topup_units;
+            ctx->diag_iters = s.unit_iters;
             float ms = 0.f;
             CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
             info->kernel_ms = ms;
+            CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_p1));
+            info->pass1_ms = ms;
+            CU(cudaEventElapsedTime(&ms, ctx->ev_p1, ctx->ev_p2));
+            info->pass2_ms = ms;
+            CU(cudaEventElapsedTime(&ms, ctx->ev_p2, ctx->ev1));
+            info->reduce_ms = ms;
         }
         return EBPMF_OK;
     }
@@ -445,6 +468,8 @@ int ebpmf_ctx_create(int device, ebpmf_ctx **out) {
     CREATE_STEP(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CREATE_STEP(cudaEventCreate(&ctx->ev0));
     CREATE_STEP(cudaEventCreate(&ctx->ev1));
+    CREATE_STEP(cudaEventCreate(&ctx->ev_p1));
+    CREATE_STEP(cudaEventCreate(&ctx->ev_p2));
     CREATE_STEP(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
     CREATE_STEP(cudaMallocHost((void **)&ctx->h_status, sizeof(Status)));
     CREATE_STEP(cudaMallocHost((void **)&ctx->h_small, sizeof(double) * 64));
@@ -467,6 +492,8 @@ int ebpmf_ctx_destroy(ebpmf_ctx *ctx) {
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_p1) cudaEventDestroy(ctx->ev_p1);
+    if (ctx->ev_p2) cudaEventDestroy(ctx->ev_p2);
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -1012,6 +1039,13 @@ int ebpmf_ctx_sim_data_log(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, int6
     ctx->K = KT; ctx->KTP = ktp; ctx->var_type = EBPMF_VAR_BY_COL;
     ctx->have_m = ctx->have_f = ctx->have_s2 = true;
     if (nnz_out) *nnz_out = nnz;
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_last_diag(ebpmf_ctx *ctx, uint64_t *topup_units, uint64_t *unit_evals) {
+    if (!ctx) return fail(ctx, EBPMF_ERR_ARG, "last_diag: ctx is NULL");
+    if (topup_units) *topup_units = ctx->diag_topups;
+    if (unit_evals) *unit_evals = ctx->diag_iters;
     return EBPMF_OK;
 }
 

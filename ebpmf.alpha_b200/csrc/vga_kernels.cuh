@@ -50,6 +50,8 @@ struct Status {           // device words shared by the passes of one solve
     int nan;              // a NaN reached the stop test
     int verify_fail;      // pass 2: some unit is not below tol at K*
     int exhausted;        // some unit hit maxiter
+    unsigned long long topup_units;   // diagnostics: units that needed pass 2 work
+    unsigned long long unit_iters;    // diagnostics: sum over units of evaluations performed
 };
 
 struct FusedArgs {
@@ -87,37 +89,41 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---------------------------------------------------------------------------------------
-// One unit: E entries per lane, all 32 lanes in lock step.  On return k is the number of
-// updates the unit has received, r[] the reciprocal of the last evaluated temp, sexp[] the last
-// evaluated S*exp(.).  Returns a bit mask: 1 converged at k, 2 exhausted, 4 NaN.
+// One unit: E entries per lane, all 32 lanes in lock step.  Per entry the loop carries
+//   m, c0 = (s2*y + beta) + 1, w = y + beta/s2, c1 = 1/s2, c2 = s2/2  [, sc = S]
+// so that  f = x - sexp - M*const1 + const3  (R/vga_solver_mat.R:25) is  fma(-m, c1, w - sexp).
+// On return k is the number of updates the unit has received, r[] the reciprocal of the last
+// evaluated temp, sexp[] / f[] the last evaluated S*exp(.) and f.
+// Returns a bit mask: 1 converged at k, 2 exhausted.  (A NaN never converges, so it exhausts
+// the loop and is detected from f[] by the caller -- R errors at the first NaN it tests, and
+// every k this unit evaluates is <= the global count, so the outcome is the same.)
 // ---------------------------------------------------------------------------------------
-template <int E, int FORMULA, int MODE>
-__device__ __forceinline__ int newton_unit(double (&m)[E], const double (&y)[E], const double (&beta)[E],
-                                           const double (&c0)[E], const double (&c1)[E], const double (&c2)[E],
-                                           const double (&sc)[E], const bool (&ok)[E],
-                                           int &k, int target, const volatile int *kstar_live,
-                                           int maxiter, double tol, const double *exptab,
-                                           double (&r)[E], double (&sexp)[E])
+template <int E, int FORMULA, int MODE, bool SCALED>
+__device__ __forceinline__ int newton_unit(double (&m)[E], const double (&c0)[E], const double (&w)[E],
+                                           const double (&c1)[E], const double (&c2)[E], const double (&sc)[E],
+                                           const bool (&ok)[E], int &k, int target,
+                                           const volatile int *kstar_live, int maxiter, double tol,
+                                           const double *exptab, double (&r)[E], double (&sexp)[E], double (&f)[E])
 {
     int flags = 0;
+#pragma unroll 1
     for (;;) {
-        bool lane_conv = true, lane_nan = false;
-        double f[E], a[E];
+        bool lane_conv = true;
+        double a[E], xx[E], ex[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const double temp = c0[e] - m[e];                                  // :22
             r[e] = rcp_fast(temp);
             a[e] = c2[e] * r[e];                                               // const2/temp
-            sexp[e] = sc[e] * exp_fast(m[e] + a[e], exptab);                   // :23
-            if (FORMULA == FORMULA_A1)
-                f[e] = fma(beta[e], c1[e], fma(-m[e], c1[e], y[e] - sexp[e])); // :25  x-sexp-M*const1+const3
-            else
-                f[e] = fma(beta[e] - m[e], c1[e], y[e] - sexp[e]);             // :84,:98
-            const bool cv = fabs(f[e]) < tol;                                  // :26 (strict <)
-            lane_conv = lane_conv && (cv || !ok[e]);
-            lane_nan = lane_nan || (ok[e] && (f[e] != f[e]));
+            xx[e] = m[e] + a[e];
         }
-        if (__any_sync(0xffffffffu, lane_nan)) { flags |= 4; break; }
+        exp_fast_n<E>(xx, ex, exptab);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            sexp[e] = SCALED ? sc[e] * ex[e] : ex[e];                          // :23
+            f[e] = fma(-m[e], c1[e], w[e] - sexp[e]);                          // :25 | :84,:98
+            lane_conv = lane_conv && ((fabs(f[e]) < tol) || !ok[e]);           // :26 (strict <)
+        }
         const bool conv = __all_sync(0xffffffffu, lane_conv);
         bool stop;
         if (MODE == MODE_FIRST) stop = conv && (k >= *kstar_live);
@@ -135,18 +141,26 @@ __device__ __forceinline__ int newton_unit(double (&m)[E], const double (&y)[E],
     return flags;
 }
 
+// shared memory of the fused kernel (dynamic): Y image, Beta image, EF rows, column constants
+template <int KTP>
+struct FusedSmem {
+    double ys[kTileCols][kRowsPerCta];
+    double bs[kTileCols][kRowsPerCta];
+    double efs[kTileCols][KTP];
+    double s2s[kTileCols], c1s[kTileCols], c2s[kTileCols], f0s[kTileCols];
+    double exptab[EBPMF_EXP_TABLE_SIZE];
+};
+
 // ---------------------------------------------------------------------------------------
 // K1 / K4: fused VGA step on CSC Y with Beta rebuilt from the flash factors.
-// grid = (column spans, row blocks), block = 256 threads.
+// grid = (column spans, row blocks), block = 256 threads, dynamic smem = sizeof(FusedSmem<KTP>).
 // ---------------------------------------------------------------------------------------
 template <int KTP, int E, int FORMULA, int MODE>
 __global__ void __launch_bounds__(kThreads, 2) vga_fused_kernel(const FusedArgs a)
 {
     static_assert(kTileCols % E == 0, "E must divide the tile width");
-    __shared__ double ys[kTileCols][kRowsPerCta];
-    __shared__ double efs[kTileCols][KTP];
-    __shared__ double s2s[kTileCols], c1s[kTileCols], c2s[kTileCols], f0s[kTileCols];
-    __shared__ double exptab[EBPMF_EXP_TABLE_SIZE];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FusedSmem<KTP> &sm = *reinterpret_cast<FusedSmem<KTP> *>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long rb = blockIdx.y;
@@ -158,11 +172,7 @@ __global__ void __launch_bounds__(kThreads, 2) vga_fused_kernel(const FusedArgs 
     const long long jc0 = a.col0 + (long long)blockIdx.x * a.cols_per_cta;
     const long long jc1 = min(a.col1, jc0 + (long long)a.cols_per_cta);
 
-    exp_table_init(exptab, tid, kThreads);
-
-    double el[KTP];
-#pragma unroll
-    for (int k = 0; k < KTP; ++k) el[k] = (row_ok && k < a.K) ? __ldg(a.EL + i + a.n * k) : 0.0;
+    exp_table_init(sm.exptab, tid, kThreads);
 
     // row-constant pieces (by_row / constant sigma2, A10's l0)
     double s2_row = 1.0, c1_row = 1.0, c2_row = 0.5, l0_i = 1.0;
@@ -176,7 +186,8 @@ __global__ void __launch_bounds__(kThreads, 2) vga_fused_kernel(const FusedArgs 
     const int target = (MODE == MODE_TOPUP) ? a.status->kstar : 0;
     const volatile int *kstar_live = &a.status->kstar;
     const double *Msrc = (MODE == MODE_FIRST) ? a.M_in : a.M_out;
-    int any_exhausted = 0;
+    int any_exhausted = 0, any_nan = 0, any_fail = 0;
+    unsigned my_topups = 0, my_iters = 0;
 
     for (long long j0 = jc0; j0 < jc1; j0 += kTileCols) {
         // ---- does this tile need work?  (also the barrier that protects the smem tile) ----
@@ -192,20 +203,20 @@ __global__ void __launch_bounds__(kThreads, 2) vga_fused_kernel(const FusedArgs 
 
         // ---- stage the tile: zero Y image, EF rows, per-column constants --------------------
 #pragma unroll
-        for (int c = 0; c < kTileCols; ++c) ys[c][tid] = 0.0;
+        for (int c = 0; c < kTileCols; ++c) sm.ys[c][tid] = 0.0;
         for (int idx = tid; idx < kTileCols * KTP; idx += kThreads) {
             const int c = idx / KTP, k = idx - c * KTP;
             const long long j = j0 + c;
-            efs[c][k] = (j < jc1) ? __ldg(a.EFt + j * KTP + k) : 0.0;
+            sm.efs[c][k] = (j < jc1) ? __ldg(a.EFt + j * KTP + k) : 0.0;
         }
         if (tid < kTileCols) {
             const long long j = j0 + tid;
             double s2 = 1.0;
             if (a.var_type == 2 && j < jc1) s2 = a.sigma2[j];
-            s2s[tid] = s2;
-            c1s[tid] = 1.0 / s2;
-            c2s[tid] = s2 / 2;
-            f0s[tid] = (FORMULA == FORMULA_A10 && j < jc1) ? a.f0[j] : 1.0;
+            sm.s2s[tid] = s2;
+            sm.c1s[tid] = 1.0 / s2;
+            sm.c2s[tid] = s2 / 2;
+            sm.f0s[tid] = (FORMULA == FORMULA_A10 && j < jc1) ? a.f0[j] : 1.0;
         }
         __syncthreads();
         // scatter the CSC non-zeros of rows [r0, r0+256) of each tile column
@@ -214,7 +225,21 @@ __global__ void __launch_bounds__(kThreads, 2) vga_fused_kernel(const FusedArgs 
             if (j < jc1) {
                 const int lo = a.rbptr[rb * a.p + j], hi = a.rbptr[(rb + 1) * a.p + j];
                 for (int q = lo + lane; q < hi; q += 32)
-                    ys[c][a.rowidx[q] - (int)r0] = __ldg(a.yx + q);
+                    sm.ys[c][a.rowidx[q] - (int)r0] = __ldg(a.yx + q);
+            }
+        }
+        // a2: this row's Beta for the 16 tile columns, K_tot FMAs each (EL row lives in registers
+        // only here; EF rows are broadcast reads from shared memory)
+        {
+            double el[KTP];
+#pragma unroll
+            for (int k = 0; k < KTP; ++k) el[k] = (row_ok && k < a.K) ? __ldg(a.EL + i + a.n * k) : 0.0;
+#pragma unroll 4
+            for (int c = 0; c < kTileCols; ++c) {
+                double b = 0.0;
+#pragma unroll
+                for (int k = 0; k < KTP; ++k) b = fma(el[k], sm.efs[c][k], b);
+                sm.bs[c][tid] = b;
             }
         }
         __syncthreads();
@@ -229,8 +254,9 @@ __global__ void __launch_bounds__(kThreads, 2) vga_fused_kernel(const FusedArgs 
             if (MODE == MODE_TOPUP) {
                 k = a.kunit[jg * a.nRW + rw];
                 if (k == target) continue;
+                ++my_topups;
             }
-            double m[E], y[E], beta[E], c0[E], c1[E], c2[E], sc[E], s2[E], r[E], sexp[E];
+            double m[E], c0[E], w[E], c1[E], c2[E], sc[E], s2[E], r[E], sexp[E], f[E];
             bool ok[E];
 #pragma unroll
             for (int e = 0; e < E; ++e) {
@@ -238,40 +264,40 @@ __global__ void __launch_bounds__(kThreads, 2) vga_fused_kernel(const FusedArgs 
                 const long long j = jb + e;
                 ok[e] = row_ok && (j < jc1);
                 m[e] = ok[e] ? ld_stream(Msrc + i + a.n * j) : 0.0;
-                y[e] = ys[c][tid];
-                double b = 0.0;
-#pragma unroll
-                for (int kk = 0; kk < KTP; ++kk) b = fma(el[kk], efs[c][kk], b);   // a2
-                beta[e] = b;
-                if (a.var_type == 2) { s2[e] = s2s[c]; c1[e] = c1s[c]; c2[e] = c2s[c]; }
+                const double y = sm.ys[c][tid], b = sm.bs[c][tid];
+                if (a.var_type == 2) { s2[e] = sm.s2s[c]; c1[e] = sm.c1s[c]; c2[e] = sm.c2s[c]; }
                 else { s2[e] = s2_row; c1[e] = c1_row; c2[e] = c2_row; }
-                c0[e] = fma(s2[e], y[e], b) + 1.0;                                 // :9 | :81,:95
-                if (FORMULA == FORMULA_A1) sc[e] = 1.0;                            // S = 1 (R/ebpmf_log.R:304)
-                else sc[e] = l0_i * f0s[c];                                        // :83,:97
+                c0[e] = fma(s2[e], y, b) + 1.0;                                    // :9 | :81,:95
+                w[e] = fma(b, c1[e], y);                                           // x + const3
+                sc[e] = (FORMULA == FORMULA_A10) ? l0_i * sm.f0s[c] : 1.0;         // :83,:97 | S = 1
                 if (MODE == MODE_FIRST) {
                     const double cap = (FORMULA == FORMULA_A1) ? (c0[e] - 1.0) : b;   // :16 | :78
                     m[e] = (m[e] < cap) ? m[e] : cap;
                 }
             }
-            const int flags = newton_unit<E, FORMULA, MODE>(m, y, beta, c0, c1, c2, sc, ok, k, target,
-                                                            kstar_live, a.maxiter, a.tol, exptab, r, sexp);
-            if (flags & 4) { if (lane == 0) a.status->nan = 1; }
+            const int k_in = k;
+            const int flags = newton_unit<E, FORMULA, MODE, FORMULA == FORMULA_A10>(
+                m, c0, w, c1, c2, sc, ok, k, target, kstar_live, a.maxiter, a.tol, sm.exptab, r, sexp, f);
+            my_iters += (unsigned)(k - k_in + 1);
             if (flags & 2) any_exhausted = 1;
-            if (MODE == MODE_TOPUP && !(flags & 3) && !(flags & 4)) { if (lane == 0) a.status->verify_fail = 1; }
+            if (MODE == MODE_TOPUP && !(flags & 3)) any_fail = 1;
 
             // ---- finalise the unit ---------------------------------------------------------
             double rowv = 0.0;
+            bool lane_nan = false;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
+                const int c = g * E + e;
                 const long long j = jb + e;
+                lane_nan = lane_nan || (ok[e] && (f[e] != f[e]));
                 if (ok[e]) st_stream(a.M_out + i + a.n * j, m[e]);
                 if (FORMULA == FORMULA_A1) {
                     const double v = s2[e] * r[e];                                  // :36 Sigma2/temp (stale if exhausted)
                     if (ok[e] && a.V_out) st_stream(a.V_out + i + a.n * j, v);
                     double ex = sexp[e];                                            // == exp(M+V/2) when S == 1 and the loop broke
-                    if (flags & 2) ex = exp_fast(fma(0.5, v, m[e]), exptab);        // exhausted: M moved after temp
+                    if (flags & 2) ex = exp_fast(fma(0.5, v, m[e]), sm.exptab);     // exhausted: M moved after temp
                     double sv = ok[e] ? v : 0.0;
-                    double sy = ok[e] ? y[e] * m[e] : 0.0;                          // R/ebpmf_log.R:316
+                    double sy = ok[e] ? sm.ys[c][tid] * m[e] : 0.0;                 // R/ebpmf_log.R:316
                     double se = ok[e] ? ex : 0.0;                                   // :317
                     double sl = ok[e] ? fma(0.5, log_fast(v), kSlogvConst) : 0.0;   // :318
                     rowv += sv;
@@ -283,6 +309,7 @@ __global__ void __launch_bounds__(kThreads, 2) vga_fused_kernel(const FusedArgs 
                     }
                 }
             }
+            if (__any_sync(0xffffffffu, lane_nan)) any_nan = 1;
             if (FORMULA == FORMULA_A1 && a.rowpart && row_ok) a.rowpart[jg * a.n + i] = rowv;
             if (lane == 0) {
                 a.kunit[jg * a.nRW + rw] = (unsigned short)k;
@@ -290,7 +317,13 @@ __global__ void __launch_bounds__(kThreads, 2) vga_fused_kernel(const FusedArgs 
             }
         }
     }
-    if (any_exhausted && lane == 0) a.status->exhausted = 1;
+    if (lane == 0) {
+        if (any_exhausted) a.status->exhausted = 1;
+        if (any_nan) a.status->nan = 1;
+        if (any_fail) a.status->verify_fail = 1;
+        if (my_topups) atomicAdd(&a.status->topup_units, (unsigned long long)my_topups);
+        if (my_iters) atomicAdd(&a.status->unit_iters, (unsigned long long)my_iters);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -319,15 +352,15 @@ __global__ void __launch_bounds__(kThreads, 2) vga_dense_kernel(const DenseArgs 
     const long long i = rb * kRowsPerCta + tid;
     const bool row_ok = i < a.n;
     const long long rw = rb * kWarps + warp;
+    exp_table_init(exptab, tid, kThreads);
+    __syncthreads();
     if (rw >= a.nRW) return;                         // no block-wide barrier below this point
     const long long jc0 = (long long)blockIdx.x * a.cols_per_cta;
     const long long jc1 = min(a.p, jc0 + (long long)a.cols_per_cta);
-    exp_table_init(exptab, tid, kThreads);
-    __syncthreads();
     const int target = (MODE == MODE_TOPUP) ? a.status->kstar : 0;
     const volatile int *kstar_live = &a.status->kstar;
     const double *Msrc = (MODE == MODE_FIRST) ? a.M_in : a.M_out;
-    int any_exhausted = 0;
+    int any_exhausted = 0, any_nan = 0, any_fail = 0;
     const long long ii = row_ok ? i : 0;
 
 #pragma unroll 1
@@ -338,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, 2) vga_dense_kernel(const DenseArgs 
             k = a.kunit[jg * a.nRW + rw];
             if (k == target) continue;
         }
-        double m[E], y[E], beta[E], c0[E], c1[E], c2[E], sc[E], s2[E], r[E], sexp[E];
+        double m[E], c0[E], w[E], c1[E], c2[E], sc[E], s2[E], r[E], sexp[E], f[E];
         bool ok[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) {
@@ -346,37 +379,44 @@ __global__ void __launch_bounds__(kThreads, 2) vga_dense_kernel(const DenseArgs 
             ok[e] = row_ok && (j < jc1);
             const long long jj = (j < jc1) ? j : jc0;
             m[e] = ok[e] ? ld_stream(Msrc + i + a.n * j) : 0.0;
-            y[e] = ok[e] ? ld_stream(a.X + i + a.n * j) : 0.0;
-            beta[e] = ok[e] ? a.Beta[ii * a.B_rs + jj * a.B_cs] : 0.0;
+            const double y = ok[e] ? ld_stream(a.X + i + a.n * j) : 0.0;
+            const double b = ok[e] ? a.Beta[ii * a.B_rs + jj * a.B_cs] : 0.0;
             s2[e] = ok[e] ? a.Sigma2[ii * a.V_rs + jj * a.V_cs] : 1.0;
             sc[e] = ok[e] ? a.S[ii * a.S_rs + jj * a.S_cs] : 1.0;
             c1[e] = 1.0 / s2[e];                                                   // :10
             c2[e] = s2[e] / 2;                                                     // :11
-            c0[e] = fma(s2[e], y[e], beta[e]) + 1.0;                               // :9
+            c0[e] = fma(s2[e], y, b) + 1.0;                                        // :9
+            w[e] = fma(b, c1[e], y);                                               // x + const3
             if (MODE == MODE_FIRST) {
                 const double cap = c0[e] - 1.0;                                    // :16
                 m[e] = (m[e] < cap) ? m[e] : cap;
             }
         }
-        const int flags = newton_unit<E, FORMULA_A1, MODE>(m, y, beta, c0, c1, c2, sc, ok, k, target,
-                                                           kstar_live, a.maxiter, a.tol, exptab, r, sexp);
-        if (flags & 4) { if (lane == 0) a.status->nan = 1; }
+        const int flags = newton_unit<E, FORMULA_A1, MODE, true>(m, c0, w, c1, c2, sc, ok, k, target, kstar_live,
+                                                                  a.maxiter, a.tol, exptab, r, sexp, f);
         if (flags & 2) any_exhausted = 1;
-        if (MODE == MODE_TOPUP && !(flags & 3) && !(flags & 4)) { if (lane == 0) a.status->verify_fail = 1; }
+        if (MODE == MODE_TOPUP && !(flags & 3)) any_fail = 1;
+        bool lane_nan = false;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const long long j = jb + e;
+            lane_nan = lane_nan || (ok[e] && (f[e] != f[e]));
             if (ok[e]) {
                 st_stream(a.M_out + i + a.n * j, m[e]);
                 if (a.V_out) st_stream(a.V_out + i + a.n * j, s2[e] * r[e]);        // :36
             }
         }
+        if (__any_sync(0xffffffffu, lane_nan)) any_nan = 1;
         if (lane == 0) {
             a.kunit[jg * a.nRW + rw] = (unsigned short)k;
             if (MODE == MODE_FIRST && k > *kstar_live) atomicMax(&a.status->kstar, k);
         }
     }
-    if (any_exhausted && lane == 0) a.status->exhausted = 1;
+    if (lane == 0) {
+        if (any_exhausted) a.status->exhausted = 1;
+        if (any_nan) a.status->nan = 1;
+        if (any_fail) a.status->verify_fail = 1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -41,35 +41,73 @@ __device__ __forceinline__ void exp_table_init(double *tab, int tid, int nthread
         tab[j] = exp2((double)j * (1.0 / EBPMF_EXP_TABLE_SIZE));
 }
 
+// libdevice exp for arguments outside the fast range (overflow, underflow, NaN, Inf); kept out of
+// line so the Newton loop body stays small.
+__device__ __noinline__ double exp_slow(double x) { return exp(x); }
+
+// Constants of exp_core in the constant bank: DFMA takes them as c[bank][off] operands, so they
+// cost neither registers nor the UMOV/IMAD.MOV rematerialisation that immediates need.
+__constant__ double kExpC[6] = {
+    92.332482616893656768,        // 64/ln2
+    -0x1.62e42fee00000p-7,        // -(ln2/64 rounded to 32 bits): n*L_HI is exact
+    -0x1.a39ef35793c76p-39,       // -(ln2/64 - L_HI)
+    1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
+
+// true when |x| >= 700 or x is NaN / Inf: decided on the high word with integer instructions
+// so the test costs no FP64-pipe slot (0x4085E000_00000000 == 700.0).
+__device__ __forceinline__ bool exp_out_of_range(double x) {
+    return (__double2hiint(x) & 0x7fffffff) >= 0x4085E000;
+}
+
+// exp(x) for |x| < 700: n = rint(x*64/ln2), r = x - n*ln2/64, 2^(j/64) from the table,
+// exp(r) - 1 = r + r^2/2 + ... + r^5/120 (the dropped r^6/720 is <= 3.5e-17 at |r| <= ln2/128).
+// Measured on the host with the same fma sequence: max rel. error 2.3e-16 on [-700,700].
+__device__ __forceinline__ double exp_core(double x, const double *tab) {
+    const double MAGIC = 6755399441055744.0;           // 1.5 * 2^52
+    const double t = fma(x, kExpC[0], MAGIC);
+    const int n = __double2loint(t);
+    const double nf = t - MAGIC;
+    double r = fma(nf, kExpC[1], x);
+    r = fma(nf, kExpC[2], r);
+    double q = fma(r, kExpC[3], kExpC[4]);
+    q = fma(q, r, kExpC[5]);
+    q = fma(q, r, 0.5);
+    q = q * r;
+    q = fma(q, r, r);                                  // q = exp(r) - 1
+    const double tj = tab[n & (EBPMF_EXP_TABLE_SIZE - 1)];
+    const double v = fma(tj, q, tj);                   // 2^(j/64) * exp(r)
+    // scale by 2^(n>>6): |x| < 700 keeps the result a normal double
+    const int hi = __double2hiint(v) + ((n >> 6) << 20);
+    return __hiloint2double(hi, __double2loint(v));
+}
+
 __device__ __forceinline__ double exp_fast(double x, const double *tab) {
 #if EBPMF_EXACT_MATH
     (void)tab;
     return exp(x);
 #else
-    // Outside [-700, 700] (overflow / underflow / NaN / Inf) defer to libdevice.
-    if (!(fabs(x) < 700.0)) return exp(x);
-    const double INV = 92.332482616893656768;          // 64/ln2
-    const double L_HI = 0x1.62e42fee00000p-7;          // ln2/64 rounded to 32 bits: n*L_HI is exact
-    const double L_LO = 0x1.a39ef35793c76p-39;         // ln2/64 - L_HI
-    const double MAGIC = 6755399441055744.0;           // 1.5 * 2^52
-    double t = fma(x, INV, MAGIC);
-    int n = __double2loint(t);
-    double nf = t - MAGIC;
-    double r = fma(nf, -L_HI, x);
-    r = fma(nf, -L_LO, r);
-    // exp(r) - 1 = r + r^2/2 + ... + r^5/120; the dropped r^6/720 is <= 3.5e-17 at |r| <= ln2/128.
-    // Measured on the host with the same fma sequence: max rel. error 2.3e-16 on [-700,700].
-    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    q = fma(q, r, 1.0 / 6.0);
-    q = fma(q, r, 0.5);
-    q = q * r;
-    q = fma(q, r, r);                                  // q = exp(r) - 1
-    const double tj = tab[n & (EBPMF_EXP_TABLE_SIZE - 1)];
-    double v = fma(tj, q, tj);                         // 2^(j/64) * exp(r)
-    // scale by 2^(n>>6): |x| < 700 keeps the result a normal double
-    const int k = n >> 6;
-    int hi = __double2hiint(v) + (k << 20);
-    return __hiloint2double(hi, __double2loint(v));
+    if (exp_out_of_range(x)) return exp_slow(x);
+    return exp_core(x, tab);
+#endif
+}
+
+// E exponentials with ONE range branch for the lot (the Newton loop's form)
+template <int E>
+__device__ __forceinline__ void exp_fast_n(const double (&x)[E], double (&out)[E], const double *tab) {
+#if EBPMF_EXACT_MATH
+#pragma unroll
+    for (int e = 0; e < E; ++e) out[e] = exp(x[e]);
+#else
+    bool oor = false;
+#pragma unroll
+    for (int e = 0; e < E; ++e) oor = oor || exp_out_of_range(x[e]);
+    if (oor) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) out[e] = exp_slow(x[e]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) out[e] = exp_core(x[e], tab);
+    }
 #endif
 }
 

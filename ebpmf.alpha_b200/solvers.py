@@ -238,7 +238,7 @@ class VgaContext:
                                                    int(n_total or self.n), int(p_total or self.p), _ptr(out)))
         return out
 
-    def vga_step_host(self, M, EL, EF, sigma2, var_type, maxiter=10, tol=1e-5, return_V=False):
+    def vga_step_host(self, M, EL, EF, sigma2, var_type, maxiter=10, tol=1e-5, return_V=False, M_out=None):
         """The whole step with host buffers (what the .Call shim does each outer iteration)."""
         if var_type not in VAR_TYPE:
             raise EbpmfError(4, "Non-supported var type")
@@ -247,7 +247,9 @@ class VgaContext:
         EF = _f(np.asarray(EF, dtype=np.float64).reshape(self.p, -1))
         s2 = _vec(sigma2)
         ln = {"by_col": self.p, "by_row": self.n, "constant": 1}[var_type]
-        Mo = np.empty((self.n, self.p), order="F")
+        Mo = np.empty((self.n, self.p), order="F") if M_out is None else M_out     # e.g. a pinned buffer
+        if Mo.shape != (self.n, self.p) or not Mo.flags.f_contiguous or Mo.dtype != np.float64:
+            raise ValueError("M_out must be an n x p column-major float64 array")
         Vo = np.empty((self.n, self.p), order="F") if return_V else None
         vs = np.empty(ln)
         info = SolveInfo()
@@ -267,6 +269,11 @@ class VgaContext:
                                                   float(pi0), float(noise), int(bool(warm_start)), C.byref(nnz)))
         self.n, self.p, self.var_type = n, p, "by_col"
         return nnz.value
+
+    def last_diag(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self._lib.ebpmf_ctx_last_diag(self._h, C.byref(a), C.byref(b)))
+        return dict(topup_units=a.value, unit_evals=b.value)
 
     def probe_fp64_tflops(self):
         out = C.c_double()

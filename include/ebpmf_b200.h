@@ -65,6 +65,9 @@ typedef struct ebpmf_solve_info {
     double  ssexp;          /* sum(exp(M+V/2))               R/ebpmf_log.R:275,317 */
     double  slogv;          /* sum(log(V)/2+0.9189385)       R/ebpmf_log.R:276,318 */
     double  kernel_ms;      /* device time of the kernels of this call (CUDA events) */
+    double  pass1_ms;       /* first pass (every unit to its own convergence)        */
+    double  pass2_ms;       /* top-up pass(es) to the global count                    */
+    double  reduce_ms;      /* partial-sum reductions (+ NCCL combine when sharded)   */
 } ebpmf_solve_info;
 
 /* ---- library / context ---------------------------------------------------------------- */
@@ -197,6 +200,10 @@ int  ebpmf_ctx_sim_data_log(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, int
                             uint64_t seed, double log_offset, double bg_lo, double bg_hi,
                             double pi0, double noise, int warm_start,
                             int64_t *nnz_out);
+
+/* diagnostics of the last fused solve: units (warp x 2 columns) that needed second-pass work and
+ * the total number of unit evaluations (each = 64 entry evaluations of f) */
+int  ebpmf_ctx_last_diag(ebpmf_ctx *ctx, uint64_t *topup_units, uint64_t *unit_evals);
 
 /* device-time micro-probe of the FP64 pipe (DFMA chains), used by bench.py for the FP64 line */
 int  ebpmf_probe_fp64_tflops(ebpmf_ctx *ctx, double *tflops);
