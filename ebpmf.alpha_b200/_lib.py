@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libebpmf_b200.so")
+LIB_PATH = os.environ.get("EBPMF_B200_LIB") or os.path.join(_HERE, "lib", "libebpmf_b200.so")   # override: A/B builds
 
 EBPMF_OK = 0
 ERR_NAMES = {1: "EBPMF_ERR_ARG", 2: "EBPMF_ERR_CUDA", 3: "EBPMF_ERR_NAN", 4: "EBPMF_ERR_VAR_TYPE",

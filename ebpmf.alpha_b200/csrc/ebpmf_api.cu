@@ -10,6 +10,7 @@
 #include <nccl.h>      // types only; the library is dlopen'ed (nccl_dyn below)
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -77,10 +78,13 @@ struct ebpmf_ctx {
     DevBuf colptr, rowidx, yx, rbptr;
     DevBuf Mcur, Malt, V;
     DevBuf EL, EF, EFt, sigma2, l0, f0;
-    DevBuf kunit, colpart, rowpart;
+    DevBuf C0;         // const0 of the last first pass (n x p)
+    DevBuf sc1, sc2;   // 1/sigma2, sigma2/2
+    DevBuf kunit, colV, unitS, rowpart;
     DevBuf red;        // [4 scalars: sym, ssexp, slogv, sumV][v_sum ...]
-    DevBuf colsums;    // p x 3
+    DevBuf colsums;    // colsym[p] | v_sum scratch[p] | unitsum[nJG][2]
     DevBuf status;     // Status
+    DevBuf tables;     // MathTables
     DevBuf misc;       // small scratch (R2, fitmax, obj terms, lfactorial partials)
     DevBuf scratch[6]; // dense-signature operands
 
@@ -156,7 +160,10 @@ int ktp_for(int K) {
     return -1;
 }
 
-constexpr int kE = 2;   // columns per unit in the fused / dense kernels
+#ifndef EBPMF_E
+#define EBPMF_E 2
+#endif
+constexpr int kE = EBPMF_E;   // columns per unit in the fused / dense kernels
 
 int cols_per_cta_for(long long p, long long nRB) {
     // enough CTAs for ~16 waves of 148 SMs x 2 resident CTAs, spans of 16..256 columns
@@ -168,9 +175,9 @@ int cols_per_cta_for(long long p, long long nRB) {
     return (int)c;
 }
 
-template <int KTP, int FORMULA, int MODE>
-int launch_fused_ktp(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
-    auto kern = vga_fused_kernel<KTP, kE, FORMULA, MODE>;
+template <int KTP, int FORMULA>
+int launch_first_ktp(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
+    auto kern = vga_fused_kernel<KTP, kE, FORMULA>;
     const int smem = (int)sizeof(FusedSmem<KTP>);
     static bool configured[8] = {false, false, false, false, false, false, false, false};   // per device
     if (ctx->device < 8 ? !configured[ctx->device] : true) {
@@ -182,18 +189,30 @@ int launch_fused_ktp(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
     return EBPMF_OK;
 }
 
-template <int FORMULA, int MODE>
-int launch_fused(ebpmf_ctx *ctx, const FusedArgs &a) {
+// pass 1 of the fused path (K1 / K4)
+template <int FORMULA>
+int launch_first(ebpmf_ctx *ctx, const FusedArgs &a) {
     const long long ncols = a.col1 - a.col0;
     if (ncols <= 0) return EBPMF_OK;
     dim3 grid((unsigned)((ncols + a.cols_per_cta - 1) / a.cols_per_cta), (unsigned)ctx->nRB);
     switch (ctx->KTP) {
-        case 8: return launch_fused_ktp<8, FORMULA, MODE>(ctx, a, grid);
-        case 16: return launch_fused_ktp<16, FORMULA, MODE>(ctx, a, grid);
-        case 24: return launch_fused_ktp<24, FORMULA, MODE>(ctx, a, grid);
-        case 32: return launch_fused_ktp<32, FORMULA, MODE>(ctx, a, grid);
+        case 8: return launch_first_ktp<8, FORMULA>(ctx, a, grid);
+        case 16: return launch_first_ktp<16, FORMULA>(ctx, a, grid);
+        case 24: return launch_first_ktp<24, FORMULA>(ctx, a, grid);
+        case 32: return launch_first_ktp<32, FORMULA>(ctx, a, grid);
     }
     return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported (max 32)", ctx->K);
+}
+
+// pass 2 (streaming top-up to the global count)
+template <int FORMULA>
+int launch_topup(ebpmf_ctx *ctx, const FusedArgs &a) {
+    const long long ncols = a.col1 - a.col0;
+    if (ncols <= 0) return EBPMF_OK;
+    dim3 grid((unsigned)((ncols + a.cols_per_cta - 1) / a.cols_per_cta), (unsigned)ctx->nRB);
+    vga_topup_kernel<kE, FORMULA><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    return EBPMF_OK;
 }
 
 int stride_for(int kind, long long n, long long *rs, long long *cs) {
@@ -253,17 +272,26 @@ int alloc_solver_state(ebpmf_ctx *ctx, long long n, long long p) {
 }
 
 // reductions of the per-unit partials into red = [sym, ssexp, slogv, sumV][v_sum...]
+// (the final M is in Malt at this point: sum(Y*M) runs over the CSC non-zeros only)
 int run_reductions(ebpmf_ctx *ctx) {
     const long long n = ctx->n, p = ctx->p;
+    const long long nJG = (p + kE - 1) / kE;
     double *red = as<double>(ctx->red);
-    double *colv = (ctx->var_type == EBPMF_VAR_BY_COL) ? red + 4 : as<double>(ctx->colsums) + 3 * p;
-    reduce_cols_kernel<<<(unsigned)((p + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(
-        as<double>(ctx->colpart), ctx->nRW, p, colv, as<double>(ctx->colsums));
+    double *colsym = as<double>(ctx->colsums);
+    double *colv = (ctx->var_type == EBPMF_VAR_BY_COL) ? red + 4 : colsym + p;
+    double *unitsum = colsym + 2 * p;
+    reduce_over_rows_kernel<1><<<(unsigned)((p + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(
+        as<double>(ctx->colV), ctx->nRW, p, colv);
     CU(cudaGetLastError());
-    reduce_scalars_kernel<<<1, 1024, 0, ctx->stream>>>(colv, as<double>(ctx->colsums), p, red);
+    reduce_over_rows_kernel<2><<<(unsigned)((nJG + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(
+        as<double>(ctx->unitS), ctx->nRW, nJG, unitsum);
+    CU(cudaGetLastError());
+    sym_nnz_kernel<<<(unsigned)((p * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+        as<int>(ctx->colptr), as<int>(ctx->rowidx), as<double>(ctx->yx), as<double>(ctx->Malt), n, p, colsym);
+    CU(cudaGetLastError());
+    reduce_scalars_kernel<<<1, 1024, 0, ctx->stream>>>(colsym, colv, p, unitsum, nJG, red);
     CU(cudaGetLastError());
     if (ctx->var_type == EBPMF_VAR_BY_ROW) {
-        const long long nJG = (p + kE - 1) / kE;
         reduce_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(as<double>(ctx->rowpart), n, nJG,
                                                                                  red + 4);
         CU(cudaGetLastError());
@@ -328,13 +356,16 @@ FusedArgs fused_args(ebpmf_ctx *ctx, int maxiter, double tol, bool want_v) {
     a.n = ctx->n; a.p = ctx->p; a.K = ctx->K; a.var_type = ctx->var_type;
     a.M_in = as<double>(ctx->Mcur); a.M_out = as<double>(ctx->Malt);
     a.V_out = want_v ? as<double>(ctx->V) : nullptr;
+    a.C0 = as<double>(ctx->C0);
     a.EL = as<double>(ctx->EL); a.EFt = as<double>(ctx->EFt); a.sigma2 = as<double>(ctx->sigma2);
+    a.sc1 = as<double>(ctx->sc1); a.sc2 = as<double>(ctx->sc2);
     a.l0 = as<double>(ctx->l0); a.f0 = as<double>(ctx->f0);
     a.rowidx = as<int>(ctx->rowidx); a.yx = as<double>(ctx->yx); a.rbptr = as<int>(ctx->rbptr);
-    a.kunit = as<unsigned short>(ctx->kunit); a.nRW = ctx->nRW;
-    a.colpart = as<double>(ctx->colpart);
+    a.kunit = as<unsigned short>(ctx->kunit); a.nRW = ctx->nRW; a.nJG = (ctx->p + kE - 1) / kE;
+    a.colV = as<double>(ctx->colV); a.unitS = as<double>(ctx->unitS);
     a.rowpart = (ctx->var_type == EBPMF_VAR_BY_ROW) ? as<double>(ctx->rowpart) : nullptr;
     a.status = as<Status>(ctx->status);
+    a.tables = as<MathTables>(ctx->tables);
     a.maxiter = maxiter; a.tol = tol;
     a.col0 = 0; a.col1 = ctx->p;
     a.cols_per_cta = cols_per_cta_for(ctx->p, ctx->nRB);
@@ -367,8 +398,12 @@ int finish_set_y(ebpmf_ctx *ctx, long long n, long long p) {
     build_rbptr_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(
         as<int>(ctx->colptr), as<int>(ctx->rowidx), p, ctx->nRB, as<int>(ctx->rbptr));
     CU(cudaGetLastError());
-    CHECK(reserve(ctx, ctx->colpart, sizeof(double) * 4 * (size_t)ctx->nRW * (size_t)p));
-    CHECK(reserve(ctx, ctx->colsums, sizeof(double) * 4 * (size_t)p));
+    const long long nJG = (p + kE - 1) / kE;
+    CHECK(reserve(ctx, ctx->colV, sizeof(double) * (size_t)ctx->nRW * (size_t)p));
+    CHECK(reserve(ctx, ctx->unitS, sizeof(double) * 2 * (size_t)ctx->nRW * (size_t)nJG));
+    CHECK(reserve(ctx, ctx->colsums, sizeof(double) * (2 * (size_t)p + 2 * (size_t)nJG)));
+    CHECK(reserve(ctx, ctx->sc1, sizeof(double) * (size_t)std::max(n, p)));
+    CHECK(reserve(ctx, ctx->sc2, sizeof(double) * (size_t)std::max(n, p)));
     CHECK(reserve(ctx, ctx->red, sizeof(double) * (4 + (size_t)std::max(n, p))));
     CHECK(reserve(ctx, ctx->misc, sizeof(double) * (size_t)(3 * std::max(n, p) + 4096)));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -473,6 +508,22 @@ int ebpmf_ctx_create(int device, ebpmf_ctx **out) {
     CREATE_STEP(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
     CREATE_STEP(cudaMallocHost((void **)&ctx->h_status, sizeof(Status)));
     CREATE_STEP(cudaMallocHost((void **)&ctx->h_small, sizeof(double) * 64));
+    CREATE_STEP(cudaMalloc(&ctx->tables.ptr, sizeof(MathTables)));
+    ctx->tables.cap = sizeof(MathTables);
+    {
+        static MathTables host_tables;          // built once on the host: every kernel uses the same bits
+        static bool built = false;
+        if (!built) {
+            for (int j = 0; j < 64; ++j) host_tables.exp2_tab[j] = std::exp2((double)j / 64.0);
+            for (int i = 0; i < 128; ++i) {
+                const float c = (float)(1.0 / (1.0 + ((double)i + 0.5) / 128.0));
+                host_tables.log_tab[i].x = (double)c;
+                host_tables.log_tab[i].y = -std::log((double)c);
+            }
+            built = true;
+        }
+        CREATE_STEP(cudaMemcpy(ctx->tables.ptr, &host_tables, sizeof(MathTables), cudaMemcpyHostToDevice));
+    }
 #undef CREATE_STEP
     *out = ctx;
     return EBPMF_OK;
@@ -485,7 +536,8 @@ int ebpmf_ctx_destroy(ebpmf_ctx *ctx) {
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     DevBuf *bufs[] = {&ctx->colptr, &ctx->rowidx, &ctx->yx, &ctx->rbptr, &ctx->Mcur, &ctx->Malt, &ctx->V,
                       &ctx->EL, &ctx->EF, &ctx->EFt, &ctx->sigma2, &ctx->l0, &ctx->f0, &ctx->kunit,
-                      &ctx->colpart, &ctx->rowpart, &ctx->red, &ctx->colsums, &ctx->status, &ctx->misc};
+                      &ctx->colV, &ctx->unitS, &ctx->rowpart, &ctx->red, &ctx->colsums, &ctx->status, &ctx->misc,
+                      &ctx->C0, &ctx->sc1, &ctx->sc2, &ctx->tables};
     for (DevBuf *b : bufs) release(*b);
     for (DevBuf &b : ctx->scratch) release(b);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
@@ -606,6 +658,9 @@ int ebpmf_ctx_set_sigma2(ebpmf_ctx *ctx, int var_type, const double *sigma2) {
         const long long nJG = (ctx->p + kE - 1) / kE;
         CHECK(reserve(ctx, ctx->rowpart, sizeof(double) * (size_t)nJG * (size_t)ctx->n));
     }
+    sigma_consts_kernel<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(as<double>(ctx->sigma2), (long long)len,
+                                                                                as<double>(ctx->sc1), as<double>(ctx->sc2));
+    CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->var_type = var_type; ctx->have_s2 = true;
     return EBPMF_OK;
@@ -618,11 +673,12 @@ int ebpmf_ctx_vga_step(ebpmf_ctx *ctx, int maxiter, double tol, int want_v, ebpm
         return fail(ctx, EBPMF_ERR_STATE, "vga_step: Y, M, factors and sigma2 must be set first");
     CHECK(ensure_common(ctx));
     if (want_v) CHECK(reserve(ctx, ctx->V, sizeof(double) * (size_t)ctx->n * (size_t)ctx->p));
+    CHECK(reserve(ctx, ctx->C0, sizeof(double) * (size_t)ctx->n * (size_t)ctx->p));
     const FusedArgs a = fused_args(ctx, maxiter, tol, want_v != 0);
     ctx->have_v = false; ctx->have_vsum = false;
     int rc = run_global_stop(
-        ctx, maxiter, [&] { return launch_fused<FORMULA_A1, MODE_FIRST>(ctx, a); },
-        [&] { return launch_fused<FORMULA_A1, MODE_TOPUP>(ctx, a); }, [&] { return run_reductions(ctx); }, info);
+        ctx, maxiter, [&] { return launch_first<FORMULA_A1>(ctx, a); },
+        [&] { return launch_topup<FORMULA_A1>(ctx, a); }, [&] { return run_reductions(ctx); }, info);
     if (rc != EBPMF_OK) return rc;
     CU(cudaMemcpyAsync(ctx->h_small, ctx->red.ptr, sizeof(double) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -709,6 +765,9 @@ int ebpmf_ctx_update_sigma2(ebpmf_ctx *ctx, const double *R2, double a0, double 
     const double *vsum = as<double>(ctx->red) + (vt == EBPMF_VAR_CONSTANT ? 3 : 4);
     update_sigma2_kernel<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(
         vsum, dR2, len, half_m, a0, b0, cap_var_mean_ratio, fitmax, as<double>(ctx->sigma2));
+    CU(cudaGetLastError());
+    sigma_consts_kernel<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(as<double>(ctx->sigma2), len,
+                                                                               as<double>(ctx->sc1), as<double>(ctx->sc2));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(sigma2_out, ctx->sigma2.ptr, sizeof(double) * (size_t)len, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -847,6 +906,7 @@ int ebpmf_vga_newton(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *M, cons
     a.S = dS; a.Beta = dB; a.Sigma2 = dV;
     a.kunit = as<unsigned short>(ctx->kunit); a.nRW = nRW;
     a.status = as<Status>(ctx->status);
+    a.tables = as<MathTables>(ctx->tables);
     a.maxiter = maxiter; a.tol = tol;
     a.cols_per_cta = cols_per_cta_for(p, nRB);
     dim3 grid((unsigned)((p + a.cols_per_cta - 1) / a.cols_per_cta), (unsigned)nRB);
@@ -892,6 +952,7 @@ int ebpmf_vga_fixed_iter(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *M, 
     a.Y = as<double>(ctx->scratch[2]);
     a.S = dS; a.Beta = dB; a.Sigma2 = dV;
     a.M_out = as<double>(ctx->scratch[1]); a.V_out = as<double>(ctx->scratch[3]);
+    a.tables = as<MathTables>(ctx->tables);
     a.maxiter = maxiter;
     const long long nRB = (n + kRowsPerCta - 1) / kRowsPerCta;
     dim3 grid((unsigned)std::min<long long>(p, 4096), (unsigned)nRB);
@@ -924,10 +985,11 @@ int ebpmf_vga_low_memory(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, const 
     CHECK(reserve(ctx, ctx->f0, sizeof(double) * (size_t)p));
     CU(cudaMemcpyAsync(ctx->l0.ptr, l0, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->f0.ptr, f0, sizeof(double) * (size_t)p, cudaMemcpyHostToDevice, ctx->stream));
+    CHECK(reserve(ctx, ctx->C0, sizeof(double) * (size_t)n * (size_t)p));
     const FusedArgs a = fused_args(ctx, maxiter, tol, false);
     int rc = run_global_stop(
-        ctx, maxiter, [&] { return launch_fused<FORMULA_A10, MODE_FIRST>(ctx, a); },
-        [&] { return launch_fused<FORMULA_A10, MODE_TOPUP>(ctx, a); }, [&] { return EBPMF_OK; }, info);
+        ctx, maxiter, [&] { return launch_first<FORMULA_A10>(ctx, a); },
+        [&] { return launch_topup<FORMULA_A10>(ctx, a); }, [&] { return EBPMF_OK; }, info);
     if (rc != EBPMF_OK) return rc;
     if (info) { info->sym = info->ssexp = info->slogv = 0.0; }
     std::swap(ctx->Mcur, ctx->Malt);
@@ -1034,6 +1096,10 @@ int ebpmf_ctx_sim_data_log(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, int6
     CHECK(finish_set_y(ctx, n, p));
     transpose_ef_kernel<<<(unsigned)((p * ktp + 255) / 256), 256, 0, ctx->stream>>>(as<double>(ctx->EF), p, KT, ktp,
                                                                                    as<double>(ctx->EFt));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    sigma_consts_kernel<<<(unsigned)((p + 255) / 256), 256, 0, ctx->stream>>>(as<double>(ctx->sigma2), p,
+                                                                             as<double>(ctx->sc1), as<double>(ctx->sc2));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->K = KT; ctx->KTP = ktp; ctx->var_type = EBPMF_VAR_BY_COL;

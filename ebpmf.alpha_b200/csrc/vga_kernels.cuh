@@ -10,27 +10,30 @@
 //
 // Layout.  M is column-major n x p (R), so consecutive THREADS own consecutive ROWS: a CTA
 // of 256 threads owns a row block of 256 rows and walks a span of columns; every global
-// access to M/V is a 2 KB contiguous segment per column.  Each thread keeps its row of EL
-// (K_tot <= KTP doubles) in registers; the EF rows, sigma2 and the dense image of the sparse
-// Y tile (16 columns x 256 rows, scattered from the CSC arrays through a per-row-block
-// offset table) live in shared memory.  Beta_ij = sum_k EL_ik EF_jk is K_tot FMAs per entry:
-// an outer-product rebuild, not a tensor-core contraction.
+// access to M/V is a 2 KB contiguous segment per column.  Per 16-column tile the CTA stages,
+// in shared memory, the dense image of the sparse Y tile (scattered from the CSC arrays through
+// a per-row-block offset table) and the Beta tile: each thread loads its row of EL
+// (K_tot <= KTP doubles, registers, only for this phase) and forms Beta_ij = sum_k EL_ik EF_jk
+// against EF rows broadcast from shared memory -- K_tot FMAs per entry, an outer-product
+// rebuild, not a tensor-core contraction.
 //
 // The GLOBAL stop rule.  R stops when max|f| < tol over ALL entries, so every entry receives
 // the same number u of Newton updates.  The kernels reproduce u exactly with
 // register-resident iterations and no per-iteration grid sync:
 //   unit      = one warp x E columns (32*E entries), iterates in lock step;
-//   pass 1    (MODE_FIRST) each unit iterates until ITS entries all satisfy |f_k| < tol at
-//             some k >= t0, where t0 is the largest such k any finished unit has published
-//             so far (never above u, because at k = u every unit is converged); it
-//             finalises speculatively (M_k, partial sums) and records k_unit; K* = max k_unit;
-//   pass 2    (MODE_TOPUP) units with k_unit < K* continue the SAME iteration sequence up to
-//             K* updates, test |f_K*| < tol and re-finalise.  If every unit passes, u = K*
-//             (it is the first k at which all entries are below tol).  Otherwise the host
-//             repeats pass 2 with K*+1 (rare: needs an entry to bounce back above tol).
+//   pass 1    (vga_fused_kernel) each unit iterates until ITS entries all satisfy |f_k| < tol at
+//             some k >= t0, where t0 is the largest such k any finished unit had published when
+//             this unit started (never above u, because at k = u every unit is converged); it
+//             finalises speculatively (M_k, const0, partial sums) and records k_unit; K* = max;
+//   pass 2    (vga_topup_kernel, streaming: reads M_k and const0 back, no tile staging) units with
+//             k_unit < K* continue the SAME iteration sequence up to K* updates, test
+//             |f_K*| < tol and re-finalise.  If every unit passes, u = K* (it is the first k at
+//             which all entries are below tol).  Otherwise the host repeats pass 2 with K*+1
+//             (rare: needs an entry to bounce back above tol).
 //   exhausted if a unit reaches maxiter updates, u = maxiter and V keeps the reciprocal of the
 //             LAST EVALUATED temp, i.e. it is one iteration stale exactly as in R (F6).
-// A NaN in f at any evaluated k <= u is what makes R's `if()` fail; it raises status.nan.
+// A NaN in f never converges, so its unit runs to maxiter and the NaN is seen in the last
+// evaluated f: R's `if()` would have failed at the first NaN it tested, which is <= u.
 #pragma once
 #include "vga_math.cuh"
 
@@ -61,18 +64,22 @@ struct FusedArgs {
     const double *M_in;             // pass 1 source
     double *M_out;                  // pass 1 destination, pass 2 in place
     double *V_out;                  // nullable
+    double *C0;                     // n x p: const0 = (Sigma2*X + Beta) + 1, written by pass 1
     const double *EL;               // n x K column-major
     const double *EFt;              // p x KTP row-major, zero padded
-    const double *sigma2;
+    const double *sigma2;           // length 1 | n | p
+    const double *sc1, *sc2;        // 1/sigma2 (const1), sigma2/2 (const2), same length
     const double *l0, *f0;          // A10 only
     const int *rowidx;              // CSC row indices (0-based within the shard)
     const double *yx;               // CSC values
     const int *rbptr;               // (nRB+1) x p: first nnz of column j with row >= rb*256
-    unsigned short *kunit;          // [p/E][nRW]
-    long long nRW;                  // ceil(n/32)
-    double *colpart;                // [nRW][p][4] : sum V, sum Y*M, sum exp(M+V/2), sum(log(V)/2+c)
-    double *rowpart;                // [ceil(p/E)][n] sum V (by_row only), else null
+    unsigned short *kunit;          // [nJG][nRW]
+    long long nRW, nJG;             // ceil(n/32), ceil(p/E)
+    double *colV;                   // [nRW][p]      sum over the warp's 32 rows of V
+    double *unitS;                  // [nRW][nJG][2] sum exp(M+V/2), sum(log(V)/2+c) of the unit
+    double *rowpart;                // [nJG][n] sum over the unit's columns of V (by_row only), else null
     Status *status;
+    const MathTables *tables;       // exp2 / log tables (device copy of the host-built tables)
     int maxiter;
     double tol;
     long long col0, col1;           // columns of this launch
@@ -82,27 +89,72 @@ struct FusedArgs {
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
 
-__device__ __forceinline__ double warp_sum(double v) {
+// ---------------------------------------------------------------------------------------
+// Sum S (4 or 8) per-lane values over the 32 lanes with a transposing butterfly: each step
+// halves the number of values a lane carries, so S values cost S-1+log2(32/S)... shuffles of a
+// double instead of 5*S.  On return every lane holds the total of slot warp_slot<S>(lane).
+// Fixed tree => deterministic.
+// ---------------------------------------------------------------------------------------
+template <int S> __device__ __forceinline__ int warp_slot(int lane) {
+    return (S == 8) ? (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1))
+                    : (((lane >> 4) & 1) * 2 + ((lane >> 3) & 1));
+}
+
+template <int S> __device__ __forceinline__ double warp_multi_sum(const double (&v)[S], int lane) {
+    static_assert(S == 4 || S == 8, "4 or 8 slots");
+    const unsigned FULL = 0xffffffffu;
+    double a[4];
+    if (S == 8) {
+        const bool hi = lane & 16;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+        for (int s = 0; s < 4; ++s) {
+            const double keep = hi ? v[s + 4] : v[s], send = hi ? v[s] : v[s + 4];
+            a[s] = keep + __shfl_xor_sync(FULL, send, 16);
+        }
+        const bool h8 = lane & 8;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const double keep = h8 ? a[s + 2] : a[s], send = h8 ? a[s] : a[s + 2];
+            a[s] = keep + __shfl_xor_sync(FULL, send, 8);
+        }
+        const bool h4 = lane & 4;
+        const double keep = h4 ? a[1] : a[0], send = h4 ? a[0] : a[1];
+        double t = keep + __shfl_xor_sync(FULL, send, 4);
+        t += __shfl_xor_sync(FULL, t, 2);
+        t += __shfl_xor_sync(FULL, t, 1);
+        return t;
+    } else {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const double keep = hi ? v[s + 2] : v[s], send = hi ? v[s] : v[s + 2];
+            a[s] = keep + __shfl_xor_sync(FULL, send, 16);
+        }
+        const bool h8 = lane & 8;
+        const double keep = h8 ? a[1] : a[0], send = h8 ? a[0] : a[1];
+        double t = keep + __shfl_xor_sync(FULL, send, 8);
+        t += __shfl_xor_sync(FULL, t, 4);
+        t += __shfl_xor_sync(FULL, t, 2);
+        t += __shfl_xor_sync(FULL, t, 1);
+        return t;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
 // One unit: E entries per lane, all 32 lanes in lock step.  Per entry the loop carries
-//   m, c0 = (s2*y + beta) + 1, w = y + beta/s2, c1 = 1/s2, c2 = s2/2  [, sc = S]
+//   m, c0 = (s2*y + beta) + 1, w = (c0 - 1)/s2 = y + beta/s2, c1 = 1/s2, c2 = s2/2 [, sc = S]
 // so that  f = x - sexp - M*const1 + const3  (R/vga_solver_mat.R:25) is  fma(-m, c1, w - sexp).
+// tol_e is tol for a live entry and +Inf for a padding entry (row >= n or column >= p).
+// `target` is t0 in the first pass (stop at the first k >= t0 at which the unit is converged)
+// and K* in the top-up pass (stop exactly at k == K*).
 // On return k is the number of updates the unit has received, r[] the reciprocal of the last
 // evaluated temp, sexp[] / f[] the last evaluated S*exp(.) and f.
-// Returns a bit mask: 1 converged at k, 2 exhausted.  (A NaN never converges, so it exhausts
-// the loop and is detected from f[] by the caller -- R errors at the first NaN it tests, and
-// every k this unit evaluates is <= the global count, so the outcome is the same.)
+// Returns a bit mask: 1 converged at k, 2 exhausted.
 // ---------------------------------------------------------------------------------------
 template <int E, int FORMULA, int MODE, bool SCALED>
 __device__ __forceinline__ int newton_unit(double (&m)[E], const double (&c0)[E], const double (&w)[E],
                                            const double (&c1)[E], const double (&c2)[E], const double (&sc)[E],
-                                           const bool (&ok)[E], int &k, int target,
-                                           const volatile int *kstar_live, int maxiter, double tol,
+                                           const double (&tol_e)[E], int &k, int target, int maxiter,
                                            const double *exptab, double (&r)[E], double (&sexp)[E], double (&f)[E])
 {
     int flags = 0;
@@ -112,28 +164,26 @@ __device__ __forceinline__ int newton_unit(double (&m)[E], const double (&c0)[E]
         double a[E], xx[E], ex[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            const double temp = c0[e] - m[e];                                  // :22
+            const double temp = __dadd_rn(c0[e], -m[e]);                       // :22
             r[e] = rcp_fast(temp);
-            a[e] = c2[e] * r[e];                                               // const2/temp
-            xx[e] = m[e] + a[e];
+            a[e] = __dmul_rn(c2[e], r[e]);                                     // const2/temp
+            xx[e] = __dadd_rn(m[e], a[e]);
         }
         exp_fast_n<E>(xx, ex, exptab);
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            sexp[e] = SCALED ? sc[e] * ex[e] : ex[e];                          // :23
-            f[e] = fma(-m[e], c1[e], w[e] - sexp[e]);                          // :25 | :84,:98
-            lane_conv = lane_conv && ((fabs(f[e]) < tol) || !ok[e]);           // :26 (strict <)
+            sexp[e] = SCALED ? __dmul_rn(sc[e], ex[e]) : ex[e];                // :23
+            f[e] = __fma_rn(-m[e], c1[e], __dadd_rn(w[e], -sexp[e]));          // :25 | :84,:98
+            lane_conv = lane_conv && (fabs(f[e]) < tol_e[e]);                  // :26 (strict <)
         }
         const bool conv = __all_sync(0xffffffffu, lane_conv);
-        bool stop;
-        if (MODE == MODE_FIRST) stop = conv && (k >= *kstar_live);
-        else stop = (k == target);
+        const bool stop = (MODE == MODE_FIRST) ? (conv && (k >= target)) : (k == target);
         if (stop) { if (conv) flags |= 1; break; }
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            const double q = (FORMULA == FORMULA_A1) ? a[e] : 0.5 * r[e];     // const2/temp^2 | 0.5*temp^-2
-            const double g = fma(-sexp[e], fma(q, r[e], 1.0), -c1[e]);        // :31 | :90,:105
-            m[e] = fma(-f[e], rcp_fast(g), m[e]);
+            const double q = (FORMULA == FORMULA_A1) ? a[e] : __dmul_rn(0.5, r[e]);   // const2/temp^2 | 0.5*temp^-2
+            const double g = __fma_rn(-sexp[e], __fma_rn(q, r[e], 1.0), -c1[e]);      // :31 | :90,:105
+            m[e] = __fma_rn(-f[e], rcp_fast(g), m[e]);
         }
         ++k;
         if (k >= maxiter) { flags |= 2; break; }
@@ -141,22 +191,73 @@ __device__ __forceinline__ int newton_unit(double (&m)[E], const double (&c0)[E]
     return flags;
 }
 
-// shared memory of the fused kernel (dynamic): Y image, Beta image, EF rows, column constants
+// ---------------------------------------------------------------------------------------
+// Finalise one unit of the fused path: store M (and V), and for the A1 step the unit's
+// partial sums: sum_rows V per column -> colV[rw][j]; sum exp(M+V/2), sum(log(V)/2+c) ->
+// unitS[rw][jg][0..1]; by_row: sum_cols V -> rowpart[jg][i].  sum(Y*M) is taken over the
+// non-zeros only by sym_nnz_kernel once M is final.  Returns true if a live entry's f is NaN.
+// ---------------------------------------------------------------------------------------
+template <int E, int FORMULA>
+__device__ __forceinline__ bool finalize_unit(const FusedArgs &a, const double (&m)[E], const double (&c2)[E],
+                                              const double (&r)[E], const double (&sexp)[E], const double (&f)[E],
+                                              const bool (&ok)[E], int flags, long long i, long long jb,
+                                              long long jg, long long rw, int lane, bool row_ok,
+                                              const double *exptab, const double2 *logtab)
+{
+    constexpr int S = (E + 2 <= 4) ? 4 : 8;
+    static_assert(E + 2 <= 8, "at most 6 columns per unit");
+    double vals[S];
+#pragma unroll
+    for (int q = 0; q < S; ++q) vals[q] = 0.0;
+    double rowv = 0.0;
+    bool lane_nan = false;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const long long j = jb + e;
+        lane_nan = lane_nan || (ok[e] && (f[e] != f[e]));
+        if (ok[e]) st_stream(a.M_out + i + a.n * j, m[e]);
+        if (FORMULA == FORMULA_A1) {
+            const double v = __dmul_rn(__dadd_rn(c2[e], c2[e]), r[e]);          // :36 Sigma2/temp (stale if exhausted)
+            if (ok[e] && a.V_out) st_stream(a.V_out + i + a.n * j, v);
+            double ex = sexp[e];                                                // == exp(M+V/2): S == 1 and the loop broke
+            if (flags & 2) ex = exp_fast(__fma_rn(0.5, v, m[e]), exptab);       // exhausted: M moved after temp
+            const double lv = fma(0.5, log_fast(v, logtab), kSlogvConst);       // R/ebpmf_log.R:318
+            if (ok[e]) { vals[e] = v; vals[E] += ex; vals[E + 1] += lv; rowv += v; }
+        }
+    }
+    if (FORMULA == FORMULA_A1) {
+        const double tot = warp_multi_sum<S>(vals, lane);
+        const int slot = warp_slot<S>(lane);
+        if ((lane & ((S == 8) ? 3 : 7)) == 0) {                                 // one writer per slot
+            if (slot < E) { if (jb + slot < a.col1) a.colV[rw * a.p + jb + slot] = tot; }
+            else if (slot < E + 2) a.unitS[(rw * a.nJG + jg) * 2 + (slot - E)] = tot;
+        }
+        if (a.rowpart && row_ok) a.rowpart[jg * a.n + i] = rowv;
+    }
+    return __any_sync(0xffffffffu, lane_nan);
+}
+
+// shared memory of the first-pass kernel (dynamic): Y image, Beta image, EF rows, column constants
 template <int KTP>
 struct FusedSmem {
     double ys[kTileCols][kRowsPerCta];
     double bs[kTileCols][kRowsPerCta];
     double efs[kTileCols][KTP];
-    double s2s[kTileCols], c1s[kTileCols], c2s[kTileCols], f0s[kTileCols];
+    double c1s[kTileCols], c2s[kTileCols], f0s[kTileCols];
     double exptab[EBPMF_EXP_TABLE_SIZE];
+    double2 logtab[EBPMF_LOG_TABLE_SIZE];
 };
 
+#ifndef EBPMF_MINB
+#define EBPMF_MINB 3          // resident CTAs per SM the register allocation is bounded for
+#endif
+
 // ---------------------------------------------------------------------------------------
-// K1 / K4: fused VGA step on CSC Y with Beta rebuilt from the flash factors.
+// K1 / K4, pass 1: fused VGA step on CSC Y with Beta rebuilt from the flash factors.
 // grid = (column spans, row blocks), block = 256 threads, dynamic smem = sizeof(FusedSmem<KTP>).
 // ---------------------------------------------------------------------------------------
-template <int KTP, int E, int FORMULA, int MODE>
-__global__ void __launch_bounds__(kThreads, 2) vga_fused_kernel(const FusedArgs a)
+template <int KTP, int E, int FORMULA>
+__global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const FusedArgs a)
 {
     static_assert(kTileCols % E == 0, "E must divide the tile width");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -172,35 +273,26 @@ __global__ void __launch_bounds__(kThreads, 2) vga_fused_kernel(const FusedArgs 
     const long long jc0 = a.col0 + (long long)blockIdx.x * a.cols_per_cta;
     const long long jc1 = min(a.col1, jc0 + (long long)a.cols_per_cta);
 
-    exp_table_init(sm.exptab, tid, kThreads);
+    exp_table_init(sm.exptab, a.tables, tid, kThreads);
+    log_table_init(sm.logtab, a.tables, tid, kThreads);
 
     // row-constant pieces (by_row / constant sigma2, A10's l0)
-    double s2_row = 1.0, c1_row = 1.0, c2_row = 0.5, l0_i = 1.0;
+    double c1_row = 1.0, c2_row = 0.5, l0_i = 1.0;
     if (a.var_type != 2) {
-        s2_row = (a.var_type == 1) ? (row_ok ? a.sigma2[i] : 1.0) : a.sigma2[0];
-        c1_row = 1.0 / s2_row;                                                 // :10
-        c2_row = s2_row / 2;                                                   // :11
+        const long long si = (a.var_type == 1) ? (row_ok ? i : 0) : 0;
+        c1_row = a.sc1[si];                                                    // :10
+        c2_row = a.sc2[si];                                                    // :11
     }
     if (FORMULA == FORMULA_A10) l0_i = row_ok ? a.l0[i] : 1.0;
 
-    const int target = (MODE == MODE_TOPUP) ? a.status->kstar : 0;
     const volatile int *kstar_live = &a.status->kstar;
-    const double *Msrc = (MODE == MODE_FIRST) ? a.M_in : a.M_out;
-    int any_exhausted = 0, any_nan = 0, any_fail = 0;
-    unsigned my_topups = 0, my_iters = 0;
+    int any_exhausted = 0, any_nan = 0;
+    unsigned my_iters = 0;
+    const double *Mrow = a.M_in + i;                 // + n*j
+    double *Crow = a.C0 + i;
 
     for (long long j0 = jc0; j0 < jc1; j0 += kTileCols) {
-        // ---- does this tile need work?  (also the barrier that protects the smem tile) ----
-        bool need = (MODE == MODE_FIRST);
-        if (MODE == MODE_TOPUP && warp_ok) {
-#pragma unroll
-            for (int g = 0; g < kTileCols / E; ++g) {
-                const long long jb = j0 + g * E;
-                if (jb < jc1) need = need || (a.kunit[(jb / E) * a.nRW + rw] != target);
-            }
-        }
-        if (!__syncthreads_or(need)) continue;
-
+        __syncthreads();                             // previous tile fully consumed
         // ---- stage the tile: zero Y image, EF rows, per-column constants --------------------
 #pragma unroll
         for (int c = 0; c < kTileCols; ++c) sm.ys[c][tid] = 0.0;
@@ -211,13 +303,16 @@ __global__ void __launch_bounds__(kThreads, 2) vga_fused_kernel(const FusedArgs 
         }
         if (tid < kTileCols) {
             const long long j = j0 + tid;
-            double s2 = 1.0;
-            if (a.var_type == 2 && j < jc1) s2 = a.sigma2[j];
-            sm.s2s[tid] = s2;
-            sm.c1s[tid] = 1.0 / s2;
-            sm.c2s[tid] = s2 / 2;
+            const bool col = (a.var_type == 2) && (j < jc1);
+            sm.c1s[tid] = col ? a.sc1[j] : 1.0;
+            sm.c2s[tid] = col ? a.sc2[j] : 0.5;
             sm.f0s[tid] = (FORMULA == FORMULA_A10 && j < jc1) ? a.f0[j] : 1.0;
         }
+        // first unit's M values: in flight while the tile is staged
+        double mnext[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            mnext[e] = (row_ok && (j0 + e < jc1)) ? ld_stream(Mrow + a.n * (j0 + e)) : 0.0;
         __syncthreads();
         // scatter the CSC non-zeros of rows [r0, r0+256) of each tile column
         for (int c = warp; c < kTileCols; c += kWarps) {
@@ -250,72 +345,114 @@ __global__ void __launch_bounds__(kThreads, 2) vga_fused_kernel(const FusedArgs 
             const long long jb = j0 + g * E;
             if (jb >= jc1 || !warp_ok) break;
             const long long jg = jb / E;
-            int k = 0;
-            if (MODE == MODE_TOPUP) {
-                k = a.kunit[jg * a.nRW + rw];
-                if (k == target) continue;
-                ++my_topups;
-            }
-            double m[E], c0[E], w[E], c1[E], c2[E], sc[E], s2[E], r[E], sexp[E], f[E];
+            // t0: the largest converged-at count any finished unit has published so far.  It never
+            // exceeds the global count u, so running this unit at least that far cannot overshoot.
+            const int t0 = *kstar_live;
+            double m[E], c0[E], w[E], c1[E], c2[E], sc[E], tol_e[E], r[E], sexp[E], f[E];
             bool ok[E];
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int c = g * E + e;
                 const long long j = jb + e;
                 ok[e] = row_ok && (j < jc1);
-                m[e] = ok[e] ? ld_stream(Msrc + i + a.n * j) : 0.0;
+                m[e] = mnext[e];
+                const long long jn = j + E;                                        // same slot of the next unit
+                mnext[e] = (row_ok && (g + 1 < kTileCols / E) && (jn < jc1)) ? ld_stream(Mrow + a.n * jn) : 0.0;
                 const double y = sm.ys[c][tid], b = sm.bs[c][tid];
-                if (a.var_type == 2) { s2[e] = sm.s2s[c]; c1[e] = sm.c1s[c]; c2[e] = sm.c2s[c]; }
-                else { s2[e] = s2_row; c1[e] = c1_row; c2[e] = c2_row; }
-                c0[e] = fma(s2[e], y, b) + 1.0;                                    // :9 | :81,:95
-                w[e] = fma(b, c1[e], y);                                           // x + const3
-                sc[e] = (FORMULA == FORMULA_A10) ? l0_i * sm.f0s[c] : 1.0;         // :83,:97 | S = 1
-                if (MODE == MODE_FIRST) {
-                    const double cap = (FORMULA == FORMULA_A1) ? (c0[e] - 1.0) : b;   // :16 | :78
-                    m[e] = (m[e] < cap) ? m[e] : cap;
-                }
+                if (a.var_type == 2) { c1[e] = sm.c1s[c]; c2[e] = sm.c2s[c]; }
+                else { c1[e] = c1_row; c2[e] = c2_row; }
+                c0[e] = __dadd_rn(__fma_rn(__dadd_rn(c2[e], c2[e]), y, b), 1.0);   // :9 | :81,:95
+                const double c0m1 = __dadd_rn(c0[e], -1.0);
+                w[e] = __dmul_rn(c0m1, c1[e]);                                     // x + const3
+                sc[e] = (FORMULA == FORMULA_A10) ? __dmul_rn(l0_i, sm.f0s[c]) : 1.0;   // :83,:97 | S = 1
+                const double cap = (FORMULA == FORMULA_A1) ? c0m1 : b;             // :16 | :78
+                m[e] = (m[e] < cap) ? m[e] : cap;
+                tol_e[e] = ok[e] ? a.tol : INFINITY;
+                if (ok[e]) st_stream(Crow + a.n * j, c0[e]);
             }
-            const int k_in = k;
-            const int flags = newton_unit<E, FORMULA, MODE, FORMULA == FORMULA_A10>(
-                m, c0, w, c1, c2, sc, ok, k, target, kstar_live, a.maxiter, a.tol, sm.exptab, r, sexp, f);
-            my_iters += (unsigned)(k - k_in + 1);
+            int k = 0;
+            const int flags = newton_unit<E, FORMULA, MODE_FIRST, FORMULA == FORMULA_A10>(
+                m, c0, w, c1, c2, sc, tol_e, k, t0, a.maxiter, sm.exptab, r, sexp, f);
+            my_iters += (unsigned)(k + 1);
             if (flags & 2) any_exhausted = 1;
-            if (MODE == MODE_TOPUP && !(flags & 3)) any_fail = 1;
-
-            // ---- finalise the unit ---------------------------------------------------------
-            double rowv = 0.0;
-            bool lane_nan = false;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int c = g * E + e;
-                const long long j = jb + e;
-                lane_nan = lane_nan || (ok[e] && (f[e] != f[e]));
-                if (ok[e]) st_stream(a.M_out + i + a.n * j, m[e]);
-                if (FORMULA == FORMULA_A1) {
-                    const double v = s2[e] * r[e];                                  // :36 Sigma2/temp (stale if exhausted)
-                    if (ok[e] && a.V_out) st_stream(a.V_out + i + a.n * j, v);
-                    double ex = sexp[e];                                            // == exp(M+V/2) when S == 1 and the loop broke
-                    if (flags & 2) ex = exp_fast(fma(0.5, v, m[e]), sm.exptab);     // exhausted: M moved after temp
-                    double sv = ok[e] ? v : 0.0;
-                    double sy = ok[e] ? sm.ys[c][tid] * m[e] : 0.0;                 // R/ebpmf_log.R:316
-                    double se = ok[e] ? ex : 0.0;                                   // :317
-                    double sl = ok[e] ? fma(0.5, log_fast(v), kSlogvConst) : 0.0;   // :318
-                    rowv += sv;
-                    sv = warp_sum(sv); sy = warp_sum(sy); se = warp_sum(se); sl = warp_sum(sl);
-                    if (lane == 0 && j < jc1) {
-                        double *dst = a.colpart + (rw * a.p + j) * 4;
-                        reinterpret_cast<double2 *>(dst)[0] = make_double2(sv, sy);
-                        reinterpret_cast<double2 *>(dst)[1] = make_double2(se, sl);
-                    }
-                }
-            }
-            if (__any_sync(0xffffffffu, lane_nan)) any_nan = 1;
-            if (FORMULA == FORMULA_A1 && a.rowpart && row_ok) a.rowpart[jg * a.n + i] = rowv;
+            if (finalize_unit<E, FORMULA>(a, m, c2, r, sexp, f, ok, flags, i, jb, jg, rw, lane, row_ok, sm.exptab,
+                                          sm.logtab))
+                any_nan = 1;
             if (lane == 0) {
                 a.kunit[jg * a.nRW + rw] = (unsigned short)k;
-                if (MODE == MODE_FIRST && k > *kstar_live) atomicMax(&a.status->kstar, k);
+                if (k > t0) atomicMax(&a.status->kstar, k);
             }
         }
+    }
+    if (lane == 0) {
+        if (any_exhausted) a.status->exhausted = 1;
+        if (any_nan) a.status->nan = 1;
+        if (my_iters) atomicAdd(&a.status->unit_iters, (unsigned long long)my_iters);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K1 / K4, pass 2: streaming top-up.  Same (column span, row block) decomposition so that
+// unit indices agree with pass 1; reads M_k and const0 back, no Y / Beta staging, no barrier
+// after the table set-up.
+// ---------------------------------------------------------------------------------------
+template <int E, int FORMULA>
+__global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_topup_kernel(const FusedArgs a)
+{
+    __shared__ double exptab[EBPMF_EXP_TABLE_SIZE];
+    __shared__ double2 logtab[EBPMF_LOG_TABLE_SIZE];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long rb = blockIdx.y;
+    const long long i = rb * kRowsPerCta + tid;
+    const bool row_ok = i < a.n;
+    const long long rw = rb * kWarps + warp;
+    exp_table_init(exptab, a.tables, tid, kThreads);
+    log_table_init(logtab, a.tables, tid, kThreads);
+    __syncthreads();
+    if (rw >= a.nRW) return;                         // no block-wide barrier below this point
+    const long long jc0 = a.col0 + (long long)blockIdx.x * a.cols_per_cta;
+    const long long jc1 = min(a.col1, jc0 + (long long)a.cols_per_cta);
+    const int target = a.status->kstar;
+    double c1_row = 1.0, c2_row = 0.5, l0_i = 1.0;
+    if (a.var_type != 2) {
+        const long long si = (a.var_type == 1) ? (row_ok ? i : 0) : 0;
+        c1_row = a.sc1[si];
+        c2_row = a.sc2[si];
+    }
+    if (FORMULA == FORMULA_A10) l0_i = row_ok ? a.l0[i] : 1.0;
+    int any_exhausted = 0, any_nan = 0, any_fail = 0;
+    unsigned my_topups = 0, my_iters = 0;
+
+#pragma unroll 1
+    for (long long jb = jc0; jb < jc1; jb += E) {
+        const long long jg = jb / E;
+        int k = a.kunit[jg * a.nRW + rw];
+        if (k == target) continue;
+        ++my_topups;
+        double m[E], c0[E], w[E], c1[E], c2[E], sc[E], tol_e[E], r[E], sexp[E], f[E];
+        bool ok[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const long long j = jb + e;
+            ok[e] = row_ok && (j < jc1);
+            const long long jj = (j < jc1) ? j : jc0;
+            m[e] = ok[e] ? ld_stream(a.M_out + i + a.n * j) : 0.0;
+            c0[e] = ok[e] ? ld_stream(a.C0 + i + a.n * j) : 2.0;
+            if (a.var_type == 2) { c1[e] = __ldg(a.sc1 + jj); c2[e] = __ldg(a.sc2 + jj); }
+            else { c1[e] = c1_row; c2[e] = c2_row; }
+            w[e] = __dmul_rn(__dadd_rn(c0[e], -1.0), c1[e]);
+            sc[e] = (FORMULA == FORMULA_A10) ? __dmul_rn(l0_i, __ldg(a.f0 + jj)) : 1.0;
+            tol_e[e] = ok[e] ? a.tol : INFINITY;
+        }
+        const int k_in = k;
+        const int flags = newton_unit<E, FORMULA, MODE_TOPUP, FORMULA == FORMULA_A10>(
+            m, c0, w, c1, c2, sc, tol_e, k, target, a.maxiter, exptab, r, sexp, f);
+        my_iters += (unsigned)(k - k_in + 1);
+        if (flags & 2) any_exhausted = 1;
+        if (!(flags & 3)) any_fail = 1;              // stopped at K* but not below tol
+        if (finalize_unit<E, FORMULA>(a, m, c2, r, sexp, f, ok, flags, i, jb, jg, rw, lane, row_ok, exptab, logtab))
+            any_nan = 1;
+        if (lane == 0) a.kunit[jg * a.nRW + rw] = (unsigned short)k;
     }
     if (lane == 0) {
         if (any_exhausted) a.status->exhausted = 1;
@@ -326,9 +463,35 @@ __global__ void __launch_bounds__(kThreads, 2) vga_fused_kernel(const FusedArgs 
     }
 }
 
+// sum(Y*M) over the non-zeros (R/ebpmf_log.R:316): one warp per column, colsym[j] = sum_q x_q M[i_q, j]
+__global__ void __launch_bounds__(256) sym_nnz_kernel(const int *colptr, const int *rowidx, const double *yx,
+                                                      const double *M, long long n, long long p, double *colsym)
+{
+    const long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (j >= p) return;
+    double acc = 0.0;
+    const double *Mc = M + n * j;
+    for (int q = colptr[j] + lane; q < colptr[j + 1]; q += 32) acc = fma(__ldg(yx + q), Mc[rowidx[q]], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) colsym[j] = acc;
+}
+
+// 1/sigma2 and sigma2/2 (const1, const2 of R/vga_solver_mat.R:10-11) for every sigma2 element
+__global__ void sigma_consts_kernel(const double *sigma2, long long len, double *sc1, double *sc2)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= len) return;
+    const double s2 = sigma2[t];
+    sc1[t] = 1.0 / s2;
+    sc2[t] = s2 / 2;
+}
+
 // ---------------------------------------------------------------------------------------
 // K2: drop-in dense-operand solver  vga_pois_solver_mat_newton(M,X,S,Beta,Sigma2,...)
-// Operands recycle through (row stride, col stride).  Same two-pass global-stop scheme.
+// Operands recycle through (row stride, col stride).  Same two-pass global-stop scheme; both
+// passes re-derive the per-entry constants from the operands.
 // ---------------------------------------------------------------------------------------
 struct DenseArgs {
     long long n, p;
@@ -339,6 +502,7 @@ struct DenseArgs {
     const double *Sigma2; long long V_rs, V_cs;
     unsigned short *kunit; long long nRW;
     Status *status;
+    const MathTables *tables;
     int maxiter; double tol;
     int cols_per_cta;
 };
@@ -352,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, 2) vga_dense_kernel(const DenseArgs 
     const long long i = rb * kRowsPerCta + tid;
     const bool row_ok = i < a.n;
     const long long rw = rb * kWarps + warp;
-    exp_table_init(exptab, tid, kThreads);
+    exp_table_init(exptab, a.tables, tid, kThreads);
     __syncthreads();
     if (rw >= a.nRW) return;                         // no block-wide barrier below this point
     const long long jc0 = (long long)blockIdx.x * a.cols_per_cta;
@@ -367,11 +531,12 @@ __global__ void __launch_bounds__(kThreads, 2) vga_dense_kernel(const DenseArgs 
     for (long long jb = jc0; jb < jc1; jb += E) {
         const long long jg = jb / E;
         int k = 0;
+        const int t0 = (MODE == MODE_FIRST) ? *kstar_live : 0;
         if (MODE == MODE_TOPUP) {
             k = a.kunit[jg * a.nRW + rw];
             if (k == target) continue;
         }
-        double m[E], c0[E], w[E], c1[E], c2[E], sc[E], s2[E], r[E], sexp[E], f[E];
+        double m[E], c0[E], w[E], c1[E], c2[E], sc[E], s2[E], tol_e[E], r[E], sexp[E], f[E];
         bool ok[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) {
@@ -385,15 +550,15 @@ __global__ void __launch_bounds__(kThreads, 2) vga_dense_kernel(const DenseArgs 
             sc[e] = ok[e] ? a.S[ii * a.S_rs + jj * a.S_cs] : 1.0;
             c1[e] = 1.0 / s2[e];                                                   // :10
             c2[e] = s2[e] / 2;                                                     // :11
-            c0[e] = fma(s2[e], y, b) + 1.0;                                        // :9
-            w[e] = fma(b, c1[e], y);                                               // x + const3
-            if (MODE == MODE_FIRST) {
-                const double cap = c0[e] - 1.0;                                    // :16
-                m[e] = (m[e] < cap) ? m[e] : cap;
-            }
+            c0[e] = __dadd_rn(__fma_rn(s2[e], y, b), 1.0);                         // :9
+            const double c0m1 = __dadd_rn(c0[e], -1.0);
+            w[e] = __dmul_rn(c0m1, c1[e]);                                         // x + const3
+            tol_e[e] = ok[e] ? a.tol : INFINITY;
+            if (MODE == MODE_FIRST) m[e] = (m[e] < c0m1) ? m[e] : c0m1;            // :16
         }
-        const int flags = newton_unit<E, FORMULA_A1, MODE, true>(m, c0, w, c1, c2, sc, ok, k, target, kstar_live,
-                                                                  a.maxiter, a.tol, exptab, r, sexp, f);
+        const int flags = newton_unit<E, FORMULA_A1, MODE, true>(m, c0, w, c1, c2, sc, tol_e, k,
+                                                                  (MODE == MODE_FIRST) ? t0 : target, a.maxiter,
+                                                                  exptab, r, sexp, f);
         if (flags & 2) any_exhausted = 1;
         if (MODE == MODE_TOPUP && !(flags & 3)) any_fail = 1;
         bool lane_nan = false;
@@ -403,13 +568,13 @@ __global__ void __launch_bounds__(kThreads, 2) vga_dense_kernel(const DenseArgs 
             lane_nan = lane_nan || (ok[e] && (f[e] != f[e]));
             if (ok[e]) {
                 st_stream(a.M_out + i + a.n * j, m[e]);
-                if (a.V_out) st_stream(a.V_out + i + a.n * j, s2[e] * r[e]);        // :36
+                if (a.V_out) st_stream(a.V_out + i + a.n * j, __dmul_rn(s2[e], r[e]));   // :36
             }
         }
         if (__any_sync(0xffffffffu, lane_nan)) any_nan = 1;
         if (lane == 0) {
             a.kunit[jg * a.nRW + rw] = (unsigned short)k;
-            if (MODE == MODE_FIRST && k > *kstar_live) atomicMax(&a.status->kstar, k);
+            if (MODE == MODE_FIRST && k > t0) atomicMax(&a.status->kstar, k);
         }
     }
     if (lane == 0) {
@@ -430,13 +595,14 @@ struct FixedArgs {
     const double *Beta; long long B_rs, B_cs;
     const double *Sigma2; long long V_rs, V_cs;
     double *M_out, *V_out;
+    const MathTables *tables;
     int maxiter;
 };
 
 __global__ void __launch_bounds__(kThreads) vga_fixed_iter_kernel(const FixedArgs a)
 {
     __shared__ double exptab[EBPMF_EXP_TABLE_SIZE];
-    exp_table_init(exptab, threadIdx.x, kThreads);
+    exp_table_init(exptab, a.tables, threadIdx.x, kThreads);
     __syncthreads();
     const long long i = (long long)blockIdx.y * kRowsPerCta + threadIdx.x;
     if (i >= a.n) return;
@@ -471,44 +637,42 @@ __global__ void __launch_bounds__(kThreads) vga_fixed_iter_kernel(const FixedArg
 // ---------------------------------------------------------------------------------------
 // reductions of the per-unit partials (fixed order => run-to-run reproducible)
 // ---------------------------------------------------------------------------------------
-// block (32, 8): x = column within a group of 32, y = slice of row-warps.
-// out[j] = v_sum[j]; colsums[j*3 + {0,1,2}] = per-column sym, ssexp, slogv.
-__global__ void __launch_bounds__(256) reduce_cols_kernel(const double *colpart, long long nRW, long long p,
-                                                          double *v_sum, double *colsums)
+// src is [R][C][W]; dst[c*W + w] = sum_r src[r][c][w].  block (32, 8): x = column, y = slice of r.
+template <int W>
+__global__ void __launch_bounds__(256) reduce_over_rows_kernel(const double *src, long long R, long long C, double *dst)
 {
-    __shared__ double sm[8][32][4];
-    const long long j = (long long)blockIdx.x * 32 + threadIdx.x;
-    double acc[4] = {0, 0, 0, 0};
-    if (j < p) {
-        for (long long rw = threadIdx.y; rw < nRW; rw += 8) {
-            const double2 *src = reinterpret_cast<const double2 *>(colpart + (rw * p + j) * 4);
-            const double2 u = src[0], w = src[1];
-            acc[0] += u.x; acc[1] += u.y; acc[2] += w.x; acc[3] += w.y;
+    __shared__ double sm[8][32][W];
+    const long long c = (long long)blockIdx.x * 32 + threadIdx.x;
+    double acc[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) acc[w] = 0.0;
+    if (c < C) {
+        for (long long r = threadIdx.y; r < R; r += 8) {
+#pragma unroll
+            for (int w = 0; w < W; ++w) acc[w] += src[(r * C + c) * W + w];
         }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) sm[threadIdx.y][threadIdx.x][q] = acc[q];
+    for (int w = 0; w < W; ++w) sm[threadIdx.y][threadIdx.x][w] = acc[w];
     __syncthreads();
-    if (threadIdx.y == 0 && j < p) {
-        double t[4] = {0, 0, 0, 0};
-        for (int s = 0; s < 8; ++s)
+    if (threadIdx.y == 0 && c < C) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) t[q] += sm[s][threadIdx.x][q];
-        v_sum[j] = t[0];
-        colsums[j * 3 + 0] = t[1]; colsums[j * 3 + 1] = t[2]; colsums[j * 3 + 2] = t[3];
+        for (int w = 0; w < W; ++w) {
+            double t = 0.0;
+            for (int s = 0; s < 8; ++s) t += sm[s][threadIdx.x][w];
+            dst[c * W + w] = t;
+        }
     }
 }
 
-// one block: scalars[0..2] = sym, ssexp, slogv ; scalars[3] = sum(V)
-__global__ void __launch_bounds__(1024) reduce_scalars_kernel(const double *v_sum, const double *colsums,
-                                                              long long p, double *scalars)
+// one block: scalars[0] = sum colsym (sym), [1] = ssexp, [2] = slogv (from unit sums [nJG][2]), [3] = sum(V)
+__global__ void __launch_bounds__(1024) reduce_scalars_kernel(const double *colsym, const double *v_sum, long long p,
+                                                              const double *unitsum, long long nJG, double *scalars)
 {
     __shared__ double sm[4][1024];
     double acc[4] = {0, 0, 0, 0};
-    for (long long j = threadIdx.x; j < p; j += 1024) {
-        acc[0] += colsums[j * 3 + 0]; acc[1] += colsums[j * 3 + 1]; acc[2] += colsums[j * 3 + 2];
-        acc[3] += v_sum[j];
-    }
+    for (long long j = threadIdx.x; j < p; j += 1024) { acc[0] += colsym[j]; acc[3] += v_sum[j]; }
+    for (long long g = threadIdx.x; g < nJG; g += 1024) { acc[1] += unitsum[g * 2]; acc[2] += unitsum[g * 2 + 1]; }
     for (int q = 0; q < 4; ++q) sm[q][threadIdx.x] = acc[q];
     __syncthreads();
     for (int s = 512; s > 0; s >>= 1) {

@@ -7,8 +7,11 @@
 //         r(1+e+e^2): 3 DFMA, result within ~1.5 ulp for normal, finite x;
 //   exp : n = rint(x*64/ln2); r = x - n*ln2/64 (Cody-Waite, 2 DFMA); 2^(j/64) from a
 //         64-entry table in shared memory; degree-5 polynomial: ~10 DP instructions, rel. err <= 2.3e-16;
-//   log : libdevice log() (only once per entry, in the epilogue).
+//   log : 128-entry (1/m_i, -log(1/m_i)) table + degree-6 log1p polynomial, ~10 DP instructions.
 // Parity budget is 1e-8 relative against the oracle (BASELINE.json); these are ~1e-15.
+// Every operation is an explicit __fma_rn/__dmul_rn/__dadd_rn so that nvcc's mul+add contraction
+// cannot differ between the two kernels that continue one iteration sequence: a unit gives
+// bit-identical iterates whichever pass executes them (run-to-run reproducible results).
 // EBPMF_EXACT_MATH=1 switches to IEEE division and libdevice exp() (used by tests to
 // bound the effect of the fast paths).
 #pragma once
@@ -27,18 +30,24 @@ __device__ __forceinline__ double rcp_fast(double x) {
 #else
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    e = fma(e, e, e);
-    return fma(r, e, r);
+    double e = __fma_rn(-x, r, 1.0);
+    e = __fma_rn(e, e, e);
+    return __fma_rn(r, e, r);
 #endif
 }
 
 // 2^(j/64), j = 0..63, filled by exp_table_init() into shared memory (64 doubles).
 #define EBPMF_EXP_TABLE_SIZE 64
 
-__device__ __forceinline__ void exp_table_init(double *tab, int tid, int nthreads) {
-    for (int j = tid; j < EBPMF_EXP_TABLE_SIZE; j += nthreads)
-        tab[j] = exp2((double)j * (1.0 / EBPMF_EXP_TABLE_SIZE));
+// The table values come from ONE place (the host, ebpmf_api.cu: math_tables()) and are copied into
+// shared memory by every kernel, so all kernels iterate with bit-identical tables.
+struct MathTables {
+    double exp2_tab[64];          // 2^(j/64)
+    double2 log_tab[128];         // (c_i, -log(c_i)), c_i = float(1/(1+(i+0.5)/128))
+};
+
+__device__ __forceinline__ void exp_table_init(double *tab, const MathTables *g, int tid, int nthreads) {
+    for (int j = tid; j < 64; j += nthreads) tab[j] = g->exp2_tab[j];
 }
 
 // libdevice exp for arguments outside the fast range (overflow, underflow, NaN, Inf); kept out of
@@ -64,18 +73,18 @@ __device__ __forceinline__ bool exp_out_of_range(double x) {
 // Measured on the host with the same fma sequence: max rel. error 2.3e-16 on [-700,700].
 __device__ __forceinline__ double exp_core(double x, const double *tab) {
     const double MAGIC = 6755399441055744.0;           // 1.5 * 2^52
-    const double t = fma(x, kExpC[0], MAGIC);
+    const double t = __fma_rn(x, kExpC[0], MAGIC);
     const int n = __double2loint(t);
-    const double nf = t - MAGIC;
-    double r = fma(nf, kExpC[1], x);
-    r = fma(nf, kExpC[2], r);
-    double q = fma(r, kExpC[3], kExpC[4]);
-    q = fma(q, r, kExpC[5]);
-    q = fma(q, r, 0.5);
-    q = q * r;
-    q = fma(q, r, r);                                  // q = exp(r) - 1
+    const double nf = __dadd_rn(t, -MAGIC);
+    double r = __fma_rn(nf, kExpC[1], x);
+    r = __fma_rn(nf, kExpC[2], r);
+    double q = __fma_rn(r, kExpC[3], kExpC[4]);
+    q = __fma_rn(q, r, kExpC[5]);
+    q = __fma_rn(q, r, 0.5);
+    q = __dmul_rn(q, r);
+    q = __fma_rn(q, r, r);                             // q = exp(r) - 1
     const double tj = tab[n & (EBPMF_EXP_TABLE_SIZE - 1)];
-    const double v = fma(tj, q, tj);                   // 2^(j/64) * exp(r)
+    const double v = __fma_rn(tj, q, tj);              // 2^(j/64) * exp(r)
     // scale by 2^(n>>6): |x| < 700 keeps the result a normal double
     const int hi = __double2hiint(v) + ((n >> 6) << 20);
     return __hiloint2double(hi, __double2loint(v));
@@ -111,8 +120,44 @@ __device__ __forceinline__ void exp_fast_n(const double (&x)[E], double (&out)[E
 #endif
 }
 
-__device__ __forceinline__ double log_fast(double x) {
+// ---------------------------------------------------------------------------------------
+// log(x): x = 2^e * m, m in [1,2); 128-entry table of c_i ~ 1/m_i (float-rounded, so
+// z = m*c_i - 1 is exact in one fma, |z| <= 0.004) and l_i = -log(c_i);
+// log(x) = e*ln2 + l_i + log1p(z), log1p by a degree-6 polynomial (next term z^7/7 <= 2.3e-18).
+// ~10 FP64-pipe instructions; measured on the host with the same fma sequence: error
+// <= 2.6e-16 * max(|log x|, 1).  Zero / negative / denormal / Inf / NaN go to libdevice.
+// ---------------------------------------------------------------------------------------
+#define EBPMF_LOG_TABLE_SIZE 128
+
+__device__ __forceinline__ void log_table_init(double2 *tab, const MathTables *g, int tid, int nthreads) {
+    for (int i = tid; i < EBPMF_LOG_TABLE_SIZE; i += nthreads) tab[i] = g->log_tab[i];
+}
+
+__device__ __noinline__ double log_slow(double x) { return log(x); }
+
+__constant__ double kLogC[5] = {-1.0 / 6.0, 0.2, -0.25, 1.0 / 3.0, 0.6931471805599453};
+
+__device__ __forceinline__ double log_fast(double x, const double2 *tab) {
+#if EBPMF_EXACT_MATH
+    (void)tab;
     return log(x);
+#else
+    const int hi = __double2hiint(x);
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log_slow(x);
+    const int idx = (hi >> 13) & (EBPMF_LOG_TABLE_SIZE - 1);
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    const double2 cl = tab[idx];
+    const double z = fma(m, cl.x, -1.0);
+    double p = fma(z, kLogC[0], kLogC[1]);
+    p = fma(p, z, kLogC[2]);
+    p = fma(p, z, kLogC[3]);
+    p = fma(p, z, -0.5);
+    p = p * z;
+    const double res = fma(p, z, z);
+    // (double)(e) without a conversion instruction: 2^52 + 2^31 magic
+    const double ed = __hiloint2double(0x43300000, ((hi >> 20) - 1023) ^ 0x80000000) - 4503601774854144.0;
+    return fma(ed, kLogC[4], cl.y) + res;
+#endif
 }
 
 }  // namespace ebpmf

@@ -1,0 +1,80 @@
+# vga_cuda.R -- R wrappers with the reference's UNCHANGED signatures over the .Call shim
+# (src/r_glue.c -> include/ebpmf_b200.h).  Drop this file into the package's R/ directory in
+# place of the bodies in R/vga_solver_mat.R:6-109 and R/ebpmf_log.R:406-447,470-472.
+# There is no CPU fallback: without a usable B200 the .Call raises an R error.
+#
+# NOT run in this repository (R is not installed); the Python mirror ebpmf.alpha_b200/solvers.py
+# marshals exactly the same arguments into the same C entry points and IS tested.
+
+.ebpmf_b200_env = new.env(parent = emptyenv())
+
+#' one GPU context per R session (external pointer with a finalizer)
+ebpmf_b200_ctx = function(device = as.integer(Sys.getenv("EBPMF_B200_DEVICE", "0"))){
+  if(is.null(.ebpmf_b200_env$ctx)){
+    .ebpmf_b200_env$ctx = .Call(C_ebpmf_ctx_new, as.integer(device))
+  }
+  .ebpmf_b200_env$ctx
+}
+
+.as_num_or_dgC = function(Y){
+  if(is(Y,'dgCMatrix')) return(Y)
+  if(is(Y,'sparseMatrix')) return(as(Y,'dgCMatrix'))
+  Y = as.matrix(Y); storage.mode(Y) = 'double'; Y
+}
+
+#'@title a matrix version of the vga solver using Newton's method   (R/vga_solver_mat.R:6)
+vga_pois_solver_mat_newton = function(M,X,S,Beta,Sigma2,maxiter=1000,tol=1e-8,return_V = TRUE){
+  storage.mode(M) = 'double'
+  .Call(C_vga_pois_solver_mat_newton, ebpmf_b200_ctx(), M, .as_num_or_dgC(X), as.double(S),
+        as.double(Beta), as.double(Sigma2), as.integer(maxiter), as.double(tol), as.logical(return_V))
+}
+
+#'@title vga solver for fixed iteration, not necessary to convergence   (R/vga_solver_mat.R:44)
+vga_pois_solver_mat_newton_fixed_iter = function(M,V,Y,S,Beta,Sigma2,maxiter=1000){
+  storage.mode(M) = 'double'
+  .Call(C_vga_pois_solver_mat_newton_fixed_iter, ebpmf_b200_ctx(), M,
+        if(is.null(V)) NULL else matrix(as.double(V),nrow(M),ncol(M)), as.matrix(Y) + 0,
+        as.double(S), as.double(Beta), as.double(Sigma2), as.integer(maxiter))
+}
+
+#'@title low memory mode   (R/vga_solver_mat.R:71)
+vga_pois_solver_mat_newton_low_memory = function(M,Y,l0,f0,EL,EF,
+                                                 sigma2,var_type,
+                                                 maxiter=1000,tol=1e-8){
+  storage.mode(M) = 'double'
+  .Call(C_vga_pois_solver_mat_newton_low_memory, ebpmf_b200_ctx(), M, .as_num_or_dgC(Y),
+        rep_len(as.double(l0), nrow(M)), rep_len(as.double(f0), ncol(M)),
+        matrix(as.double(EL), nrow(M)), matrix(as.double(EF), ncol(M)),
+        as.double(sigma2), var_type, as.integer(maxiter), as.double(tol))
+}
+
+#'@title Calc elbo   (R/ebpmf_log.R:406)
+calc_ebpmf_log_obj = function(n,p,sym,ssexp,slogv,sv,sigma2,R2,KL_LF,const,ss,a0,b0){
+  len = max(length(sv),length(sigma2),length(R2))
+  .Call(C_calc_ebpmf_log_obj, ebpmf_b200_ctx(), n, p, sym, ssexp, slogv, rep_len(as.double(sv),len),
+        rep_len(as.double(sigma2),len), rep_len(as.double(R2),len), KL_LF, const, ss, a0, b0)
+}
+
+#'@title update sigma2   (R/ebpmf_log.R:413)
+ebpmf_log_update_sigma2 = function(fit_flash,sigma2,v_sum,var_type,cap_var_mean_ratio,a0,b0,n,p){
+  R2 = fit_flash$flash_fit$R2
+  if(var_type=='constant') R2 = sum(R2)
+  EL = NULL; EF = NULL
+  if(cap_var_mean_ratio>0){ EL = fit_flash$flash_fit$EF[[1]]; EF = fit_flash$flash_fit$EF[[2]] }
+  .Call(C_ebpmf_log_update_sigma2, ebpmf_b200_ctx(), as.double(sigma2), as.double(v_sum), as.double(R2),
+        var_type, as.double(cap_var_mean_ratio), as.double(a0), as.double(b0), n, p, EL, EF)
+}
+
+#'@title calculate sum of log factorial of all elements of a sparse Matrix   (R/ebpmf_log.R:470)
+sum_lfactorial_sparseMat = function(Y){
+  .Call(C_ebpmf_sum_lfactorial, ebpmf_b200_ctx(), as.double(Y@x))
+}
+
+#' The fused VGA step for ebpmf_log's outer loop: replaces R/ebpmf_log.R:302-327 (see INTEGRATION.md).
+#' Y must have been uploaded once with ebpmf_b200_set_y(Y) (it is constant across iterations).
+ebpmf_b200_set_y = function(Y){ invisible(.Call(C_ebpmf_ctx_set_y, ebpmf_b200_ctx(), .as_num_or_dgC(Y))) }
+ebpmf_b200_vga_step = function(M,EL,EF,sigma2,var_type,maxiter,tol,want_V=FALSE){
+  storage.mode(M) = 'double'
+  .Call(C_ebpmf_vga_step, ebpmf_b200_ctx(), M, EL + 0, EF + 0, as.double(sigma2), var_type,
+        as.integer(maxiter), as.double(tol), as.logical(want_V))
+}

@@ -1,0 +1,292 @@
+/*
+ * r_glue.c -- the thin `.Call` shim between R and the plain C ABI of include/ebpmf_b200.h.
+ *
+ * NOT COMPILED IN THIS REPOSITORY'S CI: R (R.h, Rinternals.h, libR) is not installed in the build
+ * image or on the GPU box, so this file is compile-checked only where R exists
+ * (R CMD INSTALL with src/Makevars).  It is deliberately tiny: every line of arithmetic lives
+ * behind the C ABI, which IS tested (from Python/ctypes, tests/).  No Rinternals.h is faked.
+ *
+ * Conventions
+ *   - arguments are never written (R shares them, copy-on-modify); outputs are fresh
+ *     allocMatrix/allocVector results, PROTECTed until return, with dim copied from M;
+ *   - errors: the C ABI returns a status; we copy the message to a stack buffer and call
+ *     Rf_error() (a longjmp) only after nothing needs freeing;
+ *   - one context per R session lives in an external pointer with a finalizer.
+ *
+ * Replaces (paths relative to the reference root):
+ *   R/vga_solver_mat.R:6-41, :44-65, :71-109 ; R/ebpmf_log.R:302-332, :406-410, :413-447, :470-472
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <string.h>
+
+#include "ebpmf_b200.h"
+
+/* ---- helpers ---------------------------------------------------------------------------- */
+static ebpmf_ctx *get_ctx(SEXP xp)
+{
+    if (TYPEOF(xp) != EXTPTRSXP || R_ExternalPtrAddr(xp) == NULL)
+        Rf_error("ebpmf_b200: invalid or closed GPU context");
+    return (ebpmf_ctx *)R_ExternalPtrAddr(xp);
+}
+
+static void ctx_finalizer(SEXP xp)
+{
+    ebpmf_ctx *ctx = (ebpmf_ctx *)R_ExternalPtrAddr(xp);
+    if (ctx) { ebpmf_ctx_destroy(ctx); R_ClearExternalPtr(xp); }
+}
+
+static void check(ebpmf_ctx *ctx, int rc)
+{
+    if (rc == EBPMF_OK) return;
+    char msg[1024];
+    strncpy(msg, ebpmf_last_error(ctx), sizeof msg - 1);
+    msg[sizeof msg - 1] = '\0';
+    if (rc == EBPMF_ERR_NAN) Rf_error("missing value where TRUE/FALSE needed");   /* R/vga_solver_mat.R:26 */
+    if (rc == EBPMF_ERR_VAR_TYPE) Rf_error("Non-supported var type");               /* R/ebpmf_log.R:444,483 */
+    Rf_error("ebpmf_b200: %s", msg);
+}
+
+static int var_type_code(SEXP vt)
+{
+    const char *s = CHAR(STRING_ELT(vt, 0));
+    if (!strcmp(s, "constant")) return EBPMF_VAR_CONSTANT;
+    if (!strcmp(s, "by_row")) return EBPMF_VAR_BY_ROW;
+    if (!strcmp(s, "by_col")) return EBPMF_VAR_BY_COL;
+    return -1;
+}
+
+/* scalar / length-n vector / n x p matrix, as R would recycle it against an n x p matrix */
+static int operand_kind(SEXP a, R_xlen_t n, R_xlen_t p, const char *what)
+{
+    R_xlen_t len = XLENGTH(a);
+    if (len == 1) return EBPMF_OP_SCALAR;
+    if (len == n * p) return EBPMF_OP_MATRIX;
+    if (len == n) return EBPMF_OP_ROWVEC;
+    Rf_error("%s: non-conformable arrays", what);
+    return -1;
+}
+
+static int is_dgC(SEXP Y) { return Rf_isS4(Y) && Rf_inherits(Y, "dgCMatrix"); }
+
+static SEXP alloc_like(SEXP M)
+{
+    SEXP dim = Rf_getAttrib(M, R_DimSymbol);
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, INTEGER(dim)[0], INTEGER(dim)[1]));
+    SEXP dn = Rf_getAttrib(M, R_DimNamesSymbol);
+    if (dn != R_NilValue) Rf_setAttrib(out, R_DimNamesSymbol, dn);
+    UNPROTECT(1);
+    return out;
+}
+
+static SEXP info_list(const ebpmf_solve_info *info, SEXP M, SEXP V, SEXP v_sum)
+{
+    const char *names[] = {"M", "V", "v_sum", "sym", "ssexp", "slogv", "n_updates", "converged", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+    SET_VECTOR_ELT(out, 0, M);
+    SET_VECTOR_ELT(out, 1, V);
+    SET_VECTOR_ELT(out, 2, v_sum);
+    SET_VECTOR_ELT(out, 3, Rf_ScalarReal(info->sym));
+    SET_VECTOR_ELT(out, 4, Rf_ScalarReal(info->ssexp));
+    SET_VECTOR_ELT(out, 5, Rf_ScalarReal(info->slogv));
+    SET_VECTOR_ELT(out, 6, Rf_ScalarInteger(info->n_updates));
+    SET_VECTOR_ELT(out, 7, Rf_ScalarLogical(info->converged));
+    UNPROTECT(1);
+    return out;
+}
+
+/* ---- context ----------------------------------------------------------------------------- */
+SEXP C_ebpmf_ctx_new(SEXP device)
+{
+    ebpmf_ctx *ctx = NULL;
+    int rc = ebpmf_ctx_create(Rf_asInteger(device), &ctx);
+    if (rc != EBPMF_OK) Rf_error("ebpmf_b200: %s", ebpmf_last_error(NULL));   /* no CPU fallback */
+    SEXP xp = PROTECT(R_MakeExternalPtr(ctx, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(xp, ctx_finalizer, TRUE);
+    UNPROTECT(1);
+    return xp;
+}
+
+/* Y: numeric matrix (as.matrix(Y), R/ebpmf_log.R:202) or dgCMatrix (slots p, i, x, Dim) */
+SEXP C_ebpmf_ctx_set_y(SEXP xp, SEXP Y)
+{
+    ebpmf_ctx *ctx = get_ctx(xp);
+    if (is_dgC(Y)) {
+        SEXP Dim = R_do_slot(Y, Rf_install("Dim"));
+        check(ctx, ebpmf_ctx_set_y_csc(ctx, INTEGER(Dim)[0], INTEGER(Dim)[1], INTEGER(R_do_slot(Y, Rf_install("p"))),
+                                       INTEGER(R_do_slot(Y, Rf_install("i"))), REAL(R_do_slot(Y, Rf_install("x")))));
+    } else {
+        if (!Rf_isMatrix(Y) || TYPEOF(Y) != REALSXP) Rf_error("Y must be a numeric matrix or a dgCMatrix");
+        check(ctx, ebpmf_ctx_set_y_dense(ctx, Rf_nrows(Y), Rf_ncols(Y), REAL(Y)));
+    }
+    return R_NilValue;
+}
+
+/* const = -sum_lfactorial_sparseMat(Y)  R/ebpmf_log.R:172-176, :470-472 */
+SEXP C_ebpmf_sum_lfactorial(SEXP xp, SEXP x)
+{
+    ebpmf_ctx *ctx = get_ctx(xp);
+    double out = 0.0;
+    if (x == R_NilValue) check(ctx, ebpmf_ctx_sum_lfactorial(ctx, &out));          /* resident Y */
+    else check(ctx, ebpmf_sum_lfactorial(ctx, (int64_t)XLENGTH(x), REAL(x), &out));
+    return Rf_ScalarReal(out);
+}
+
+/* ---- the fused VGA step of the outer loop, R/ebpmf_log.R:302-327 ----------------------------
+ * list(M, V|NULL, v_sum, sym, ssexp, slogv, n_updates, converged) */
+SEXP C_ebpmf_vga_step(SEXP xp, SEXP M, SEXP EL, SEXP EF, SEXP sigma2, SEXP var_type, SEXP maxiter, SEXP tol,
+                      SEXP want_V)
+{
+    ebpmf_ctx *ctx = get_ctx(xp);
+    const int vt = var_type_code(var_type);
+    if (vt < 0) Rf_error("Non-supported var type");
+    const R_xlen_t n = Rf_nrows(M), p = Rf_ncols(M);
+    if (Rf_nrows(EL) != n || Rf_nrows(EF) != p || Rf_ncols(EL) != Rf_ncols(EF)) Rf_error("non-conformable arguments");
+    const R_xlen_t want = vt == EBPMF_VAR_BY_COL ? p : vt == EBPMF_VAR_BY_ROW ? n : 1;
+    if (XLENGTH(sigma2) != want) Rf_error("sigma2 has the wrong length for this var_type");
+    const int wv = Rf_asLogical(want_V);
+    SEXP Mo = PROTECT(alloc_like(M));
+    SEXP Vo = PROTECT(wv ? alloc_like(M) : R_NilValue);
+    SEXP vs = PROTECT(Rf_allocVector(REALSXP, want));
+    ebpmf_solve_info info;
+    int rc = ebpmf_vga_step_host(ctx, REAL(M), Rf_ncols(EL), REAL(EL), REAL(EF), vt, REAL(sigma2),
+                                 Rf_asInteger(maxiter), Rf_asReal(tol), REAL(Mo), wv ? REAL(Vo) : NULL, REAL(vs), &info);
+    if (rc != EBPMF_OK) { UNPROTECT(3); check(ctx, rc); }
+    SEXP out = info_list(&info, Mo, Vo, vs);
+    UNPROTECT(3);
+    return out;
+}
+
+/* ---- vga_pois_solver_mat_newton(M,X,S,Beta,Sigma2,maxiter,tol,return_V)  R/vga_solver_mat.R:6 */
+SEXP C_vga_pois_solver_mat_newton(SEXP xp, SEXP M, SEXP X, SEXP S, SEXP Beta, SEXP Sigma2, SEXP maxiter, SEXP tol,
+                                  SEXP return_V)
+{
+    ebpmf_ctx *ctx = get_ctx(xp);
+    const R_xlen_t n = Rf_nrows(M), p = Rf_ncols(M);
+    const int rv = Rf_asLogical(return_V);
+    const int ks = operand_kind(S, n, p, "S"), kb = operand_kind(Beta, n, p, "Beta"),
+              kv = operand_kind(Sigma2, n, p, "Sigma2");
+    SEXP Mo = PROTECT(alloc_like(M));
+    SEXP Vo = PROTECT(rv ? alloc_like(M) : R_NilValue);
+    ebpmf_solve_info info;
+    int rc;
+    if (is_dgC(X))
+        rc = ebpmf_vga_newton(ctx, n, p, REAL(M), NULL, INTEGER(R_do_slot(X, Rf_install("p"))),
+                              INTEGER(R_do_slot(X, Rf_install("i"))), REAL(R_do_slot(X, Rf_install("x"))), REAL(S), ks,
+                              REAL(Beta), kb, REAL(Sigma2), kv, Rf_asInteger(maxiter), Rf_asReal(tol), REAL(Mo),
+                              rv ? REAL(Vo) : NULL, &info);
+    else
+        rc = ebpmf_vga_newton(ctx, n, p, REAL(M), REAL(X), NULL, NULL, NULL, REAL(S), ks, REAL(Beta), kb, REAL(Sigma2),
+                              kv, Rf_asInteger(maxiter), Rf_asReal(tol), REAL(Mo), rv ? REAL(Vo) : NULL, &info);
+    if (rc != EBPMF_OK) { UNPROTECT(2); check(ctx, rc); }
+    SEXP out;
+    if (rv) {                                                   /* list(M=M, V=Sigma2/temp)  :36 */
+        const char *names[] = {"M", "V", ""};
+        out = PROTECT(Rf_mkNamed(VECSXP, names));
+        SET_VECTOR_ELT(out, 0, Mo);
+        SET_VECTOR_ELT(out, 1, Vo);
+        UNPROTECT(1);
+    } else {
+        out = Mo;                                               /* return(M)  :38 */
+    }
+    UNPROTECT(2);
+    return out;
+}
+
+/* ---- vga_pois_solver_mat_newton_fixed_iter(M,V,Y,S,Beta,Sigma2,maxiter)  R/vga_solver_mat.R:44 */
+SEXP C_vga_pois_solver_mat_newton_fixed_iter(SEXP xp, SEXP M, SEXP V, SEXP Y, SEXP S, SEXP Beta, SEXP Sigma2,
+                                             SEXP maxiter)
+{
+    ebpmf_ctx *ctx = get_ctx(xp);
+    const R_xlen_t n = Rf_nrows(M), p = Rf_ncols(M);
+    const int ks = operand_kind(S, n, p, "S"), kb = operand_kind(Beta, n, p, "Beta"),
+              kv = operand_kind(Sigma2, n, p, "Sigma2");
+    SEXP Mo = PROTECT(alloc_like(M));
+    SEXP Vo = PROTECT(alloc_like(M));
+    int rc = ebpmf_vga_fixed_iter(ctx, n, p, REAL(M), V == R_NilValue ? NULL : REAL(V), REAL(Y), REAL(S), ks, REAL(Beta),
+                                  kb, REAL(Sigma2), kv, Rf_asInteger(maxiter), REAL(Mo), REAL(Vo));
+    if (rc != EBPMF_OK) { UNPROTECT(2); check(ctx, rc); }
+    const char *names[] = {"M", "V", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+    SET_VECTOR_ELT(out, 0, Mo);
+    SET_VECTOR_ELT(out, 1, Vo);
+    UNPROTECT(3);
+    return out;
+}
+
+/* ---- vga_pois_solver_mat_newton_low_memory(M,Y,l0,f0,EL,EF,sigma2,var_type,maxiter,tol)  :71 */
+SEXP C_vga_pois_solver_mat_newton_low_memory(SEXP xp, SEXP M, SEXP Y, SEXP l0, SEXP f0, SEXP EL, SEXP EF, SEXP sigma2,
+                                             SEXP var_type, SEXP maxiter, SEXP tol)
+{
+    ebpmf_ctx *ctx = get_ctx(xp);
+    const int vt = var_type_code(var_type);
+    if (vt < 0) Rf_error("Non-supported var type");
+    const R_xlen_t n = Rf_nrows(M), p = Rf_ncols(M);
+    SEXP Mo = PROTECT(alloc_like(M));
+    ebpmf_solve_info info;
+    int rc;
+    if (is_dgC(Y))
+        rc = ebpmf_vga_low_memory(ctx, n, p, Rf_ncols(EL), REAL(M), NULL, INTEGER(R_do_slot(Y, Rf_install("p"))),
+                                  INTEGER(R_do_slot(Y, Rf_install("i"))), REAL(R_do_slot(Y, Rf_install("x"))), REAL(l0),
+                                  REAL(f0), REAL(EL), REAL(EF), REAL(sigma2), vt, Rf_asInteger(maxiter), Rf_asReal(tol),
+                                  REAL(Mo), &info);
+    else
+        rc = ebpmf_vga_low_memory(ctx, n, p, Rf_ncols(EL), REAL(M), REAL(Y), NULL, NULL, NULL, REAL(l0), REAL(f0),
+                                  REAL(EL), REAL(EF), REAL(sigma2), vt, Rf_asInteger(maxiter), Rf_asReal(tol), REAL(Mo),
+                                  &info);
+    if (rc != EBPMF_OK) { UNPROTECT(1); check(ctx, rc); }
+    UNPROTECT(1);
+    return Mo;                                                  /* return(as.matrix(M))  :108 */
+}
+
+/* ---- ebpmf_log_update_sigma2(fit_flash,sigma2,v_sum,var_type,cap,a0,b0,n,p)  R/ebpmf_log.R:413
+ * The R wrapper passes R2 = fit_flash$flash_fit$R2 (summed for 'constant') and, when cap > 0,
+ * EL = flash_fit$EF[[1]], EF = flash_fit$EF[[2]] (else NULL). */
+SEXP C_ebpmf_log_update_sigma2(SEXP xp, SEXP sigma2, SEXP v_sum, SEXP R2, SEXP var_type, SEXP cap, SEXP a0, SEXP b0,
+                               SEXP n, SEXP p, SEXP EL, SEXP EF)
+{
+    ebpmf_ctx *ctx = get_ctx(xp);
+    const int vt = var_type_code(var_type);
+    if (vt < 0) Rf_error("Non-supported var type");
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, XLENGTH(sigma2)));
+    const int have_f = EL != R_NilValue && EF != R_NilValue;
+    int rc = ebpmf_update_sigma2(ctx, vt, (int64_t)Rf_asReal(n), (int64_t)Rf_asReal(p), REAL(sigma2), REAL(v_sum),
+                                 REAL(R2), Rf_asReal(a0), Rf_asReal(b0), Rf_asReal(cap), have_f ? Rf_ncols(EL) : 0,
+                                 have_f ? REAL(EL) : NULL, have_f ? REAL(EF) : NULL, REAL(out));
+    if (rc != EBPMF_OK) { UNPROTECT(1); check(ctx, rc); }
+    UNPROTECT(1);
+    return out;
+}
+
+/* ---- calc_ebpmf_log_obj(n,p,sym,ssexp,slogv,sv,sigma2,R2,KL_LF,const,ss,a0,b0)  R/ebpmf_log.R:406
+ * sv / sigma2 / R2 are recycled to a common length by the R wrapper. */
+SEXP C_calc_ebpmf_log_obj(SEXP xp, SEXP n, SEXP p, SEXP sym, SEXP ssexp, SEXP slogv, SEXP sv, SEXP sigma2, SEXP R2,
+                          SEXP KL_LF, SEXP const_, SEXP ss, SEXP a0, SEXP b0)
+{
+    ebpmf_ctx *ctx = get_ctx(xp);
+    double obj = 0.0;
+    check(ctx, ebpmf_calc_obj(ctx, (int64_t)Rf_asReal(n), (int64_t)Rf_asReal(p), Rf_asReal(sym), Rf_asReal(ssexp),
+                              Rf_asReal(slogv), (int64_t)XLENGTH(sigma2), REAL(sv), REAL(sigma2), REAL(R2),
+                              Rf_asReal(KL_LF), Rf_asReal(const_), Rf_asReal(ss), Rf_asReal(a0), Rf_asReal(b0), &obj));
+    return Rf_ScalarReal(obj);
+}
+
+/* ---- registration ------------------------------------------------------------------------ */
+static const R_CallMethodDef call_methods[] = {
+    {"C_ebpmf_ctx_new", (DL_FUNC)&C_ebpmf_ctx_new, 1},
+    {"C_ebpmf_ctx_set_y", (DL_FUNC)&C_ebpmf_ctx_set_y, 2},
+    {"C_ebpmf_sum_lfactorial", (DL_FUNC)&C_ebpmf_sum_lfactorial, 2},
+    {"C_ebpmf_vga_step", (DL_FUNC)&C_ebpmf_vga_step, 9},
+    {"C_vga_pois_solver_mat_newton", (DL_FUNC)&C_vga_pois_solver_mat_newton, 9},
+    {"C_vga_pois_solver_mat_newton_fixed_iter", (DL_FUNC)&C_vga_pois_solver_mat_newton_fixed_iter, 8},
+    {"C_vga_pois_solver_mat_newton_low_memory", (DL_FUNC)&C_vga_pois_solver_mat_newton_low_memory, 11},
+    {"C_ebpmf_log_update_sigma2", (DL_FUNC)&C_ebpmf_log_update_sigma2, 12},
+    {"C_calc_ebpmf_log_obj", (DL_FUNC)&C_calc_ebpmf_log_obj, 14},
+    {NULL, NULL, 0}};
+
+void R_init_ebpmf_alpha(DllInfo *dll)
+{
+    R_registerRoutines(dll, NULL, call_methods, NULL, NULL);
+    R_useDynamicSymbols(dll, FALSE);
+}
