@@ -70,6 +70,7 @@ struct ebpmf_ctx {
     long long nRB = 0, nRW = 0;
     int K = 0, KTP = 0;
     int var_type = -1;
+    int pipeline = 0;          // 0: fused first pass, 1: split (const0 kernel + streaming Newton)
     bool can_rewind = false;
     unsigned long long diag_topups = 0, diag_iters = 0;
     bool have_y = false, have_m = false, have_f = false, have_s2 = false, have_v = false, have_vsum = false;
@@ -189,12 +190,34 @@ int launch_first_ktp(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
     return EBPMF_OK;
 }
 
-// pass 1 of the fused path (K1 / K4)
+template <int KTP, int FORMULA>
+int launch_prep_ktp(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
+    auto kern = vga_prep_kernel<KTP, FORMULA>;
+    const int smem = (int)sizeof(PrepSmem<KTP>);
+    kern<<<grid, dim3(kThreads), smem, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    return EBPMF_OK;
+}
+
+// pass 1 of the fused path (K1 / K4): either ONE fused kernel (tile staging + Beta rebuild +
+// register-resident Newton), or the split pipeline: const0 kernel, then streaming Newton.
 template <int FORMULA>
 int launch_first(ebpmf_ctx *ctx, const FusedArgs &a) {
     const long long ncols = a.col1 - a.col0;
     if (ncols <= 0) return EBPMF_OK;
     dim3 grid((unsigned)((ncols + a.cols_per_cta - 1) / a.cols_per_cta), (unsigned)ctx->nRB);
+    if (ctx->pipeline == 1) {
+        switch (ctx->KTP) {
+            case 8: CHECK((launch_prep_ktp<8, FORMULA>(ctx, a, grid))); break;
+            case 16: CHECK((launch_prep_ktp<16, FORMULA>(ctx, a, grid))); break;
+            case 24: CHECK((launch_prep_ktp<24, FORMULA>(ctx, a, grid))); break;
+            case 32: CHECK((launch_prep_ktp<32, FORMULA>(ctx, a, grid))); break;
+            default: return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported (max 32)", ctx->K);
+        }
+        vga_stream_kernel<kE, FORMULA, MODE_FIRST><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
+        CU(cudaGetLastError());
+        return EBPMF_OK;
+    }
     switch (ctx->KTP) {
         case 8: return launch_first_ktp<8, FORMULA>(ctx, a, grid);
         case 16: return launch_first_ktp<16, FORMULA>(ctx, a, grid);
@@ -210,7 +233,7 @@ int launch_topup(ebpmf_ctx *ctx, const FusedArgs &a) {
     const long long ncols = a.col1 - a.col0;
     if (ncols <= 0) return EBPMF_OK;
     dim3 grid((unsigned)((ncols + a.cols_per_cta - 1) / a.cols_per_cta), (unsigned)ctx->nRB);
-    vga_topup_kernel<kE, FORMULA><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
+    vga_stream_kernel<kE, FORMULA, MODE_TOPUP><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
     CU(cudaGetLastError());
     return EBPMF_OK;
 }
@@ -490,6 +513,7 @@ int ebpmf_ctx_create(int device, ebpmf_ctx **out) {
     ctx = new (std::nothrow) ebpmf_ctx();
     if (!ctx) return fail(nullptr, EBPMF_ERR_NOMEM, "out of host memory");
     ctx->device = device;
+    if (const char *pl = getenv("EBPMF_B200_PIPELINE")) ctx->pipeline = (strcmp(pl, "split") == 0) ? 1 : 0;
     cudaError_t ce;
 #define CREATE_STEP(call)                                                                                        \
     ce = (call);                                                                                                 \

@@ -144,7 +144,8 @@ template <int S> __device__ __forceinline__ double warp_multi_sum(const double (
 // One unit: E entries per lane, all 32 lanes in lock step.  Per entry the loop carries
 //   m, c0 = (s2*y + beta) + 1, w = (c0 - 1)/s2 = y + beta/s2, c1 = 1/s2, c2 = s2/2 [, sc = S]
 // so that  f = x - sexp - M*const1 + const3  (R/vga_solver_mat.R:25) is  fma(-m, c1, w - sexp).
-// tol_e is tol for a live entry and +Inf for a padding entry (row >= n or column >= p).
+// tol_lane is tol for a live row and +Inf for a padding row (row >= n); a padding COLUMN (p not a
+// multiple of E) is given the values of the lane's previous column, so it converges with it.
 // `target` is t0 in the first pass (stop at the first k >= t0 at which the unit is converged)
 // and K* in the top-up pass (stop exactly at k == K*).
 // On return k is the number of updates the unit has received, r[] the reciprocal of the last
@@ -152,12 +153,17 @@ template <int S> __device__ __forceinline__ double warp_multi_sum(const double (
 // Returns a bit mask: 1 converged at k, 2 exhausted.
 // ---------------------------------------------------------------------------------------
 template <int E, int FORMULA, int MODE, bool SCALED>
-__device__ __forceinline__ int newton_unit(double (&m)[E], const double (&c0)[E], const double (&w)[E],
+__device__ __forceinline__ int newton_unit(double (&m)[E], const double (&c0)[E], double (&w)[E],
                                            const double (&c1)[E], const double (&c2)[E], const double (&sc)[E],
-                                           const double (&tol_e)[E], int &k, int target, int maxiter,
+                                           double tol_lane, int &k, int target, int maxiter,
                                            const double *exptab, double (&r)[E], double (&sexp)[E], double (&f)[E])
 {
     int flags = 0;
+    // keep w (and the lane tolerance) in registers: without this the compiler re-derives
+    // (c0-1)*c1 in every iteration -- 2 extra FP64-pipe instructions per entry per iteration
+#pragma unroll
+    for (int e = 0; e < E; ++e) asm volatile("" : "+d"(w[e]));
+    asm volatile("" : "+d"(tol_lane));
 #pragma unroll 1
     for (;;) {
         bool lane_conv = true;
@@ -174,7 +180,7 @@ __device__ __forceinline__ int newton_unit(double (&m)[E], const double (&c0)[E]
         for (int e = 0; e < E; ++e) {
             sexp[e] = SCALED ? __dmul_rn(sc[e], ex[e]) : ex[e];                // :23
             f[e] = __fma_rn(-m[e], c1[e], __dadd_rn(w[e], -sexp[e]));          // :25 | :84,:98
-            lane_conv = lane_conv && (fabs(f[e]) < tol_e[e]);                  // :26 (strict <)
+            lane_conv = lane_conv && (fabs(f[e]) < tol_lane);                  // :26 (strict <)
         }
         const bool conv = __all_sync(0xffffffffu, lane_conv);
         const bool stop = (MODE == MODE_FIRST) ? (conv && (k >= target)) : (k == target);
@@ -200,9 +206,13 @@ __device__ __forceinline__ int newton_unit(double (&m)[E], const double (&c0)[E]
 template <int E, int FORMULA>
 __device__ __forceinline__ bool finalize_unit(const FusedArgs &a, const double (&m)[E], const double (&c2)[E],
                                               const double (&r)[E], const double (&sexp)[E], const double (&f)[E],
-                                              const bool (&ok)[E], int flags, long long i, long long jb,
-                                              long long jg, long long rw, int lane, bool row_ok,
-                                              const double *exptab, const double2 *logtab)
+                                              const bool (&ok)[E], int flags,
+                                              size_t off,      // i + n*jb : entry (i, jb) of the n x p matrices
+                                              size_t cv_idx,   // rw*p + jb : slot of (rw, jb) in colV
+                                              size_t us_idx,   // (rw*nJG + jg)*2 : slot of the unit in unitS
+                                              size_t rp_idx,   // jg*n + i : slot in rowpart
+                                              int cols_left,   // p - jb
+                                              int lane, bool row_ok, const double *exptab, const double2 *logtab)
 {
     constexpr int S = (E + 2 <= 4) ? 4 : 8;
     static_assert(E + 2 <= 8, "at most 6 columns per unit");
@@ -211,14 +221,14 @@ __device__ __forceinline__ bool finalize_unit(const FusedArgs &a, const double (
     for (int q = 0; q < S; ++q) vals[q] = 0.0;
     double rowv = 0.0;
     bool lane_nan = false;
+    const size_t n = (size_t)a.n;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-        const long long j = jb + e;
         lane_nan = lane_nan || (ok[e] && (f[e] != f[e]));
-        if (ok[e]) st_stream(a.M_out + i + a.n * j, m[e]);
+        if (ok[e]) st_stream(a.M_out + off + e * n, m[e]);
         if (FORMULA == FORMULA_A1) {
             const double v = __dmul_rn(__dadd_rn(c2[e], c2[e]), r[e]);          // :36 Sigma2/temp (stale if exhausted)
-            if (ok[e] && a.V_out) st_stream(a.V_out + i + a.n * j, v);
+            if (ok[e] && a.V_out) st_stream(a.V_out + off + e * n, v);
             double ex = sexp[e];                                                // == exp(M+V/2): S == 1 and the loop broke
             if (flags & 2) ex = exp_fast(__fma_rn(0.5, v, m[e]), exptab);       // exhausted: M moved after temp
             const double lv = fma(0.5, log_fast(v, logtab), kSlogvConst);       // R/ebpmf_log.R:318
@@ -229,10 +239,10 @@ __device__ __forceinline__ bool finalize_unit(const FusedArgs &a, const double (
         const double tot = warp_multi_sum<S>(vals, lane);
         const int slot = warp_slot<S>(lane);
         if ((lane & ((S == 8) ? 3 : 7)) == 0) {                                 // one writer per slot
-            if (slot < E) { if (jb + slot < a.col1) a.colV[rw * a.p + jb + slot] = tot; }
-            else if (slot < E + 2) a.unitS[(rw * a.nJG + jg) * 2 + (slot - E)] = tot;
+            if (slot < E) { if (slot < cols_left) a.colV[cv_idx + slot] = tot; }
+            else if (slot < E + 2) a.unitS[us_idx + (slot - E)] = tot;
         }
-        if (a.rowpart && row_ok) a.rowpart[jg * a.n + i] = rowv;
+        if (a.rowpart && row_ok) a.rowpart[rp_idx] = rowv;
     }
     return __any_sync(0xffffffffu, lane_nan);
 }
@@ -263,15 +273,17 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FusedSmem<KTP> &sm = *reinterpret_cast<FusedSmem<KTP> *>(smem_raw);
 
+    // rows of a shard and columns fit 32 bits (dgCMatrix Dim is int); only n*j products are 64-bit
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long rb = blockIdx.y;
-    const long long r0 = rb * kRowsPerCta;
-    const long long i = r0 + tid;
-    const bool row_ok = i < a.n;
-    const long long rw = rb * kWarps + warp;
-    const bool warp_ok = rw < a.nRW;                 // false: every row of this warp is beyond n
-    const long long jc0 = a.col0 + (long long)blockIdx.x * a.cols_per_cta;
-    const long long jc1 = min(a.col1, jc0 + (long long)a.cols_per_cta);
+    const int n = (int)a.n, p = (int)a.p;
+    const int rb = blockIdx.y;
+    const int r0 = rb * kRowsPerCta;
+    const int i = r0 + tid;
+    const bool row_ok = i < n;
+    const int rw = rb * kWarps + warp;
+    const bool warp_ok = rw < (int)a.nRW;            // false: every row of this warp is beyond n
+    const int jc0 = (int)a.col0 + blockIdx.x * a.cols_per_cta;
+    const int jc1 = min((int)a.col1, jc0 + a.cols_per_cta);
 
     exp_table_init(sm.exptab, a.tables, tid, kThreads);
     log_table_init(sm.logtab, a.tables, tid, kThreads);
@@ -279,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
     // row-constant pieces (by_row / constant sigma2, A10's l0)
     double c1_row = 1.0, c2_row = 0.5, l0_i = 1.0;
     if (a.var_type != 2) {
-        const long long si = (a.var_type == 1) ? (row_ok ? i : 0) : 0;
+        const int si = (a.var_type == 1) ? (row_ok ? i : 0) : 0;
         c1_row = a.sc1[si];                                                    // :10
         c2_row = a.sc2[si];                                                    // :11
     }
@@ -288,47 +300,53 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
     const volatile int *kstar_live = &a.status->kstar;
     int any_exhausted = 0, any_nan = 0;
     unsigned my_iters = 0;
-    const double *Mrow = a.M_in + i;                 // + n*j
-    double *Crow = a.C0 + i;
+    const size_t ns = (size_t)n;
+    const bool by_col = a.var_type == 2;
+    int t0_next = *kstar_live;
 
-    for (long long j0 = jc0; j0 < jc1; j0 += kTileCols) {
+    for (int j0 = jc0; j0 < jc1; j0 += kTileCols) {
         __syncthreads();                             // previous tile fully consumed
         // ---- stage the tile: zero Y image, EF rows, per-column constants --------------------
 #pragma unroll
         for (int c = 0; c < kTileCols; ++c) sm.ys[c][tid] = 0.0;
-        for (int idx = tid; idx < kTileCols * KTP; idx += kThreads) {
-            const int c = idx / KTP, k = idx - c * KTP;
-            const long long j = j0 + c;
-            sm.efs[c][k] = (j < jc1) ? __ldg(a.EFt + j * KTP + k) : 0.0;
+        {
+            const double *eft = a.EFt + (size_t)j0 * KTP;
+            const int lim = (jc1 - j0) * KTP;        // rows of EFt beyond jc1 are not read
+            for (int idx = tid; idx < kTileCols * KTP; idx += kThreads)
+                (&sm.efs[0][0])[idx] = (idx < lim) ? __ldg(eft + idx) : 0.0;
         }
         if (tid < kTileCols) {
-            const long long j = j0 + tid;
-            const bool col = (a.var_type == 2) && (j < jc1);
+            const int j = j0 + tid;
+            const bool col = by_col && (j < jc1);
             sm.c1s[tid] = col ? a.sc1[j] : 1.0;
             sm.c2s[tid] = col ? a.sc2[j] : 0.5;
             sm.f0s[tid] = (FORMULA == FORMULA_A10 && j < jc1) ? a.f0[j] : 1.0;
         }
         // first unit's M values: in flight while the tile is staged
+        size_t off = (size_t)i + ns * (size_t)j0;    // entry (i, j0)
         double mnext[E];
 #pragma unroll
         for (int e = 0; e < E; ++e)
-            mnext[e] = (row_ok && (j0 + e < jc1)) ? ld_stream(Mrow + a.n * (j0 + e)) : 0.0;
+            mnext[e] = (row_ok && (j0 + e < jc1)) ? ld_stream(a.M_in + off + e * ns) : 0.0;
         __syncthreads();
         // scatter the CSC non-zeros of rows [r0, r0+256) of each tile column
-        for (int c = warp; c < kTileCols; c += kWarps) {
-            const long long j = j0 + c;
-            if (j < jc1) {
-                const int lo = a.rbptr[rb * a.p + j], hi = a.rbptr[(rb + 1) * a.p + j];
-                for (int q = lo + lane; q < hi; q += 32)
-                    sm.ys[c][a.rowidx[q] - (int)r0] = __ldg(a.yx + q);
+        {
+            const int *rp0 = a.rbptr + (size_t)rb * p + j0, *rp1 = rp0 + p;
+            for (int c = warp; c < kTileCols; c += kWarps) {
+                if (j0 + c < jc1) {
+                    const int lo = rp0[c], hi = rp1[c];
+                    for (int q = lo + lane; q < hi; q += 32)
+                        sm.ys[c][a.rowidx[q] - r0] = __ldg(a.yx + q);
+                }
             }
         }
         // a2: this row's Beta for the 16 tile columns, K_tot FMAs each (EL row lives in registers
         // only here; EF rows are broadcast reads from shared memory)
         {
             double el[KTP];
+            const double *elp = a.EL + i;
 #pragma unroll
-            for (int k = 0; k < KTP; ++k) el[k] = (row_ok && k < a.K) ? __ldg(a.EL + i + a.n * k) : 0.0;
+            for (int k = 0; k < KTP; ++k) el[k] = (row_ok && k < a.K) ? __ldg(elp + k * ns) : 0.0;
 #pragma unroll 4
             for (int c = 0; c < kTileCols; ++c) {
                 double b = 0.0;
@@ -339,27 +357,34 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
         }
         __syncthreads();
 
-        // ---- units -----------------------------------------------------------------------
+        // ---- units: running offsets, no 64-bit multiplies in the loop ------------------------
+        const int jg0 = j0 / E;
+        size_t ku_idx = (size_t)jg0 * (size_t)a.nRW + rw;          // kunit[jg][rw]
+        size_t cv_idx = (size_t)rw * p + j0;                        // colV[rw][j]
+        size_t us_idx = ((size_t)rw * (size_t)a.nJG + jg0) * 2;     // unitS[rw][jg][2]
+        size_t rp_idx = (size_t)jg0 * ns + i;                       // rowpart[jg][i]
 #pragma unroll 1
         for (int g = 0; g < kTileCols / E; ++g) {
-            const long long jb = j0 + g * E;
+            const int jb = j0 + g * E;
             if (jb >= jc1 || !warp_ok) break;
-            const long long jg = jb / E;
-            // t0: the largest converged-at count any finished unit has published so far.  It never
-            // exceeds the global count u, so running this unit at least that far cannot overshoot.
-            const int t0 = *kstar_live;
-            double m[E], c0[E], w[E], c1[E], c2[E], sc[E], tol_e[E], r[E], sexp[E], f[E];
+            // t0: the largest converged-at count any finished unit had published when the PREVIOUS
+            // unit of this warp started (read one unit ahead so the L2 latency is off the critical
+            // path).  It never exceeds the global count u, so running this unit at least that far
+            // cannot overshoot.
+            const int t0 = t0_next;
+            t0_next = *kstar_live;
+            double m[E], c0[E], w[E], c1[E], c2[E], sc[E], r[E], sexp[E], f[E];
             bool ok[E];
+            const bool more = (g + 1 < kTileCols / E);
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int c = g * E + e;
-                const long long j = jb + e;
-                ok[e] = row_ok && (j < jc1);
+                const bool colok = jb + e < jc1;
+                ok[e] = row_ok && colok;
                 m[e] = mnext[e];
-                const long long jn = j + E;                                        // same slot of the next unit
-                mnext[e] = (row_ok && (g + 1 < kTileCols / E) && (jn < jc1)) ? ld_stream(Mrow + a.n * jn) : 0.0;
+                mnext[e] = (row_ok && more && (jb + E + e < jc1)) ? ld_stream(a.M_in + off + (E + e) * ns) : 0.0;
                 const double y = sm.ys[c][tid], b = sm.bs[c][tid];
-                if (a.var_type == 2) { c1[e] = sm.c1s[c]; c2[e] = sm.c2s[c]; }
+                if (by_col) { c1[e] = sm.c1s[c]; c2[e] = sm.c2s[c]; }
                 else { c1[e] = c1_row; c2[e] = c2_row; }
                 c0[e] = __dadd_rn(__fma_rn(__dadd_rn(c2[e], c2[e]), y, b), 1.0);   // :9 | :81,:95
                 const double c0m1 = __dadd_rn(c0[e], -1.0);
@@ -367,21 +392,25 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
                 sc[e] = (FORMULA == FORMULA_A10) ? __dmul_rn(l0_i, sm.f0s[c]) : 1.0;   // :83,:97 | S = 1
                 const double cap = (FORMULA == FORMULA_A1) ? c0m1 : b;             // :16 | :78
                 m[e] = (m[e] < cap) ? m[e] : cap;
-                tol_e[e] = ok[e] ? a.tol : INFINITY;
-                if (ok[e]) st_stream(Crow + a.n * j, c0[e]);
+                if (ok[e]) st_stream(a.C0 + off + e * ns, c0[e]);
+                if (e > 0 && !colok) {          // padding column (p % E != 0): shadow the previous one
+                    m[e] = m[e - 1]; c0[e] = c0[e - 1]; w[e] = w[e - 1]; c1[e] = c1[e - 1]; c2[e] = c2[e - 1];
+                    sc[e] = sc[e - 1];
+                }
             }
             int k = 0;
             const int flags = newton_unit<E, FORMULA, MODE_FIRST, FORMULA == FORMULA_A10>(
-                m, c0, w, c1, c2, sc, tol_e, k, t0, a.maxiter, sm.exptab, r, sexp, f);
+                m, c0, w, c1, c2, sc, row_ok ? a.tol : INFINITY, k, t0, a.maxiter, sm.exptab, r, sexp, f);
             my_iters += (unsigned)(k + 1);
             if (flags & 2) any_exhausted = 1;
-            if (finalize_unit<E, FORMULA>(a, m, c2, r, sexp, f, ok, flags, i, jb, jg, rw, lane, row_ok, sm.exptab,
-                                          sm.logtab))
+            if (finalize_unit<E, FORMULA>(a, m, c2, r, sexp, f, ok, flags, off, cv_idx, us_idx, rp_idx, p - jb, lane,
+                                          row_ok, sm.exptab, sm.logtab))
                 any_nan = 1;
             if (lane == 0) {
-                a.kunit[jg * a.nRW + rw] = (unsigned short)k;
+                a.kunit[ku_idx] = (unsigned short)k;
                 if (k > t0) atomicMax(&a.status->kstar, k);
             }
+            off += E * ns; ku_idx += (size_t)a.nRW; cv_idx += E; us_idx += 2; rp_idx += ns;
         }
     }
     if (lane == 0) {
@@ -392,67 +421,198 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
 }
 
 // ---------------------------------------------------------------------------------------
-// K1 / K4, pass 2: streaming top-up.  Same (column span, row block) decomposition so that
-// unit indices agree with pass 1; reads M_k and const0 back, no Y / Beta staging, no barrier
-// after the table set-up.
+// Split pipeline, stage A: const0 = (Sigma2*Y + Beta) + 1 for every entry (R/vga_solver_mat.R:9,
+// :81, :95), Beta rebuilt from the factors against the staged CSC tile.  Writes C0 (n x p).  For
+// the low_memory formula it also applies the clamp M = Pmin(M, Beta) (:78), M_in -> M_out, because
+// Beta alone cannot be recovered from const0 later.
 // ---------------------------------------------------------------------------------------
-template <int E, int FORMULA>
-__global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_topup_kernel(const FusedArgs a)
+template <int KTP>
+struct PrepSmem {
+    double ys[kTileCols][kRowsPerCta];
+    double efs[kTileCols][KTP];
+    double s2s[kTileCols];
+};
+
+template <int KTP, int FORMULA>
+__global__ void __launch_bounds__(kThreads, 3) vga_prep_kernel(const FusedArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PrepSmem<KTP> &sm = *reinterpret_cast<PrepSmem<KTP> *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = (int)a.n, p = (int)a.p;
+    const int rb = blockIdx.y;
+    const int r0 = rb * kRowsPerCta;
+    const int i = r0 + tid;
+    const bool row_ok = i < n;
+    const int jc0 = (int)a.col0 + blockIdx.x * a.cols_per_cta;
+    const int jc1 = min((int)a.col1, jc0 + a.cols_per_cta);
+    const size_t ns = (size_t)n;
+    const bool by_col = a.var_type == 2;
+    double s2_row = 1.0;
+    if (!by_col) s2_row = __dadd_rn(a.sc2[(a.var_type == 1) ? (row_ok ? i : 0) : 0], a.sc2[(a.var_type == 1) ? (row_ok ? i : 0) : 0]);
+    double el[KTP];
+    {
+        const double *elp = a.EL + i;
+#pragma unroll
+        for (int k = 0; k < KTP; ++k) el[k] = (row_ok && k < a.K) ? __ldg(elp + k * ns) : 0.0;
+    }
+    for (int j0 = jc0; j0 < jc1; j0 += kTileCols) {
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < kTileCols; ++c) sm.ys[c][tid] = 0.0;
+        {
+            const double *eft = a.EFt + (size_t)j0 * KTP;
+            const int lim = (jc1 - j0) * KTP;
+            for (int idx = tid; idx < kTileCols * KTP; idx += kThreads)
+                (&sm.efs[0][0])[idx] = (idx < lim) ? __ldg(eft + idx) : 0.0;
+        }
+        if (tid < kTileCols) {
+            const int j = j0 + tid;
+            sm.s2s[tid] = (by_col && j < jc1) ? __dadd_rn(a.sc2[j], a.sc2[j]) : 1.0;    // sigma2 = 2*const2, exact
+        }
+        __syncthreads();
+        {
+            const int *rp0 = a.rbptr + (size_t)rb * p + j0, *rp1 = rp0 + p;
+            for (int c = warp; c < kTileCols; c += kWarps) {
+                if (j0 + c < jc1) {
+                    const int lo = rp0[c], hi = rp1[c];
+                    for (int q = lo + lane; q < hi; q += 32)
+                        sm.ys[c][a.rowidx[q] - r0] = __ldg(a.yx + q);
+                }
+            }
+        }
+        __syncthreads();
+        size_t off = (size_t)i + ns * (size_t)j0;
+#pragma unroll 4
+        for (int c = 0; c < kTileCols; ++c, off += ns) {
+            double b = 0.0;
+#pragma unroll
+            for (int k = 0; k < KTP; ++k) b = fma(el[k], sm.efs[c][k], b);          // a2: Beta_ij
+            if (row_ok && j0 + c < jc1) {
+                const double s2 = by_col ? sm.s2s[c] : s2_row;
+                st_stream(a.C0 + off, __dadd_rn(__fma_rn(s2, sm.ys[c][tid], b), 1.0));   // :9 | :81,:95
+                if (FORMULA == FORMULA_A10) {
+                    const double m0 = ld_stream(a.M_in + off);
+                    st_stream(a.M_out + off, (m0 < b) ? m0 : b);                     // :78
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Split pipeline, stage B (MODE_FIRST) and the top-up pass of both pipelines (MODE_TOPUP):
+// streaming Newton.  Reads M and const0, no tile staging, no barrier after the table set-up.
+// Same (column span, row block) decomposition as the other kernels so unit indices agree.
+// ---------------------------------------------------------------------------------------
+#ifndef EBPMF_STREAM_MINB
+#define EBPMF_STREAM_MINB 3
+#endif
+template <int E, int FORMULA, int MODE>
+__global__ void __launch_bounds__(kThreads, EBPMF_STREAM_MINB) vga_stream_kernel(const FusedArgs a)
 {
     __shared__ double exptab[EBPMF_EXP_TABLE_SIZE];
     __shared__ double2 logtab[EBPMF_LOG_TABLE_SIZE];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long rb = blockIdx.y;
-    const long long i = rb * kRowsPerCta + tid;
-    const bool row_ok = i < a.n;
-    const long long rw = rb * kWarps + warp;
+    const int n = (int)a.n, p = (int)a.p;
+    const int rb = blockIdx.y;
+    const int i = rb * kRowsPerCta + tid;
+    const bool row_ok = i < n;
+    const int rw = rb * kWarps + warp;
     exp_table_init(exptab, a.tables, tid, kThreads);
     log_table_init(logtab, a.tables, tid, kThreads);
     __syncthreads();
-    if (rw >= a.nRW) return;                         // no block-wide barrier below this point
-    const long long jc0 = a.col0 + (long long)blockIdx.x * a.cols_per_cta;
-    const long long jc1 = min(a.col1, jc0 + (long long)a.cols_per_cta);
-    const int target = a.status->kstar;
+    if (rw >= (int)a.nRW) return;                    // no block-wide barrier below this point
+    const int jc0 = (int)a.col0 + blockIdx.x * a.cols_per_cta;
+    const int jc1 = min((int)a.col1, jc0 + a.cols_per_cta);
+    const volatile int *kstar_live = &a.status->kstar;
+    const int target = (MODE == MODE_TOPUP) ? a.status->kstar : 0;
+    const bool by_col = a.var_type == 2;
     double c1_row = 1.0, c2_row = 0.5, l0_i = 1.0;
-    if (a.var_type != 2) {
-        const long long si = (a.var_type == 1) ? (row_ok ? i : 0) : 0;
+    if (!by_col) {
+        const int si = (a.var_type == 1) ? (row_ok ? i : 0) : 0;
         c1_row = a.sc1[si];
         c2_row = a.sc2[si];
     }
     if (FORMULA == FORMULA_A10) l0_i = row_ok ? a.l0[i] : 1.0;
+    // first pass of A1 reads the caller's M and clamps it; A10's prep kernel already wrote the
+    // clamped M to M_out; the top-up pass continues in place on M_out
+    const double *Msrc = (MODE == MODE_FIRST && FORMULA == FORMULA_A1) ? a.M_in : a.M_out;
     int any_exhausted = 0, any_nan = 0, any_fail = 0;
     unsigned my_topups = 0, my_iters = 0;
+    const size_t ns = (size_t)n;
+    const int jg0 = jc0 / E;
+    size_t off = (size_t)i + ns * (size_t)jc0;
+    size_t ku_idx = (size_t)jg0 * (size_t)a.nRW + rw;
+    size_t cv_idx = (size_t)rw * p + jc0;
+    size_t us_idx = ((size_t)rw * (size_t)a.nJG + jg0) * 2;
+    size_t rp_idx = (size_t)jg0 * ns + i;
+    int t0_next = (MODE == MODE_FIRST) ? *kstar_live : 0;
+    const double tol_lane = row_ok ? a.tol : INFINITY;
+
+    // first pass: register prefetch of the next unit's (M, const0)
+    double mnext[E], cnext[E];
+    if (MODE == MODE_FIRST) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const bool okn = row_ok && (jc0 + e < jc1);
+            mnext[e] = okn ? ld_stream(Msrc + off + e * ns) : 0.0;
+            cnext[e] = okn ? ld_stream(a.C0 + off + e * ns) : 2.0;
+        }
+    }
 
 #pragma unroll 1
-    for (long long jb = jc0; jb < jc1; jb += E) {
-        const long long jg = jb / E;
-        int k = a.kunit[jg * a.nRW + rw];
-        if (k == target) continue;
-        ++my_topups;
-        double m[E], c0[E], w[E], c1[E], c2[E], sc[E], tol_e[E], r[E], sexp[E], f[E];
+    for (int jb = jc0; jb < jc1; jb += E, off += E * ns, ku_idx += (size_t)a.nRW, cv_idx += E, us_idx += 2, rp_idx += ns) {
+        int k = 0;
+        int t0 = 0;
+        if (MODE == MODE_TOPUP) {
+            k = a.kunit[ku_idx];
+            if (k == target) continue;
+            ++my_topups;
+        } else {
+            t0 = t0_next;                            // read one unit ahead: off the critical path, still <= u
+            t0_next = *kstar_live;
+        }
+        double m[E], c0[E], w[E], c1[E], c2[E], sc[E], r[E], sexp[E], f[E];
         bool ok[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            const long long j = jb + e;
-            ok[e] = row_ok && (j < jc1);
-            const long long jj = (j < jc1) ? j : jc0;
-            m[e] = ok[e] ? ld_stream(a.M_out + i + a.n * j) : 0.0;
-            c0[e] = ok[e] ? ld_stream(a.C0 + i + a.n * j) : 2.0;
-            if (a.var_type == 2) { c1[e] = __ldg(a.sc1 + jj); c2[e] = __ldg(a.sc2 + jj); }
+            const bool colok = jb + e < jc1;
+            ok[e] = row_ok && colok;
+            const int jj = colok ? jb + e : jc0;
+            if (MODE == MODE_FIRST) {
+                m[e] = mnext[e]; c0[e] = cnext[e];
+                const bool okn = row_ok && (jb + E + e < jc1);
+                mnext[e] = okn ? ld_stream(Msrc + off + (E + e) * ns) : 0.0;
+                cnext[e] = okn ? ld_stream(a.C0 + off + (E + e) * ns) : 2.0;
+            } else {
+                m[e] = ok[e] ? ld_stream(Msrc + off + e * ns) : 0.0;
+                c0[e] = ok[e] ? ld_stream(a.C0 + off + e * ns) : 2.0;
+            }
+            if (by_col) { c1[e] = __ldg(a.sc1 + jj); c2[e] = __ldg(a.sc2 + jj); }
             else { c1[e] = c1_row; c2[e] = c2_row; }
-            w[e] = __dmul_rn(__dadd_rn(c0[e], -1.0), c1[e]);
+            const double c0m1 = __dadd_rn(c0[e], -1.0);
+            w[e] = __dmul_rn(c0m1, c1[e]);
             sc[e] = (FORMULA == FORMULA_A10) ? __dmul_rn(l0_i, __ldg(a.f0 + jj)) : 1.0;
-            tol_e[e] = ok[e] ? a.tol : INFINITY;
+            if (MODE == MODE_FIRST && FORMULA == FORMULA_A1) m[e] = (m[e] < c0m1) ? m[e] : c0m1;   // :16
+            if (e > 0 && !colok) {                   // padding column (p % E != 0): shadow the previous one
+                m[e] = m[e - 1]; c0[e] = c0[e - 1]; w[e] = w[e - 1]; c1[e] = c1[e - 1]; c2[e] = c2[e - 1];
+                sc[e] = sc[e - 1];
+            }
         }
         const int k_in = k;
-        const int flags = newton_unit<E, FORMULA, MODE_TOPUP, FORMULA == FORMULA_A10>(
-            m, c0, w, c1, c2, sc, tol_e, k, target, a.maxiter, exptab, r, sexp, f);
+        const int flags = newton_unit<E, FORMULA, MODE, FORMULA == FORMULA_A10>(
+            m, c0, w, c1, c2, sc, tol_lane, k, (MODE == MODE_FIRST) ? t0 : target, a.maxiter, exptab, r, sexp, f);
         my_iters += (unsigned)(k - k_in + 1);
         if (flags & 2) any_exhausted = 1;
-        if (!(flags & 3)) any_fail = 1;              // stopped at K* but not below tol
-        if (finalize_unit<E, FORMULA>(a, m, c2, r, sexp, f, ok, flags, i, jb, jg, rw, lane, row_ok, exptab, logtab))
+        if (MODE == MODE_TOPUP && !(flags & 3)) any_fail = 1;      // stopped at K* but not below tol
+        if (finalize_unit<E, FORMULA>(a, m, c2, r, sexp, f, ok, flags, off, cv_idx, us_idx, rp_idx, p - jb, lane, row_ok,
+                                      exptab, logtab))
             any_nan = 1;
-        if (lane == 0) a.kunit[jg * a.nRW + rw] = (unsigned short)k;
+        if (lane == 0) {
+            a.kunit[ku_idx] = (unsigned short)k;
+            if (MODE == MODE_FIRST && k > t0) atomicMax(&a.status->kstar, k);
+        }
     }
     if (lane == 0) {
         if (any_exhausted) a.status->exhausted = 1;
@@ -536,27 +696,26 @@ __global__ void __launch_bounds__(kThreads, 2) vga_dense_kernel(const DenseArgs 
             k = a.kunit[jg * a.nRW + rw];
             if (k == target) continue;
         }
-        double m[E], c0[E], w[E], c1[E], c2[E], sc[E], s2[E], tol_e[E], r[E], sexp[E], f[E];
+        double m[E], c0[E], w[E], c1[E], c2[E], sc[E], s2[E], r[E], sexp[E], f[E];
         bool ok[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const long long j = jb + e;
             ok[e] = row_ok && (j < jc1);
-            const long long jj = (j < jc1) ? j : jc0;
-            m[e] = ok[e] ? ld_stream(Msrc + i + a.n * j) : 0.0;
-            const double y = ok[e] ? ld_stream(a.X + i + a.n * j) : 0.0;
-            const double b = ok[e] ? a.Beta[ii * a.B_rs + jj * a.B_cs] : 0.0;
-            s2[e] = ok[e] ? a.Sigma2[ii * a.V_rs + jj * a.V_cs] : 1.0;
-            sc[e] = ok[e] ? a.S[ii * a.S_rs + jj * a.S_cs] : 1.0;
+            const long long jj = (j < jc1) ? j : jb;                               // padding column shadows column jb
+            m[e] = row_ok ? ld_stream(Msrc + i + a.n * jj) : 0.0;
+            const double y = row_ok ? ld_stream(a.X + i + a.n * jj) : 0.0;
+            const double b = row_ok ? a.Beta[ii * a.B_rs + jj * a.B_cs] : 0.0;
+            s2[e] = row_ok ? a.Sigma2[ii * a.V_rs + jj * a.V_cs] : 1.0;
+            sc[e] = row_ok ? a.S[ii * a.S_rs + jj * a.S_cs] : 1.0;
             c1[e] = 1.0 / s2[e];                                                   // :10
             c2[e] = s2[e] / 2;                                                     // :11
             c0[e] = __dadd_rn(__fma_rn(s2[e], y, b), 1.0);                         // :9
             const double c0m1 = __dadd_rn(c0[e], -1.0);
             w[e] = __dmul_rn(c0m1, c1[e]);                                         // x + const3
-            tol_e[e] = ok[e] ? a.tol : INFINITY;
             if (MODE == MODE_FIRST) m[e] = (m[e] < c0m1) ? m[e] : c0m1;            // :16
         }
-        const int flags = newton_unit<E, FORMULA_A1, MODE, true>(m, c0, w, c1, c2, sc, tol_e, k,
+        const int flags = newton_unit<E, FORMULA_A1, MODE, true>(m, c0, w, c1, c2, sc, row_ok ? a.tol : INFINITY, k,
                                                                   (MODE == MODE_FIRST) ? t0 : target, a.maxiter,
                                                                   exptab, r, sexp, f);
         if (flags & 2) any_exhausted = 1;

@@ -1,12 +1,13 @@
 #!/bin/bash
-# Build kernel variants (E columns per unit, MINB resident CTAs) for A/B timing under gpurun.
+# Build kernel variants for A/B timing under gpurun: "E MINB STREAM_MINB"
 set -e
 cd "$(dirname "$0")/../ebpmf.alpha_b200/csrc"
 mkdir -p ../lib/variants
-for v in "2 2" "4 2" "2 3" "4 1"; do
+rm -f ../lib/variants/*.so
+for v in "2 3 4" "2 3 5" "4 2 2"; do
   set -- $v
-  nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -DEBPMF_E=$1 -DEBPMF_MINB=$2 \
-       -shared -o ../lib/variants/libebpmf_E$1_B$2.so ebpmf_api.cu -lcudart -ldl &
+  nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -DEBPMF_E=$1 -DEBPMF_MINB=$2 -DEBPMF_STREAM_MINB=$3 \
+       -shared -o ../lib/variants/libebpmf_E$1_B$2_S$3.so ebpmf_api.cu -lcudart -ldl &
 done
 wait
-ls -la ../lib/variants
+ls ../lib/variants
