@@ -102,6 +102,14 @@ class ClockSampler:
                     power_w_max=max(float(r[2]) for r in self.rows), samples=len(self.rows))
 
 
+def host_cores():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, so ask the OS)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_sample_inputs(ctx, rows):
     """Rows [0, rows) of the device-generated workload, pulled to the host for the CPU arm."""
     import scipy.sparse as sp
@@ -116,7 +124,7 @@ def cpu_baseline(sample, reps=2):
     """The oracle's C transcription of R/ebpmf_log.R:302-327 (OpenMP, all cores) on the sample."""
     from oracle import c_oracle
     rows, p = sample["Y"].shape
-    cores = c_oracle.max_threads()
+    cores = host_cores()
     best, out = None, None
     for _ in range(reps):
         t = time.perf_counter()
@@ -147,7 +155,7 @@ def run_reference(args, wl, rank, world):
     p, K = wl["p"], wl["K"]
     sim = simdata.sim_data_log(rows, p, K=K, seed=SEED, log_offset=wl["log_offset"])
     st = simdata.solver_state(sim, start="cold")
-    cores = c_oracle.max_threads()
+    cores = host_cores()
     times = []
     for it in range(args.warmup + args.steps):
         t = time.perf_counter()
