@@ -51,6 +51,7 @@ WORKLOADS = {
                label="BASELINE config 2: 10000 x 2000, K=5 (+2 offset cols)"),
 }
 MAXITER_VGA, VGA_TOL = 10, 1e-5
+DELTA = 1e-14
 SEED = 12345
 
 
@@ -259,6 +260,24 @@ def main():
     p2 = sum(i.pass2_ms for i in infos) / args.steps
     rd = sum(i.reduce_ms for i in infos) / args.steps
 
+    # ---- the same step in delta mode (option, not the default) ----------------
+    ctx.set_option("delta", DELTA)
+    dinfos = []
+    for it in range(1 + args.steps):
+        inf = ctx.vga_step(MAXITER_VGA, VGA_TOL)
+        ctx.rewind_m()
+        if it > 0:
+            dinfos.append(inf)
+    barrier()
+    ctx.set_option("delta", 0.0)
+    d_ms = allmax(sum(i.kernel_ms for i in dinfos)) / args.steps
+    delta_mode = {"delta": DELTA, "value": entries / (d_ms * 1e-3), "unit": "entries/s", "ms_per_step": d_ms,
+                  "n_updates": dinfos[-1].n_updates,
+                  "pass_ms": {"first": sum(i.pass1_ms for i in dinfos) / args.steps,
+                              "topup": sum(i.pass2_ms for i in dinfos) / args.steps},
+                  "note": "units whose next Newton update is <= delta (and |f| < tol/16) are frozen; M, V within "
+                          "~delta of the exact-count result, n_updates identical; NOT the headline value"}
+
     # ---- roofline (HBM line of the dominant kernel = first pass) --------------------------------
     peak, peak_src = read_peaks()
     alg_bytes_per_entry = 16.0 + 12.0 * density            # read M 8 + write M 8 + CSC (x 8 + i 4) * density
@@ -268,9 +287,10 @@ def main():
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_entry": alg_bytes_per_entry,
                 "note": "the FP64 pipe, not HBM, binds this kernel for u > 0 (see fp64)"}
-    # FP64 line: DP-pipe instructions per entry from the SASS of the Newton loop:
-    # 18 per evaluation + 8 per update + K_tot FMAs for Beta per pass + ~40 in the epilogue
-    dp_instr = 18.0 * (u + 2) + 8.0 * u + 2.0 * (K + 2) + 40.0
+    # FP64 line: FP64-pipe instructions per entry, counted in the SASS of the Newton loop:
+    # 19 per evaluation of f (u+1 of them, +1 for the 58 % of units redone in pass 2), 6.5 per update,
+    # K_tot FMAs for Beta, ~20 in the epilogue
+    dp_instr = 19.0 * (u + 1.6) + 6.5 * u + 1.0 * (K + 2) + 20.0
     fp64 = {"dfma_tflops_measured": fp64_tf, "dp_instr_per_entry_model": dp_instr,
             "line_entries_per_s": (fp64_tf * 1e12 / 2.0) / dp_instr,
             "frac_of_fp64_line": (value / world) / ((fp64_tf * 1e12 / 2.0) / dp_instr)}
@@ -286,7 +306,8 @@ def main():
         "n_updates": u, "converged": bool(infos[-1].converged), "passes": infos[-1].passes,
         "pass_ms": {"first": p1, "topup": p2, "reduce": rd}, "wall_ms_per_step": 1e3 * wall / args.steps,
         "topup_units_frac": diag["topup_units"] / max(1.0, ((n + 31) // 32) * ((p + 1) // 2)),
-        "roofline": roofline, "fp64": fp64, "gpu_launches": 4 * args.steps, "clocks": clk.summary(),
+        "roofline": roofline, "fp64": fp64, "delta_mode": delta_mode,
+        "gpu_launches": 7 * args.steps, "clocks": clk.summary(),
     }
 
     # ---- parity gate + CPU baseline on a bounded row sample (rank 0) -----------------------------

@@ -72,6 +72,7 @@ SIGNATURES = {
                                     _int, _dbl, _vp, _PI]),
     "ebpmf_ctx_sim_data_log": (_int, [_vp, _i64, _i64, _i64, _i64, C.c_uint64, _dbl, _dbl, _dbl, _dbl, _dbl, _int,
                                       C.POINTER(_i64)]),
+    "ebpmf_ctx_set_option": (_int, [_vp, C.c_char_p, _dbl]),
     "ebpmf_ctx_last_diag": (_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ebpmf_probe_fp64_tflops": (_int, [_vp, C.POINTER(_dbl)]),
 }

@@ -71,6 +71,7 @@ struct ebpmf_ctx {
     int K = 0, KTP = 0;
     int var_type = -1;
     int pipeline = 0;          // 0: fused first pass, 1: split (const0 kernel + streaming Newton)
+    double delta = 0.0;        // 0: exact update count (default); > 0: delta mode (ebpmf_ctx_set_option)
     bool can_rewind = false;
     unsigned long long diag_topups = 0, diag_iters = 0;
     bool have_y = false, have_m = false, have_f = false, have_s2 = false, have_v = false, have_vsum = false;
@@ -176,9 +177,9 @@ int cols_per_cta_for(long long p, long long nRB) {
     return (int)c;
 }
 
-template <int KTP, int FORMULA>
-int launch_first_ktp(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
-    auto kern = vga_fused_kernel<KTP, kE, FORMULA>;
+template <int KTP, int FORMULA, bool DELTA>
+int launch_first_ktp2(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
+    auto kern = vga_fused_kernel<KTP, kE, FORMULA, DELTA>;
     const int smem = (int)sizeof(FusedSmem<KTP>);
     static bool configured[8] = {false, false, false, false, false, false, false, false};   // per device
     if (ctx->device < 8 ? !configured[ctx->device] : true) {
@@ -188,6 +189,12 @@ int launch_first_ktp(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
     kern<<<grid, dim3(kThreads), smem, ctx->stream>>>(a);
     CU(cudaGetLastError());
     return EBPMF_OK;
+}
+
+template <int KTP, int FORMULA>
+int launch_first_ktp(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
+    return a.delta > 0 ? launch_first_ktp2<KTP, FORMULA, true>(ctx, a, grid)
+                       : launch_first_ktp2<KTP, FORMULA, false>(ctx, a, grid);
 }
 
 template <int KTP, int FORMULA>
@@ -214,7 +221,8 @@ int launch_first(ebpmf_ctx *ctx, const FusedArgs &a) {
             case 32: CHECK((launch_prep_ktp<32, FORMULA>(ctx, a, grid))); break;
             default: return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported (max 32)", ctx->K);
         }
-        vga_stream_kernel<kE, FORMULA, MODE_FIRST><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
+        if (a.delta > 0) vga_stream_kernel<kE, FORMULA, MODE_FIRST, true><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
+        else vga_stream_kernel<kE, FORMULA, MODE_FIRST, false><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
         CU(cudaGetLastError());
         return EBPMF_OK;
     }
@@ -233,7 +241,8 @@ int launch_topup(ebpmf_ctx *ctx, const FusedArgs &a) {
     const long long ncols = a.col1 - a.col0;
     if (ncols <= 0) return EBPMF_OK;
     dim3 grid((unsigned)((ncols + a.cols_per_cta - 1) / a.cols_per_cta), (unsigned)ctx->nRB);
-    vga_stream_kernel<kE, FORMULA, MODE_TOPUP><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
+    if (a.delta > 0) vga_stream_kernel<kE, FORMULA, MODE_TOPUP, true><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
+    else vga_stream_kernel<kE, FORMULA, MODE_TOPUP, false><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
     CU(cudaGetLastError());
     return EBPMF_OK;
 }
@@ -389,7 +398,7 @@ FusedArgs fused_args(ebpmf_ctx *ctx, int maxiter, double tol, bool want_v) {
     a.rowpart = (ctx->var_type == EBPMF_VAR_BY_ROW) ? as<double>(ctx->rowpart) : nullptr;
     a.status = as<Status>(ctx->status);
     a.tables = as<MathTables>(ctx->tables);
-    a.maxiter = maxiter; a.tol = tol;
+    a.maxiter = maxiter; a.tol = tol; a.delta = ctx->delta;
     a.col0 = 0; a.col1 = ctx->p;
     a.cols_per_cta = cols_per_cta_for(ctx->p, ctx->nRB);
     return a;
@@ -514,6 +523,7 @@ int ebpmf_ctx_create(int device, ebpmf_ctx **out) {
     if (!ctx) return fail(nullptr, EBPMF_ERR_NOMEM, "out of host memory");
     ctx->device = device;
     if (const char *pl = getenv("EBPMF_B200_PIPELINE")) ctx->pipeline = (strcmp(pl, "split") == 0) ? 1 : 0;
+    if (const char *dl = getenv("EBPMF_B200_DELTA")) ctx->delta = atof(dl);
     cudaError_t ce;
 #define CREATE_STEP(call)                                                                                        \
     ce = (call);                                                                                                 \
@@ -1130,6 +1140,17 @@ int ebpmf_ctx_sim_data_log(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, int6
     ctx->have_m = ctx->have_f = ctx->have_s2 = true;
     if (nnz_out) *nnz_out = nnz;
     return EBPMF_OK;
+}
+
+int ebpmf_ctx_set_option(ebpmf_ctx *ctx, const char *name, double value) {
+    if (!ctx || !name) return fail(ctx, EBPMF_ERR_ARG, "set_option: bad arguments");
+    if (!strcmp(name, "delta")) {
+        if (!(value >= 0.0) || value > 1e-10) return fail(ctx, EBPMF_ERR_ARG, "set_option: delta must be in [0, 1e-10]");
+        ctx->delta = value;
+        return EBPMF_OK;
+    }
+    if (!strcmp(name, "pipeline")) { ctx->pipeline = value != 0.0 ? 1 : 0; return EBPMF_OK; }
+    return fail(ctx, EBPMF_ERR_ARG, "set_option: unknown option '%s'", name);
 }
 
 int ebpmf_ctx_last_diag(ebpmf_ctx *ctx, uint64_t *topup_units, uint64_t *unit_evals) {

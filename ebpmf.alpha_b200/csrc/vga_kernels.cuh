@@ -82,6 +82,7 @@ struct FusedArgs {
     const MathTables *tables;       // exp2 / log tables (device copy of the host-built tables)
     int maxiter;
     double tol;
+    double delta;                   // 0: exact update count for every entry; > 0: delta mode
     long long col0, col1;           // columns of this launch
     int cols_per_cta;               // multiple of kTileCols
 };
@@ -150,20 +151,24 @@ template <int S> __device__ __forceinline__ double warp_multi_sum(const double (
 // and K* in the top-up pass (stop exactly at k == K*).
 // On return k is the number of updates the unit has received, r[] the reciprocal of the last
 // evaluated temp, sexp[] / f[] the last evaluated S*exp(.) and f.
-// Returns a bit mask: 1 converged at k, 2 exhausted.
+// Returns a bit mask: 1 converged at k, 2 exhausted, 8 frozen (delta mode only).
 // ---------------------------------------------------------------------------------------
-template <int E, int FORMULA, int MODE, bool SCALED>
+constexpr int kFrozen = 0xFFFF;     // kunit marker: unit is at its numerical fixed point (delta mode)
+
+template <int E, int FORMULA, int MODE, bool SCALED, bool DELTA>
 __device__ __forceinline__ int newton_unit(double (&m)[E], const double (&c0)[E], double (&w)[E],
                                            const double (&c1)[E], const double (&c2)[E], const double (&sc)[E],
-                                           double tol_lane, int &k, int target, int maxiter,
-                                           const double *exptab, double (&r)[E], double (&sexp)[E], double (&f)[E])
+                                           double tol_lane, int &k, int &kb, int target, int maxiter, double delta,
+                                           unsigned exptab, double (&r)[E], double (&sexp)[E], double (&f)[E])
 {
     int flags = 0;
+    kb = -1;                        // first k at which the unit was converged (what K* is the max of)
     // keep w (and the lane tolerance) in registers: without this the compiler re-derives
     // (c0-1)*c1 in every iteration -- 2 extra FP64-pipe instructions per entry per iteration
 #pragma unroll
     for (int e = 0; e < E; ++e) asm volatile("" : "+d"(w[e]));
     asm volatile("" : "+d"(tol_lane));
+    asm volatile("" : "+r"(exptab));        // likewise the table's shared-window address
 #pragma unroll 1
     for (;;) {
         bool lane_conv = true;
@@ -183,13 +188,35 @@ __device__ __forceinline__ int newton_unit(double (&m)[E], const double (&c0)[E]
             lane_conv = lane_conv && (fabs(f[e]) < tol_lane);                  // :26 (strict <)
         }
         const bool conv = __all_sync(0xffffffffu, lane_conv);
+        if (conv && kb < 0) kb = k;
         const bool stop = (MODE == MODE_FIRST) ? (conv && (k >= target)) : (k == target);
-        if (stop) { if (conv) flags |= 1; break; }
+        if (!DELTA || !conv) {
+            if (stop) { if (conv) flags |= 1; break; }
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const double q = (FORMULA == FORMULA_A1) ? a[e] : __dmul_rn(0.5, r[e]);   // const2/temp^2 | 0.5*temp^-2
-            const double g = __fma_rn(-sexp[e], __fma_rn(q, r[e], 1.0), -c1[e]);      // :31 | :90,:105
-            m[e] = __fma_rn(-f[e], rcp_fast(g), m[e]);
+            for (int e = 0; e < E; ++e) {
+                const double q = (FORMULA == FORMULA_A1) ? a[e] : __dmul_rn(0.5, r[e]);   // const2/temp^2 | 0.5*temp^-2
+                const double g = __fma_rn(-sexp[e], __fma_rn(q, r[e], 1.0), -c1[e]);      // :31 | :90,:105
+                m[e] = __fma_rn(-f[e], rcp_fast(g), m[e]);
+            }
+        } else {
+            // delta mode, unit converged: form the update and FREEZE the unit if every entry's update
+            // is a numerical no-op (|f/g| <= delta, |f| < tol/16): all later iterates equal this one
+            // to within delta, so the unit is final for any global count.
+            double mn[E];
+            bool lane_small = true;
+            const double tol16 = tol_lane * 0.0625;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const double q = (FORMULA == FORMULA_A1) ? a[e] : __dmul_rn(0.5, r[e]);
+                const double g = __fma_rn(-sexp[e], __fma_rn(q, r[e], 1.0), -c1[e]);
+                const double rg = rcp_fast(g);
+                mn[e] = __fma_rn(-f[e], rg, m[e]);
+                lane_small = lane_small && (fabs(__dmul_rn(f[e], rg)) <= delta) && (fabs(f[e]) < tol16);
+            }
+            if (__all_sync(0xffffffffu, lane_small)) { flags |= 1 | 8; break; }
+            if (stop) { flags |= 1; break; }
+#pragma unroll
+            for (int e = 0; e < E; ++e) m[e] = mn[e];
         }
         ++k;
         if (k >= maxiter) { flags |= 2; break; }
@@ -212,14 +239,15 @@ __device__ __forceinline__ bool finalize_unit(const FusedArgs &a, const double (
                                               size_t us_idx,   // (rw*nJG + jg)*2 : slot of the unit in unitS
                                               size_t rp_idx,   // jg*n + i : slot in rowpart
                                               int cols_left,   // p - jb
-                                              int lane, bool row_ok, const double *exptab, const double2 *logtab)
+                                              int lane, bool row_ok, unsigned exptab, unsigned logtab)
 {
     constexpr int S = (E + 2 <= 4) ? 4 : 8;
     static_assert(E + 2 <= 8, "at most 6 columns per unit");
     double vals[S];
 #pragma unroll
     for (int q = 0; q < S; ++q) vals[q] = 0.0;
-    double rowv = 0.0;
+    double rowv = 0.0, vprod = 1.0;
+    int nlive = 0;
     bool lane_nan = false;
     const size_t n = (size_t)a.n;
 #pragma unroll
@@ -231,9 +259,13 @@ __device__ __forceinline__ bool finalize_unit(const FusedArgs &a, const double (
             if (ok[e] && a.V_out) st_stream(a.V_out + off + e * n, v);
             double ex = sexp[e];                                                // == exp(M+V/2): S == 1 and the loop broke
             if (flags & 2) ex = exp_fast(__fma_rn(0.5, v, m[e]), exptab);       // exhausted: M moved after temp
-            const double lv = fma(0.5, log_fast(v, logtab), kSlogvConst);       // R/ebpmf_log.R:318
-            if (ok[e]) { vals[e] = v; vals[E] += ex; vals[E + 1] += lv; rowv += v; }
+            if (ok[e]) { vals[e] = v; vals[E] += ex; rowv += v; vprod *= v; ++nlive; }
         }
+    }
+    if (FORMULA == FORMULA_A1) {
+        // sum_e (log(V_e)/2 + c) = log(prod_e V_e)/2 + nlive*c : one log per lane instead of E
+        // (V in (0, sigma2]; a product of E <= 4 such values stays far from underflow)
+        vals[E + 1] = (nlive > 0) ? fma(0.5, log_fast(vprod, logtab), kSlogvConst * nlive) : 0.0;   // R/ebpmf_log.R:318
     }
     if (FORMULA == FORMULA_A1) {
         const double tot = warp_multi_sum<S>(vals, lane);
@@ -266,7 +298,7 @@ struct FusedSmem {
 // K1 / K4, pass 1: fused VGA step on CSC Y with Beta rebuilt from the flash factors.
 // grid = (column spans, row blocks), block = 256 threads, dynamic smem = sizeof(FusedSmem<KTP>).
 // ---------------------------------------------------------------------------------------
-template <int KTP, int E, int FORMULA>
+template <int KTP, int E, int FORMULA, bool DELTA>
 __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const FusedArgs a)
 {
     static_assert(kTileCols % E == 0, "E must divide the tile width");
@@ -287,6 +319,7 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
 
     exp_table_init(sm.exptab, a.tables, tid, kThreads);
     log_table_init(sm.logtab, a.tables, tid, kThreads);
+    const unsigned exptab_s = smem_addr(sm.exptab), logtab_s = smem_addr(sm.logtab);
 
     // row-constant pieces (by_row / constant sigma2, A10's l0)
     double c1_row = 1.0, c2_row = 0.5, l0_i = 1.0;
@@ -398,17 +431,17 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
                     sc[e] = sc[e - 1];
                 }
             }
-            int k = 0;
-            const int flags = newton_unit<E, FORMULA, MODE_FIRST, FORMULA == FORMULA_A10>(
-                m, c0, w, c1, c2, sc, row_ok ? a.tol : INFINITY, k, t0, a.maxiter, sm.exptab, r, sexp, f);
+            int k = 0, kb;
+            const int flags = newton_unit<E, FORMULA, MODE_FIRST, FORMULA == FORMULA_A10, DELTA>(
+                m, c0, w, c1, c2, sc, row_ok ? a.tol : INFINITY, k, kb, t0, a.maxiter, a.delta, exptab_s, r, sexp, f);
             my_iters += (unsigned)(k + 1);
-            if (flags & 2) any_exhausted = 1;
+            if (flags & 2) { any_exhausted = 1; kb = k; }
             if (finalize_unit<E, FORMULA>(a, m, c2, r, sexp, f, ok, flags, off, cv_idx, us_idx, rp_idx, p - jb, lane,
-                                          row_ok, sm.exptab, sm.logtab))
+                                          row_ok, exptab_s, logtab_s))
                 any_nan = 1;
             if (lane == 0) {
-                a.kunit[ku_idx] = (unsigned short)k;
-                if (k > t0) atomicMax(&a.status->kstar, k);
+                a.kunit[ku_idx] = (unsigned short)((flags & 8) ? kFrozen : k);
+                if (kb > t0) atomicMax(&a.status->kstar, kb);      // K* = max over units of the first converged k
             }
             off += E * ns; ku_idx += (size_t)a.nRW; cv_idx += E; us_idx += 2; rp_idx += ns;
         }
@@ -508,7 +541,7 @@ __global__ void __launch_bounds__(kThreads, 3) vga_prep_kernel(const FusedArgs a
 #ifndef EBPMF_STREAM_MINB
 #define EBPMF_STREAM_MINB 3
 #endif
-template <int E, int FORMULA, int MODE>
+template <int E, int FORMULA, int MODE, bool DELTA>
 __global__ void __launch_bounds__(kThreads, EBPMF_STREAM_MINB) vga_stream_kernel(const FusedArgs a)
 {
     __shared__ double exptab[EBPMF_EXP_TABLE_SIZE];
@@ -521,6 +554,7 @@ __global__ void __launch_bounds__(kThreads, EBPMF_STREAM_MINB) vga_stream_kernel
     const int rw = rb * kWarps + warp;
     exp_table_init(exptab, a.tables, tid, kThreads);
     log_table_init(logtab, a.tables, tid, kThreads);
+    const unsigned exptab_s = smem_addr(exptab), logtab_s = smem_addr(logtab);
     __syncthreads();
     if (rw >= (int)a.nRW) return;                    // no block-wide barrier below this point
     const int jc0 = (int)a.col0 + blockIdx.x * a.cols_per_cta;
@@ -567,7 +601,7 @@ __global__ void __launch_bounds__(kThreads, EBPMF_STREAM_MINB) vga_stream_kernel
         int t0 = 0;
         if (MODE == MODE_TOPUP) {
             k = a.kunit[ku_idx];
-            if (k == target) continue;
+            if (k == target || k == kFrozen) continue;
             ++my_topups;
         } else {
             t0 = t0_next;                            // read one unit ahead: off the critical path, still <= u
@@ -601,17 +635,19 @@ __global__ void __launch_bounds__(kThreads, EBPMF_STREAM_MINB) vga_stream_kernel
             }
         }
         const int k_in = k;
-        const int flags = newton_unit<E, FORMULA, MODE, FORMULA == FORMULA_A10>(
-            m, c0, w, c1, c2, sc, tol_lane, k, (MODE == MODE_FIRST) ? t0 : target, a.maxiter, exptab, r, sexp, f);
+        int kb;
+        const int flags = newton_unit<E, FORMULA, MODE, FORMULA == FORMULA_A10, DELTA>(
+            m, c0, w, c1, c2, sc, tol_lane, k, kb, (MODE == MODE_FIRST) ? t0 : target, a.maxiter, a.delta, exptab_s, r,
+            sexp, f);
         my_iters += (unsigned)(k - k_in + 1);
-        if (flags & 2) any_exhausted = 1;
+        if (flags & 2) { any_exhausted = 1; kb = k; }
         if (MODE == MODE_TOPUP && !(flags & 3)) any_fail = 1;      // stopped at K* but not below tol
         if (finalize_unit<E, FORMULA>(a, m, c2, r, sexp, f, ok, flags, off, cv_idx, us_idx, rp_idx, p - jb, lane, row_ok,
-                                      exptab, logtab))
+                                      exptab_s, logtab_s))
             any_nan = 1;
         if (lane == 0) {
-            a.kunit[ku_idx] = (unsigned short)k;
-            if (MODE == MODE_FIRST && k > t0) atomicMax(&a.status->kstar, k);
+            a.kunit[ku_idx] = (unsigned short)((flags & 8) ? kFrozen : k);
+            if (MODE == MODE_FIRST && kb > t0) atomicMax(&a.status->kstar, kb);
         }
     }
     if (lane == 0) {
@@ -677,6 +713,7 @@ __global__ void __launch_bounds__(kThreads, 2) vga_dense_kernel(const DenseArgs 
     const bool row_ok = i < a.n;
     const long long rw = rb * kWarps + warp;
     exp_table_init(exptab, a.tables, tid, kThreads);
+    const unsigned exptab_s = smem_addr(exptab);
     __syncthreads();
     if (rw >= a.nRW) return;                         // no block-wide barrier below this point
     const long long jc0 = (long long)blockIdx.x * a.cols_per_cta;
@@ -715,9 +752,11 @@ __global__ void __launch_bounds__(kThreads, 2) vga_dense_kernel(const DenseArgs 
             w[e] = __dmul_rn(c0m1, c1[e]);                                         // x + const3
             if (MODE == MODE_FIRST) m[e] = (m[e] < c0m1) ? m[e] : c0m1;            // :16
         }
-        const int flags = newton_unit<E, FORMULA_A1, MODE, true>(m, c0, w, c1, c2, sc, row_ok ? a.tol : INFINITY, k,
-                                                                  (MODE == MODE_FIRST) ? t0 : target, a.maxiter,
-                                                                  exptab, r, sexp, f);
+        int kb;
+        const int flags = newton_unit<E, FORMULA_A1, MODE, true, false>(m, c0, w, c1, c2, sc, row_ok ? a.tol : INFINITY,
+                                                                         k, kb, (MODE == MODE_FIRST) ? t0 : target,
+                                                                         a.maxiter, 0.0, exptab_s, r, sexp, f);
+        if (flags & 2) kb = k;
         if (flags & 2) any_exhausted = 1;
         if (MODE == MODE_TOPUP && !(flags & 3)) any_fail = 1;
         bool lane_nan = false;
@@ -733,7 +772,7 @@ __global__ void __launch_bounds__(kThreads, 2) vga_dense_kernel(const DenseArgs 
         if (__any_sync(0xffffffffu, lane_nan)) any_nan = 1;
         if (lane == 0) {
             a.kunit[jg * a.nRW + rw] = (unsigned short)k;
-            if (MODE == MODE_FIRST && k > t0) atomicMax(&a.status->kstar, k);
+            if (MODE == MODE_FIRST && kb > t0) atomicMax(&a.status->kstar, kb);
         }
     }
     if (lane == 0) {
@@ -762,6 +801,7 @@ __global__ void __launch_bounds__(kThreads) vga_fixed_iter_kernel(const FixedArg
 {
     __shared__ double exptab[EBPMF_EXP_TABLE_SIZE];
     exp_table_init(exptab, a.tables, threadIdx.x, kThreads);
+    const unsigned exptab_s = smem_addr(exptab);
     __syncthreads();
     const long long i = (long long)blockIdx.y * kRowsPerCta + threadIdx.x;
     if (i >= a.n) return;
@@ -775,18 +815,18 @@ __global__ void __launch_bounds__(kThreads) vga_fixed_iter_kernel(const FixedArg
         double v = a.V_in ? ld_stream(a.V_in + e) : s2 / 2;                         // :48
         const double is2 = 1.0 / s2;
         for (int it = 0; it < a.maxiter; ++it) {                                    // :52
-            double temp = s * exp_fast(fma(0.5, v, m), exptab);                     // :54
+            double temp = s * exp_fast(fma(0.5, v, m), exptab_s);                     // :54
             double rt = rcp_fast(temp);
             // :56  M - (Y/temp - 1 - (M-Beta)/Sigma2/temp) / (-1 - 1/Sigma2/temp)
             const double num = fma(-(m - be) * is2, rt, fma(y, rt, -1.0));
             const double den = fma(-is2, rt, -1.0);
             m = fma(-num, rcp_fast(den), m);
-            temp = s * exp_fast(fma(0.5, v, m), exptab) * v * 0.5;                  // :58
+            temp = s * exp_fast(fma(0.5, v, m), exptab_s) * v * 0.5;                  // :58
             rt = rcp_fast(temp);
             const double h = 0.5 * v * is2 * rt;                                    // V/2/Sigma2/temp
             const double numv = fma(0.5, rt, -1.0 - h);                             // :62 numerator
             const double denv = -(1.0 + 0.5 * v) - h;                               // :62 denominator
-            v = v * exp_fast(-numv * rcp_fast(denv), exptab);                       // V / exp(.)
+            v = v * exp_fast(-numv * rcp_fast(denv), exptab_s);                       // V / exp(.)
         }
         st_stream(a.M_out + e, m);
         st_stream(a.V_out + e, v);

@@ -39,6 +39,9 @@ __device__ __forceinline__ double rcp_fast(double x) {
 // 2^(j/64), j = 0..63, filled by exp_table_init() into shared memory (64 doubles).
 #define EBPMF_EXP_TABLE_SIZE 64
 
+// shared-space byte address of a __shared__ object
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
 // The table values come from ONE place (the host, ebpmf_api.cu: math_tables()) and are copied into
 // shared memory by every kernel, so all kernels iterate with bit-identical tables.
 struct MathTables {
@@ -71,7 +74,9 @@ __device__ __forceinline__ bool exp_out_of_range(double x) {
 // exp(x) for |x| < 700: n = rint(x*64/ln2), r = x - n*ln2/64, 2^(j/64) from the table,
 // exp(r) - 1 = r + r^2/2 + ... + r^5/120 (the dropped r^6/720 is <= 3.5e-17 at |r| <= ln2/128).
 // Measured on the host with the same fma sequence: max rel. error 2.3e-16 on [-700,700].
-__device__ __forceinline__ double exp_core(double x, const double *tab) {
+// tab_s: shared-space byte address of the 64-entry table (from smem_addr()); a plain LDS, no
+// generic->shared window arithmetic in the loop.
+__device__ __forceinline__ double exp_core(double x, unsigned tab_s) {
     const double MAGIC = 6755399441055744.0;           // 1.5 * 2^52
     const double t = __fma_rn(x, kExpC[0], MAGIC);
     const int n = __double2loint(t);
@@ -83,26 +88,27 @@ __device__ __forceinline__ double exp_core(double x, const double *tab) {
     q = __fma_rn(q, r, 0.5);
     q = __dmul_rn(q, r);
     q = __fma_rn(q, r, r);                             // q = exp(r) - 1
-    const double tj = tab[n & (EBPMF_EXP_TABLE_SIZE - 1)];
+    double tj;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab_s + ((unsigned)(n & (EBPMF_EXP_TABLE_SIZE - 1)) << 3)));
     const double v = __fma_rn(tj, q, tj);              // 2^(j/64) * exp(r)
     // scale by 2^(n>>6): |x| < 700 keeps the result a normal double
-    const int hi = __double2hiint(v) + ((n >> 6) << 20);
+    const int hi = __double2hiint(v) + ((n & ~(EBPMF_EXP_TABLE_SIZE - 1)) << 14);   // + (n>>6)<<20
     return __hiloint2double(hi, __double2loint(v));
 }
 
-__device__ __forceinline__ double exp_fast(double x, const double *tab) {
+__device__ __forceinline__ double exp_fast(double x, unsigned tab_s) {
 #if EBPMF_EXACT_MATH
-    (void)tab;
+    (void)tab_s;
     return exp(x);
 #else
     if (exp_out_of_range(x)) return exp_slow(x);
-    return exp_core(x, tab);
+    return exp_core(x, tab_s);
 #endif
 }
 
 // E exponentials with ONE range branch for the lot (the Newton loop's form)
 template <int E>
-__device__ __forceinline__ void exp_fast_n(const double (&x)[E], double (&out)[E], const double *tab) {
+__device__ __forceinline__ void exp_fast_n(const double (&x)[E], double (&out)[E], unsigned tab_s) {
 #if EBPMF_EXACT_MATH
 #pragma unroll
     for (int e = 0; e < E; ++e) out[e] = exp(x[e]);
@@ -115,7 +121,7 @@ __device__ __forceinline__ void exp_fast_n(const double (&x)[E], double (&out)[E
         for (int e = 0; e < E; ++e) out[e] = exp_slow(x[e]);
     } else {
 #pragma unroll
-        for (int e = 0; e < E; ++e) out[e] = exp_core(x[e], tab);
+        for (int e = 0; e < E; ++e) out[e] = exp_core(x[e], tab_s);
     }
 #endif
 }
@@ -137,16 +143,16 @@ __device__ __noinline__ double log_slow(double x) { return log(x); }
 
 __constant__ double kLogC[5] = {-1.0 / 6.0, 0.2, -0.25, 1.0 / 3.0, 0.6931471805599453};
 
-__device__ __forceinline__ double log_fast(double x, const double2 *tab) {
+__device__ __forceinline__ double log_fast(double x, unsigned tab_s) {
 #if EBPMF_EXACT_MATH
-    (void)tab;
+    (void)tab_s;
     return log(x);
 #else
     const int hi = __double2hiint(x);
     if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log_slow(x);
-    const int idx = (hi >> 13) & (EBPMF_LOG_TABLE_SIZE - 1);
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
-    const double2 cl = tab[idx];
+    double2 cl;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(cl.x), "=d"(cl.y) : "r"(tab_s + (((unsigned)hi >> 9) & ((EBPMF_LOG_TABLE_SIZE - 1) << 4))));
     const double z = fma(m, cl.x, -1.0);
     double p = fma(z, kLogC[0], kLogC[1]);
     p = fma(p, z, kLogC[2]);

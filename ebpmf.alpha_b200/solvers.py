@@ -270,6 +270,10 @@ class VgaContext:
         self.n, self.p, self.var_type = n, p, "by_col"
         return nnz.value
 
+    def set_option(self, name, value):
+        """'delta' (0 = exact update count, the default) or 'pipeline' (0 fused / 1 split)."""
+        self._ck(self._lib.ebpmf_ctx_set_option(self._h, name.encode(), float(value)))
+
     def last_diag(self):
         a, b = C.c_uint64(), C.c_uint64()
         self._ck(self._lib.ebpmf_ctx_last_diag(self._h, C.byref(a), C.byref(b)))

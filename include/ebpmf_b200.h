@@ -201,6 +201,14 @@ int  ebpmf_ctx_sim_data_log(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, int
                             double pi0, double noise, int warm_start,
                             int64_t *nnz_out);
 
+/* Options of the fused step (defaults reproduce R's update count for EVERY entry):
+ *   "delta"    0 (default): exact mode.  d > 0 (<= 1e-10): delta mode -- a unit whose entries all
+ *              satisfy |f| < tol/16 and whose next Newton update |f/f'| <= d is frozen: its remaining
+ *              updates are numerical no-ops and are skipped, so M and V differ from exact mode by at
+ *              most ~d (absolute); the global update count n_updates is still R's.  DESIGN.md §3b.
+ *   "pipeline" 0 (default): fused first pass; 1: const0 kernel + streaming Newton kernel. */
+int  ebpmf_ctx_set_option(ebpmf_ctx *ctx, const char *name, double value);
+
 /* diagnostics of the last fused solve: units (warp x 2 columns) that needed second-pass work and
  * the total number of unit evaluations (each = 64 entry evaluations of f) */
 int  ebpmf_ctx_last_diag(ebpmf_ctx *ctx, uint64_t *topup_units, uint64_t *unit_evals);

@@ -1,4 +1,4 @@
-"""Time the resident VGA step for the library in $EBPMF_B200_LIB (A/B of kernel variants)."""
+"""Time the resident VGA step for the library in $EBPMF_B200_LIB (A/B of kernel variants / options)."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -16,6 +16,6 @@ for (mi, tol) in ((10, 1e-5),):
         res.append(dict(u=i.n_updates, ms=round(i.kernel_ms, 2), p1=round(i.pass1_ms, 2), p2=round(i.pass2_ms, 2),
                         rd=round(i.reduce_ms, 2), ge_s=round(n * p / i.kernel_ms / 1e6, 2)))
 d = ctx.last_diag()
-print(os.environ.get("EBPMF_B200_LIB", "default").split("/")[-1], wl, "dens=%.4f" % (nnz / n / p), res[-1],
-      "topup_frac=%.3f evals/unit=%.2f" % (d["topup_units"] / (((n + 31) // 32) * ((p + 3) // 4 if "E4" in os.environ.get("EBPMF_B200_LIB", "E4") else (p + 1) // 2)),
-                                          d["unit_evals"] / max(1, d["topup_units"])))
+units = ((n + 31) // 32) * ((p + 1) // 2)
+print(os.environ.get("EBPMF_B200_LIB", "default").split("/")[-1], wl, "pipeline=%s delta=%s" % (os.environ.get("EBPMF_B200_PIPELINE", "fused"), os.environ.get("EBPMF_B200_DELTA", "0")),
+      "dens=%.4f" % (nnz / n / p), res[-1], "topup_frac=%.3f evals/unit=%.2f" % (d["topup_units"] / units, d["unit_evals"] / units))

@@ -262,3 +262,40 @@ def test_device_sim_data_matches_oracle(gpu_ctx):
         assert abs(getattr(info, k) - ref[k]) <= RTOL * max(abs(ref[k]), 1.0)
     rows = gpu_ctx.get_rows(1000, 257)
     assert np.array_equal(rows, gpu_ctx.get_m()[1000:1257])
+
+
+# ---------------------------------------------------------------------------------------
+# options: delta mode (frozen units) and the split pipeline
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pipeline", [0, 1])
+@pytest.mark.parametrize("delta", [0.0, 1e-14])
+@pytest.mark.parametrize("var_type,maxiter,tol", [("by_col", 10, 1e-5), ("by_row", 1000, 1e-8), ("constant", 3, 1e-5)])
+def test_options_delta_and_pipeline(pkg, pipeline, delta, var_type, maxiter, tol):
+    """Both options keep the 1e-8 parity and R's update count; delta mode stays within ~delta of exact mode."""
+    sim, st = make_case(1300, 301, 5, 0.10, var_type=var_type)
+    ctx = pkg.VgaContext(0)
+    try:
+        ctx.set_option("pipeline", pipeline)
+        ctx.set_option("delta", delta)
+        ctx.set_y(sp.csc_matrix(sim["Y"]))
+        res = ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], var_type, maxiter, tol, return_V=True)
+        ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], var_type, maxiter, tol)
+        check_step(res, ref, var_type)
+        ctx.set_option("pipeline", 0)
+        ctx.set_option("delta", 0.0)
+        exact = ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], var_type, maxiter, tol, return_V=True)
+        if delta == 0.0:
+            assert np.array_equal(res["M"], exact["M"]) and np.array_equal(res["V"], exact["V"])   # bit-identical
+        else:
+            assert np.max(np.abs(res["M"] - exact["M"])) < 1e-12 and rel(res["V"], exact["V"]) < 1e-12
+    finally:
+        ctx.close()
+
+
+def test_option_validation(pkg):
+    ctx = pkg.VgaContext(0)
+    with pytest.raises(pkg.EbpmfError):
+        ctx.set_option("delta", 1e-3)          # would break the 1e-8 contract: refused
+    with pytest.raises(pkg.EbpmfError):
+        ctx.set_option("no_such_option", 1)
+    ctx.close()
