@@ -307,7 +307,7 @@ def main():
         "pass_ms": {"first": p1, "topup": p2, "reduce": rd}, "wall_ms_per_step": 1e3 * wall / args.steps,
         "topup_units_frac": diag["topup_units"] / max(1.0, ((n + 31) // 32) * ((p + 1) // 2)),
         "roofline": roofline, "fp64": fp64, "delta_mode": delta_mode,
-        "gpu_launches": 7 * args.steps, "clocks": clk.summary(),
+        "gpu_launches": 6 * args.steps, "clocks": clk.summary(),
     }
 
     # ---- parity gate + CPU baseline on a bounded row sample (rank 0) -----------------------------

@@ -299,3 +299,72 @@ def test_option_validation(pkg):
     with pytest.raises(pkg.EbpmfError):
         ctx.set_option("no_such_option", 1)
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------
+# large size: size-independent properties + an oracle row slab with the global count forced
+# ---------------------------------------------------------------------------------------
+def test_large_size_properties(pkg):
+    """60 000 x 6 000 (3.6e8 entries, device-generated, ~5 % non-zero): the reductions returned by the step
+    equal the same sums recomputed from the downloaded M, V (linearity / checksum-of-checksums), V obeys
+    V*(sigma2*Y + Beta + 1 - M) = sigma2, |f| < tol everywhere, and a row slab matches the oracle run with
+    the global update count forced."""
+    ctx = pkg.VgaContext(0)
+    try:
+        n, p, K = 60000, 6000, 10
+        nnz = ctx.sim_data_log(n, p, K, seed=2024, log_offset=-4.644)
+        assert 0.03 < nnz / (n * p) < 0.08
+        info = ctx.vga_step(10, 1e-5, want_v=True)
+        assert info.converged and 3 <= info.n_updates <= 10
+        M = ctx.get_m(); V = ctx.get_v(); vs = ctx.get_v_sum()
+        s2 = ctx.get_sigma2()
+        cp, ri, x = ctx.get_y_csc()
+        Y = sp.csc_matrix((x, ri, cp), shape=(n, p))
+        # checksums: column sums of V, scalar partials
+        assert rel(vs, V.sum(axis=0, dtype=np.longdouble).astype(np.float64)) < 1e-10
+        ssexp = float(np.sum(np.exp(M + V / 2), dtype=np.longdouble))
+        slogv = float(np.sum(np.log(V) / 2 + 0.9189385, dtype=np.longdouble))
+        cols = np.repeat(np.arange(p), np.diff(cp))
+        sym = float(np.sum(x * M[ri, cols], dtype=np.longdouble))
+        assert abs(info.ssexp - ssexp) < 1e-10 * abs(ssexp)
+        assert abs(info.slogv - slogv) < 1e-10 * abs(slogv)
+        assert abs(info.sym - sym) < 1e-10 * abs(sym)
+        # a row slab against the oracle with the GLOBAL update count forced (tol = 0 => exactly u updates)
+        rows = slice(12345, 12345 + 700)
+        EL, EF = ctx.get_factors()
+        Beta = EL[rows] @ EF.T
+        S2 = np.repeat(s2[None, :], 700, axis=0)
+        Yr = Y[rows].toarray()
+        ctx.rewind_m(); M0 = ctx.get_rows(12345, 700)
+        ref = vga_numpy.vga_pois_solver_mat_newton(M0, Yr, 1, Beta, S2, info.n_updates, 0.0)["M"]
+        assert relM(M[rows], ref) < RTOL
+        # invariants on the slab: fresh V and stationarity at the global count
+        temp = S2 * Yr + Beta + 1 - M[rows]
+        assert rel(V[rows] * temp, S2) < 1e-12
+        f = Yr - np.exp(M[rows] + V[rows] / 2) - (M[rows] - Beta) / S2
+        assert np.max(np.abs(f)) < 1e-5
+    finally:
+        ctx.close()
+
+
+def test_idempotence_second_step_needs_no_update(gpu_ctx):
+    """A converged M is a fixed point of the step: the second call breaks at iteration 1 (u = 0) and
+    returns M unchanged, V recomputed from it -- as R would."""
+    sim, st = make_case(2000, 257, 4, 0.10)
+    gpu_ctx.set_y(sp.csc_matrix(sim["Y"]))
+    r1 = gpu_ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], "by_col", 100, 1e-7, return_V=True)
+    r2 = gpu_ctx.vga_step_host(r1["M"], st["EL"], st["EF"], st["sigma2"], "by_col", 100, 1e-7, return_V=True)
+    assert r1["converged"] and r2["converged"] and r2["n_updates"] == 0
+    assert np.array_equal(r2["M"], r1["M"])
+    ref = vga_numpy.ebpmf_log_vga_step(r1["M"], sim["Y"], st["EL"], st["EF"], st["sigma2"], "by_col", 100, 1e-7)
+    check_step(r2, ref, "by_col")
+
+
+def test_maxiter_one(gpu_ctx):
+    """maxiter = 1: one evaluation; either it breaks (u = 0) or one update is applied and V is stale."""
+    sim, st = make_case(700, 90, 3, 0.2)
+    gpu_ctx.set_y(sp.csc_matrix(sim["Y"]))
+    res = gpu_ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], "by_col", 1, 1e-5, return_V=True)
+    ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], "by_col", 1, 1e-5)
+    check_step(res, ref, "by_col")
+    assert res["n_updates"] == 1 and not res["converged"]
