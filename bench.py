@@ -283,8 +283,11 @@ def main():
     alg_bytes_per_entry = 16.0 + 12.0 * density            # read M 8 + write M 8 + CSC (x 8 + i 4) * density
     alg_bytes = alg_bytes_per_entry * n * p                 # per launch of the first-pass kernel (one slab)
     achieved = alg_bytes / (p1 * 1e-3) / 1e9
+    # DRAM bytes of that kernel from the committed ncu capture (profiles/r01_ncu_summary.md), this workload only
+    traffic = 95.81 if (args.workload == "c4slab" and os.environ.get("EBPMF_B200_PIPELINE", "fused") == "fused") else None
     roofline = {"bound": "hbm", "kernel": "vga_fused_kernel<MODE_FIRST>", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write)",
+                "algorithmic_gb_per_launch": alg_bytes / 1e9, "peak_source": peak_src,
                 "algorithmic_bytes_per_entry": alg_bytes_per_entry,
                 "note": "the FP64 pipe, not HBM, binds this kernel for u > 0 (see fp64)"}
     # FP64 line: FP64-pipe instructions per entry, counted in the SASS of the Newton loop:

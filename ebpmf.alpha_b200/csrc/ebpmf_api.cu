@@ -16,6 +16,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <vector>
 
 using namespace ebpmf;
 
@@ -481,6 +483,70 @@ int sum_lfactorial_dev(ebpmf_ctx *ctx, const double *dx, long long len, double *
     return EBPMF_OK;
 }
 
+
+// host matrix (rows x cols, leading dimension ld >= rows) <-> packed device matrix (ld == rows)
+int copy_in_ld(ebpmf_ctx *ctx, void *dst, const double *src, long long rows, long long cols, long long ld) {
+    if (ld == rows) {
+        CU(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)rows * (size_t)cols, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        CU(cudaMemcpy2DAsync(dst, sizeof(double) * (size_t)rows, src, sizeof(double) * (size_t)ld,
+                             sizeof(double) * (size_t)rows, (size_t)cols, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return EBPMF_OK;
+}
+
+int copy_out_ld(ebpmf_ctx *ctx, double *dst, const void *src, long long rows, long long cols, long long ld) {
+    if (ld == rows) {
+        CU(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)rows * (size_t)cols, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        CU(cudaMemcpy2DAsync(dst, sizeof(double) * (size_t)ld, src, sizeof(double) * (size_t)rows,
+                             sizeof(double) * (size_t)rows, (size_t)cols, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return EBPMF_OK;
+}
+
+int set_m_ld(ebpmf_ctx *ctx, const double *M, long long ld) {
+    if (!ctx || !M) return fail(ctx, EBPMF_ERR_ARG, "set_m: bad arguments");
+    if (!ctx->have_y) return fail(ctx, EBPMF_ERR_STATE, "set_m: Y not set");
+    CHECK(ensure_common(ctx));
+    const size_t bytes = sizeof(double) * (size_t)ctx->n * (size_t)ctx->p;
+    CHECK(reserve(ctx, ctx->Mcur, bytes));
+    CHECK(reserve(ctx, ctx->Malt, bytes));
+    CHECK(copy_in_ld(ctx, ctx->Mcur.ptr, M, ctx->n, ctx->p, ld));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->have_m = true; ctx->can_rewind = false;
+    return EBPMF_OK;
+}
+
+int set_factors_ld(ebpmf_ctx *ctx, int64_t K, const double *EL, long long ldl, const double *EF) {
+    if (!ctx || !EL || !EF || K < 1) return fail(ctx, EBPMF_ERR_ARG, "set_factors: bad arguments");
+    if (!ctx->have_y) return fail(ctx, EBPMF_ERR_STATE, "set_factors: Y not set");
+    const int ktp = ktp_for((int)K);
+    if (ktp < 0) return fail(ctx, EBPMF_ERR_ARG, "K = %lld factor columns not supported (max 32)", (long long)K);
+    CHECK(ensure_common(ctx));
+    const long long n = ctx->n, p = ctx->p;
+    CHECK(reserve(ctx, ctx->EL, sizeof(double) * (size_t)n * (size_t)K));
+    CHECK(reserve(ctx, ctx->EF, sizeof(double) * (size_t)p * (size_t)K));
+    CHECK(reserve(ctx, ctx->EFt, sizeof(double) * (size_t)p * (size_t)ktp));
+    CHECK(copy_in_ld(ctx, ctx->EL.ptr, EL, n, K, ldl));
+    CU(cudaMemcpyAsync(ctx->EF.ptr, EF, sizeof(double) * (size_t)p * (size_t)K, cudaMemcpyHostToDevice, ctx->stream));
+    transpose_ef_kernel<<<(unsigned)((p * ktp + 255) / 256), 256, 0, ctx->stream>>>(as<double>(ctx->EF), p, (int)K, ktp,
+                                                                                   as<double>(ctx->EFt));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->K = (int)K; ctx->KTP = ktp; ctx->have_f = true;
+    return EBPMF_OK;
+}
+
+int get_matrix_ld(ebpmf_ctx *ctx, bool want_v, double *out, long long ld) {
+    if (!ctx || !out) return fail(ctx, EBPMF_ERR_ARG, "get: bad arguments");
+    if (want_v ? !ctx->have_v : !ctx->have_m) return fail(ctx, EBPMF_ERR_STATE, want_v ? "get_v: the last step did not materialise V (want_v = 0)" : "get_m: M not set");
+    CHECK(ensure_common(ctx));
+    CHECK(copy_out_ld(ctx, out, want_v ? ctx->V.ptr : ctx->Mcur.ptr, ctx->n, ctx->p, ld));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return EBPMF_OK;
+}
+
 }  // namespace
 
 // =========================================================================================
@@ -647,37 +713,10 @@ int ebpmf_sum_lfactorial(ebpmf_ctx *ctx, int64_t len, const double *x, double *o
     return sum_lfactorial_dev(ctx, as<double>(ctx->scratch[0]), len, out);
 }
 
-int ebpmf_ctx_set_m(ebpmf_ctx *ctx, const double *M) {
-    if (!ctx || !M) return fail(ctx, EBPMF_ERR_ARG, "set_m: bad arguments");
-    if (!ctx->have_y) return fail(ctx, EBPMF_ERR_STATE, "set_m: Y not set");
-    CHECK(ensure_common(ctx));
-    const size_t bytes = sizeof(double) * (size_t)ctx->n * (size_t)ctx->p;
-    CHECK(reserve(ctx, ctx->Mcur, bytes));
-    CHECK(reserve(ctx, ctx->Malt, bytes));
-    CU(cudaMemcpyAsync(ctx->Mcur.ptr, M, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    ctx->have_m = true; ctx->can_rewind = false;
-    return EBPMF_OK;
-}
+int ebpmf_ctx_set_m(ebpmf_ctx *ctx, const double *M) { return set_m_ld(ctx, M, ctx ? ctx->n : 0); }
 
 int ebpmf_ctx_set_factors(ebpmf_ctx *ctx, int64_t K, const double *EL, const double *EF) {
-    if (!ctx || !EL || !EF || K < 1) return fail(ctx, EBPMF_ERR_ARG, "set_factors: bad arguments");
-    if (!ctx->have_y) return fail(ctx, EBPMF_ERR_STATE, "set_factors: Y not set");
-    const int ktp = ktp_for((int)K);
-    if (ktp < 0) return fail(ctx, EBPMF_ERR_ARG, "K = %lld factor columns not supported (max 32)", (long long)K);
-    CHECK(ensure_common(ctx));
-    const long long n = ctx->n, p = ctx->p;
-    CHECK(reserve(ctx, ctx->EL, sizeof(double) * (size_t)n * (size_t)K));
-    CHECK(reserve(ctx, ctx->EF, sizeof(double) * (size_t)p * (size_t)K));
-    CHECK(reserve(ctx, ctx->EFt, sizeof(double) * (size_t)p * (size_t)ktp));
-    CU(cudaMemcpyAsync(ctx->EL.ptr, EL, sizeof(double) * (size_t)n * (size_t)K, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->EF.ptr, EF, sizeof(double) * (size_t)p * (size_t)K, cudaMemcpyHostToDevice, ctx->stream));
-    transpose_ef_kernel<<<(unsigned)((p * ktp + 255) / 256), 256, 0, ctx->stream>>>(as<double>(ctx->EF), p, (int)K, ktp,
-                                                                                   as<double>(ctx->EFt));
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(ctx->stream));
-    ctx->K = (int)K; ctx->KTP = ktp; ctx->have_f = true;
-    return EBPMF_OK;
+    return set_factors_ld(ctx, K, EL, ctx ? ctx->n : 0, EF);
 }
 
 int ebpmf_ctx_set_sigma2(ebpmf_ctx *ctx, int var_type, const double *sigma2) {
@@ -730,23 +769,9 @@ int ebpmf_ctx_rewind_m(ebpmf_ctx *ctx) {
     return EBPMF_OK;
 }
 
-int ebpmf_ctx_get_m(ebpmf_ctx *ctx, double *M) {
-    if (!ctx || !M) return fail(ctx, EBPMF_ERR_ARG, "get_m: bad arguments");
-    if (!ctx->have_m) return fail(ctx, EBPMF_ERR_STATE, "get_m: M not set");
-    CHECK(ensure_common(ctx));
-    CU(cudaMemcpyAsync(M, ctx->Mcur.ptr, sizeof(double) * (size_t)ctx->n * (size_t)ctx->p, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    return EBPMF_OK;
-}
+int ebpmf_ctx_get_m(ebpmf_ctx *ctx, double *M) { return get_matrix_ld(ctx, false, M, ctx ? ctx->n : 0); }
 
-int ebpmf_ctx_get_v(ebpmf_ctx *ctx, double *V) {
-    if (!ctx || !V) return fail(ctx, EBPMF_ERR_ARG, "get_v: bad arguments");
-    if (!ctx->have_v) return fail(ctx, EBPMF_ERR_STATE, "get_v: the last step did not materialise V (want_v = 0)");
-    CHECK(ensure_common(ctx));
-    CU(cudaMemcpyAsync(V, ctx->V.ptr, sizeof(double) * (size_t)ctx->n * (size_t)ctx->p, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    return EBPMF_OK;
-}
+int ebpmf_ctx_get_v(ebpmf_ctx *ctx, double *V) { return get_matrix_ld(ctx, true, V, ctx ? ctx->n : 0); }
 
 int ebpmf_ctx_get_v_sum(ebpmf_ctx *ctx, double *v_sum) {
     if (!ctx || !v_sum) return fail(ctx, EBPMF_ERR_ARG, "get_v_sum: bad arguments");
@@ -1175,6 +1200,173 @@ int ebpmf_probe_fp64_tflops(ebpmf_ctx *ctx, double *tflops) {
     CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     const double flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
     *tflops = flops / (ms * 1e-3) / 1e12;
+    return EBPMF_OK;
+}
+
+
+// ---- single-process multi-GPU group (what an R session uses: R is one process) -------------
+}  // extern "C"
+
+struct ebpmf_group {
+    std::vector<ebpmf_ctx *> ctx;
+    std::vector<long long> row0, nrows;
+    long long n = 0, p = 0;
+    std::string err;
+};
+
+namespace {
+int gfail(ebpmf_group *g, int code, const std::string &msg) {
+    if (g) g->err = msg;
+    g_last_error = msg;
+    return code;
+}
+
+// one host thread per GPU; every thread runs fn(rank) against its own context.  The per-context
+// calls are synchronous, so the threads are what overlaps the GPUs (and they meet in the NCCL
+// collectives inside ebpmf_ctx_vga_step).
+template <typename F> int run_ranks(ebpmf_group *g, F fn) {
+    const int N = (int)g->ctx.size();
+    std::vector<int> rc(N, EBPMF_OK);
+    std::vector<std::thread> th;
+    for (int r = 1; r < N; ++r) th.emplace_back([&, r] { rc[r] = fn(r); });
+    rc[0] = fn(0);
+    for (auto &t : th) t.join();
+    for (int r = 0; r < N; ++r)
+        if (rc[r] != EBPMF_OK) return gfail(g, rc[r], std::string("rank ") + std::to_string(r) + ": " + g->ctx[r]->err);
+    return EBPMF_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ebpmf_group_create(int ndev, const int *devices, ebpmf_group **out) {
+    if (!out || ndev < 1) return gfail(nullptr, EBPMF_ERR_ARG, "group_create: bad arguments");
+    *out = nullptr;
+    ebpmf_group *g = new (std::nothrow) ebpmf_group();
+    if (!g) return gfail(nullptr, EBPMF_ERR_NOMEM, "out of host memory");
+    for (int r = 0; r < ndev; ++r) {
+        ebpmf_ctx *c = nullptr;
+        int rc = ebpmf_ctx_create(devices ? devices[r] : r, &c);
+        if (rc != EBPMF_OK) {
+            for (ebpmf_ctx *q : g->ctx) ebpmf_ctx_destroy(q);
+            delete g;
+            return rc;
+        }
+        g->ctx.push_back(c);
+    }
+    if (ndev > 1) {
+        unsigned char id[128];
+        int rc = ebpmf_nccl_unique_id(id);
+        if (rc == EBPMF_OK) rc = run_ranks(g, [&](int r) { return ebpmf_ctx_comm_init(g->ctx[r], r, ndev, id); });
+        if (rc != EBPMF_OK) {
+            const std::string msg = g->err.empty() ? g_last_error : g->err;
+            for (ebpmf_ctx *q : g->ctx) ebpmf_ctx_destroy(q);
+            delete g;
+            return gfail(nullptr, rc, msg);
+        }
+    }
+    *out = g;
+    return EBPMF_OK;
+}
+
+int ebpmf_group_destroy(ebpmf_group *g) {
+    if (!g) return EBPMF_OK;
+    for (ebpmf_ctx *c : g->ctx) ebpmf_ctx_destroy(c);
+    delete g;
+    return EBPMF_OK;
+}
+
+const char *ebpmf_group_last_error(const ebpmf_group *g) { return g ? g->err.c_str() : g_last_error.c_str(); }
+
+int ebpmf_group_size(const ebpmf_group *g) { return g ? (int)g->ctx.size() : 0; }
+
+// Rows are dealt to the GPUs in 256-row blocks (the kernels' row-block size), as evenly as possible.
+int ebpmf_group_set_y_csc(ebpmf_group *g, int64_t n, int64_t p, const int32_t *colptr, const int32_t *rowidx,
+                          const double *x) {
+    if (!g || n < 1 || p < 1 || !colptr) return gfail(g, EBPMF_ERR_ARG, "group_set_y_csc: bad arguments");
+    const int N = (int)g->ctx.size();
+    const long long nblk = (n + kRowsPerCta - 1) / kRowsPerCta;
+    if (nblk < N) return gfail(g, EBPMF_ERR_ARG, "group_set_y_csc: fewer 256-row blocks than GPUs; use a smaller group");
+    g->row0.assign(N, 0); g->nrows.assign(N, 0);
+    long long r0 = 0;
+    for (int r = 0; r < N; ++r) {
+        long long rows = (nblk / N + (r < nblk % N ? 1 : 0)) * kRowsPerCta;
+        rows = std::max(0LL, std::min(rows, (long long)n - r0));
+        g->row0[r] = r0; g->nrows[r] = rows; r0 += rows;
+    }
+    g->n = n; g->p = p;
+    return run_ranks(g, [&](int r) {
+        // the row slice Y[row0:row0+nrows, ] as its own dgCMatrix (what `Y[b,]` does in R/ebpmf_log.R:199)
+        const long long lo = g->row0[r], hi = lo + g->nrows[r];
+        std::vector<int32_t> cp((size_t)p + 1, 0);
+        for (long long j = 0; j < p; ++j) {
+            int c = 0;
+            for (int q = colptr[j]; q < colptr[j + 1]; ++q) c += (rowidx[q] >= lo && rowidx[q] < hi);
+            cp[(size_t)j + 1] = cp[(size_t)j] + c;
+        }
+        std::vector<int32_t> ri((size_t)std::max(1, cp[(size_t)p]));
+        std::vector<double> xx((size_t)std::max(1, cp[(size_t)p]));
+        for (long long j = 0; j < p; ++j) {
+            int w = cp[(size_t)j];
+            for (int q = colptr[j]; q < colptr[j + 1]; ++q)
+                if (rowidx[q] >= lo && rowidx[q] < hi) { ri[(size_t)w] = (int32_t)(rowidx[q] - lo); xx[(size_t)w] = x[q]; ++w; }
+        }
+        return ebpmf_ctx_set_y_csc(g->ctx[r], g->nrows[r], p, cp.data(), ri.data(), xx.data());
+    });
+}
+
+int ebpmf_group_set_option(ebpmf_group *g, const char *name, double value) {
+    if (!g) return gfail(g, EBPMF_ERR_ARG, "group_set_option: group is NULL");
+    for (ebpmf_ctx *c : g->ctx) {
+        int rc = ebpmf_ctx_set_option(c, name, value);
+        if (rc != EBPMF_OK) return gfail(g, rc, c->err);
+    }
+    return EBPMF_OK;
+}
+
+// The whole VGA step on the FULL host matrices; each GPU works on its row shard (strided copies out
+// of / into the column-major host arrays), the shards meet in the NCCL combine.  v_sum has length
+// p ('by_col'), n ('by_row', written shard by shard) or 1.
+int ebpmf_group_vga_step_host(ebpmf_group *g, const double *M_in, int64_t K, const double *EL, const double *EF,
+                              int var_type, const double *sigma2, int maxiter, double tol, double *M_out,
+                              double *V_out, double *v_sum, ebpmf_solve_info *info) {
+    if (!g || !M_in || !M_out || !EL || !EF || !sigma2) return gfail(g, EBPMF_ERR_ARG, "group_vga_step_host: bad arguments");
+    if (g->n < 1) return gfail(g, EBPMF_ERR_STATE, "group_vga_step_host: Y not set");
+    const int N = (int)g->ctx.size();
+    std::vector<ebpmf_solve_info> infos((size_t)N);
+    const long long n = g->n;
+    int rc = run_ranks(g, [&](int r) {
+        ebpmf_ctx *c = g->ctx[r];
+        const long long lo = g->row0[r];
+        CHECK(set_factors_ld(c, K, EL + lo, n, EF));
+        CHECK(ebpmf_ctx_set_sigma2(c, var_type, var_type == EBPMF_VAR_BY_ROW ? sigma2 + lo : sigma2));
+        CHECK(set_m_ld(c, M_in + lo, n));
+        CHECK(ebpmf_ctx_vga_step(c, maxiter, tol, V_out != nullptr, &infos[(size_t)r]));
+        CHECK(get_matrix_ld(c, false, M_out + lo, n));
+        if (V_out) CHECK(get_matrix_ld(c, true, V_out + lo, n));
+        if (v_sum) {
+            if (var_type == EBPMF_VAR_BY_ROW) CHECK(ebpmf_ctx_get_v_sum(c, v_sum + lo));
+            else if (r == 0) CHECK(ebpmf_ctx_get_v_sum(c, v_sum));
+        }
+        return (int)EBPMF_OK;
+    });
+    if (rc != EBPMF_OK) return rc;
+    if (info) {
+        *info = infos[0];                       // sums and the update count are global after the combine
+        for (int r = 1; r < N; ++r) info->kernel_ms = std::max(info->kernel_ms, infos[(size_t)r].kernel_ms);
+    }
+    return EBPMF_OK;
+}
+
+// sum(lfactorial(Y@x)) over all shards
+int ebpmf_group_sum_lfactorial(ebpmf_group *g, double *out) {
+    if (!g || !out) return gfail(g, EBPMF_ERR_ARG, "group_sum_lfactorial: bad arguments");
+    std::vector<double> part(g->ctx.size(), 0.0);
+    int rc = run_ranks(g, [&](int r) { return ebpmf_ctx_sum_lfactorial(g->ctx[r], &part[(size_t)r]); });
+    if (rc != EBPMF_OK) return rc;
+    double s = 0.0;
+    for (double v : part) s += v;
+    *out = s;
     return EBPMF_OK;
 }
 

@@ -285,6 +285,68 @@ class VgaContext:
         return out.value
 
 
+class VgaGroup:
+    """One process driving several GPUs (what a single R session does): owns an ``ebpmf_group`` --
+    one context per GPU, one host thread per GPU per call, rows dealt in 256-row blocks, the
+    library's NCCL combine of the update count and of v_sum / ELBO partials."""
+
+    def __init__(self, devices):
+        self._lib = _lib.load()
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        _lib.check(self._lib.ebpmf_group_create(len(devices), devs, C.byref(h)))
+        self._h = h
+        self.n = self.p = None
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self._lib.ebpmf_group_last_error(self._h)
+            raise EbpmfError(rc, msg.decode() if msg else "")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ebpmf_group_destroy(self._h)
+            self._h = None
+
+    def size(self):
+        return int(self._lib.ebpmf_group_size(self._h))
+
+    def set_option(self, name, value):
+        self._ck(self._lib.ebpmf_group_set_option(self._h, name.encode(), float(value)))
+
+    def set_y(self, Y):
+        n, p = Y.shape
+        cp, ri, x = _csc_slots(Y if _is_sparse(Y) else _sp.csc_matrix(np.asarray(Y)))
+        self._ck(self._lib.ebpmf_group_set_y_csc(self._h, n, p, _ptr(cp), _ptr(ri), _ptr(x)))
+        self.n, self.p = n, p
+
+    def sum_lfactorial(self):
+        out = C.c_double()
+        self._ck(self._lib.ebpmf_group_sum_lfactorial(self._h, C.byref(out)))
+        return out.value
+
+    def vga_step_host(self, M, EL, EF, sigma2, var_type, maxiter=10, tol=1e-5, return_V=False, M_out=None):
+        if var_type not in VAR_TYPE:
+            raise EbpmfError(4, "Non-supported var type")
+        M = _f(M)
+        EL = _f(np.asarray(EL, dtype=np.float64).reshape(self.n, -1))
+        EF = _f(np.asarray(EF, dtype=np.float64).reshape(self.p, -1))
+        s2 = _vec(sigma2)
+        ln = {"by_col": self.p, "by_row": self.n, "constant": 1}[var_type]
+        if s2.size != ln:
+            raise ValueError("sigma2 has the wrong length for var_type %r" % var_type)
+        Mo = np.empty((self.n, self.p), order="F") if M_out is None else M_out
+        Vo = np.empty((self.n, self.p), order="F") if return_V else None
+        vs = np.empty(ln)
+        info = SolveInfo()
+        self._ck(self._lib.ebpmf_group_vga_step_host(self._h, _ptr(M), EL.shape[1], _ptr(EL), _ptr(EF),
+                                                     VAR_TYPE[var_type], _ptr(s2), int(maxiter), float(tol), _ptr(Mo),
+                                                     _ptr(Vo), _ptr(vs), C.byref(info)))
+        return dict(M=Mo, V=Vo, v_sum=(vs if var_type != "constant" else float(vs[0])), sym=info.sym,
+                    ssexp=info.ssexp, slogv=info.slogv, n_updates=info.n_updates,
+                    converged=bool(info.converged), passes=info.passes, kernel_ms=info.kernel_ms)
+
+
 # ---------------------------------------------------------------------------
 # drop-in solver signatures
 # ---------------------------------------------------------------------------

@@ -161,6 +161,25 @@ int  ebpmf_vga_step_host(ebpmf_ctx *ctx, const double *M_in, int64_t K, const do
                          int maxiter, double tol,
                          double *M_out, double *V_out, double *v_sum, ebpmf_solve_info *info);
 
+/* ---- one process, several GPUs (an R session is one process) -------------------------------
+ * A group owns one context per GPU and one NCCL communicator over them; every group call runs one
+ * host thread per GPU.  set_y takes the FULL dgCMatrix and deals its rows to the GPUs in 256-row
+ * blocks; vga_step_host takes the FULL n x p / n x K host matrices (column-major) and each GPU
+ * copies its row shard with strided transfers.  Results are those of ebpmf_vga_step_host. */
+typedef struct ebpmf_group ebpmf_group;
+int  ebpmf_group_create(int ndev, const int *devices /* NULL: 0..ndev-1 */, ebpmf_group **out);
+int  ebpmf_group_destroy(ebpmf_group *g);
+const char *ebpmf_group_last_error(const ebpmf_group *g);
+int  ebpmf_group_size(const ebpmf_group *g);
+int  ebpmf_group_set_option(ebpmf_group *g, const char *name, double value);
+int  ebpmf_group_set_y_csc(ebpmf_group *g, int64_t n, int64_t p,
+                           const int32_t *colptr, const int32_t *rowidx, const double *x);
+int  ebpmf_group_sum_lfactorial(ebpmf_group *g, double *out);
+int  ebpmf_group_vga_step_host(ebpmf_group *g, const double *M_in, int64_t K, const double *EL,
+                               const double *EF, int var_type, const double *sigma2,
+                               int maxiter, double tol,
+                               double *M_out, double *V_out, double *v_sum, ebpmf_solve_info *info);
+
 /* ---- drop-in solver signatures (dense operands, as R passes them) ------------------------ */
 
 /* vga_pois_solver_mat_newton(M,X,S,Beta,Sigma2,maxiter,tol,return_V)  R/vga_solver_mat.R:6-41
