@@ -39,6 +39,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's version / debug banner goes to a file instead
+os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/ebpmf_b200_nccl_%h_%p.log")
 
 # per-GPU slab of BASELINE.json config 4; log offsets calibrated so that mean(1-exp(-lambda)) hits
 # the target density (oracle/simdata.offset_for_density on a 4096^2 sample): K=20 @5 %: -5.3828
