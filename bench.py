@@ -39,8 +39,18 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's version / debug banner goes to a file instead
-os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/ebpmf_b200_nccl_%h_%p.log")
+# stdout carries exactly one JSON line.  Libraries (NCCL's version banner) write to fd 1 behind
+# Python's back, so fd 1 is pointed at stderr while the benchmark runs and restored for the result.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.dup2(_REAL_STDOUT, 1)
+    print(line, flush=True)
+    os.dup2(2, 1)
+
 
 # per-GPU slab of BASELINE.json config 4; log offsets calibrated so that mean(1-exp(-lambda)) hits
 # the target density (oracle/simdata.offset_for_density on a 4096^2 sample): K=20 @5 %: -5.3828
@@ -171,7 +181,7 @@ def run_reference(args, wl, rank, world):
     sample = ("%d x %d row sample of the workload per step (NumPy-generated sim_data_log, same DGP), u=%d; C "
               "transcription of the R code with OpenMP -- R is not installed, this is not the R interpreter"
               % (rows, p, out["n_updates"]))
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "VGA Newton entries/sec (fp64, N x p)", "value": val, "unit": "entries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -366,7 +376,7 @@ def main():
                                 "PCIe-bound" % (er, p), "n_updates": r["n_updates"], "ms_per_step": 1e3 * e_wall / args.steps}
         ectx.close()
     if rank == 0:
-        print(json.dumps(out))
+        emit(json.dumps(out))
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
