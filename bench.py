@@ -321,6 +321,8 @@ def main():
         "n_updates": u, "converged": bool(infos[-1].converged), "passes": infos[-1].passes,
         "pass_ms": {"first": p1, "topup": p2, "reduce": rd}, "wall_ms_per_step": 1e3 * wall / args.steps,
         "topup_units_frac": diag["topup_units"] / max(1.0, ((n + 31) // 32) * ((p + 1) // 2)),
+        "peer_kstar_sharing": {"peers_mapped": ctx.peer_count() if world > 1 else 0,
+                               "how": "pass-1 kernels read the other GPUs' published update count over NVLink peer memory"},
         "roofline": roofline, "fp64": fp64, "delta_mode": delta_mode,
         "gpu_launches": 6 * args.steps, "clocks": clk.summary(),
     }

@@ -52,6 +52,7 @@ SIGNATURES = {
     "ebpmf_ctx_set_sigma2": (_int, [_vp, _int, _vp]),
     "ebpmf_ctx_vga_step": (_int, [_vp, _int, _dbl, _int, _PI]),
     "ebpmf_ctx_get_m": (_int, [_vp, _vp]),
+    "ebpmf_ctx_peer_count": (_int, [_vp, C.POINTER(_int)]),
     "ebpmf_ctx_rewind_m": (_int, [_vp]),
     "ebpmf_ctx_get_v": (_int, [_vp, _vp]),
     "ebpmf_ctx_get_v_sum": (_int, [_vp, _vp]),

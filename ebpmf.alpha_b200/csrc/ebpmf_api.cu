@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>      // types only; the library is dlopen'ed (nccl_dyn below)
 
 #include <algorithm>
@@ -31,6 +32,7 @@ struct NcclDyn {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool load(std::string &err) {
         if (handle) return true;
@@ -47,6 +49,7 @@ struct NcclDyn {
         EBPMF_SYM(CommInitRank, "ncclCommInitRank");
         EBPMF_SYM(CommDestroy, "ncclCommDestroy");
         EBPMF_SYM(AllReduce, "ncclAllReduce");
+        EBPMF_SYM(AllGather, "ncclAllGather");
         EBPMF_SYM(GetErrorString, "ncclGetErrorString");
 #undef EBPMF_SYM
         return true;
@@ -98,6 +101,11 @@ struct ebpmf_ctx {
     // NCCL
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    // the other ranks' Status words mapped into this device's address space (NVLink peer memory)
+    DevBuf peer_ptrs;               // Status* [npeers]
+    int npeers = 0;
+    std::vector<void *> ipc_opened; // pointers to close at destroy
+    unsigned epoch = 0;             // solve counter, identical on every rank
 };
 
 namespace {
@@ -287,7 +295,7 @@ int set_target(ebpmf_ctx *ctx, int target) {
     memset(&s, 0, sizeof s);
     s.kstar = target;
     *ctx->h_status = s;
-    CU(cudaMemcpyAsync(ctx->status.ptr, ctx->h_status, sizeof(Status), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->status.ptr, ctx->h_status, kStatusResetBytes, cudaMemcpyHostToDevice, ctx->stream));
     return EBPMF_OK;
 }
 
@@ -341,7 +349,8 @@ int run_reductions(ebpmf_ctx *ctx) {
 // first / topup are callables that enqueue one pass on ctx->stream.
 template <typename First, typename Topup, typename After>
 int run_global_stop(ebpmf_ctx *ctx, int maxiter, First first, Topup topup, After after, ebpmf_solve_info *info) {
-    CU(cudaMemsetAsync(ctx->status.ptr, 0, sizeof(Status), ctx->stream));
+    CU(cudaMemsetAsync(ctx->status.ptr, 0, kStatusResetBytes, ctx->stream));     // `pub` survives (epoch-tagged)
+    ++ctx->epoch;
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     CHECK(first());
     CU(cudaEventRecord(ctx->ev_p1, ctx->stream));
@@ -399,6 +408,9 @@ FusedArgs fused_args(ebpmf_ctx *ctx, int maxiter, double tol, bool want_v) {
     a.colV = as<double>(ctx->colV); a.unitS = as<double>(ctx->unitS);
     a.rowpart = (ctx->var_type == EBPMF_VAR_BY_ROW) ? as<double>(ctx->rowpart) : nullptr;
     a.status = as<Status>(ctx->status);
+    a.peers = reinterpret_cast<const Status *const *>(ctx->peer_ptrs.ptr);
+    a.npeers = ctx->npeers;
+    a.epoch = ctx->epoch + 1;      // run_global_stop increments the counter before the first launch
     a.tables = as<MathTables>(ctx->tables);
     a.maxiter = maxiter; a.tol = tol; a.delta = ctx->delta;
     a.col0 = 0; a.col1 = ctx->p;
@@ -547,6 +559,61 @@ int get_matrix_ld(ebpmf_ctx *ctx, bool want_v, double *out, long long ld) {
     return EBPMF_OK;
 }
 
+
+// Map the other ranks' Status words into this device's address space so the pass-1 kernels can read
+// their published counts over NVLink.  Same process (ebpmf_group): raw pointers + peer access;
+// other processes (torchrun): CUDA IPC handles, exchanged with one ncclAllGather.  Best effort: any
+// failure leaves npeers = 0 and the ranks only meet in the all-reduce between the passes.
+struct PeerInfo {
+    long long pid;
+    int device, valid;
+    unsigned long long raw;
+    cudaIpcMemHandle_t handle;
+};
+
+int setup_peers(ebpmf_ctx *ctx) {
+    ctx->npeers = 0;
+    if (!ctx->comm || ctx->world < 2 || getenv("EBPMF_B200_NO_PEER")) return EBPMF_OK;
+    const int W = ctx->world;
+    PeerInfo mine;
+    memset(&mine, 0, sizeof mine);
+    mine.pid = (long long)getpid(); mine.device = ctx->device; mine.raw = (unsigned long long)ctx->status.ptr;
+    mine.valid = (cudaIpcGetMemHandle(&mine.handle, ctx->status.ptr) == cudaSuccess) ? 1 : 0;
+    (void)cudaGetLastError();
+    CHECK(reserve(ctx, ctx->scratch[0], sizeof(PeerInfo) * (size_t)(W + 1)));
+    PeerInfo *d = as<PeerInfo>(ctx->scratch[0]);
+    CU(cudaMemcpyAsync(d + W, &mine, sizeof mine, cudaMemcpyHostToDevice, ctx->stream));
+    NC(g_nccl.AllGather(d + W, d, sizeof(PeerInfo), ncclChar, ctx->comm, ctx->stream));
+    std::vector<PeerInfo> all((size_t)W);
+    CU(cudaMemcpyAsync(all.data(), d, sizeof(PeerInfo) * (size_t)W, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::vector<void *> ptrs;
+    for (int r = 0; r < W; ++r) {
+        if (r == ctx->rank) continue;
+        void *p = nullptr;
+        if (all[(size_t)r].pid == mine.pid) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, ctx->device, all[(size_t)r].device) == cudaSuccess && can) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(all[(size_t)r].device, 0);
+                if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) p = (void *)all[(size_t)r].raw;
+            }
+        } else if (all[(size_t)r].valid) {
+            if (cudaIpcOpenMemHandle(&p, all[(size_t)r].handle, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess)
+                ctx->ipc_opened.push_back(p);
+            else
+                p = nullptr;
+        }
+        (void)cudaGetLastError();
+        if (p) ptrs.push_back(p);
+    }
+    if (ptrs.empty()) return EBPMF_OK;
+    CHECK(reserve(ctx, ctx->peer_ptrs, sizeof(void *) * ptrs.size()));
+    CU(cudaMemcpyAsync(ctx->peer_ptrs.ptr, ptrs.data(), sizeof(void *) * ptrs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->npeers = (int)ptrs.size();
+    return EBPMF_OK;
+}
+
 }  // namespace
 
 // =========================================================================================
@@ -610,6 +677,9 @@ int ebpmf_ctx_create(int device, ebpmf_ctx **out) {
     CREATE_STEP(cudaMallocHost((void **)&ctx->h_small, sizeof(double) * 64));
     CREATE_STEP(cudaMalloc(&ctx->tables.ptr, sizeof(MathTables)));
     ctx->tables.cap = sizeof(MathTables);
+    CREATE_STEP(cudaMalloc(&ctx->status.ptr, sizeof(Status)));
+    ctx->status.cap = sizeof(Status);
+    CREATE_STEP(cudaMemset(ctx->status.ptr, 0, sizeof(Status)));
     {
         static MathTables host_tables;          // built once on the host: every kernel uses the same bits
         static bool built = false;
@@ -633,11 +703,12 @@ int ebpmf_ctx_destroy(ebpmf_ctx *ctx) {
     if (!ctx) return EBPMF_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (void *q : ctx->ipc_opened) cudaIpcCloseMemHandle(q);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     DevBuf *bufs[] = {&ctx->colptr, &ctx->rowidx, &ctx->yx, &ctx->rbptr, &ctx->Mcur, &ctx->Malt, &ctx->V,
                       &ctx->EL, &ctx->EF, &ctx->EFt, &ctx->sigma2, &ctx->l0, &ctx->f0, &ctx->kunit,
                       &ctx->colV, &ctx->unitS, &ctx->rowpart, &ctx->red, &ctx->colsums, &ctx->status, &ctx->misc,
-                      &ctx->C0, &ctx->sc1, &ctx->sc2, &ctx->tables};
+                      &ctx->C0, &ctx->sc1, &ctx->sc2, &ctx->tables, &ctx->peer_ptrs};
     for (DevBuf *b : bufs) release(*b);
     for (DevBuf &b : ctx->scratch) release(b);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
@@ -674,8 +745,7 @@ int ebpmf_ctx_comm_init(ebpmf_ctx *ctx, int rank, int world, const void *id128) 
     memcpy(&id, id128, sizeof id);
     NC(g_nccl.CommInitRank(&ctx->comm, world, id, rank));
     ctx->rank = rank; ctx->world = world;
-    CHECK(reserve(ctx, ctx->status, sizeof(Status)));
-    return EBPMF_OK;
+    return setup_peers(ctx);
 }
 
 int ebpmf_ctx_set_y_csc(ebpmf_ctx *ctx, int64_t n, int64_t p, const int32_t *colptr, const int32_t *rowidx,
@@ -1176,6 +1246,12 @@ int ebpmf_ctx_set_option(ebpmf_ctx *ctx, const char *name, double value) {
     }
     if (!strcmp(name, "pipeline")) { ctx->pipeline = value != 0.0 ? 1 : 0; return EBPMF_OK; }
     return fail(ctx, EBPMF_ERR_ARG, "set_option: unknown option '%s'", name);
+}
+
+int ebpmf_ctx_peer_count(ebpmf_ctx *ctx, int *npeers) {
+    if (!ctx || !npeers) return fail(ctx, EBPMF_ERR_ARG, "peer_count: bad arguments");
+    *npeers = ctx->npeers;
+    return EBPMF_OK;
 }
 
 int ebpmf_ctx_last_diag(ebpmf_ctx *ctx, uint64_t *topup_units, uint64_t *unit_evals) {

@@ -55,7 +55,11 @@ struct Status {           // device words shared by the passes of one solve
     int exhausted;        // some unit hit maxiter
     unsigned long long topup_units;   // diagnostics: units that needed pass 2 work
     unsigned long long unit_iters;    // diagnostics: sum over units of evaluations performed
+    // --- not reset per solve: (epoch << 32 | kstar), raised with atomicMax; what the OTHER GPUs read
+    // over NVLink during pass 1 so that every rank learns the global count while it is still working.
+    unsigned long long pub;
 };
+constexpr size_t kStatusResetBytes = 32;    // the words before `pub`
 
 struct FusedArgs {
     long long n, p;                 // rows of this shard, columns
@@ -79,6 +83,9 @@ struct FusedArgs {
     double *unitS;                  // [nRW][nJG][2] sum exp(M+V/2), sum(log(V)/2+c) of the unit
     double *rowpart;                // [nJG][n] sum over the unit's columns of V (by_row only), else null
     Status *status;
+    const Status *const *peers;     // the other ranks' Status words, mapped peer memory (NVLink); may be null
+    int npeers;
+    unsigned epoch;                 // solve counter, identical on every rank
     const MathTables *tables;       // exp2 / log tables (device copy of the host-built tables)
     int maxiter;
     double tol;
@@ -86,6 +93,24 @@ struct FusedArgs {
     long long col0, col1;           // columns of this launch
     int cols_per_cta;               // multiple of kTileCols
 };
+
+// publish a unit's first-converged count locally and to the peers' view
+__device__ __forceinline__ void publish_kstar(Status *st, unsigned epoch, int kb) {
+    atomicMax(&st->kstar, kb);
+    atomicMax(&st->pub, ((unsigned long long)epoch << 32) | (unsigned)kb);
+}
+// one peer's published word (a plain load over NVLink; 0 when there are no peers)
+__device__ __forceinline__ unsigned long long peek_peer(const FusedArgs &a, unsigned which) {
+    if (a.npeers <= 0) return 0ull;
+    return *reinterpret_cast<const volatile unsigned long long *>(&a.peers[which % (unsigned)a.npeers]->pub);
+}
+// fold a peeked word into the local count if it belongs to this solve: a peer's K* is <= the global u
+__device__ __forceinline__ void absorb_peer(Status *st, unsigned epoch, unsigned long long pv) {
+    if ((unsigned)(pv >> 32) == epoch) {
+        const int k = (int)(unsigned)pv;
+        if (k > *reinterpret_cast<volatile int *>(&st->kstar)) atomicMax(&st->kstar, k);
+    }
+}
 
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
@@ -339,6 +364,10 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
 
     for (int j0 = jc0; j0 < jc1; j0 += kTileCols) {
         __syncthreads();                             // previous tile fully consumed
+        // one thread per CTA peeks at one peer GPU's published count (round robin); the word is
+        // consumed after the tile's units, so the NVLink latency is never waited for
+        unsigned long long peer_word = 0ull;
+        if (tid == 0) peer_word = peek_peer(a, (unsigned)(j0 / kTileCols) + blockIdx.x + blockIdx.y);
         // ---- stage the tile: zero Y image, EF rows, per-column constants --------------------
 #pragma unroll
         for (int c = 0; c < kTileCols; ++c) sm.ys[c][tid] = 0.0;
@@ -441,10 +470,11 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
                 any_nan = 1;
             if (lane == 0) {
                 a.kunit[ku_idx] = (unsigned short)((flags & 8) ? kFrozen : k);
-                if (kb > t0) atomicMax(&a.status->kstar, kb);      // K* = max over units of the first converged k
+                if (kb > t0) publish_kstar(a.status, a.epoch, kb);   // K* = max over units of the first converged k
             }
             off += E * ns; ku_idx += (size_t)a.nRW; cv_idx += E; us_idx += 2; rp_idx += ns;
         }
+        if (tid == 0) absorb_peer(a.status, a.epoch, peer_word);
     }
     if (lane == 0) {
         if (any_exhausted) a.status->exhausted = 1;
@@ -595,10 +625,15 @@ __global__ void __launch_bounds__(kThreads, EBPMF_STREAM_MINB) vga_stream_kernel
         }
     }
 
+    unsigned long long peer_word = 0ull;
 #pragma unroll 1
     for (int jb = jc0; jb < jc1; jb += E, off += E * ns, ku_idx += (size_t)a.nRW, cv_idx += E, us_idx += 2, rp_idx += ns) {
         int k = 0;
         int t0 = 0;
+        if (MODE == MODE_FIRST && tid == 0 && ((jb - jc0) & (8 * E - 1)) == 0) {
+            absorb_peer(a.status, a.epoch, peer_word);           // the word peeked 8 units ago
+            peer_word = peek_peer(a, (unsigned)(jb / E) + blockIdx.x + blockIdx.y);
+        }
         if (MODE == MODE_TOPUP) {
             k = a.kunit[ku_idx];
             if (k == target || k == kFrozen) continue;
@@ -647,7 +682,7 @@ __global__ void __launch_bounds__(kThreads, EBPMF_STREAM_MINB) vga_stream_kernel
             any_nan = 1;
         if (lane == 0) {
             a.kunit[ku_idx] = (unsigned short)((flags & 8) ? kFrozen : k);
-            if (MODE == MODE_FIRST && kb > t0) atomicMax(&a.status->kstar, kb);
+            if (MODE == MODE_FIRST && kb > t0) publish_kstar(a.status, a.epoch, kb);
         }
     }
     if (lane == 0) {

@@ -126,6 +126,11 @@ class VgaContext:
         buf = C.create_string_buffer(bytes(unique_id), 128)
         self._ck(self._lib.ebpmf_ctx_comm_init(self._h, int(rank), int(world), buf))
 
+    def peer_count(self):
+        out = C.c_int()
+        self._ck(self._lib.ebpmf_ctx_peer_count(self._h, C.byref(out)))
+        return out.value
+
     # -- resident state ---------------------------------------------------
     def set_y(self, Y):
         """Y: scipy sparse (-> dgCMatrix slots) or dense n x p."""

@@ -116,6 +116,10 @@ int  ebpmf_ctx_set_sigma2(ebpmf_ctx *ctx, int var_type, const double *sigma2);
 int  ebpmf_ctx_vga_step(ebpmf_ctx *ctx, int maxiter, double tol, int want_v, ebpmf_solve_info *info);
 
 int  ebpmf_ctx_get_m(ebpmf_ctx *ctx, double *M);
+/* number of peer GPUs whose published update count this context can read over NVLink during
+ * pass 1 (0: none; the ranks then only meet in the all-reduce between the passes) */
+int  ebpmf_ctx_peer_count(ebpmf_ctx *ctx, int *npeers);
+
 /* undo the M <- res$M of the last step: the resident M is again the step's input (the input
  * buffer is never written by a step).  Lets a benchmark repeat the same step without a copy. */
 int  ebpmf_ctx_rewind_m(ebpmf_ctx *ctx);

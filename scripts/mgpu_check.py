@@ -18,6 +18,7 @@ ctx = pkg.VgaContext(local)
 uid = [pkg.VgaContext.nccl_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
 ctx.comm_init(rank, world, uid[0])
+print("rank", rank, "peers mapped over NVLink:", ctx.peer_count(), flush=True)
 
 ok = True
 for (n, p, K, var_type, mi, tol) in [(5000, 700, 5, "by_col", 10, 1e-5), (3001, 333, 3, "by_col", 1000, 1e-8),

@@ -27,6 +27,11 @@ def gpu_ctx(pkg):
 
 
 @pytest.fixture(scope="session", autouse=True)
-def _build_oracle():
+def _build_everything_once():
+    """The oracle's C transcription and (if it did not travel with the snapshot) the CUDA library:
+    nvcc cross-compiles sm_100a without a GPU, so the CPU suite can check the ABI."""
     from oracle import c_oracle
     c_oracle.lib()
+    import __graft_entry__ as ge
+    if not os.path.exists(os.path.join(ge.PKG_DIR, "lib", "libebpmf_b200.so")):
+        ge.build()
