@@ -73,7 +73,7 @@ struct ebpmf_ctx {
     // shapes
     long long n = 0, p = 0, nnz = 0;
     long long nRB = 0, nRW = 0;
-    int K = 0, KTP = 0;
+    int K = 0, KTP = 0, ldk = 0;
     int var_type = -1;
     int pipeline = 0;          // 0: fused first pass, 1: split (const0 kernel + streaming Newton)
     double delta = 0.0;        // 0: exact update count (default); > 0: delta mode (ebpmf_ctx_set_option)
@@ -164,13 +164,17 @@ void release(DevBuf &b) {
 
 template <typename T> T *as(DevBuf &b) { return reinterpret_cast<T *>(b.ptr); }
 
+// register tile of factor columns: 8/16/24/32; more than 32 columns are walked in chunks of 32
 int ktp_for(int K) {
     if (K <= 8) return 8;
     if (K <= 16) return 16;
     if (K <= 24) return 24;
-    if (K <= 32) return 32;
+    if (K <= 4096) return 32;
     return -1;
 }
+
+// row length of the transposed, zero-padded EF (EFt): KTP, or the next multiple of 32 when K > 32
+int ldk_for(int K) { return K <= 32 ? ktp_for(K) : ((K + 31) / 32) * 32; }
 
 #ifndef EBPMF_E
 #define EBPMF_E 2
@@ -229,7 +233,7 @@ int launch_first(ebpmf_ctx *ctx, const FusedArgs &a) {
             case 16: CHECK((launch_prep_ktp<16, FORMULA>(ctx, a, grid))); break;
             case 24: CHECK((launch_prep_ktp<24, FORMULA>(ctx, a, grid))); break;
             case 32: CHECK((launch_prep_ktp<32, FORMULA>(ctx, a, grid))); break;
-            default: return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported (max 32)", ctx->K);
+            default: return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported", ctx->K);
         }
         if (a.delta > 0) vga_stream_kernel<kE, FORMULA, MODE_FIRST, true><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
         else vga_stream_kernel<kE, FORMULA, MODE_FIRST, false><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
@@ -242,7 +246,7 @@ int launch_first(ebpmf_ctx *ctx, const FusedArgs &a) {
         case 24: return launch_first_ktp<24, FORMULA>(ctx, a, grid);
         case 32: return launch_first_ktp<32, FORMULA>(ctx, a, grid);
     }
-    return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported (max 32)", ctx->K);
+    return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported", ctx->K);
 }
 
 // pass 2 (streaming top-up to the global count)
@@ -400,7 +404,7 @@ FusedArgs fused_args(ebpmf_ctx *ctx, int maxiter, double tol, bool want_v) {
     a.M_in = as<double>(ctx->Mcur); a.M_out = as<double>(ctx->Malt);
     a.V_out = want_v ? as<double>(ctx->V) : nullptr;
     a.C0 = as<double>(ctx->C0);
-    a.EL = as<double>(ctx->EL); a.EFt = as<double>(ctx->EFt); a.sigma2 = as<double>(ctx->sigma2);
+    a.EL = as<double>(ctx->EL); a.EFt = as<double>(ctx->EFt); a.ldk = ctx->ldk; a.sigma2 = as<double>(ctx->sigma2);
     a.sc1 = as<double>(ctx->sc1); a.sc2 = as<double>(ctx->sc2);
     a.l0 = as<double>(ctx->l0); a.f0 = as<double>(ctx->f0);
     a.rowidx = as<int>(ctx->rowidx); a.yx = as<double>(ctx->yx); a.rbptr = as<int>(ctx->rbptr);
@@ -534,19 +538,20 @@ int set_factors_ld(ebpmf_ctx *ctx, int64_t K, const double *EL, long long ldl, c
     if (!ctx || !EL || !EF || K < 1) return fail(ctx, EBPMF_ERR_ARG, "set_factors: bad arguments");
     if (!ctx->have_y) return fail(ctx, EBPMF_ERR_STATE, "set_factors: Y not set");
     const int ktp = ktp_for((int)K);
-    if (ktp < 0) return fail(ctx, EBPMF_ERR_ARG, "K = %lld factor columns not supported (max 32)", (long long)K);
+    if (ktp < 0) return fail(ctx, EBPMF_ERR_ARG, "K = %lld factor columns not supported (max 4096)", (long long)K);
+    const int ldk = ldk_for((int)K);
     CHECK(ensure_common(ctx));
     const long long n = ctx->n, p = ctx->p;
     CHECK(reserve(ctx, ctx->EL, sizeof(double) * (size_t)n * (size_t)K));
     CHECK(reserve(ctx, ctx->EF, sizeof(double) * (size_t)p * (size_t)K));
-    CHECK(reserve(ctx, ctx->EFt, sizeof(double) * (size_t)p * (size_t)ktp));
+    CHECK(reserve(ctx, ctx->EFt, sizeof(double) * (size_t)p * (size_t)ldk));
     CHECK(copy_in_ld(ctx, ctx->EL.ptr, EL, n, K, ldl));
     CU(cudaMemcpyAsync(ctx->EF.ptr, EF, sizeof(double) * (size_t)p * (size_t)K, cudaMemcpyHostToDevice, ctx->stream));
-    transpose_ef_kernel<<<(unsigned)((p * ktp + 255) / 256), 256, 0, ctx->stream>>>(as<double>(ctx->EF), p, (int)K, ktp,
+    transpose_ef_kernel<<<(unsigned)((p * ldk + 255) / 256), 256, 0, ctx->stream>>>(as<double>(ctx->EF), p, (int)K, ldk,
                                                                                    as<double>(ctx->EFt));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->K = (int)K; ctx->KTP = ktp; ctx->have_f = true;
+    ctx->K = (int)K; ctx->KTP = ktp; ctx->ldk = ldk; ctx->have_f = true;
     return EBPMF_OK;
 }
 
@@ -1188,7 +1193,7 @@ int ebpmf_ctx_sim_data_log(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, int6
         return fail(ctx, EBPMF_ERR_ARG, "sim_data_log: bad arguments");
     const int KT = (int)K + 2;
     const int ktp = ktp_for(KT);
-    if (ktp < 0) return fail(ctx, EBPMF_ERR_ARG, "sim_data_log: K + 2 = %d factor columns not supported (max 32)", KT);
+    if (ktp < 0 || KT > 32) return fail(ctx, EBPMF_ERR_ARG, "sim_data_log: K + 2 = %d factor columns not supported (max 32)", KT);
     CHECK(ensure_common(ctx));
     const size_t NP = (size_t)n * (size_t)p;
     CHECK(reserve(ctx, ctx->Mcur, sizeof(double) * NP));
@@ -1231,7 +1236,7 @@ int ebpmf_ctx_sim_data_log(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, int6
                                                                              as<double>(ctx->sc1), as<double>(ctx->sc2));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->K = KT; ctx->KTP = ktp; ctx->var_type = EBPMF_VAR_BY_COL;
+    ctx->K = KT; ctx->KTP = ktp; ctx->ldk = ktp; ctx->var_type = EBPMF_VAR_BY_COL;
     ctx->have_m = ctx->have_f = ctx->have_s2 = true;
     if (nnz_out) *nnz_out = nnz;
     return EBPMF_OK;

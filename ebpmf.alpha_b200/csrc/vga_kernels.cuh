@@ -70,7 +70,8 @@ struct FusedArgs {
     double *V_out;                  // nullable
     double *C0;                     // n x p: const0 = (Sigma2*X + Beta) + 1, written by pass 1
     const double *EL;               // n x K column-major
-    const double *EFt;              // p x KTP row-major, zero padded
+    const double *EFt;              // p x ldk row-major, zero padded (ldk = KTP, or a multiple of 32 when K > 32)
+    int ldk;
     const double *sigma2;           // length 1 | n | p
     const double *sc1, *sc2;        // 1/sigma2 (const1), sigma2/2 (const2), same length
     const double *l0, *f0;          // A10 only
@@ -304,6 +305,15 @@ __device__ __forceinline__ bool finalize_unit(const FusedArgs &a, const double (
     return __any_sync(0xffffffffu, lane_nan);
 }
 
+// stage EF rows [j0, j0+16) x factor columns [k0, k0+KTP) into efs[16][KTP] (zero beyond jc1)
+template <int KTP>
+__device__ __forceinline__ void stage_ef_chunk(double *efs, const double *EFt, int ldk, int j0, int jc1, int k0, int tid) {
+    for (int idx = tid; idx < kTileCols * KTP; idx += kThreads) {
+        const int c = idx / KTP, k = idx - c * KTP;
+        efs[idx] = (j0 + c < jc1) ? __ldg(EFt + (size_t)(j0 + c) * ldk + k0 + k) : 0.0;
+    }
+}
+
 // shared memory of the first-pass kernel (dynamic): Y image, Beta image, EF rows, column constants
 template <int KTP>
 struct FusedSmem {
@@ -371,12 +381,7 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
         // ---- stage the tile: zero Y image, EF rows, per-column constants --------------------
 #pragma unroll
         for (int c = 0; c < kTileCols; ++c) sm.ys[c][tid] = 0.0;
-        {
-            const double *eft = a.EFt + (size_t)j0 * KTP;
-            const int lim = (jc1 - j0) * KTP;        // rows of EFt beyond jc1 are not read
-            for (int idx = tid; idx < kTileCols * KTP; idx += kThreads)
-                (&sm.efs[0][0])[idx] = (idx < lim) ? __ldg(eft + idx) : 0.0;
-        }
+        stage_ef_chunk<KTP>(&sm.efs[0][0], a.EFt, a.ldk, j0, jc1, 0, tid);
         if (tid < kTileCols) {
             const int j = j0 + tid;
             const bool col = by_col && (j < jc1);
@@ -403,15 +408,21 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
             }
         }
         // a2: this row's Beta for the 16 tile columns, K_tot FMAs each (EL row lives in registers
-        // only here; EF rows are broadcast reads from shared memory)
-        {
+        // only here; EF rows are broadcast reads from shared memory).  K_tot > KTP (only possible
+        // with KTP = 32) walks the factor columns in chunks of KTP, restaging the EF rows.
+        for (int k0 = 0; k0 < a.K; k0 += KTP) {
+            if (k0 > 0) {
+                __syncthreads();
+                stage_ef_chunk<KTP>(&sm.efs[0][0], a.EFt, a.ldk, j0, jc1, k0, tid);
+                __syncthreads();
+            }
             double el[KTP];
-            const double *elp = a.EL + i;
+            const double *elp = a.EL + i + (size_t)k0 * ns;
 #pragma unroll
-            for (int k = 0; k < KTP; ++k) el[k] = (row_ok && k < a.K) ? __ldg(elp + k * ns) : 0.0;
+            for (int k = 0; k < KTP; ++k) el[k] = (row_ok && k0 + k < a.K) ? __ldg(elp + k * ns) : 0.0;
 #pragma unroll 4
             for (int c = 0; c < kTileCols; ++c) {
-                double b = 0.0;
+                double b = (k0 > 0) ? sm.bs[c][tid] : 0.0;
 #pragma unroll
                 for (int k = 0; k < KTP; ++k) b = fma(el[k], sm.efs[c][k], b);
                 sm.bs[c][tid] = b;
@@ -513,22 +524,11 @@ __global__ void __launch_bounds__(kThreads, 3) vga_prep_kernel(const FusedArgs a
     const bool by_col = a.var_type == 2;
     double s2_row = 1.0;
     if (!by_col) s2_row = __dadd_rn(a.sc2[(a.var_type == 1) ? (row_ok ? i : 0) : 0], a.sc2[(a.var_type == 1) ? (row_ok ? i : 0) : 0]);
-    double el[KTP];
-    {
-        const double *elp = a.EL + i;
-#pragma unroll
-        for (int k = 0; k < KTP; ++k) el[k] = (row_ok && k < a.K) ? __ldg(elp + k * ns) : 0.0;
-    }
     for (int j0 = jc0; j0 < jc1; j0 += kTileCols) {
         __syncthreads();
 #pragma unroll
         for (int c = 0; c < kTileCols; ++c) sm.ys[c][tid] = 0.0;
-        {
-            const double *eft = a.EFt + (size_t)j0 * KTP;
-            const int lim = (jc1 - j0) * KTP;
-            for (int idx = tid; idx < kTileCols * KTP; idx += kThreads)
-                (&sm.efs[0][0])[idx] = (idx < lim) ? __ldg(eft + idx) : 0.0;
-        }
+        stage_ef_chunk<KTP>(&sm.efs[0][0], a.EFt, a.ldk, j0, jc1, 0, tid);
         if (tid < kTileCols) {
             const int j = j0 + tid;
             sm.s2s[tid] = (by_col && j < jc1) ? __dadd_rn(a.sc2[j], a.sc2[j]) : 1.0;    // sigma2 = 2*const2, exact
@@ -544,13 +544,31 @@ __global__ void __launch_bounds__(kThreads, 3) vga_prep_kernel(const FusedArgs a
                 }
             }
         }
+        // Beta accumulates in registers over chunks of KTP factor columns (one chunk when K_tot <= KTP)
+        double beta[kTileCols];
+#pragma unroll
+        for (int c = 0; c < kTileCols; ++c) beta[c] = 0.0;
+        for (int k0 = 0; k0 < a.K; k0 += KTP) {
+            if (k0 > 0) {
+                __syncthreads();
+                stage_ef_chunk<KTP>(&sm.efs[0][0], a.EFt, a.ldk, j0, jc1, k0, tid);
+                __syncthreads();
+            }
+            double el[KTP];
+            const double *elp = a.EL + i + (size_t)k0 * ns;
+#pragma unroll
+            for (int k = 0; k < KTP; ++k) el[k] = (row_ok && k0 + k < a.K) ? __ldg(elp + k * ns) : 0.0;
+#pragma unroll
+            for (int c = 0; c < kTileCols; ++c) {
+#pragma unroll
+                for (int k = 0; k < KTP; ++k) beta[c] = fma(el[k], sm.efs[c][k], beta[c]);          // a2: Beta_ij
+            }
+        }
         __syncthreads();
         size_t off = (size_t)i + ns * (size_t)j0;
-#pragma unroll 4
-        for (int c = 0; c < kTileCols; ++c, off += ns) {
-            double b = 0.0;
 #pragma unroll
-            for (int k = 0; k < KTP; ++k) b = fma(el[k], sm.efs[c][k], b);          // a2: Beta_ij
+        for (int c = 0; c < kTileCols; ++c, off += ns) {
+            const double b = beta[c];
             if (row_ok && j0 + c < jc1) {
                 const double s2 = by_col ? sm.s2s[c] : s2_row;
                 st_stream(a.C0 + off, __dadd_rn(__fma_rn(s2, sm.ys[c][tid], b), 1.0));   // :9 | :81,:95

@@ -32,7 +32,7 @@ extern "C" {
 #endif
 
 #define EBPMF_OK            0
-#define EBPMF_ERR_ARG       1   /* bad argument (NULL, maxiter < 1, shapes that do not conform) */
+#define EBPMF_ERR_ARG       1   /* bad argument (NULL, maxiter outside [1,65535], shapes that do not conform) */
 #define EBPMF_ERR_CUDA      2   /* CUDA runtime failure / no usable GPU */
 #define EBPMF_ERR_NAN       3   /* a NaN reached the stop test: R stops with "missing value where
                                    TRUE/FALSE needed" at R/vga_solver_mat.R:26,85,100 */

@@ -368,3 +368,24 @@ def test_maxiter_one(gpu_ctx):
     ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], "by_col", 1, 1e-5)
     check_step(res, ref, "by_col")
     assert res["n_updates"] == 1 and not res["converged"]
+
+
+@pytest.mark.parametrize("K,pipeline", [(31, 0), (45, 0), (45, 1), (70, 0)])
+def test_many_factors(pkg, K, pipeline):
+    """K_tot = K + 2 above the 32-column register tile: Beta is accumulated over chunks of 32 factor columns
+    (flash_control$Kmax defaults to 30, R/ebpmf_log_controls.R:74, but greedy additions can exceed it)."""
+    c = simdata.offset_for_density(0.10, K=4)
+    sim = simdata.sim_data_log(700, 150, K=4, seed=5, log_offset=c)
+    rng = np.random.default_rng(K)
+    st = simdata.solver_state(sim, start="cold")
+    EL = np.hstack([st["EL"], 0.05 * rng.normal(size=(700, K - 4))])
+    EF = np.hstack([st["EF"], 0.05 * rng.normal(size=(150, K - 4))])
+    ctx = pkg.VgaContext(0)
+    try:
+        ctx.set_option("pipeline", pipeline)
+        ctx.set_y(sp.csc_matrix(sim["Y"]))
+        res = ctx.vga_step_host(st["M0"], EL, EF, st["sigma2"], "by_col", 100, 1e-8, return_V=True)
+        ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], EL, EF, st["sigma2"], "by_col", 100, 1e-8)
+        check_step(res, ref, "by_col")
+    finally:
+        ctx.close()
