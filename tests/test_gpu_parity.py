@@ -389,3 +389,22 @@ def test_many_factors(pkg, K, pipeline):
         check_step(res, ref, "by_col")
     finally:
         ctx.close()
+
+
+def test_fast_math_vs_exact_math(pkg, tmp_path):
+    """The fast reciprocal / exp / log of vga_math.cuh against the same library built with
+    EBPMF_EXACT_MATH=1 (IEEE division, libdevice exp/log): same update count, results within 1e-12."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exact = os.path.join(os.path.dirname(pkg.LIB_PATH), "libebpmf_b200_exactmath.so")
+    assert os.path.exists(exact), "build with make -C ebpmf.alpha_b200/csrc (or __graft_entry__.build())"
+    outs = []
+    for tag, lib in (("fast", pkg.LIB_PATH), ("exact", exact)):
+        o = str(tmp_path / (tag + ".npz"))
+        env = dict(os.environ, EBPMF_B200_LIB=lib)
+        subprocess.run([sys.executable, os.path.join(root, "scripts", "run_case_dump.py"), o], check=True, env=env)
+        outs.append(np.load(o))
+    a, b = outs
+    assert a["s"][3] == b["s"][3]
+    assert np.max(np.abs(a["M"] - b["M"])) < 1e-12 and rel(a["V"], b["V"]) < 1e-12
+    assert rel(a["v_sum"], b["v_sum"]) < 1e-12 and rel(a["s"][:3], b["s"][:3]) < 1e-12
