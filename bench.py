@@ -76,7 +76,8 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock, power and throttle reasons sampled DURING the timed region (NVML every 50 ms;
+    nvidia-smi polling as a fallback)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -84,18 +85,43 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], threading.Event()
         self.t = threading.Thread(target=self.run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    def sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        bit = lambda name: "Active" if (r & getattr(n, name, 0)) else "Not Active"
+        return [str(sm), str(self.max), str(pw), bit("nvmlClocksThrottleReasonHwSlowdown"),
+                bit("nvmlClocksThrottleReasonHwThermalSlowdown"), bit("nvmlClocksThrottleReasonSwThermalSlowdown"),
+                bit("nvmlClocksThrottleReasonSwPowerCap")]
 
     def run(self):
         while not self.stop.is_set():
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in o.strip().split(",")]
-                if len(f) >= 7:
-                    self.rows.append(f)
+                if self.nvml is not None:
+                    self.rows.append(self.sample_nvml())
+                else:
+                    o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                        "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    f = [x.strip() for x in o.strip().split(",")]
+                    if len(f) >= 7:
+                        self.rows.append(f)
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.05 if self.nvml is not None else 0.2)
 
     def __enter__(self):
         self.t.start(); return self
@@ -112,7 +138,8 @@ class ClockSampler:
             if any(r[i].lower().startswith("active") for r in self.rows):
                 reasons.append(name)
         return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(self.rows[0][1]), reasons=reasons,
-                    power_w_max=max(float(r[2]) for r in self.rows), samples=len(self.rows))
+                    power_w_max=max(float(r[2]) for r in self.rows), samples=len(self.rows),
+                    source="nvml" if self.nvml is not None else "nvidia-smi")
 
 
 def host_cores():
