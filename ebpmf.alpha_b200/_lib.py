@@ -66,6 +66,7 @@ SIGNATURES = {
     "ebpmf_calc_obj": (_int, [_vp, _i64, _i64, _dbl, _dbl, _dbl, _i64, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl,
                               _dbl, C.POINTER(_dbl)]),
     "ebpmf_vga_step_host": (_int, [_vp, _vp, _i64, _vp, _vp, _int, _vp, _int, _dbl, _vp, _vp, _vp, _PI]),
+    "ebpmf_vga_step_resident_host": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _int, _dbl, _vp, _vp, _vp, _PI]),
     "ebpmf_group_create": (_int, [_int, _vp, C.POINTER(_vp)]),
     "ebpmf_group_destroy": (_int, [_vp]),
     "ebpmf_group_last_error": (C.c_char_p, [_vp]),

@@ -982,6 +982,24 @@ int ebpmf_vga_step_host(ebpmf_ctx *ctx, const double *M_in, int64_t K, const dou
     return EBPMF_OK;
 }
 
+// The per-iteration call of ebpmf_log's outer loop once M lives on the device: R feeds res$M back
+// unchanged (fit_flash$flash_fit$Y = res$M, R/ebpmf_log.R:309; flash_init(fit_flash$flash_fit$Y, ..),
+// R/ebpmf_log_flash_update.R:35), so the step's input M IS the resident M left by the previous step
+// and only the factors and sigma2 cross PCIe on the way in.
+int ebpmf_vga_step_resident_host(ebpmf_ctx *ctx, int64_t K, const double *EL, const double *EF, int var_type,
+                                 const double *sigma2, int maxiter, double tol, double *M_out, double *V_out,
+                                 double *v_sum, ebpmf_solve_info *info) {
+    if (!ctx || !M_out) return fail(ctx, EBPMF_ERR_ARG, "vga_step_resident_host: bad arguments");
+    if (!ctx->have_m) return fail(ctx, EBPMF_ERR_STATE, "vga_step_resident_host: upload M once with ebpmf_ctx_set_m");
+    CHECK(ebpmf_ctx_set_factors(ctx, K, EL, EF));
+    CHECK(ebpmf_ctx_set_sigma2(ctx, var_type, sigma2));
+    CHECK(ebpmf_ctx_vga_step(ctx, maxiter, tol, V_out != nullptr, info));
+    CHECK(ebpmf_ctx_get_m(ctx, M_out));
+    if (V_out) CHECK(ebpmf_ctx_get_v(ctx, V_out));
+    if (v_sum) CHECK(ebpmf_ctx_get_v_sum(ctx, v_sum));
+    return EBPMF_OK;
+}
+
 // ---- drop-in dense signatures ------------------------------------------------------------
 
 int ebpmf_vga_newton(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *M, const double *X,

@@ -78,3 +78,11 @@ ebpmf_b200_vga_step = function(M,EL,EF,sigma2,var_type,maxiter,tol,want_V=FALSE)
   .Call(C_ebpmf_vga_step, ebpmf_b200_ctx(), M, EL + 0, EF + 0, as.double(sigma2), var_type,
         as.integer(maxiter), as.double(tol), as.logical(want_V))
 }
+
+#' Resident-M variant used by ebpmf_log's loop: upload M_init once, then every iteration sends only
+#' the factors and sigma2 and receives res$M (R feeds res$M back unchanged, R/ebpmf_log.R:309).
+ebpmf_b200_set_m = function(M){ storage.mode(M) = 'double'; invisible(.Call(C_ebpmf_ctx_set_m, ebpmf_b200_ctx(), M)) }
+ebpmf_b200_vga_step_resident = function(n,p,EL,EF,sigma2,var_type,maxiter,tol,want_V=FALSE){
+  .Call(C_ebpmf_vga_step_resident, ebpmf_b200_ctx(), as.integer(c(n,p)), EL + 0, EF + 0, as.double(sigma2), var_type,
+        as.integer(maxiter), as.double(tol), as.logical(want_V))
+}

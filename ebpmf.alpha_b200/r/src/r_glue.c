@@ -158,6 +158,41 @@ SEXP C_ebpmf_vga_step(SEXP xp, SEXP M, SEXP EL, SEXP EF, SEXP sigma2, SEXP var_t
     return out;
 }
 
+/* M_init -> device, once per ebpmf_log() call (the latent M then stays resident: every later step's
+ * input is the previous step's output, R/ebpmf_log.R:309) */
+SEXP C_ebpmf_ctx_set_m(SEXP xp, SEXP M)
+{
+    ebpmf_ctx *ctx = get_ctx(xp);
+    if (!Rf_isMatrix(M) || TYPEOF(M) != REALSXP) Rf_error("M must be a numeric matrix");
+    check(ctx, ebpmf_ctx_set_m(ctx, REAL(M)));
+    return R_NilValue;
+}
+
+/* The per-iteration VGA step on the resident M: factors and sigma2 in, list(M, V|NULL, v_sum, sym,
+ * ssexp, slogv, n_updates, converged) out.  dims = c(n, p) of the resident matrices. */
+SEXP C_ebpmf_vga_step_resident(SEXP xp, SEXP dims, SEXP EL, SEXP EF, SEXP sigma2, SEXP var_type, SEXP maxiter,
+                               SEXP tol, SEXP want_V)
+{
+    ebpmf_ctx *ctx = get_ctx(xp);
+    const int vt = var_type_code(var_type);
+    if (vt < 0) Rf_error("Non-supported var type");
+    const int n = INTEGER(dims)[0], p = INTEGER(dims)[1];
+    if (Rf_nrows(EL) != n || Rf_nrows(EF) != p || Rf_ncols(EL) != Rf_ncols(EF)) Rf_error("non-conformable arguments");
+    const R_xlen_t want = vt == EBPMF_VAR_BY_COL ? p : vt == EBPMF_VAR_BY_ROW ? n : 1;
+    if (XLENGTH(sigma2) != want) Rf_error("sigma2 has the wrong length for this var_type");
+    const int wv = Rf_asLogical(want_V);
+    SEXP Mo = PROTECT(Rf_allocMatrix(REALSXP, n, p));
+    SEXP Vo = PROTECT(wv ? Rf_allocMatrix(REALSXP, n, p) : R_NilValue);
+    SEXP vs = PROTECT(Rf_allocVector(REALSXP, want));
+    ebpmf_solve_info info;
+    int rc = ebpmf_vga_step_resident_host(ctx, Rf_ncols(EL), REAL(EL), REAL(EF), vt, REAL(sigma2), Rf_asInteger(maxiter),
+                                          Rf_asReal(tol), REAL(Mo), wv ? REAL(Vo) : NULL, REAL(vs), &info);
+    if (rc != EBPMF_OK) { UNPROTECT(3); check(ctx, rc); }
+    SEXP out = info_list(&info, Mo, Vo, vs);
+    UNPROTECT(3);
+    return out;
+}
+
 /* ---- vga_pois_solver_mat_newton(M,X,S,Beta,Sigma2,maxiter,tol,return_V)  R/vga_solver_mat.R:6 */
 SEXP C_vga_pois_solver_mat_newton(SEXP xp, SEXP M, SEXP X, SEXP S, SEXP Beta, SEXP Sigma2, SEXP maxiter, SEXP tol,
                                   SEXP return_V)
@@ -278,6 +313,8 @@ static const R_CallMethodDef call_methods[] = {
     {"C_ebpmf_ctx_set_y", (DL_FUNC)&C_ebpmf_ctx_set_y, 2},
     {"C_ebpmf_sum_lfactorial", (DL_FUNC)&C_ebpmf_sum_lfactorial, 2},
     {"C_ebpmf_vga_step", (DL_FUNC)&C_ebpmf_vga_step, 9},
+    {"C_ebpmf_ctx_set_m", (DL_FUNC)&C_ebpmf_ctx_set_m, 2},
+    {"C_ebpmf_vga_step_resident", (DL_FUNC)&C_ebpmf_vga_step_resident, 9},
     {"C_vga_pois_solver_mat_newton", (DL_FUNC)&C_vga_pois_solver_mat_newton, 9},
     {"C_vga_pois_solver_mat_newton_fixed_iter", (DL_FUNC)&C_vga_pois_solver_mat_newton_fixed_iter, 8},
     {"C_vga_pois_solver_mat_newton_low_memory", (DL_FUNC)&C_vga_pois_solver_mat_newton_low_memory, 11},

@@ -266,6 +266,27 @@ class VgaContext:
                     ssexp=info.ssexp, slogv=info.slogv, n_updates=info.n_updates,
                     converged=bool(info.converged), passes=info.passes, kernel_ms=info.kernel_ms)
 
+    def vga_step_resident_host(self, EL, EF, sigma2, var_type, maxiter=10, tol=1e-5, return_V=False, M_out=None):
+        """The per-iteration call of ebpmf_log's loop once M is resident (set_m once): factors and
+        sigma2 in, M [, V], v_sum out.  R feeds res$M back unchanged, so nothing else is needed."""
+        if var_type not in VAR_TYPE:
+            raise EbpmfError(4, "Non-supported var type")
+        EL = _f(np.asarray(EL, dtype=np.float64).reshape(self.n, -1))
+        EF = _f(np.asarray(EF, dtype=np.float64).reshape(self.p, -1))
+        s2 = _vec(sigma2)
+        ln = {"by_col": self.p, "by_row": self.n, "constant": 1}[var_type]
+        Mo = np.empty((self.n, self.p), order="F") if M_out is None else M_out
+        Vo = np.empty((self.n, self.p), order="F") if return_V else None
+        vs = np.empty(ln)
+        info = SolveInfo()
+        self._ck(self._lib.ebpmf_vga_step_resident_host(self._h, EL.shape[1], _ptr(EL), _ptr(EF), VAR_TYPE[var_type],
+                                                        _ptr(s2), int(maxiter), float(tol), _ptr(Mo), _ptr(Vo),
+                                                        _ptr(vs), C.byref(info)))
+        self.var_type = var_type
+        return dict(M=Mo, V=Vo, v_sum=(vs if var_type != "constant" else float(vs[0])), sym=info.sym,
+                    ssexp=info.ssexp, slogv=info.slogv, n_updates=info.n_updates,
+                    converged=bool(info.converged), passes=info.passes, kernel_ms=info.kernel_ms)
+
     def sim_data_log(self, n, p, K, row0=0, seed=12345, log_offset=0.0, background_unif_range=(1.0, 2.0),
                      pi0=0.8, noise=0.2, warm_start=False):
         nnz = C.c_int64()

@@ -165,6 +165,14 @@ int  ebpmf_vga_step_host(ebpmf_ctx *ctx, const double *M_in, int64_t K, const do
                          int maxiter, double tol,
                          double *M_out, double *V_out, double *v_sum, ebpmf_solve_info *info);
 
+/* The same step when M already lives on the device: ebpmf_log feeds res$M back unchanged
+ * (fit_flash$flash_fit$Y = res$M, R/ebpmf_log.R:309; flash_init(fit_flash$flash_fit$Y, ...),
+ * R/ebpmf_log_flash_update.R:35), so after one ebpmf_ctx_set_m(M_init) the input of every later step is
+ * the resident M left by the previous one.  In: factors and sigma2.  Out: M [, V], v_sum, info. */
+int  ebpmf_vga_step_resident_host(ebpmf_ctx *ctx, int64_t K, const double *EL, const double *EF,
+                                  int var_type, const double *sigma2, int maxiter, double tol,
+                                  double *M_out, double *V_out, double *v_sum, ebpmf_solve_info *info);
+
 /* ---- one process, several GPUs (an R session is one process) -------------------------------
  * A group owns one context per GPU and one NCCL communicator over them; every group call runs one
  * host thread per GPU.  set_y takes the FULL dgCMatrix and deals its rows to the GPUs in 256-row

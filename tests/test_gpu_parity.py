@@ -408,3 +408,22 @@ def test_fast_math_vs_exact_math(pkg, tmp_path):
     assert a["s"][3] == b["s"][3]
     assert np.max(np.abs(a["M"] - b["M"])) < 1e-12 and rel(a["V"], b["V"]) < 1e-12
     assert rel(a["v_sum"], b["v_sum"]) < 1e-12 and rel(a["s"][:3], b["s"][:3]) < 1e-12
+
+
+def test_resident_m_loop_equals_full_roundtrip(gpu_ctx):
+    """ebpmf_log's loop with M resident (set_m once, then factors/sigma2 in, M out) gives exactly what
+    passing M in and out every iteration gives: three outer iterations with changing factors."""
+    sim, st = make_case(1100, 190, 4, 0.10)
+    rng = np.random.default_rng(11)
+    gpu_ctx.set_y(sp.csc_matrix(sim["Y"]))
+    facs = [(st["EL"] + 0.02 * t * rng.normal(size=st["EL"].shape), st["EF"] + 0.02 * t * rng.normal(size=st["EF"].shape),
+             st["sigma2"] * (1 + 0.1 * t)) for t in range(3)]
+    M = st["M0"]; full = []
+    for EL, EF, s2 in facs:
+        r = gpu_ctx.vga_step_host(M, EL, EF, s2, "by_col", 10, 1e-5)
+        M = r["M"]; full.append(r)
+    gpu_ctx.set_m(st["M0"])
+    for (EL, EF, s2), rf in zip(facs, full):
+        r = gpu_ctx.vga_step_resident_host(EL, EF, s2, "by_col", 10, 1e-5)
+        assert r["n_updates"] == rf["n_updates"] and np.array_equal(r["M"], rf["M"])
+        assert np.array_equal(r["v_sum"], rf["v_sum"]) and r["sym"] == rf["sym"]
