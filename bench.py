@@ -337,6 +337,20 @@ def main():
             "line_entries_per_s": (fp64_tf * 1e12 / 2.0) / dp_instr,
             "frac_of_fp64_line": (value / world) / ((fp64_tf * 1e12 / 2.0) / dp_instr)}
 
+    # Issue-port line (what binds pass 1): FP64 instructions hold a sub-partition's
+    # issue port for 2 cycles (3 with three distinct register sources), everything else 1 cycle.  The
+    # instruction counts per 32 entries come from the committed ncu capture of this workload
+    # (profiles/r01_ncu_summary.md); the cycles are measured live.
+    issue = None
+    if args.workload == "c4slab" and os.environ.get("EBPMF_B200_PIPELINE", "fused") == "fused":
+        clk_mhz = 1965.0
+        cycles_per_32 = p1 * 1e-3 * clk_mhz * 1e6 * 148 * 4 / (n * p / 32.0)
+        slots = 671.0 + 278.0 + 25.0
+        issue = {"bound": "issue port (FP64 = 2 slots)", "slots_per_32_entries": slots,
+                 "inst_per_32_entries": 671, "fp64_inst_per_32_entries": 278, "three_register_dfma_per_32_entries": 25,
+                 "cycles_per_32_entries_measured": cycles_per_32, "frac": slots / cycles_per_32,
+                 "sm_mhz_assumed": clk_mhz, "source": "profiles/r01_ncu_summary.md + scripts/probes"}
+
     out = {
         "metric": "VGA Newton entries/sec (fp64, N x p)", "value": value, "unit": "entries/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -350,7 +364,7 @@ def main():
         "topup_units_frac": diag["topup_units"] / max(1.0, ((n + 31) // 32) * ((p + 1) // 2)),
         "peer_kstar_sharing": {"peers_mapped": ctx.peer_count() if world > 1 else 0,
                                "how": "pass-1 kernels read the other GPUs' published update count over NVLink peer memory"},
-        "roofline": roofline, "fp64": fp64, "delta_mode": delta_mode,
+        "roofline": roofline, "fp64": fp64, "issue_roofline": issue, "delta_mode": delta_mode,
         "gpu_launches": 6 * args.steps, "clocks": clk.summary(),
     }
 
