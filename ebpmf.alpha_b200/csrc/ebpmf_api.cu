@@ -5,6 +5,8 @@
 #include "vga_kernels.cuh"
 #include "simgen.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <unistd.h>
@@ -75,7 +77,7 @@ struct ebpmf_ctx {
     long long nRB = 0, nRW = 0;
     int K = 0, KTP = 0, ldk = 0;
     int var_type = -1;
-    int pipeline = 0;          // 0: fused first pass, 1: split (const0 kernel + streaming Newton)
+    int pipeline = 0;          // 0: fused first pass, 1: split (const0 kernel + streaming Newton), 2: ordered split
     double delta = 0.0;        // 0: exact update count (default); > 0: delta mode (ebpmf_ctx_set_option)
     bool can_rewind = false;
     unsigned long long diag_topups = 0, diag_iters = 0;
@@ -92,6 +94,7 @@ struct ebpmf_ctx {
     DevBuf colsums;    // colsym[p] | v_sum scratch[p] | unitsum[nJG][2]
     DevBuf status;     // Status
     DevBuf tables;     // MathTables
+    DevBuf score, score_sorted, cta_ids, perm, cub_tmp;   // ordered pipeline (pipeline == 2)
     DevBuf misc;       // small scratch (R2, fitmax, obj terms, lfactorial partials)
     DevBuf scratch[6]; // dense-signature operands
 
@@ -220,6 +223,75 @@ int launch_prep_ktp(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
     return EBPMF_OK;
 }
 
+template <int FORMULA>
+int launch_prep(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
+    switch (ctx->KTP) {
+        case 8: return launch_prep_ktp<8, FORMULA>(ctx, a, grid);
+        case 16: return launch_prep_ktp<16, FORMULA>(ctx, a, grid);
+        case 24: return launch_prep_ktp<24, FORMULA>(ctx, a, grid);
+        case 32: return launch_prep_ktp<32, FORMULA>(ctx, a, grid);
+    }
+    return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported", ctx->K);
+}
+
+template <int KTP>
+int launch_iter0_ktp(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
+    auto kern = vga_fused_kernel<KTP, kE, FORMULA_A1, false, true>;
+    const int smem = (int)sizeof(FusedSmem<KTP>);
+    static bool configured[8] = {false, false, false, false, false, false, false, false};   // per device
+    if (ctx->device < 8 ? !configured[ctx->device] : true) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (ctx->device < 8) configured[ctx->device] = true;
+    }
+    kern<<<grid, dim3(kThreads), smem, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    return EBPMF_OK;
+}
+
+__global__ void iota_kernel(int *ids, int count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < count) ids[t] = t;
+}
+
+// Ordered pipeline (pipeline == 2, FORMULA_A1, maxiter >= 2): stage A (the fused kernel's ITER0_ONLY
+// form) performs Newton iteration 0 and scores every CTA by its largest first step; the streaming kernel
+// then walks the CTAs by decreasing score, so the slowest entries -- the ones that set the global update count --
+// are met first and almost no unit finishes below K* (the top-up pass becomes nearly empty).
+template <bool DELTA>
+int launch_first_ordered(ebpmf_ctx *ctx, FusedArgs a, dim3 grid) {
+    const int ncta = (int)(grid.x * grid.y);
+    CHECK(reserve(ctx, ctx->score, sizeof(float) * (size_t)ncta));
+    CHECK(reserve(ctx, ctx->score_sorted, sizeof(float) * (size_t)ncta));
+    CHECK(reserve(ctx, ctx->cta_ids, sizeof(int) * (size_t)ncta));
+    CHECK(reserve(ctx, ctx->perm, sizeof(int) * (size_t)ncta));
+    a.score = as<float>(ctx->score);
+    a.perm = nullptr;
+    a.nspans = (int)grid.x;
+    switch (ctx->KTP) {   // stage A: tile staging + Beta + Newton iteration 0 (the fused kernel's ITER0_ONLY form)
+        case 8: CHECK((launch_iter0_ktp<8>(ctx, a, grid))); break;
+        case 16: CHECK((launch_iter0_ktp<16>(ctx, a, grid))); break;
+        case 24: CHECK((launch_iter0_ktp<24>(ctx, a, grid))); break;
+        case 32: CHECK((launch_iter0_ktp<32>(ctx, a, grid))); break;
+        default: return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported", ctx->K);
+    }
+    if (ctx->comm)    // "some entry is not converged at k = 0" is a property of the WHOLE matrix
+        NC(g_nccl.AllReduce(&as<Status>(ctx->status)->notconv0, &as<Status>(ctx->status)->notconv0, 1, ncclInt32,
+                            ncclMax, ctx->comm, ctx->stream));
+    iota_kernel<<<(ncta + 255) / 256, 256, 0, ctx->stream>>>(as<int>(ctx->cta_ids), ncta);
+    CU(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, as<float>(ctx->score), as<float>(ctx->score_sorted),
+                                                 as<int>(ctx->cta_ids), as<int>(ctx->perm), ncta, 0, 32, ctx->stream));
+    CHECK(reserve(ctx, ctx->cub_tmp, tmp_bytes));
+    CU(cub::DeviceRadixSort::SortPairsDescending(ctx->cub_tmp.ptr, tmp_bytes, as<float>(ctx->score),
+                                                 as<float>(ctx->score_sorted), as<int>(ctx->cta_ids), as<int>(ctx->perm),
+                                                 ncta, 0, 32, ctx->stream));
+    a.perm = as<int>(ctx->perm);
+    vga_stream_kernel<kE, FORMULA_A1, MODE_FIRST, DELTA><<<dim3((unsigned)ncta), dim3(kThreads), 0, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    return EBPMF_OK;
+}
+
 // pass 1 of the fused path (K1 / K4): either ONE fused kernel (tile staging + Beta rebuild +
 // register-resident Newton), or the split pipeline: const0 kernel, then streaming Newton.
 template <int FORMULA>
@@ -227,14 +299,10 @@ int launch_first(ebpmf_ctx *ctx, const FusedArgs &a) {
     const long long ncols = a.col1 - a.col0;
     if (ncols <= 0) return EBPMF_OK;
     dim3 grid((unsigned)((ncols + a.cols_per_cta - 1) / a.cols_per_cta), (unsigned)ctx->nRB);
-    if (ctx->pipeline == 1) {
-        switch (ctx->KTP) {
-            case 8: CHECK((launch_prep_ktp<8, FORMULA>(ctx, a, grid))); break;
-            case 16: CHECK((launch_prep_ktp<16, FORMULA>(ctx, a, grid))); break;
-            case 24: CHECK((launch_prep_ktp<24, FORMULA>(ctx, a, grid))); break;
-            case 32: CHECK((launch_prep_ktp<32, FORMULA>(ctx, a, grid))); break;
-            default: return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported", ctx->K);
-        }
+    if (ctx->pipeline == 2 && FORMULA == FORMULA_A1 && a.maxiter >= 2 && a.col0 == 0 && a.col1 == ctx->p)
+        return a.delta > 0 ? launch_first_ordered<true>(ctx, a, grid) : launch_first_ordered<false>(ctx, a, grid);
+    if (ctx->pipeline >= 1) {
+        CHECK((launch_prep<FORMULA>(ctx, a, grid)));
         if (a.delta > 0) vga_stream_kernel<kE, FORMULA, MODE_FIRST, true><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
         else vga_stream_kernel<kE, FORMULA, MODE_FIRST, false><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
         CU(cudaGetLastError());
@@ -660,7 +728,8 @@ int ebpmf_ctx_create(int device, ebpmf_ctx **out) {
     ctx = new (std::nothrow) ebpmf_ctx();
     if (!ctx) return fail(nullptr, EBPMF_ERR_NOMEM, "out of host memory");
     ctx->device = device;
-    if (const char *pl = getenv("EBPMF_B200_PIPELINE")) ctx->pipeline = (strcmp(pl, "split") == 0) ? 1 : 0;
+    if (const char *pl = getenv("EBPMF_B200_PIPELINE"))
+        ctx->pipeline = !strcmp(pl, "ordered") ? 2 : !strcmp(pl, "split") ? 1 : 0;
     if (const char *dl = getenv("EBPMF_B200_DELTA")) ctx->delta = atof(dl);
     cudaError_t ce;
 #define CREATE_STEP(call)                                                                                        \
@@ -713,7 +782,8 @@ int ebpmf_ctx_destroy(ebpmf_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->colptr, &ctx->rowidx, &ctx->yx, &ctx->rbptr, &ctx->Mcur, &ctx->Malt, &ctx->V,
                       &ctx->EL, &ctx->EF, &ctx->EFt, &ctx->sigma2, &ctx->l0, &ctx->f0, &ctx->kunit,
                       &ctx->colV, &ctx->unitS, &ctx->rowpart, &ctx->red, &ctx->colsums, &ctx->status, &ctx->misc,
-                      &ctx->C0, &ctx->sc1, &ctx->sc2, &ctx->tables, &ctx->peer_ptrs};
+                      &ctx->C0, &ctx->sc1, &ctx->sc2, &ctx->tables, &ctx->peer_ptrs,
+                      &ctx->score, &ctx->score_sorted, &ctx->cta_ids, &ctx->perm, &ctx->cub_tmp};
     for (DevBuf *b : bufs) release(*b);
     for (DevBuf &b : ctx->scratch) release(b);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
@@ -1267,7 +1337,11 @@ int ebpmf_ctx_set_option(ebpmf_ctx *ctx, const char *name, double value) {
         ctx->delta = value;
         return EBPMF_OK;
     }
-    if (!strcmp(name, "pipeline")) { ctx->pipeline = value != 0.0 ? 1 : 0; return EBPMF_OK; }
+    if (!strcmp(name, "pipeline")) {
+        if (value != 0.0 && value != 1.0 && value != 2.0) return fail(ctx, EBPMF_ERR_ARG, "set_option: pipeline is 0, 1 or 2");
+        ctx->pipeline = (int)value;
+        return EBPMF_OK;
+    }
     return fail(ctx, EBPMF_ERR_ARG, "set_option: unknown option '%s'", name);
 }
 

@@ -55,11 +55,13 @@ struct Status {           // device words shared by the passes of one solve
     int exhausted;        // some unit hit maxiter
     unsigned long long topup_units;   // diagnostics: units that needed pass 2 work
     unsigned long long unit_iters;    // diagnostics: sum over units of evaluations performed
+    int notconv0;         // ordered pipeline: some entry fails |f_0| < tol (so iteration 0's update counts)
+    int pad0;
     // --- not reset per solve: (epoch << 32 | kstar), raised with atomicMax; what the OTHER GPUs read
     // over NVLink during pass 1 so that every rank learns the global count while it is still working.
     unsigned long long pub;
 };
-constexpr size_t kStatusResetBytes = 32;    // the words before `pub`
+constexpr size_t kStatusResetBytes = 40;    // the words before `pub`
 
 struct FusedArgs {
     long long n, p;                 // rows of this shard, columns
@@ -83,6 +85,9 @@ struct FusedArgs {
     double *colV;                   // [nRW][p]      sum over the warp's 32 rows of V
     double *unitS;                  // [nRW][nJG][2] sum exp(M+V/2), sum(log(V)/2+c) of the unit
     double *rowpart;                // [nJG][n] sum over the unit's columns of V (by_row only), else null
+    float *score;                   // ordered pipeline: per-CTA max |f_0/f_0'| written by the const0 kernel
+    const int *perm;                // ordered pipeline: CTA ids by decreasing score (null: natural order)
+    int nspans;                     // column spans per row block (grid.x of the natural decomposition)
     Status *status;
     const Status *const *peers;     // the other ranks' Status words, mapped peer memory (NVLink); may be null
     int npeers;
@@ -323,6 +328,8 @@ struct FusedSmem {
     double c1s[kTileCols], c2s[kTileCols], f0s[kTileCols];
     double exptab[EBPMF_EXP_TABLE_SIZE];
     double2 logtab[EBPMF_LOG_TABLE_SIZE];
+    float wmax[kWarps];
+    int wnot[kWarps];
 };
 
 #ifndef EBPMF_MINB
@@ -333,7 +340,12 @@ struct FusedSmem {
 // K1 / K4, pass 1: fused VGA step on CSC Y with Beta rebuilt from the flash factors.
 // grid = (column spans, row blocks), block = 256 threads, dynamic smem = sizeof(FusedSmem<KTP>).
 // ---------------------------------------------------------------------------------------
-template <int KTP, int E, int FORMULA, bool DELTA>
+// ITER0_ONLY (ordered pipeline, stage A): the same tile staging and prologue, but each unit performs
+// exactly Newton iteration 0 -- evaluate f_0, record |f_0| < tol, form and apply the update -- and
+// writes M_1 and const0; no finalisation.  The CTA's largest first step max|f_0/f_0'| goes to
+// a.score: it predicts where the slowest entries are (the CTA holding the entry that sets the global
+// count ranks in the first few % by this score on every case tried, cold or warm start).
+template <int KTP, int E, int FORMULA, bool DELTA, bool ITER0_ONLY = false>
 __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const FusedArgs a)
 {
     static_assert(kTileCols % E == 0, "E must divide the tile width");
@@ -370,14 +382,16 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
     unsigned my_iters = 0;
     const size_t ns = (size_t)n;
     const bool by_col = a.var_type == 2;
-    int t0_next = *kstar_live;
+    int t0_next = ITER0_ONLY ? 0 : *kstar_live;
+    double it0_step = 0.0;                           // ITER0_ONLY: max |f_0/f_0'| of this thread's entries
+    int it0_notconv = 0;
 
     for (int j0 = jc0; j0 < jc1; j0 += kTileCols) {
         __syncthreads();                             // previous tile fully consumed
         // one thread per CTA peeks at one peer GPU's published count (round robin); the word is
         // consumed after the tile's units, so the NVLink latency is never waited for
         unsigned long long peer_word = 0ull;
-        if (tid == 0) peer_word = peek_peer(a, (unsigned)(j0 / kTileCols) + blockIdx.x + blockIdx.y);
+        if (tid == 0 && !ITER0_ONLY) peer_word = peek_peer(a, (unsigned)(j0 / kTileCols) + blockIdx.x + blockIdx.y);
         // ---- stage the tile: zero Y image, EF rows, per-column constants --------------------
 #pragma unroll
         for (int c = 0; c < kTileCols; ++c) sm.ys[c][tid] = 0.0;
@@ -445,7 +459,7 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
             // path).  It never exceeds the global count u, so running this unit at least that far
             // cannot overshoot.
             const int t0 = t0_next;
-            t0_next = *kstar_live;
+            if (!ITER0_ONLY) t0_next = *kstar_live;
             double m[E], c0[E], w[E], c1[E], c2[E], sc[E], r[E], sexp[E], f[E];
             bool ok[E];
             const bool more = (g + 1 < kTileCols / E);
@@ -471,6 +485,30 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
                     sc[e] = sc[e - 1];
                 }
             }
+            if (ITER0_ONLY) {
+                // iteration 0 with newton_unit's instruction sequence (bit-identical iterates)
+                double aa[E], xx[E], ex[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    r[e] = rcp_fast(__dadd_rn(c0[e], -m[e]));                      // :22
+                    aa[e] = __dmul_rn(c2[e], r[e]);
+                    xx[e] = __dadd_rn(m[e], aa[e]);
+                }
+                exp_fast_n<E>(xx, ex, exptab_s);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    f[e] = __fma_rn(-m[e], c1[e], __dadd_rn(w[e], -ex[e]));        // :25 (S = 1)
+                    const double g = __fma_rn(-ex[e], __fma_rn(aa[e], r[e], 1.0), -c1[e]);   // :31
+                    const double rg = rcp_fast(g);
+                    if (ok[e]) {
+                        if (!(fabs(f[e]) < a.tol)) it0_notconv = 1;                // :26
+                        it0_step = fmax(it0_step, fabs(__dmul_rn(f[e], rg)));
+                        st_stream(a.M_out + off + e * ns, __fma_rn(-f[e], rg, m[e]));       // M_1
+                    }
+                }
+                off += E * ns; ku_idx += (size_t)a.nRW; cv_idx += E; us_idx += 2; rp_idx += ns;
+                continue;
+            }
             int k = 0, kb;
             const int flags = newton_unit<E, FORMULA, MODE_FIRST, FORMULA == FORMULA_A10, DELTA>(
                 m, c0, w, c1, c2, sc, row_ok ? a.tol : INFINITY, k, kb, t0, a.maxiter, a.delta, exptab_s, r, sexp, f);
@@ -485,7 +523,26 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
             }
             off += E * ns; ku_idx += (size_t)a.nRW; cv_idx += E; us_idx += 2; rp_idx += ns;
         }
-        if (tid == 0) absorb_peer(a.status, a.epoch, peer_word);
+        if (tid == 0 && !ITER0_ONLY) absorb_peer(a.status, a.epoch, peer_word);
+    }
+    if (ITER0_ONLY) {
+        float smx = (float)fmin(it0_step, 3.0e38);
+        int nc = it0_notconv;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            smx = fmaxf(smx, __shfl_xor_sync(0xffffffffu, smx, o));
+            nc |= __shfl_xor_sync(0xffffffffu, nc, o);
+        }
+        __syncthreads();
+        if (lane == 0) { sm.wmax[warp] = smx; sm.wnot[warp] = nc; }
+        __syncthreads();
+        if (tid == 0) {
+            float mx = 0.f; int any = 0;
+            for (int q = 0; q < kWarps; ++q) { mx = fmaxf(mx, sm.wmax[q]); any |= sm.wnot[q]; }
+            a.score[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = mx;
+            if (any) a.status->notconv0 = 1;
+        }
+        return;
     }
     if (lane == 0) {
         if (any_exhausted) a.status->exhausted = 1;
@@ -523,7 +580,10 @@ __global__ void __launch_bounds__(kThreads, 3) vga_prep_kernel(const FusedArgs a
     const size_t ns = (size_t)n;
     const bool by_col = a.var_type == 2;
     double s2_row = 1.0;
-    if (!by_col) s2_row = __dadd_rn(a.sc2[(a.var_type == 1) ? (row_ok ? i : 0) : 0], a.sc2[(a.var_type == 1) ? (row_ok ? i : 0) : 0]);
+    if (!by_col) {
+        const int si = (a.var_type == 1) ? (row_ok ? i : 0) : 0;
+        s2_row = __dadd_rn(a.sc2[si], a.sc2[si]);
+    }
     for (int j0 = jc0; j0 < jc1; j0 += kTileCols) {
         __syncthreads();
 #pragma unroll
@@ -571,7 +631,8 @@ __global__ void __launch_bounds__(kThreads, 3) vga_prep_kernel(const FusedArgs a
             const double b = beta[c];
             if (row_ok && j0 + c < jc1) {
                 const double s2 = by_col ? sm.s2s[c] : s2_row;
-                st_stream(a.C0 + off, __dadd_rn(__fma_rn(s2, sm.ys[c][tid], b), 1.0));   // :9 | :81,:95
+                const double c0 = __dadd_rn(__fma_rn(s2, sm.ys[c][tid], b), 1.0);         // :9 | :81,:95
+                st_stream(a.C0 + off, c0);
                 if (FORMULA == FORMULA_A10) {
                     const double m0 = ld_stream(a.M_in + off);
                     st_stream(a.M_out + off, (m0 < b) ? m0 : b);                     // :78
@@ -596,7 +657,13 @@ __global__ void __launch_bounds__(kThreads, EBPMF_STREAM_MINB) vga_stream_kernel
     __shared__ double2 logtab[EBPMF_LOG_TABLE_SIZE];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = (int)a.n, p = (int)a.p;
-    const int rb = blockIdx.y;
+    // ordered pipeline: a 1-D grid walks the CTAs by decreasing predicted hardness (a.perm)
+    int bx = blockIdx.x, rb = blockIdx.y;
+    if (MODE == MODE_FIRST && a.perm) {
+        const int id = a.perm[blockIdx.x];
+        rb = id / a.nspans;
+        bx = id - rb * a.nspans;
+    }
     const int i = rb * kRowsPerCta + tid;
     const bool row_ok = i < n;
     const int rw = rb * kWarps + warp;
@@ -605,10 +672,13 @@ __global__ void __launch_bounds__(kThreads, EBPMF_STREAM_MINB) vga_stream_kernel
     const unsigned exptab_s = smem_addr(exptab), logtab_s = smem_addr(logtab);
     __syncthreads();
     if (rw >= (int)a.nRW) return;                    // no block-wide barrier below this point
-    const int jc0 = (int)a.col0 + blockIdx.x * a.cols_per_cta;
+    const int jc0 = (int)a.col0 + bx * a.cols_per_cta;
     const int jc1 = min((int)a.col1, jc0 + a.cols_per_cta);
     const volatile int *kstar_live = &a.status->kstar;
     const int target = (MODE == MODE_TOPUP) ? a.status->kstar : 0;
+    // ordered pipeline: the const0 kernel has already applied iteration 0 (M_1 is in M_out) unless every
+    // entry of every rank passed |f_0| < tol, in which case R breaks at i = 1 and M_0 (clamped) is final
+    const bool from_prep = (MODE == MODE_FIRST) && a.perm && (a.status->notconv0 != 0);
     const bool by_col = a.var_type == 2;
     double c1_row = 1.0, c2_row = 0.5, l0_i = 1.0;
     if (!by_col) {
@@ -619,7 +689,8 @@ __global__ void __launch_bounds__(kThreads, EBPMF_STREAM_MINB) vga_stream_kernel
     if (FORMULA == FORMULA_A10) l0_i = row_ok ? a.l0[i] : 1.0;
     // first pass of A1 reads the caller's M and clamps it; A10's prep kernel already wrote the
     // clamped M to M_out; the top-up pass continues in place on M_out
-    const double *Msrc = (MODE == MODE_FIRST && FORMULA == FORMULA_A1) ? a.M_in : a.M_out;
+    const double *Msrc = (MODE == MODE_FIRST && FORMULA == FORMULA_A1 && !from_prep) ? a.M_in : a.M_out;
+    const int k_first = from_prep ? 1 : 0;
     int any_exhausted = 0, any_nan = 0, any_fail = 0;
     unsigned my_topups = 0, my_iters = 0;
     const size_t ns = (size_t)n;
@@ -646,11 +717,11 @@ __global__ void __launch_bounds__(kThreads, EBPMF_STREAM_MINB) vga_stream_kernel
     unsigned long long peer_word = 0ull;
 #pragma unroll 1
     for (int jb = jc0; jb < jc1; jb += E, off += E * ns, ku_idx += (size_t)a.nRW, cv_idx += E, us_idx += 2, rp_idx += ns) {
-        int k = 0;
+        int k = k_first;
         int t0 = 0;
         if (MODE == MODE_FIRST && tid == 0 && ((jb - jc0) & (8 * E - 1)) == 0) {
             absorb_peer(a.status, a.epoch, peer_word);           // the word peeked 8 units ago
-            peer_word = peek_peer(a, (unsigned)(jb / E) + blockIdx.x + blockIdx.y);
+            peer_word = peek_peer(a, (unsigned)(jb / E) + bx + rb);
         }
         if (MODE == MODE_TOPUP) {
             k = a.kunit[ku_idx];
@@ -681,7 +752,7 @@ __global__ void __launch_bounds__(kThreads, EBPMF_STREAM_MINB) vga_stream_kernel
             const double c0m1 = __dadd_rn(c0[e], -1.0);
             w[e] = __dmul_rn(c0m1, c1[e]);
             sc[e] = (FORMULA == FORMULA_A10) ? __dmul_rn(l0_i, __ldg(a.f0 + jj)) : 1.0;
-            if (MODE == MODE_FIRST && FORMULA == FORMULA_A1) m[e] = (m[e] < c0m1) ? m[e] : c0m1;   // :16
+            if (MODE == MODE_FIRST && FORMULA == FORMULA_A1 && !from_prep) m[e] = (m[e] < c0m1) ? m[e] : c0m1;   // :16
             if (e > 0 && !colok) {                   // padding column (p % E != 0): shadow the previous one
                 m[e] = m[e - 1]; c0[e] = c0[e - 1]; w[e] = w[e - 1]; c1[e] = c1[e - 1]; c2[e] = c2[e - 1];
                 sc[e] = sc[e - 1];

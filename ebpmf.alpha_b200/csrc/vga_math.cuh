@@ -116,9 +116,9 @@ __device__ __forceinline__ void exp_fast_n(const double (&x)[E], double (&out)[E
     bool oor = false;
 #pragma unroll
     for (int e = 0; e < E; ++e) oor = oor || exp_out_of_range(x[e]);
-    if (oor) {
+    if (oor) {          // rare; each entry still gets the value it would get on its own
 #pragma unroll
-        for (int e = 0; e < E; ++e) out[e] = exp_slow(x[e]);
+        for (int e = 0; e < E; ++e) out[e] = exp_out_of_range(x[e]) ? exp_slow(x[e]) : exp_core(x[e], tab_s);
     } else {
 #pragma unroll
         for (int e = 0; e < E; ++e) out[e] = exp_core(x[e], tab_s);

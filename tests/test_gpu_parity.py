@@ -267,7 +267,7 @@ def test_device_sim_data_matches_oracle(gpu_ctx):
 # ---------------------------------------------------------------------------------------
 # options: delta mode (frozen units) and the split pipeline
 # ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize("pipeline", [0, 1])
+@pytest.mark.parametrize("pipeline", [0, 1, 2])
 @pytest.mark.parametrize("delta", [0.0, 1e-14])
 @pytest.mark.parametrize("var_type,maxiter,tol", [("by_col", 10, 1e-5), ("by_row", 1000, 1e-8), ("constant", 3, 1e-5)])
 def test_options_delta_and_pipeline(pkg, pipeline, delta, var_type, maxiter, tol):
@@ -370,7 +370,7 @@ def test_maxiter_one(gpu_ctx):
     assert res["n_updates"] == 1 and not res["converged"]
 
 
-@pytest.mark.parametrize("K,pipeline", [(31, 0), (45, 0), (45, 1), (70, 0)])
+@pytest.mark.parametrize("K,pipeline", [(31, 0), (45, 0), (45, 1), (70, 0), (45, 2)])
 def test_many_factors(pkg, K, pipeline):
     """K_tot = K + 2 above the 32-column register tile: Beta is accumulated over chunks of 32 factor columns
     (flash_control$Kmax defaults to 30, R/ebpmf_log_controls.R:74, but greedy additions can exceed it)."""
@@ -427,3 +427,33 @@ def test_resident_m_loop_equals_full_roundtrip(gpu_ctx):
         r = gpu_ctx.vga_step_resident_host(EL, EF, s2, "by_col", 10, 1e-5)
         assert r["n_updates"] == rf["n_updates"] and np.array_equal(r["M"], rf["M"])
         assert np.array_equal(r["v_sum"], rf["v_sum"]) and r["sym"] == rf["sym"]
+
+
+@pytest.mark.parametrize("var_type", ["by_col", "by_row"])
+def test_ordered_pipeline_edge_cases(pkg, var_type):
+    """pipeline 2 (iteration 0 inside the const0 kernel, CTAs by decreasing first step): u = 0 (R breaks at
+    i = 1, M_0 final), maxiter = 1 (falls back), maxiter = 2 (exhaustion right after the moved iteration),
+    NaN; always bit-identical to the fused pipeline."""
+    sim, st = make_case(1500, 200, 4, 0.10, var_type=var_type)
+    a, b = pkg.VgaContext(0), pkg.VgaContext(0)
+    try:
+        b.set_option("pipeline", 2)
+        for c in (a, b):
+            c.set_y(sp.csc_matrix(sim["Y"]))
+        ra = a.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], var_type, 100, 1e-7, return_V=True)
+        rb = b.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], var_type, 100, 1e-7, return_V=True)
+        assert ra["n_updates"] == rb["n_updates"] and np.array_equal(ra["M"], rb["M"]) and np.array_equal(ra["V"], rb["V"])
+        for mi, tol, M0 in ((100, 1e-7, ra["M"]), (1, 1e-5, st["M0"]), (2, 1e-5, st["M0"]), (3, 1e-12, st["M0"])):
+            xa = a.vga_step_host(M0, st["EL"], st["EF"], st["sigma2"], var_type, mi, tol, return_V=True)
+            xb = b.vga_step_host(M0, st["EL"], st["EF"], st["sigma2"], var_type, mi, tol, return_V=True)
+            ref = vga_numpy.ebpmf_log_vga_step(M0, sim["Y"], st["EL"], st["EF"], st["sigma2"], var_type, mi, tol)
+            check_step(xb, ref, var_type)
+            assert xa["n_updates"] == xb["n_updates"] and xa["converged"] == xb["converged"]
+            assert np.array_equal(xa["M"], xb["M"]) and np.array_equal(xa["V"], xb["V"])
+            assert np.array_equal(np.atleast_1d(xa["v_sum"]), np.atleast_1d(xb["v_sum"]))
+        EL = st["EL"].copy(); EL[5, 1] = np.nan
+        with pytest.raises(pkg.EbpmfError) as ei:
+            b.vga_step_host(st["M0"], EL, st["EF"], st["sigma2"], var_type, 10, 1e-5)
+        assert ei.value.code == 3
+    finally:
+        a.close(); b.close()
