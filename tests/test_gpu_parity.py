@@ -457,3 +457,34 @@ def test_ordered_pipeline_edge_cases(pkg, var_type):
         assert ei.value.code == 3
     finally:
         a.close(); b.close()
+
+
+def test_config5_variants_medium_size(gpu_ctx, pkg):
+    """BASELINE config 5 (fixed_iter vs low_memory variants, K = 10) at 20 000 x 2 000: tolerance and
+    iteration-count parity against the C transcription of the oracle."""
+    c = simdata.offset_for_density(0.05, K=10)
+    sim = simdata.sim_data_log(20000, 2000, K=10, seed=12345, log_offset=c)
+    st = simdata.solver_state(sim, start="cold")
+    n, p = sim["Y"].shape
+    Ys = sp.csc_matrix(sim["Y"])
+    Beta = st["EL"] @ st["EF"].T
+    S2 = vga_numpy.adjust_var_shape(st["sigma2"], "by_col", n, p)
+    for mi in (1, 10):        # maxiter = 1 is _fixed_iter's only call site (inst/code/Poisson_MF_splitting.R:212-214)
+        g = pkg.vga_pois_solver_mat_newton_fixed_iter(st["M0"], None, sim["Y"], 1, Beta, S2, mi, ctx=gpu_ctx)
+        r = c_oracle.vga_fixed_iter(st["M0"], None, sim["Y"], 1, Beta, S2, mi)
+        assert relM(g["M"], r["M"]) < RTOL and rel(g["V"], r["V"]) < RTOL
+    l0 = sim["L0"] * np.exp(sim["log_offset"]); f0 = sim["F0"]
+    EL, EF = st["EL"][:, 2:], st["EF"][:, 2:]
+    M0 = np.log(sim["Y"] + 0.5) - np.log(l0)[:, None] - np.log(f0)[None, :]
+    for vt, s2 in (("by_col", st["sigma2"]), ("by_row", np.random.default_rng(3).uniform(0.05, 1, n)), ("constant", np.array([0.4]))):
+        gi = {}
+        g = pkg.vga_pois_solver_mat_newton_low_memory(M0, Ys, l0, f0, EL, EF, s2, vt, 1000, 1e-5, info=gi, ctx=gpu_ctx)
+        r = c_oracle.vga_low_memory(M0, sim["Y"], l0, f0, EL, EF, s2, vt, 1000, 1e-5)
+        assert gi["n_updates"] == r["n_updates"] and gi["converged"] == r["converged"]
+        assert relM(g, r["M"]) < RTOL
+    # a1 on the same data: same root as a10 (l0, f0 as S), different update count (F8)
+    i1 = {}
+    pkg.vga_pois_solver_mat_newton(np.minimum(M0, EL @ EF.T), Ys, np.outer(l0, f0), EL @ EF.T, S2, 1000, 1e-5,
+                                   return_V=False, info=i1, ctx=gpu_ctx)
+    r1 = c_oracle.vga_newton(np.minimum(M0, EL @ EF.T), sim["Y"], np.outer(l0, f0), EL @ EF.T, S2, 1000, 1e-5)
+    assert i1["n_updates"] == r1["n_updates"]
