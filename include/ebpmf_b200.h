@@ -30,6 +30,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden: only this ABI is exported */
+#endif
 
 #define EBPMF_OK            0
 #define EBPMF_ERR_ARG       1   /* bad argument (NULL, maxiter outside [1,65535], shapes that do not conform) */
@@ -249,6 +252,9 @@ int  ebpmf_ctx_last_diag(ebpmf_ctx *ctx, uint64_t *topup_units, uint64_t *unit_e
 /* device-time micro-probe of the FP64 pipe (DFMA chains), used by bench.py for the FP64 line */
 int  ebpmf_probe_fp64_tflops(ebpmf_ctx *ctx, double *tflops);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

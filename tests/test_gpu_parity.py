@@ -488,3 +488,31 @@ def test_config5_variants_medium_size(gpu_ctx, pkg):
                                    return_V=False, info=i1, ctx=gpu_ctx)
     r1 = c_oracle.vga_newton(np.minimum(M0, EL @ EF.T), sim["Y"], np.outer(l0, f0), EL @ EF.T, S2, 1000, 1e-5)
     assert i1["n_updates"] == r1["n_updates"]
+
+
+def test_randomised_configurations(pkg):
+    """40 random small configurations (shape, K, density, var_type, maxiter, tol, start, pipeline, delta):
+    every one must match the oracle to 1e-8 with the same update count."""
+    rng = np.random.default_rng(20261019)
+    ctx = pkg.VgaContext(0)
+    try:
+        for trial in range(40):
+            n = int(rng.integers(1, 700)); p = int(rng.integers(1, 90)); K = int(rng.integers(1, 41))
+            vt = ["by_col", "by_row", "constant"][int(rng.integers(3))]
+            maxiter = int(rng.choice([1, 2, 3, 5, 10, 50, 1000])); tol = float(rng.choice([1e-3, 1e-5, 1e-8, 1e-10]))
+            dens = float(rng.choice([0.0, 0.02, 0.1, 0.5, 0.9]))
+            sim = simdata.sim_data_log(n, p, K=K, seed=1000 + trial, pi0=0.9,
+                                       log_offset=(simdata.offset_for_density(dens, K=K, pi0=0.9) if dens > 0 else -40.0))
+            st = simdata.solver_state(sim, start=["cold", "warm"][int(rng.integers(2))], var_type=vt, seed=trial, noise=0.1)
+            ctx.set_option("pipeline", int(rng.integers(3)))
+            ctx.set_option("delta", float(rng.choice([0.0, 0.0, 1e-14])))
+            ctx.set_y(sp.csc_matrix(sim["Y"]) if rng.integers(2) else sim["Y"])
+            res = ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], vt, maxiter, tol, return_V=True)
+            ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], vt, maxiter, tol)
+            try:
+                check_step(res, ref, vt)
+            except AssertionError as e:
+                raise AssertionError("trial %d: n=%d p=%d K=%d %s maxiter=%d tol=%g dens=%g: %s"
+                                     % (trial, n, p, K, vt, maxiter, tol, dens, e))
+    finally:
+        ctx.close()
