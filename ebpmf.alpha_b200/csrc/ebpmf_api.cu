@@ -79,6 +79,7 @@ struct ebpmf_ctx {
     int var_type = -1;
     int pipeline = 0;          // 0: fused first pass, 1: split (const0 kernel + streaming Newton), 2: ordered split
     double delta = 0.0;        // 0: exact update count (default); > 0: delta mode (ebpmf_ctx_set_option)
+    double debug_verify_scale = 1.0;   // test hook: pass 2 verifies against tol*scale (exercises the retry loop)
     bool can_rewind = false;
     unsigned long long diag_topups = 0, diag_iters = 0;
     bool have_y = false, have_m = false, have_f = false, have_s2 = false, have_v = false, have_vsum = false;
@@ -484,7 +485,7 @@ FusedArgs fused_args(ebpmf_ctx *ctx, int maxiter, double tol, bool want_v) {
     a.npeers = ctx->npeers;
     a.epoch = ctx->epoch + 1;      // run_global_stop increments the counter before the first launch
     a.tables = as<MathTables>(ctx->tables);
-    a.maxiter = maxiter; a.tol = tol; a.delta = ctx->delta;
+    a.maxiter = maxiter; a.tol = tol; a.delta = ctx->delta; a.tol_verify = tol * ctx->debug_verify_scale;
     a.col0 = 0; a.col1 = ctx->p;
     a.cols_per_cta = cols_per_cta_for(ctx->p, ctx->nRB);
     return a;
@@ -1335,6 +1336,11 @@ int ebpmf_ctx_set_option(ebpmf_ctx *ctx, const char *name, double value) {
     if (!strcmp(name, "delta")) {
         if (!(value >= 0.0) || value > 1e-10) return fail(ctx, EBPMF_ERR_ARG, "set_option: delta must be in [0, 1e-10]");
         ctx->delta = value;
+        return EBPMF_OK;
+    }
+    if (!strcmp(name, "debug_verify_scale")) {
+        if (!(value > 0.0) || value > 1.0) return fail(ctx, EBPMF_ERR_ARG, "set_option: debug_verify_scale must be in (0, 1]");
+        ctx->debug_verify_scale = value;
         return EBPMF_OK;
     }
     if (!strcmp(name, "pipeline")) {

@@ -96,6 +96,7 @@ struct FusedArgs {
     int maxiter;
     double tol;
     double delta;                   // 0: exact update count for every entry; > 0: delta mode
+    double tol_verify;              // == tol; a test hook scales it to exercise the K*+1 retry path
     long long col0, col1;           // columns of this launch
     int cols_per_cta;               // multiple of kTileCols
 };
@@ -518,8 +519,11 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
                                           row_ok, exptab_s, logtab_s))
                 any_nan = 1;
             if (lane == 0) {
+                // K* = max over units of the count at which the unit stopped (its first converged k >= t0, which
+                // is <= u), or of the first converged k for a frozen unit: every live unit then has k_unit <= K*
+                const int kpub = (flags & 8) ? kb : k;
                 a.kunit[ku_idx] = (unsigned short)((flags & 8) ? kFrozen : k);
-                if (kb > t0) publish_kstar(a.status, a.epoch, kb);   // K* = max over units of the first converged k
+                if (kpub > t0) publish_kstar(a.status, a.epoch, kpub);
             }
             off += E * ns; ku_idx += (size_t)a.nRW; cv_idx += E; us_idx += 2; rp_idx += ns;
         }
@@ -701,7 +705,7 @@ __global__ void __launch_bounds__(kThreads, EBPMF_STREAM_MINB) vga_stream_kernel
     size_t us_idx = ((size_t)rw * (size_t)a.nJG + jg0) * 2;
     size_t rp_idx = (size_t)jg0 * ns + i;
     int t0_next = (MODE == MODE_FIRST) ? *kstar_live : 0;
-    const double tol_lane = row_ok ? a.tol : INFINITY;
+    const double tol_lane = row_ok ? ((MODE == MODE_TOPUP) ? a.tol_verify : a.tol) : INFINITY;
 
     // first pass: register prefetch of the next unit's (M, const0)
     double mnext[E], cnext[E];
@@ -725,7 +729,7 @@ __global__ void __launch_bounds__(kThreads, EBPMF_STREAM_MINB) vga_stream_kernel
         }
         if (MODE == MODE_TOPUP) {
             k = a.kunit[ku_idx];
-            if (k == target || k == kFrozen) continue;
+            if (k >= target) continue;               // at K* already (k > K* cannot happen), or frozen (0xFFFF)
             ++my_topups;
         } else {
             t0 = t0_next;                            // read one unit ahead: off the critical path, still <= u
@@ -770,8 +774,9 @@ __global__ void __launch_bounds__(kThreads, EBPMF_STREAM_MINB) vga_stream_kernel
                                       exptab_s, logtab_s))
             any_nan = 1;
         if (lane == 0) {
+            const int kpub = (flags & 8) ? kb : k;
             a.kunit[ku_idx] = (unsigned short)((flags & 8) ? kFrozen : k);
-            if (MODE == MODE_FIRST && kb > t0) publish_kstar(a.status, a.epoch, kb);
+            if (MODE == MODE_FIRST && kpub > t0) publish_kstar(a.status, a.epoch, kpub);
         }
     }
     if (lane == 0) {
@@ -855,7 +860,7 @@ __global__ void __launch_bounds__(kThreads, 2) vga_dense_kernel(const DenseArgs 
         const int t0 = (MODE == MODE_FIRST) ? *kstar_live : 0;
         if (MODE == MODE_TOPUP) {
             k = a.kunit[jg * a.nRW + rw];
-            if (k == target) continue;
+            if (k >= target) continue;
         }
         double m[E], c0[E], w[E], c1[E], c2[E], sc[E], s2[E], r[E], sexp[E], f[E];
         bool ok[E];
@@ -896,7 +901,7 @@ __global__ void __launch_bounds__(kThreads, 2) vga_dense_kernel(const DenseArgs 
         if (__any_sync(0xffffffffu, lane_nan)) any_nan = 1;
         if (lane == 0) {
             a.kunit[jg * a.nRW + rw] = (unsigned short)k;
-            if (MODE == MODE_FIRST && kb > t0) atomicMax(&a.status->kstar, kb);
+            if (MODE == MODE_FIRST && k > t0) atomicMax(&a.status->kstar, k);
         }
     }
     if (lane == 0) {

@@ -242,7 +242,9 @@ int  ebpmf_ctx_sim_data_log(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, int
  *              most ~d (absolute); the global update count n_updates is still R's.  DESIGN.md §3b.
  *   "pipeline" 0 (default): fused first pass; 1: const0 kernel + streaming Newton kernel; 2: as 1, and the
  *              const0 kernel also performs Newton iteration 0 and scores each CTA by its largest first step,
- *              so that the streaming kernel meets the slowest entries first (same results, bit for bit). */
+ *              so that the streaming kernel meets the slowest entries first (same results, bit for bit).
+ *   "debug_verify_scale" (0,1], default 1: TEST HOOK -- the top-up pass verifies against tol*scale, which
+ *              forces the host's K*+1 retry loop to run (tests/test_gpu_parity.py::test_retry_loop_...). */
 int  ebpmf_ctx_set_option(ebpmf_ctx *ctx, const char *name, double value);
 
 /* diagnostics of the last fused solve: units (warp x 2 columns) that needed second-pass work and

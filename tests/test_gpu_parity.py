@@ -516,3 +516,30 @@ def test_randomised_configurations(pkg):
                                      % (trial, n, p, K, vt, maxiter, tol, dens, e))
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("pipeline", [0, 2])
+def test_retry_loop_when_verification_fails(pkg, pipeline):
+    """The host's K*+1 retry loop (pass 2 repeated until every unit is below tol) is exercised with a test
+    hook: pass 1 finds K* for tol, pass 2 verifies against tol*1e-8, fails, and the loop must walk up to the
+    count R would reach with tol*1e-8 -- results equal the oracle's for that tolerance."""
+    sim, st = make_case(1800, 220, 4, 0.10)
+    ctx = pkg.VgaContext(0)
+    try:
+        ctx.set_option("pipeline", pipeline)
+        ctx.set_option("debug_verify_scale", 1e-8)
+        ctx.set_y(sp.csc_matrix(sim["Y"]))
+        res = ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], "by_col", 50, 1e-2, return_V=True)
+        loose = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], "by_col", 50, 1e-2)
+        ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], "by_col", 50, 1e-10)
+        assert ref["n_updates"][0] > loose["n_updates"][0]          # the hook really forces extra passes
+        assert res["passes"] == 2 + ref["n_updates"][0] - loose["n_updates"][0]
+        check_step(res, ref, "by_col")
+        # exhaustion reached through the retry loop: maxiter just above K*
+        mi = loose["n_updates"][0] + 1
+        res = ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], "by_col", mi, 1e-2, return_V=True)
+        ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], "by_col", mi, 1e-10)
+        check_step(res, ref, "by_col")
+        assert not res["converged"] and res["n_updates"] == mi
+    finally:
+        ctx.close()
