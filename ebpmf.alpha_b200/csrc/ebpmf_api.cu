@@ -759,7 +759,7 @@ int ebpmf_ctx_create(int device, ebpmf_ctx **out) {
         static MathTables host_tables;          // built once on the host: every kernel uses the same bits
         static bool built = false;
         if (!built) {
-            for (int j = 0; j < 64; ++j) host_tables.exp2_tab[j] = std::exp2((double)j / 64.0);
+            for (int j = 0; j < EBPMF_EXP_TABLE_SIZE; ++j) host_tables.exp2_tab[j] = std::exp2((double)j / EBPMF_EXP_TABLE_SIZE);
             for (int i = 0; i < 128; ++i) {
                 const float c = (float)(1.0 / (1.0 + ((double)i + 0.5) / 128.0));
                 host_tables.log_tab[i].x = (double)c;

@@ -5,8 +5,8 @@
 // (R/vga_solver_mat.R:22-31, R/ebpmf_log.R:317-318) are replaced by
 //   rcp : MUFU.RCP64H seed (rcp.approx.ftz.f64, rel. err <= 2^-20) + one cubic Newton step
 //         r(1+e+e^2): 3 DFMA, result within ~1.5 ulp for normal, finite x;
-//   exp : n = rint(x*64/ln2); r = x - n*ln2/64 (Cody-Waite, 2 DFMA); 2^(j/64) from a
-//         64-entry table in shared memory; degree-5 polynomial: ~10 DP instructions, rel. err <= 2.3e-16;
+//   exp : n = rint(x*256/ln2); r = x - n*ln2/256 (Cody-Waite, 2 DFMA); 2^(j/256) from a
+//         256-entry table in shared memory; degree-4 polynomial: 9 DP instructions, rel. err <= 2.4e-16;
 //   log : 128-entry (1/m_i, -log(1/m_i)) table + degree-6 log1p polynomial, ~10 DP instructions.
 // Parity budget is 1e-8 relative against the oracle (BASELINE.json); these are ~1e-15.
 // Every operation is an explicit __fma_rn/__dmul_rn/__dadd_rn so that nvcc's mul+add contraction
@@ -36,8 +36,8 @@ __device__ __forceinline__ double rcp_fast(double x) {
 #endif
 }
 
-// 2^(j/64), j = 0..63, filled by exp_table_init() into shared memory (64 doubles).
-#define EBPMF_EXP_TABLE_SIZE 64
+// 2^(j/256), j = 0..255, copied by exp_table_init() into shared memory (2 KB).
+#define EBPMF_EXP_TABLE_SIZE 256
 
 // shared-space byte address of a __shared__ object
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -45,12 +45,12 @@ __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)
 // The table values come from ONE place (the host, ebpmf_api.cu: math_tables()) and are copied into
 // shared memory by every kernel, so all kernels iterate with bit-identical tables.
 struct MathTables {
-    double exp2_tab[64];          // 2^(j/64)
+    double exp2_tab[EBPMF_EXP_TABLE_SIZE];   // 2^(j/256)
     double2 log_tab[128];         // (c_i, -log(c_i)), c_i = float(1/(1+(i+0.5)/128))
 };
 
 __device__ __forceinline__ void exp_table_init(double *tab, const MathTables *g, int tid, int nthreads) {
-    for (int j = tid; j < 64; j += nthreads) tab[j] = g->exp2_tab[j];
+    for (int j = tid; j < EBPMF_EXP_TABLE_SIZE; j += nthreads) tab[j] = g->exp2_tab[j];
 }
 
 // libdevice exp for arguments outside the fast range (overflow, underflow, NaN, Inf); kept out of
@@ -59,11 +59,11 @@ __device__ __noinline__ double exp_slow(double x) { return exp(x); }
 
 // Constants of exp_core in the constant bank: DFMA takes them as c[bank][off] operands, so they
 // cost neither registers nor the UMOV/IMAD.MOV rematerialisation that immediates need.
-__constant__ double kExpC[6] = {
-    92.332482616893656768,        // 64/ln2
-    -0x1.62e42fee00000p-7,        // -(ln2/64 rounded to 32 bits): n*L_HI is exact
-    -0x1.a39ef35793c76p-39,       // -(ln2/64 - L_HI)
-    1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
+__constant__ double kExpC[5] = {
+    369.3299304675746,            // 256/ln2
+    -0x1.62e42fe800000p-9,        // -(ln2/256 rounded to 30 bits): n*L_HI is exact for |n| < 2^18
+    -0x1.e8e7bcd5e4f1ep-39,       // -(ln2/256 - L_HI)
+    1.0 / 24.0, 1.0 / 6.0};
 
 // true when |x| >= 700 or x is NaN / Inf: decided on the high word with integer instructions
 // so the test costs no FP64-pipe slot (0x4085E000_00000000 == 700.0).
@@ -71,10 +71,11 @@ __device__ __forceinline__ bool exp_out_of_range(double x) {
     return (__double2hiint(x) & 0x7fffffff) >= 0x4085E000;
 }
 
-// exp(x) for |x| < 700: n = rint(x*64/ln2), r = x - n*ln2/64, 2^(j/64) from the table,
-// exp(r) - 1 = r + r^2/2 + ... + r^5/120 (the dropped r^6/720 is <= 3.5e-17 at |r| <= ln2/128).
-// Measured on the host with the same fma sequence: max rel. error 2.3e-16 on [-700,700].
-// tab_s: shared-space byte address of the 64-entry table (from smem_addr()); a plain LDS, no
+// exp(x) for |x| < 700: n = rint(x*256/ln2), r = x - n*ln2/256, 2^(j/256) from the table,
+// exp(r) - 1 = r + r^2/2 + r^3/6 + r^4/24 (the dropped r^5/120 is <= 3.8e-17 at |r| <= ln2/512).
+// 9 FP64 instructions.  Measured on the host with the same fma sequence: max rel. error 2.4e-16
+// on [-700,700].
+// tab_s: shared-space byte address of the 256-entry table (from smem_addr()); a plain LDS, no
 // generic->shared window arithmetic in the loop.
 __device__ __forceinline__ double exp_core(double x, unsigned tab_s) {
     const double MAGIC = 6755399441055744.0;           // 1.5 * 2^52
@@ -84,15 +85,14 @@ __device__ __forceinline__ double exp_core(double x, unsigned tab_s) {
     double r = __fma_rn(nf, kExpC[1], x);
     r = __fma_rn(nf, kExpC[2], r);
     double q = __fma_rn(r, kExpC[3], kExpC[4]);
-    q = __fma_rn(q, r, kExpC[5]);
     q = __fma_rn(q, r, 0.5);
     q = __dmul_rn(q, r);
     q = __fma_rn(q, r, r);                             // q = exp(r) - 1
     double tj;
     asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab_s + ((unsigned)(n & (EBPMF_EXP_TABLE_SIZE - 1)) << 3)));
-    const double v = __fma_rn(tj, q, tj);              // 2^(j/64) * exp(r)
-    // scale by 2^(n>>6): |x| < 700 keeps the result a normal double
-    const int hi = __double2hiint(v) + ((n & ~(EBPMF_EXP_TABLE_SIZE - 1)) << 14);   // + (n>>6)<<20
+    const double v = __fma_rn(tj, q, tj);              // 2^(j/256) * exp(r)
+    // scale by 2^(n>>8): |x| < 700 keeps the result a normal double
+    const int hi = __double2hiint(v) + ((n & ~(EBPMF_EXP_TABLE_SIZE - 1)) << 12);   // + (n>>8)<<20
     return __hiloint2double(hi, __double2loint(v));
 }
 
