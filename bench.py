@@ -446,6 +446,29 @@ def main():
                                      "call": "ebpmf_vga_step_host: M in AND out every step (the stand-alone drop-in signature)",
                                      "ms_per_step": 1e3 * full_wall / args.steps}
         ectx.close()
+        # (c) ebpmf_log's batched branch (general_control$batch_size < n, R/ebpmf_log.R:254-300): one solve per row
+        #     batch with the stop test scoped to the batch, M in and out from pinned host memory, the batches
+        #     pipelined through 3 worker contexts so H2D, solve and D2H of different batches overlap
+        import scipy.sparse as sp
+        bs = max(256, er // 8)
+        bh = pkg.VgaBatched(local_rank, 3)
+        bh.set_y(sp.csc_matrix((sx, sri, scp), shape=(er, p)), batch_size=bs)
+        for _ in range(2):
+            rb_ = bh.vga_step_host(M0, ELp, EFp, s2, "by_col", MAXITER_VGA, VGA_TOL, M_out=Mo)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            rb_ = bh.vga_step_host(M0, ELp, EFp, s2, "by_col", MAXITER_VGA, VGA_TOL, M_out=Mo)
+        torch.cuda.synchronize()
+        b_wall = allmax(time.perf_counter() - t0)
+        out["e2e_batched"] = {"value": er * p * world / (b_wall / args.steps), "unit": "entries/s",
+                              "h2d_bytes_per_step": int(8 * er * p + 8 * (er + p * (len(bh.batch_row0) - 1)) * (K + 2) + 8 * p),
+                              "d2h_bytes_per_step": int(8 * er * p + 8 * p * (len(bh.batch_row0) - 1) + 64),
+                              "call": "ebpmf_batched_vga_step_host: ebpmf_log's batched branch (batch_size = %d rows, %d "
+                                      "batches, per-batch stop as in R/ebpmf_log.R:259-268), M in AND out, 3 pipelined "
+                                      "worker contexts" % (bs, len(bh.batch_row0) - 1),
+                              "n_updates_per_batch": rb_["n_updates"], "ms_per_step": 1e3 * b_wall / args.steps}
+        bh.close()
     if rank == 0:
         emit(json.dumps(out))
     ctx.close()

@@ -77,8 +77,10 @@ struct ebpmf_ctx {
     long long nRB = 0, nRW = 0;
     int K = 0, KTP = 0, ldk = 0;
     int var_type = -1;
-    int pipeline = 0;          // 0: fused first pass, 1: split (const0 kernel + streaming Newton), 2: ordered split
+    int pipeline = 0;          // 0: fused first pass, 1: split (const0 kernel + streaming Newton), 2: ordered split,
+                               // 3: scored (FP32 scoring pass, then the fused first pass in score order)
     double delta = 0.0;        // 0: exact update count (default); > 0: delta mode (ebpmf_ctx_set_option)
+    unsigned scored_min_ctas = 2 * 148 * 3;   // scored pipeline: below two waves of CTAs the order cannot matter
     double debug_verify_scale = 1.0;   // test hook: pass 2 verifies against tol*scale (exercises the retry loop)
     bool can_rewind = false;
     unsigned long long diag_topups = 0, diag_iters = 0;
@@ -254,6 +256,64 @@ __global__ void iota_kernel(int *ids, int count) {
     if (t < count) ids[t] = t;
 }
 
+int reserve_order_buffers(ebpmf_ctx *ctx, int ncta) {
+    CHECK(reserve(ctx, ctx->score, sizeof(float) * (size_t)ncta));
+    CHECK(reserve(ctx, ctx->score_sorted, sizeof(float) * (size_t)ncta));
+    CHECK(reserve(ctx, ctx->cta_ids, sizeof(int) * (size_t)ncta));
+    CHECK(reserve(ctx, ctx->perm, sizeof(int) * (size_t)ncta));
+    return EBPMF_OK;
+}
+
+// ctx->perm = CTA ids by decreasing ctx->score (cub radix sort, ~60 us for 57 k CTAs)
+int sort_ctas_by_score(ebpmf_ctx *ctx, int ncta) {
+    iota_kernel<<<(ncta + 255) / 256, 256, 0, ctx->stream>>>(as<int>(ctx->cta_ids), ncta);
+    CU(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, as<float>(ctx->score), as<float>(ctx->score_sorted),
+                                                 as<int>(ctx->cta_ids), as<int>(ctx->perm), ncta, 0, 32, ctx->stream));
+    CHECK(reserve(ctx, ctx->cub_tmp, tmp_bytes));
+    CU(cub::DeviceRadixSort::SortPairsDescending(ctx->cub_tmp.ptr, tmp_bytes, as<float>(ctx->score),
+                                                 as<float>(ctx->score_sorted), as<int>(ctx->cta_ids), as<int>(ctx->perm),
+                                                 ncta, 0, 32, ctx->stream));
+    return EBPMF_OK;
+}
+
+template <int KTP>
+int launch_score_ktp(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
+    auto kern = vga_score_kernel<KTP>;
+    const int smem = (int)sizeof(ScoreSmem<KTP>);
+    static bool configured[8] = {false, false, false, false, false, false, false, false};   // per device
+    if (ctx->device < 8 ? !configured[ctx->device] : true) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (ctx->device < 8) configured[ctx->device] = true;
+    }
+    kern<<<grid, dim3(kThreads), smem, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    return EBPMF_OK;
+}
+
+// Scored pipeline (pipeline == 3, FORMULA_A1): an FP32 scoring pass ranks the tiles by their largest
+// first Newton step, then the SAME fused kernel takes them in that order.  The slowest entries are
+// met first, K* is published early and (almost) every unit runs to the global count inside pass 1,
+// in registers; the top-up pass finds next to nothing to do.  Results are bit-identical to
+// pipeline 0 (a unit's iterates do not depend on the order the units are taken in).
+int launch_score_and_sort(ebpmf_ctx *ctx, FusedArgs &a, dim3 grid) {
+    const int ncta = (int)(grid.x * grid.y);
+    CHECK(reserve_order_buffers(ctx, ncta));
+    a.score = as<float>(ctx->score);
+    a.perm = nullptr;
+    switch (ctx->KTP) {
+        case 8: CHECK((launch_score_ktp<8>(ctx, a, grid))); break;
+        case 16: CHECK((launch_score_ktp<16>(ctx, a, grid))); break;
+        case 24: CHECK((launch_score_ktp<24>(ctx, a, grid))); break;
+        case 32: CHECK((launch_score_ktp<32>(ctx, a, grid))); break;
+        default: return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported", ctx->K);
+    }
+    CHECK(sort_ctas_by_score(ctx, ncta));
+    a.perm = as<int>(ctx->perm);
+    return EBPMF_OK;
+}
+
 // Ordered pipeline (pipeline == 2, FORMULA_A1, maxiter >= 2): stage A (the fused kernel's ITER0_ONLY
 // form) performs Newton iteration 0 and scores every CTA by its largest first step; the streaming kernel
 // then walks the CTAs by decreasing score, so the slowest entries -- the ones that set the global update count --
@@ -261,10 +321,7 @@ __global__ void iota_kernel(int *ids, int count) {
 template <bool DELTA>
 int launch_first_ordered(ebpmf_ctx *ctx, FusedArgs a, dim3 grid) {
     const int ncta = (int)(grid.x * grid.y);
-    CHECK(reserve(ctx, ctx->score, sizeof(float) * (size_t)ncta));
-    CHECK(reserve(ctx, ctx->score_sorted, sizeof(float) * (size_t)ncta));
-    CHECK(reserve(ctx, ctx->cta_ids, sizeof(int) * (size_t)ncta));
-    CHECK(reserve(ctx, ctx->perm, sizeof(int) * (size_t)ncta));
+    CHECK(reserve_order_buffers(ctx, ncta));
     a.score = as<float>(ctx->score);
     a.perm = nullptr;
     a.nspans = (int)grid.x;
@@ -278,15 +335,7 @@ int launch_first_ordered(ebpmf_ctx *ctx, FusedArgs a, dim3 grid) {
     if (ctx->comm)    // "some entry is not converged at k = 0" is a property of the WHOLE matrix
         NC(g_nccl.AllReduce(&as<Status>(ctx->status)->notconv0, &as<Status>(ctx->status)->notconv0, 1, ncclInt32,
                             ncclMax, ctx->comm, ctx->stream));
-    iota_kernel<<<(ncta + 255) / 256, 256, 0, ctx->stream>>>(as<int>(ctx->cta_ids), ncta);
-    CU(cudaGetLastError());
-    size_t tmp_bytes = 0;
-    CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, as<float>(ctx->score), as<float>(ctx->score_sorted),
-                                                 as<int>(ctx->cta_ids), as<int>(ctx->perm), ncta, 0, 32, ctx->stream));
-    CHECK(reserve(ctx, ctx->cub_tmp, tmp_bytes));
-    CU(cub::DeviceRadixSort::SortPairsDescending(ctx->cub_tmp.ptr, tmp_bytes, as<float>(ctx->score),
-                                                 as<float>(ctx->score_sorted), as<int>(ctx->cta_ids), as<int>(ctx->perm),
-                                                 ncta, 0, 32, ctx->stream));
+    CHECK(sort_ctas_by_score(ctx, ncta));
     a.perm = as<int>(ctx->perm);
     vga_stream_kernel<kE, FORMULA_A1, MODE_FIRST, DELTA><<<dim3((unsigned)ncta), dim3(kThreads), 0, ctx->stream>>>(a);
     CU(cudaGetLastError());
@@ -302,18 +351,23 @@ int launch_first(ebpmf_ctx *ctx, const FusedArgs &a) {
     dim3 grid((unsigned)((ncols + a.cols_per_cta - 1) / a.cols_per_cta), (unsigned)ctx->nRB);
     if (ctx->pipeline == 2 && FORMULA == FORMULA_A1 && a.maxiter >= 2 && a.col0 == 0 && a.col1 == ctx->p)
         return a.delta > 0 ? launch_first_ordered<true>(ctx, a, grid) : launch_first_ordered<false>(ctx, a, grid);
-    if (ctx->pipeline >= 1) {
+    if (ctx->pipeline == 1 || ctx->pipeline == 2) {
         CHECK((launch_prep<FORMULA>(ctx, a, grid)));
         if (a.delta > 0) vga_stream_kernel<kE, FORMULA, MODE_FIRST, true><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
         else vga_stream_kernel<kE, FORMULA, MODE_FIRST, false><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
         CU(cudaGetLastError());
         return EBPMF_OK;
     }
+    FusedArgs b = a;
+    b.perm = nullptr;
+    if (ctx->pipeline == 3 && FORMULA == FORMULA_A1 && a.maxiter >= 2 && ctx->K <= 32 && a.cols_per_cta <= kMaxSpanCols &&
+        grid.x * grid.y >= ctx->scored_min_ctas)
+        CHECK(launch_score_and_sort(ctx, b, grid));
     switch (ctx->KTP) {
-        case 8: return launch_first_ktp<8, FORMULA>(ctx, a, grid);
-        case 16: return launch_first_ktp<16, FORMULA>(ctx, a, grid);
-        case 24: return launch_first_ktp<24, FORMULA>(ctx, a, grid);
-        case 32: return launch_first_ktp<32, FORMULA>(ctx, a, grid);
+        case 8: return launch_first_ktp<8, FORMULA>(ctx, b, grid);
+        case 16: return launch_first_ktp<16, FORMULA>(ctx, b, grid);
+        case 24: return launch_first_ktp<24, FORMULA>(ctx, b, grid);
+        case 32: return launch_first_ktp<32, FORMULA>(ctx, b, grid);
     }
     return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported", ctx->K);
 }
@@ -509,6 +563,21 @@ int upload_csc(ebpmf_ctx *ctx, long long n, long long p, const int32_t *colptr, 
 }
 
 // after colptr/rowidx/yx are resident: shapes, row-block offset table, partial buffers
+// shape-dependent scratch of the fused step (grow-only), and nRB / nRW
+int reserve_shape_buffers(ebpmf_ctx *ctx, long long n, long long p) {
+    ctx->n = n; ctx->p = p;
+    CHECK(alloc_solver_state(ctx, n, p));
+    const long long nJG = (p + kE - 1) / kE;
+    CHECK(reserve(ctx, ctx->colV, sizeof(double) * (size_t)ctx->nRW * (size_t)p));
+    CHECK(reserve(ctx, ctx->unitS, sizeof(double) * 2 * (size_t)ctx->nRW * (size_t)nJG));
+    CHECK(reserve(ctx, ctx->colsums, sizeof(double) * (2 * (size_t)p + 2 * (size_t)nJG)));
+    CHECK(reserve(ctx, ctx->sc1, sizeof(double) * (size_t)std::max(n, p)));
+    CHECK(reserve(ctx, ctx->sc2, sizeof(double) * (size_t)std::max(n, p)));
+    CHECK(reserve(ctx, ctx->red, sizeof(double) * (4 + (size_t)std::max(n, p))));
+    CHECK(reserve(ctx, ctx->misc, sizeof(double) * (size_t)(3 * std::max(n, p) + 4096)));
+    return EBPMF_OK;
+}
+
 int finish_set_y(ebpmf_ctx *ctx, long long n, long long p) {
     ctx->n = n; ctx->p = p;
     CHECK(alloc_solver_state(ctx, n, p));
@@ -730,7 +799,7 @@ int ebpmf_ctx_create(int device, ebpmf_ctx **out) {
     if (!ctx) return fail(nullptr, EBPMF_ERR_NOMEM, "out of host memory");
     ctx->device = device;
     if (const char *pl = getenv("EBPMF_B200_PIPELINE"))
-        ctx->pipeline = !strcmp(pl, "ordered") ? 2 : !strcmp(pl, "split") ? 1 : 0;
+        ctx->pipeline = !strcmp(pl, "scored") ? 3 : !strcmp(pl, "ordered") ? 2 : !strcmp(pl, "split") ? 1 : 0;
     if (const char *dl = getenv("EBPMF_B200_DELTA")) ctx->delta = atof(dl);
     cudaError_t ce;
 #define CREATE_STEP(call)                                                                                        \
@@ -1344,8 +1413,14 @@ int ebpmf_ctx_set_option(ebpmf_ctx *ctx, const char *name, double value) {
         return EBPMF_OK;
     }
     if (!strcmp(name, "pipeline")) {
-        if (value != 0.0 && value != 1.0 && value != 2.0) return fail(ctx, EBPMF_ERR_ARG, "set_option: pipeline is 0, 1 or 2");
+        if (value != 0.0 && value != 1.0 && value != 2.0 && value != 3.0)
+            return fail(ctx, EBPMF_ERR_ARG, "set_option: pipeline is 0, 1, 2 or 3");
         ctx->pipeline = (int)value;
+        return EBPMF_OK;
+    }
+    if (!strcmp(name, "scored_min_ctas")) {
+        if (!(value >= 0.0) || value > 1e9) return fail(ctx, EBPMF_ERR_ARG, "set_option: scored_min_ctas must be in [0, 1e9]");
+        ctx->scored_min_ctas = (unsigned)value;
         return EBPMF_OK;
     }
     return fail(ctx, EBPMF_ERR_ARG, "set_option: unknown option '%s'", name);
@@ -1546,6 +1621,243 @@ int ebpmf_group_sum_lfactorial(ebpmf_group *g, double *out) {
     double s = 0.0;
     for (double v : part) s += v;
     *out = s;
+    return EBPMF_OK;
+}
+
+}  // extern "C"
+
+// ---- batch_size-faithful, host-streamed step (R/ebpmf_log.R:195-203, :254-300) ---------------
+namespace {
+// the Y part of a context: swapped into a worker context for the duration of one batch
+struct YState {
+    DevBuf colptr, rowidx, yx, rbptr;
+    long long n = 0, nnz = 0;
+};
+
+void swap_y(ebpmf_ctx *c, YState &y) {
+    std::swap(c->colptr, y.colptr); std::swap(c->rowidx, y.rowidx);
+    std::swap(c->yx, y.yx); std::swap(c->rbptr, y.rbptr);
+    std::swap(c->n, y.n); std::swap(c->nnz, y.nnz);
+}
+}  // namespace
+
+struct ebpmf_batched {
+    int device = 0;
+    std::vector<ebpmf_ctx *> slot;
+    std::vector<YState> ys;             // one per batch, resident
+    std::vector<long long> row0;        // nbatch + 1
+    long long n = 0, p = 0;
+    double lfact = 0.0;                 // sum(lfactorial(Y@x)) of the whole matrix
+    std::string err;
+};
+
+namespace {
+int bfail(ebpmf_batched *h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    g_last_error = msg;
+    return code;
+}
+
+void release_batches(ebpmf_batched *h) {
+    cudaSetDevice(h->device);
+    for (YState &y : h->ys) { release(y.colptr); release(y.rowidx); release(y.yx); release(y.rbptr); }
+    h->ys.clear();
+}
+
+// worker context c takes batch y: Y pointers, shapes, shape-dependent scratch
+int attach_batch(ebpmf_ctx *c, YState &y, long long p) {
+    swap_y(c, y);
+    CHECK(ensure_common(c));
+    CHECK(reserve_shape_buffers(c, c->n, p));
+    c->have_y = true;
+    c->have_m = c->have_f = c->have_s2 = c->have_v = c->have_vsum = false;
+    return EBPMF_OK;
+}
+
+void detach_batch(ebpmf_ctx *c, YState &y) {
+    swap_y(c, y);
+    c->have_y = false;
+}
+}  // namespace
+
+extern "C" {
+
+int ebpmf_batched_create(int device, int nslots, ebpmf_batched **out) {
+    if (!out || nslots < 1 || nslots > 8) return bfail(nullptr, EBPMF_ERR_ARG, "batched_create: nslots must be in 1..8");
+    *out = nullptr;
+    ebpmf_batched *h = new (std::nothrow) ebpmf_batched();
+    if (!h) return bfail(nullptr, EBPMF_ERR_NOMEM, "out of host memory");
+    h->device = device;
+    for (int s = 0; s < nslots; ++s) {
+        ebpmf_ctx *c = nullptr;
+        int rc = ebpmf_ctx_create(device, &c);
+        if (rc != EBPMF_OK) {
+            for (ebpmf_ctx *q : h->slot) ebpmf_ctx_destroy(q);
+            delete h;
+            return rc;
+        }
+        h->slot.push_back(c);
+    }
+    *out = h;
+    return EBPMF_OK;
+}
+
+int ebpmf_batched_destroy(ebpmf_batched *h) {
+    if (!h) return EBPMF_OK;
+    release_batches(h);
+    for (ebpmf_ctx *c : h->slot) ebpmf_ctx_destroy(c);
+    delete h;
+    return EBPMF_OK;
+}
+
+const char *ebpmf_batched_last_error(const ebpmf_batched *h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int ebpmf_batched_set_option(ebpmf_batched *h, const char *name, double value) {
+    if (!h) return bfail(h, EBPMF_ERR_ARG, "batched_set_option: handle is NULL");
+    for (ebpmf_ctx *c : h->slot) {
+        int rc = ebpmf_ctx_set_option(c, name, value);
+        if (rc != EBPMF_OK) return bfail(h, rc, c->err);
+    }
+    return EBPMF_OK;
+}
+
+// Y[b,] for every batch b (what `lapply(batches, function(b) Y[b,])` does, R/ebpmf_log.R:199): two passes
+// over the non-zeros, then one upload per batch; each slab becomes its own resident CSC with its own
+// row-block offset table.
+int ebpmf_batched_set_y_csc(ebpmf_batched *h, int64_t n, int64_t p, const int32_t *colptr, const int32_t *rowidx,
+                            const double *x, int64_t nbatch, const int64_t *batch_row0) {
+    if (!h || n < 1 || p < 1 || !colptr || nbatch < 1 || !batch_row0)
+        return bfail(h, EBPMF_ERR_ARG, "batched_set_y_csc: bad arguments");
+    if (batch_row0[0] != 0 || batch_row0[nbatch] != n) return bfail(h, EBPMF_ERR_ARG, "batched_set_y_csc: batch_row0 must run from 0 to n");
+    for (int64_t b = 0; b < nbatch; ++b)
+        if (batch_row0[b + 1] <= batch_row0[b]) return bfail(h, EBPMF_ERR_ARG, "batched_set_y_csc: empty or unordered batch");
+    const long long nnz = colptr[p];
+    if (nnz > 0 && (!rowidx || !x)) return bfail(h, EBPMF_ERR_ARG, "batched_set_y_csc: bad arguments");
+    release_batches(h);
+    h->n = n; h->p = p;
+    h->row0.assign(batch_row0, batch_row0 + nbatch + 1);
+    std::vector<int32_t> batch_of((size_t)n);
+    for (int64_t b = 0; b < nbatch; ++b)
+        for (long long i = batch_row0[b]; i < batch_row0[b + 1]; ++i) batch_of[(size_t)i] = (int32_t)b;
+    std::vector<std::vector<int32_t>> cp((size_t)nbatch, std::vector<int32_t>((size_t)p + 1, 0));
+    for (long long j = 0; j < p; ++j)
+        for (int q = colptr[j]; q < colptr[j + 1]; ++q) {
+            if (rowidx[q] < 0 || rowidx[q] >= n) return bfail(h, EBPMF_ERR_ARG, "batched_set_y_csc: row index out of range");
+            ++cp[(size_t)batch_of[(size_t)rowidx[q]]][(size_t)j + 1];
+        }
+    std::vector<std::vector<int32_t>> ri((size_t)nbatch);
+    std::vector<std::vector<double>> xx((size_t)nbatch);
+    for (int64_t b = 0; b < nbatch; ++b) {
+        for (long long j = 0; j < p; ++j) cp[(size_t)b][(size_t)j + 1] += cp[(size_t)b][(size_t)j];
+        ri[(size_t)b].resize((size_t)std::max(1, cp[(size_t)b][(size_t)p]));
+        xx[(size_t)b].resize((size_t)std::max(1, cp[(size_t)b][(size_t)p]));
+    }
+    {
+        std::vector<int32_t> fill((size_t)nbatch);
+        for (long long j = 0; j < p; ++j) {
+            for (int64_t b = 0; b < nbatch; ++b) fill[(size_t)b] = cp[(size_t)b][(size_t)j];
+            for (int q = colptr[j]; q < colptr[j + 1]; ++q) {
+                const int32_t b = batch_of[(size_t)rowidx[q]];
+                const int32_t w = fill[(size_t)b]++;
+                ri[(size_t)b][(size_t)w] = (int32_t)(rowidx[q] - batch_row0[b]);
+                xx[(size_t)b][(size_t)w] = x[q];
+            }
+        }
+    }
+    ebpmf_ctx *c0 = h->slot[0];
+    h->ys.resize((size_t)nbatch);
+    for (int64_t b = 0; b < nbatch; ++b) {
+        const long long nb = batch_row0[b + 1] - batch_row0[b];
+        int rc = ebpmf_ctx_set_y_csc(c0, nb, p, cp[(size_t)b].data(), ri[(size_t)b].data(), xx[(size_t)b].data());
+        if (rc != EBPMF_OK) return bfail(h, rc, c0->err);
+        swap_y(c0, h->ys[(size_t)b]);           // the slab now belongs to the batch store
+        c0->have_y = false;
+        std::vector<int32_t>().swap(ri[(size_t)b]);
+        std::vector<double>().swap(xx[(size_t)b]);
+    }
+    h->lfact = 0.0;
+    if (nnz > 0) {
+        // needs a context with scratch: borrow batch 0
+        int rc = attach_batch(c0, h->ys[0], p);
+        if (rc == EBPMF_OK) rc = ebpmf_sum_lfactorial(c0, nnz, x, &h->lfact);
+        detach_batch(c0, h->ys[0]);
+        if (rc != EBPMF_OK) return bfail(h, rc, c0->err);
+    }
+    return EBPMF_OK;
+}
+
+int ebpmf_batched_sum_lfactorial(ebpmf_batched *h, double *out) {
+    if (!h || !out) return bfail(h, EBPMF_ERR_ARG, "batched_sum_lfactorial: bad arguments");
+    if (h->n < 1) return bfail(h, EBPMF_ERR_STATE, "batched_sum_lfactorial: Y not set");
+    *out = h->lfact;
+    return EBPMF_OK;
+}
+
+int ebpmf_batched_vga_step_host(ebpmf_batched *h, const double *M_in, int64_t K, const double *EL, const double *EF,
+                                int var_type, const double *sigma2, int maxiter, double tol, double *M_out,
+                                double *V_out, double *v_sum, ebpmf_solve_info *info, int32_t *n_updates,
+                                int32_t *converged) {
+    if (!h || !M_in || !M_out || !EL || !EF || !sigma2) return bfail(h, EBPMF_ERR_ARG, "batched_vga_step_host: bad arguments");
+    if (h->n < 1 || h->ys.empty()) return bfail(h, EBPMF_ERR_STATE, "batched_vga_step_host: Y not set");
+    const int S = (int)h->slot.size();
+    const long long n = h->n, p = h->p;
+    const int nb = (int)h->ys.size();
+    std::vector<ebpmf_solve_info> infos((size_t)nb);
+    std::vector<double> vcol;                                  // per-batch colSums(V_b) / sum(V_b), added in batch order
+    const size_t vlen = (var_type == EBPMF_VAR_BY_COL) ? (size_t)p : 1;
+    if (v_sum && var_type != EBPMF_VAR_BY_ROW) vcol.assign((size_t)nb * vlen, 0.0);
+    std::vector<int> rc((size_t)S, EBPMF_OK);
+    std::vector<int> failed_batch((size_t)S, -1);
+    auto work = [&](int s) -> int {
+        ebpmf_ctx *c = h->slot[(size_t)s];
+        for (int b = s; b < nb; b += S) {
+            const long long lo = h->row0[(size_t)b];
+            YState &y = h->ys[(size_t)b];
+            int r = attach_batch(c, y, p);
+            if (r == EBPMF_OK) r = set_factors_ld(c, K, EL + lo, n, EF);                                   // EF[[1]][b,], :266
+            if (r == EBPMF_OK) r = ebpmf_ctx_set_sigma2(c, var_type, var_type == EBPMF_VAR_BY_ROW ? sigma2 + lo : sigma2);   // :267
+            if (r == EBPMF_OK) r = set_m_ld(c, M_in + lo, n);                                              // flash_fit$Y[b,], :263
+            if (r == EBPMF_OK) r = ebpmf_ctx_vga_step(c, maxiter, tol, V_out != nullptr, &infos[(size_t)b]);
+            if (r == EBPMF_OK) r = get_matrix_ld(c, false, M_out + lo, n);                                 // :270
+            if (r == EBPMF_OK && V_out) r = get_matrix_ld(c, true, V_out + lo, n);
+            if (r == EBPMF_OK && v_sum)
+                r = ebpmf_ctx_get_v_sum(c, var_type == EBPMF_VAR_BY_ROW ? v_sum + lo : vcol.data() + (size_t)b * vlen);
+            detach_batch(c, y);
+            if (r != EBPMF_OK) { failed_batch[(size_t)s] = b; return r; }
+        }
+        return EBPMF_OK;
+    };
+    {
+        std::vector<std::thread> th;
+        for (int s = 1; s < S; ++s) th.emplace_back([&, s] { rc[(size_t)s] = work(s); });
+        rc[0] = work(0);
+        for (auto &t : th) t.join();
+    }
+    for (int s = 0; s < S; ++s)
+        if (rc[(size_t)s] != EBPMF_OK)
+            return bfail(h, rc[(size_t)s], std::string("batch ") + std::to_string(failed_batch[(size_t)s]) + ": " + h->slot[(size_t)s]->err);
+    if (v_sum && var_type != EBPMF_VAR_BY_ROW) {
+        for (size_t q = 0; q < vlen; ++q) v_sum[q] = 0.0;                                                  // v_sum = 0, :255
+        for (int b = 0; b < nb; ++b)
+            for (size_t q = 0; q < vlen; ++q) v_sum[q] += vcol[(size_t)b * vlen + q];                      // :284, :286
+    }
+    if (info) {
+        memset(info, 0, sizeof *info);
+        info->converged = 1;
+        for (int b = 0; b < nb; ++b) {
+            const ebpmf_solve_info &ib = infos[(size_t)b];
+            info->sym += ib.sym; info->ssexp += ib.ssexp; info->slogv += ib.slogv;                         // :274-276
+            info->n_updates = std::max(info->n_updates, ib.n_updates);
+            info->converged = info->converged && ib.converged;
+            info->passes = std::max(info->passes, ib.passes);
+            info->kernel_ms += ib.kernel_ms; info->pass1_ms += ib.pass1_ms;
+            info->pass2_ms += ib.pass2_ms; info->reduce_ms += ib.reduce_ms;
+        }
+    }
+    for (int b = 0; b < nb; ++b) {
+        if (n_updates) n_updates[b] = infos[(size_t)b].n_updates;
+        if (converged) converged[b] = infos[(size_t)b].converged;
+    }
     return EBPMF_OK;
 }
 

@@ -356,13 +356,20 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
     // rows of a shard and columns fit 32 bits (dgCMatrix Dim is int); only n*j products are 64-bit
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = (int)a.n, p = (int)a.p;
-    const int rb = blockIdx.y;
+    // scored pipeline: the CTAs take the (column span, row block) tiles by decreasing predicted
+    // hardness (a.perm, from vga_score_kernel); CTAs are dispatched in linear order, x fastest
+    int span = blockIdx.x, rb = blockIdx.y;
+    if (!ITER0_ONLY && a.perm) {
+        const int id = a.perm[blockIdx.y * gridDim.x + blockIdx.x];
+        rb = id / (int)gridDim.x;
+        span = id - rb * (int)gridDim.x;
+    }
     const int r0 = rb * kRowsPerCta;
     const int i = r0 + tid;
     const bool row_ok = i < n;
     const int rw = rb * kWarps + warp;
     const bool warp_ok = rw < (int)a.nRW;            // false: every row of this warp is beyond n
-    const int jc0 = (int)a.col0 + blockIdx.x * a.cols_per_cta;
+    const int jc0 = (int)a.col0 + span * a.cols_per_cta;
     const int jc1 = min((int)a.col1, jc0 + a.cols_per_cta);
 
     exp_table_init(sm.exptab, a.tables, tid, kThreads);
@@ -552,6 +559,140 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
         if (any_exhausted) a.status->exhausted = 1;
         if (any_nan) a.status->nan = 1;
         if (my_iters) atomicAdd(&a.status->unit_iters, (unsigned long long)my_iters);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Scored pipeline, stage 0: rank the (column span, row block) tiles of the first pass by predicted
+// hardness.  The score is the tile's largest FIRST Newton step max|f_0/f_0'| (R/vga_solver_mat.R:22-31
+// evaluated once), computed in FP32 from the high words of M: it only decides the ORDER in which the
+// fused kernel takes the tiles, never a result, so single precision and approximate MUFU functions
+// are enough and the kernel runs near the rate at which M streams from HBM.  Same grid and tile
+// decomposition as vga_fused_kernel; writes a.score[row block * spans + span].  FORMULA_A1 only.
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxSpanCols = 256;      // cols_per_cta never exceeds this (cols_per_cta_for in ebpmf_api.cu)
+
+template <int KTP>
+struct ScoreSmem {
+    float efs[kMaxSpanCols][KTP];       // EF rows of the CTA's whole column span
+    float c1s[kMaxSpanCols], c2s[kMaxSpanCols];
+    float ys[kWarps][kTileCols][32];    // per-warp Y image: 32 rows x 16 columns
+    float wmax[kWarps];
+};
+
+// float from the high word of a double (20 mantissa bits kept; |x| < 2^-126 -> 0, huge -> garbage/Inf,
+// which the caller's clamp turns into "hard")
+__device__ __forceinline__ float float_from_hi(unsigned hi) {
+    const unsigned e = hi & 0x7fffffffu;
+    const unsigned bits = (hi & 0x80000000u) | ((e - 0x38000000u) << 3);
+    return (e < 0x38100000u) ? 0.f : __uint_as_float(bits);
+}
+
+// One barrier per CTA (after the span's EF rows are staged); afterwards every warp walks its own
+// 32 rows x 16 columns tiles with warp-level synchronisation only, so the CSC look-ups of one warp
+// hide behind the arithmetic of the others.  K_tot <= KTP (the host skips scoring otherwise).
+template <int KTP>
+__global__ void __launch_bounds__(kThreads, 3) vga_score_kernel(const FusedArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScoreSmem<KTP> &sm = *reinterpret_cast<ScoreSmem<KTP> *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = (int)a.n, p = (int)a.p;
+    const int rb = blockIdx.y;
+    const int r0 = rb * kRowsPerCta;
+    const int i = r0 + tid;
+    const bool row_ok = i < n;
+    const int jc0 = (int)a.col0 + blockIdx.x * a.cols_per_cta;
+    const int jc1 = min((int)a.col1, jc0 + a.cols_per_cta);
+    const size_t ns = (size_t)n;
+    const bool by_col = a.var_type == 2;
+    float c1_row = 1.f, c2_row = 0.5f;
+    if (!by_col) {
+        const int si = (a.var_type == 1) ? (row_ok ? i : 0) : 0;
+        c1_row = (float)a.sc1[si];
+        c2_row = (float)a.sc2[si];
+    }
+    for (int idx = tid; idx < (jc1 - jc0) * KTP; idx += kThreads) {
+        const int c = idx / KTP, k = idx - c * KTP;
+        sm.efs[c][k] = (k < a.K) ? (float)__ldg(a.EFt + (size_t)(jc0 + c) * a.ldk + k) : 0.f;
+    }
+    for (int c = tid; c < jc1 - jc0; c += kThreads) {
+        sm.c1s[c] = by_col ? (float)a.sc1[jc0 + c] : 1.f;
+        sm.c2s[c] = by_col ? (float)a.sc2[jc0 + c] : 0.5f;
+    }
+    float el[KTP];
+#pragma unroll
+    for (int k = 0; k < KTP; ++k) el[k] = (row_ok && k < a.K) ? (float)__ldg(a.EL + i + k * ns) : 0.f;
+    __syncthreads();
+
+    float (*yw)[32] = sm.ys[warp];
+    const int wr0 = r0 + warp * 32;                       // this warp's first row
+    const int *rpb = a.rbptr + (size_t)rb * p;            // CSC offsets of this row block, per column
+    float best = 0.f;
+    int lo_n = 0, hi_n = 0;                               // lane c: non-zero range of the next tile's column c
+    if (lane < kTileCols && jc0 + lane < jc1) { lo_n = rpb[jc0 + lane]; hi_n = rpb[p + jc0 + lane]; }
+    for (int j0 = jc0; j0 < jc1; j0 += kTileCols) {
+        const int lo_t = lo_n, hi_t = hi_n;
+        lo_n = hi_n = 0;
+        if (lane < kTileCols && j0 + kTileCols + lane < jc1) {
+            lo_n = rpb[j0 + kTileCols + lane];
+            hi_n = rpb[p + j0 + kTileCols + lane];
+        }
+        unsigned mhi[kTileCols];                          // high words of the tile's M values
+        {
+            const unsigned *mp = reinterpret_cast<const unsigned *>(a.M_in + (size_t)i + ns * (size_t)j0) + 1;
+#pragma unroll
+            for (int c = 0; c < kTileCols; ++c)
+                mhi[c] = (row_ok && j0 + c < jc1) ? __ldcs(mp + 2 * ns * (size_t)c) : 0u;
+        }
+#pragma unroll
+        for (int c = 0; c < kTileCols; ++c) yw[c][lane] = 0.f;
+        __syncwarp();
+#pragma unroll 4
+        for (int c = 0; c < kTileCols; ++c) {
+            const int lo = __shfl_sync(0xffffffffu, lo_t, c), hi = __shfl_sync(0xffffffffu, hi_t, c);
+            for (int q = lo + lane; q < hi; q += 32) {
+                const int r = a.rowidx[q] - wr0;
+                const float y = (float)__ldg(a.yx + q);
+                if ((unsigned)r < 32u) yw[c][r] = y;
+            }
+        }
+        __syncwarp();
+        const int cs0 = j0 - jc0;
+#pragma unroll
+        for (int c = 0; c < kTileCols; ++c) {
+            const float4 *ef4 = reinterpret_cast<const float4 *>(&sm.efs[cs0 + c][0]);
+            float b0 = 0.f, b1 = 0.f;
+#pragma unroll
+            for (int k4 = 0; k4 < KTP / 4; ++k4) {
+                const float4 e = ef4[k4];
+                b0 = fmaf(el[4 * k4 + 0], e.x, b0);
+                b1 = fmaf(el[4 * k4 + 1], e.y, b1);
+                b0 = fmaf(el[4 * k4 + 2], e.z, b0);
+                b1 = fmaf(el[4 * k4 + 3], e.w, b1);
+            }
+            const float c1 = by_col ? sm.c1s[cs0 + c] : c1_row, c2 = by_col ? sm.c2s[cs0 + c] : c2_row;
+            const float cap = fmaf(c2 + c2, yw[c][lane], b0 + b1);                 // const0 - 1
+            const float m = fminf(float_from_hi(mhi[c]), cap);                     // :16
+            const float r = __frcp_rn((cap + 1.f) - m);                            // :22
+            const float aa = c2 * r;
+            const float ex = __expf(m + aa);
+            const float f = fmaf(-m, c1, fmaf(cap, c1, -ex));                      // :25
+            const float g = fmaf(-ex, fmaf(aa, r, 1.f), -c1);                      // :31
+            float step = fabsf(__fdividef(f, g));
+            if (!(step <= 3.0e38f)) step = 3.0e38f;                                // Inf/NaN: take this tile early
+            if (row_ok && j0 + c < jc1) best = fmaxf(best, step);
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) sm.wmax[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+        float mx = 0.f;
+        for (int q = 0; q < kWarps; ++q) mx = fmaxf(mx, sm.wmax[q]);
+        a.score[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = mx;
     }
 }
 

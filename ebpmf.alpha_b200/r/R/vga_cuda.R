@@ -86,3 +86,18 @@ ebpmf_b200_vga_step_resident = function(n,p,EL,EF,sigma2,var_type,maxiter,tol,wa
   .Call(C_ebpmf_vga_step_resident, ebpmf_b200_ctx(), as.integer(c(n,p)), EL + 0, EF + 0, as.double(sigma2), var_type,
         as.integer(maxiter), as.double(tol), as.logical(want_V))
 }
+
+#' Batched branch of ebpmf_log's loop (general_control$batch_size < n): replaces R/ebpmf_log.R:254-293.
+#' `batches` is the list made at R/ebpmf_log.R:197 (contiguous ranges); Y is the ORIGINAL dgCMatrix, uploaded
+#' once; every call streams M through the GPU batch by batch with the stop test scoped to each batch.
+ebpmf_b200_batched_new = function(Y, batches, device = 0L, nslots = 3L){
+  row0 = c(vapply(batches, function(b) b[1] - 1, 0), nrow(Y))
+  h = .Call(C_ebpmf_batched_new, as(Y,'dgCMatrix'), as.double(row0), as.integer(device), as.integer(nslots))
+  attr(h, 'n_batch') = length(batches)
+  h
+}
+ebpmf_b200_batched_vga_step = function(h,M,EL,EF,sigma2,var_type,maxiter,tol,want_V=FALSE){
+  storage.mode(M) = 'double'
+  .Call(C_ebpmf_batched_vga_step, h, M, EL + 0, EF + 0, as.double(sigma2), var_type,
+        as.integer(maxiter), as.double(tol), as.logical(want_V), as.integer(attr(h,'n_batch')))
+}

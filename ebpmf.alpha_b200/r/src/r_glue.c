@@ -308,6 +308,81 @@ SEXP C_calc_ebpmf_log_obj(SEXP xp, SEXP n, SEXP p, SEXP sym, SEXP ssexp, SEXP sl
 }
 
 /* ---- registration ------------------------------------------------------------------------ */
+/* ---- the batched branch of the outer loop, R/ebpmf_log.R:195-203, :254-300 --------------------
+ * C_ebpmf_batched_new(Y dgCMatrix, batch_row0 integer/double vector of 0-based batch starts, device, nslots):
+ * external pointer; C_ebpmf_batched_vga_step(...): list(M, V|NULL, v_sum, sym, ssexp, slogv, n_updates
+ * (max over batches), converged (all batches)) with attribute "n_updates_per_batch". */
+static void batched_finalizer(SEXP xp)
+{
+    ebpmf_batched *h = (ebpmf_batched *)R_ExternalPtrAddr(xp);
+    if (h) { ebpmf_batched_destroy(h); R_ClearExternalPtr(xp); }
+}
+
+static ebpmf_batched *get_batched(SEXP xp)
+{
+    if (TYPEOF(xp) != EXTPTRSXP || R_ExternalPtrAddr(xp) == NULL)
+        Rf_error("ebpmf_b200: invalid or closed batched GPU handle");
+    return (ebpmf_batched *)R_ExternalPtrAddr(xp);
+}
+
+static void check_batched(ebpmf_batched *h, int rc)
+{
+    if (rc == EBPMF_OK) return;
+    char msg[1024];
+    strncpy(msg, ebpmf_batched_last_error(h), sizeof msg - 1);
+    msg[sizeof msg - 1] = '\0';
+    if (rc == EBPMF_ERR_NAN) Rf_error("missing value where TRUE/FALSE needed");   /* R/vga_solver_mat.R:26 */
+    if (rc == EBPMF_ERR_VAR_TYPE) Rf_error("Non-supported var type");
+    Rf_error("ebpmf_b200: %s", msg);
+}
+
+SEXP C_ebpmf_batched_new(SEXP Y, SEXP batch_row0, SEXP device, SEXP nslots)
+{
+    if (!is_dgC(Y)) Rf_error("Y must be a dgCMatrix");
+    ebpmf_batched *h = NULL;
+    int rc = ebpmf_batched_create(Rf_asInteger(device), Rf_asInteger(nslots), &h);
+    if (rc != EBPMF_OK) Rf_error("ebpmf_b200: %s", ebpmf_batched_last_error(NULL));
+    SEXP xp = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(xp, batched_finalizer, TRUE);
+    const R_xlen_t nb1 = XLENGTH(batch_row0);
+    int64_t *row0 = (int64_t *)R_alloc((size_t)nb1, sizeof(int64_t));
+    SEXP r0 = PROTECT(Rf_coerceVector(batch_row0, REALSXP));
+    for (R_xlen_t b = 0; b < nb1; ++b) row0[b] = (int64_t)REAL(r0)[b];
+    SEXP Dim = R_do_slot(Y, Rf_install("Dim"));
+    rc = ebpmf_batched_set_y_csc(h, INTEGER(Dim)[0], INTEGER(Dim)[1], INTEGER(R_do_slot(Y, Rf_install("p"))),
+                                 INTEGER(R_do_slot(Y, Rf_install("i"))), REAL(R_do_slot(Y, Rf_install("x"))),
+                                 (int64_t)nb1 - 1, row0);
+    UNPROTECT(2);
+    check_batched(h, rc);
+    return xp;
+}
+
+SEXP C_ebpmf_batched_vga_step(SEXP xp, SEXP M, SEXP EL, SEXP EF, SEXP sigma2, SEXP var_type, SEXP maxiter, SEXP tol,
+                              SEXP want_V, SEXP nbatch)
+{
+    ebpmf_batched *h = get_batched(xp);
+    const int vt = var_type_code(var_type);
+    if (vt < 0) Rf_error("Non-supported var type");
+    const R_xlen_t n = Rf_nrows(M), p = Rf_ncols(M);
+    if (Rf_nrows(EL) != n || Rf_nrows(EF) != p || Rf_ncols(EL) != Rf_ncols(EF)) Rf_error("non-conformable arguments");
+    const R_xlen_t want = vt == EBPMF_VAR_BY_COL ? p : vt == EBPMF_VAR_BY_ROW ? n : 1;
+    if (XLENGTH(sigma2) != want) Rf_error("sigma2 has the wrong length for this var_type");
+    const int wv = Rf_asLogical(want_V);
+    SEXP Mo = PROTECT(alloc_like(M));
+    SEXP Vo = PROTECT(wv ? alloc_like(M) : R_NilValue);
+    SEXP vs = PROTECT(Rf_allocVector(REALSXP, want));
+    SEXP nu = PROTECT(Rf_allocVector(INTSXP, Rf_asInteger(nbatch)));
+    ebpmf_solve_info info;
+    int rc = ebpmf_batched_vga_step_host(h, REAL(M), Rf_ncols(EL), REAL(EL), REAL(EF), vt, REAL(sigma2),
+                                         Rf_asInteger(maxiter), Rf_asReal(tol), REAL(Mo), wv ? REAL(Vo) : NULL, REAL(vs),
+                                         &info, INTEGER(nu), NULL);
+    if (rc != EBPMF_OK) { UNPROTECT(4); check_batched(h, rc); }
+    SEXP out = PROTECT(info_list(&info, Mo, Vo, vs));
+    Rf_setAttrib(out, Rf_install("n_updates_per_batch"), nu);
+    UNPROTECT(5);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"C_ebpmf_ctx_new", (DL_FUNC)&C_ebpmf_ctx_new, 1},
     {"C_ebpmf_ctx_set_y", (DL_FUNC)&C_ebpmf_ctx_set_y, 2},
@@ -315,6 +390,8 @@ static const R_CallMethodDef call_methods[] = {
     {"C_ebpmf_vga_step", (DL_FUNC)&C_ebpmf_vga_step, 9},
     {"C_ebpmf_ctx_set_m", (DL_FUNC)&C_ebpmf_ctx_set_m, 2},
     {"C_ebpmf_vga_step_resident", (DL_FUNC)&C_ebpmf_vga_step_resident, 9},
+    {"C_ebpmf_batched_new", (DL_FUNC)&C_ebpmf_batched_new, 4},
+    {"C_ebpmf_batched_vga_step", (DL_FUNC)&C_ebpmf_batched_vga_step, 10},
     {"C_vga_pois_solver_mat_newton", (DL_FUNC)&C_vga_pois_solver_mat_newton, 9},
     {"C_vga_pois_solver_mat_newton_fixed_iter", (DL_FUNC)&C_vga_pois_solver_mat_newton_fixed_iter, 8},
     {"C_vga_pois_solver_mat_newton_low_memory", (DL_FUNC)&C_vga_pois_solver_mat_newton_low_memory, 11},

@@ -297,7 +297,7 @@ class VgaContext:
         return nnz.value
 
     def set_option(self, name, value):
-        """'delta' (0 = exact update count, the default) or 'pipeline' (0 fused / 1 split)."""
+        """'delta' (0 = exact update count, the default), 'pipeline' (0 fused / 1 split / 2 ordered / 3 scored), ...: see include/ebpmf_b200.h."""
         self._ck(self._lib.ebpmf_ctx_set_option(self._h, name.encode(), float(value)))
 
     def last_diag(self):
@@ -371,6 +371,88 @@ class VgaGroup:
         return dict(M=Mo, V=Vo, v_sum=(vs if var_type != "constant" else float(vs[0])), sym=info.sym,
                     ssexp=info.ssexp, slogv=info.slogv, n_updates=info.n_updates,
                     converged=bool(info.converged), passes=info.passes, kernel_ms=info.kernel_ms)
+
+
+def r_batches(n, batch_size):
+    """Row ranges of ebpmf_log's batches: ``n_batch = ceiling(n/batch_size)``; ``split(1:n, cut(seq_along(1:n),
+    n_batch, labels=FALSE))`` (R/ebpmf_log.R:195-197).  base::cut with a break count uses n_batch+1 equally
+    spaced breaks on [1, n], the outer two widened by (n-1)/1000, intervals right-closed; the batches are
+    therefore contiguous.  Returns the int64 array of n_batch+1 batch starts (0-based, last = n); empty bins
+    are dropped, as split() drops them."""
+    n = int(n)
+    n_batch = int(np.ceil(n / float(batch_size)))
+    if n_batch <= 1:
+        return np.array([0, n], dtype=np.int64)
+    dx = float(n - 1) if n > 1 else 1.0
+    breaks = np.linspace(1.0, float(n), n_batch + 1)
+    breaks[0] = 1.0 - dx / 1000
+    breaks[-1] = float(n) + dx / 1000
+    code = np.searchsorted(breaks, np.arange(1, n + 1, dtype=np.float64), side="left")   # x in (b_k, b_{k+1}]
+    starts = [0] + [int(i) for i in np.nonzero(np.diff(code))[0] + 1] + [n]
+    return np.asarray(starts, dtype=np.int64)
+
+
+class VgaBatched:
+    """ebpmf_log's batched branch (``general_control$batch_size < n``, R/ebpmf_log.R:195-203, :254-300): one
+    solve per contiguous row batch with the stop test scoped to the batch, batches pipelined through
+    ``nslots`` worker contexts so host<->device copies overlap the solves; M lives on the host."""
+
+    def __init__(self, device=0, nslots=3):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._lib.ebpmf_batched_create(int(device), int(nslots), C.byref(h)))
+        self._h = h
+        self.n = self.p = self.batch_row0 = None
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self._lib.ebpmf_batched_last_error(self._h)
+            raise EbpmfError(rc, msg.decode() if msg else "")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ebpmf_batched_destroy(self._h)
+            self._h = None
+
+    def set_option(self, name, value):
+        self._ck(self._lib.ebpmf_batched_set_option(self._h, name.encode(), float(value)))
+
+    def set_y(self, Y, batch_size=None, batch_row0=None):
+        """``batch_size`` as in general_control (rows per batch, cut as R cuts them) or explicit ``batch_row0``."""
+        n, p = Y.shape
+        row0 = r_batches(n, batch_size) if batch_row0 is None else np.ascontiguousarray(batch_row0, dtype=np.int64)
+        cp, ri, x = _csc_slots(Y if _is_sparse(Y) else _sp.csc_matrix(np.asarray(Y)))
+        self._ck(self._lib.ebpmf_batched_set_y_csc(self._h, n, p, _ptr(cp), _ptr(ri), _ptr(x), len(row0) - 1, _ptr(row0)))
+        self.n, self.p, self.batch_row0 = n, p, row0
+
+    def sum_lfactorial(self):
+        out = C.c_double()
+        self._ck(self._lib.ebpmf_batched_sum_lfactorial(self._h, C.byref(out)))
+        return out.value
+
+    def vga_step_host(self, M, EL, EF, sigma2, var_type, maxiter=10, tol=1e-5, return_V=False, M_out=None):
+        if var_type not in VAR_TYPE:
+            raise EbpmfError(4, "Non-supported var type")
+        M = _f(M)
+        EL = _f(np.asarray(EL, dtype=np.float64).reshape(self.n, -1))
+        EF = _f(np.asarray(EF, dtype=np.float64).reshape(self.p, -1))
+        s2 = _vec(sigma2)
+        ln = {"by_col": self.p, "by_row": self.n, "constant": 1}[var_type]
+        if s2.size != ln:
+            raise ValueError("sigma2 has the wrong length for var_type %r" % var_type)
+        Mo = np.empty((self.n, self.p), order="F") if M_out is None else M_out
+        Vo = np.empty((self.n, self.p), order="F") if return_V else None
+        vs = np.empty(ln)
+        nb = len(self.batch_row0) - 1
+        nu = np.zeros(nb, dtype=np.int32)
+        cv = np.zeros(nb, dtype=np.int32)
+        info = SolveInfo()
+        self._ck(self._lib.ebpmf_batched_vga_step_host(self._h, _ptr(M), EL.shape[1], _ptr(EL), _ptr(EF),
+                                                       VAR_TYPE[var_type], _ptr(s2), int(maxiter), float(tol),
+                                                       _ptr(Mo), _ptr(Vo), _ptr(vs), C.byref(info), _ptr(nu), _ptr(cv)))
+        return dict(M=Mo, V=Vo, v_sum=(vs if var_type != "constant" else float(vs[0])), sym=info.sym,
+                    ssexp=info.ssexp, slogv=info.slogv, n_updates=[int(v) for v in nu],
+                    converged=[bool(v) for v in cv], kernel_ms=info.kernel_ms)
 
 
 # ---------------------------------------------------------------------------

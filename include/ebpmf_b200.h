@@ -195,6 +195,35 @@ int  ebpmf_group_vga_step_host(ebpmf_group *g, const double *M_in, int64_t K, co
                                int maxiter, double tol,
                                double *M_out, double *V_out, double *v_sum, ebpmf_solve_info *info);
 
+/* ---- batch_size-faithful, host-streamed step (R/ebpmf_log.R:195-203, :254-300) -------------
+ * With general_control$batch_size < n, ebpmf_log cuts the rows into n_batch contiguous batches
+ * (split(1:n, cut(...)), :195-199) and runs vga_pois_solver_mat_newton once per batch: the stop test
+ * max(abs(f)) < tol is scoped to the batch (:263-268), M_b is written back (:270), sym/ssexp/slogv
+ * add up in batch order (:274-276), v_sum adds up ('by_col', 'constant') or concatenates ('by_row')
+ * (:281-293).  ebpmf_batched reproduces that branch: every batch's Y slab stays resident as its own
+ * CSC, NO M is kept on the device between calls, and the batches are pipelined through `nslots`
+ * worker contexts (one stream and one host thread each), so the H2D copy of one batch overlaps the
+ * solve of another and the D2H copy of a third.  Device memory holds nslots batches of M, so the
+ * matrix may be larger than HBM.  batch_row0 has nbatch+1 increasing entries, [0] = 0, [nbatch] = n
+ * (R's cut() gives contiguous ranges; the caller computes them).
+ * vga_step_host: full n x p / n x K column-major host matrices in and out (M_out may alias M_in);
+ * v_sum has length p / n / 1; info carries the sums over batches, n_updates = max and converged =
+ * all over batches; n_updates / converged (length nbatch, may be NULL) give the per-batch values. */
+typedef struct ebpmf_batched ebpmf_batched;
+int  ebpmf_batched_create(int device, int nslots, ebpmf_batched **out);
+int  ebpmf_batched_destroy(ebpmf_batched *h);
+const char *ebpmf_batched_last_error(const ebpmf_batched *h);
+int  ebpmf_batched_set_option(ebpmf_batched *h, const char *name, double value);
+int  ebpmf_batched_set_y_csc(ebpmf_batched *h, int64_t n, int64_t p, const int32_t *colptr,
+                             const int32_t *rowidx, const double *x,
+                             int64_t nbatch, const int64_t *batch_row0);
+int  ebpmf_batched_sum_lfactorial(ebpmf_batched *h, double *out);
+int  ebpmf_batched_vga_step_host(ebpmf_batched *h, const double *M_in, int64_t K, const double *EL,
+                                 const double *EF, int var_type, const double *sigma2,
+                                 int maxiter, double tol,
+                                 double *M_out, double *V_out, double *v_sum, ebpmf_solve_info *info,
+                                 int32_t *n_updates, int32_t *converged);
+
 /* ---- drop-in solver signatures (dense operands, as R passes them) ------------------------ */
 
 /* vga_pois_solver_mat_newton(M,X,S,Beta,Sigma2,maxiter,tol,return_V)  R/vga_solver_mat.R:6-41
@@ -242,7 +271,10 @@ int  ebpmf_ctx_sim_data_log(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, int
  *              most ~d (absolute); the global update count n_updates is still R's.  DESIGN.md §3b.
  *   "pipeline" 0 (default): fused first pass; 1: const0 kernel + streaming Newton kernel; 2: as 1, and the
  *              const0 kernel also performs Newton iteration 0 and scores each CTA by its largest first step,
- *              so that the streaming kernel meets the slowest entries first (same results, bit for bit).
+ *              so that the streaming kernel meets the slowest entries first (same results, bit for bit);
+ *              3: an FP32 scoring pass ranks the (column span, row block) tiles by their largest first Newton
+ *              step and the fused first pass takes them in that order (same results, bit for bit).
+ *   "scored_min_ctas" (default 888 = two waves): pipeline 3 skips the scoring pass below this many tiles.
  *   "debug_verify_scale" (0,1], default 1: TEST HOOK -- the top-up pass verifies against tol*scale, which
  *              forces the host's K*+1 retry loop to run (tests/test_gpu_parity.py::test_retry_loop_...). */
 int  ebpmf_ctx_set_option(ebpmf_ctx *ctx, const char *name, double value);

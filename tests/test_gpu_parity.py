@@ -267,7 +267,7 @@ def test_device_sim_data_matches_oracle(gpu_ctx):
 # ---------------------------------------------------------------------------------------
 # options: delta mode (frozen units) and the split pipeline
 # ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize("pipeline", [0, 1, 2])
+@pytest.mark.parametrize("pipeline", [0, 1, 2, 3])
 @pytest.mark.parametrize("delta", [0.0, 1e-14])
 @pytest.mark.parametrize("var_type,maxiter,tol", [("by_col", 10, 1e-5), ("by_row", 1000, 1e-8), ("constant", 3, 1e-5)])
 def test_options_delta_and_pipeline(pkg, pipeline, delta, var_type, maxiter, tol):
@@ -276,6 +276,7 @@ def test_options_delta_and_pipeline(pkg, pipeline, delta, var_type, maxiter, tol
     ctx = pkg.VgaContext(0)
     try:
         ctx.set_option("pipeline", pipeline)
+        ctx.set_option("scored_min_ctas", 0)
         ctx.set_option("delta", delta)
         ctx.set_y(sp.csc_matrix(sim["Y"]))
         res = ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], var_type, maxiter, tol, return_V=True)
@@ -370,7 +371,7 @@ def test_maxiter_one(gpu_ctx):
     assert res["n_updates"] == 1 and not res["converged"]
 
 
-@pytest.mark.parametrize("K,pipeline", [(31, 0), (45, 0), (45, 1), (70, 0), (45, 2)])
+@pytest.mark.parametrize("K,pipeline", [(31, 0), (45, 0), (45, 1), (70, 0), (45, 2), (45, 3), (70, 3)])
 def test_many_factors(pkg, K, pipeline):
     """K_tot = K + 2 above the 32-column register tile: Beta is accumulated over chunks of 32 factor columns
     (flash_control$Kmax defaults to 30, R/ebpmf_log_controls.R:74, but greedy additions can exceed it)."""
@@ -383,6 +384,7 @@ def test_many_factors(pkg, K, pipeline):
     ctx = pkg.VgaContext(0)
     try:
         ctx.set_option("pipeline", pipeline)
+        ctx.set_option("scored_min_ctas", 0)
         ctx.set_y(sp.csc_matrix(sim["Y"]))
         res = ctx.vga_step_host(st["M0"], EL, EF, st["sigma2"], "by_col", 100, 1e-8, return_V=True)
         ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], EL, EF, st["sigma2"], "by_col", 100, 1e-8)
@@ -429,15 +431,18 @@ def test_resident_m_loop_equals_full_roundtrip(gpu_ctx):
         assert np.array_equal(r["v_sum"], rf["v_sum"]) and r["sym"] == rf["sym"]
 
 
+@pytest.mark.parametrize("pipeline", [2, 3])
 @pytest.mark.parametrize("var_type", ["by_col", "by_row"])
-def test_ordered_pipeline_edge_cases(pkg, var_type):
-    """pipeline 2 (iteration 0 inside the const0 kernel, CTAs by decreasing first step): u = 0 (R breaks at
-    i = 1, M_0 final), maxiter = 1 (falls back), maxiter = 2 (exhaustion right after the moved iteration),
-    NaN; always bit-identical to the fused pipeline."""
+def test_ordered_pipeline_edge_cases(pkg, var_type, pipeline):
+    """pipeline 2 (iteration 0 inside the const0 kernel, CTAs by decreasing first step) and pipeline 3 (FP32
+    scoring pass, fused kernel in score order): u = 0 (R breaks at i = 1, M_0 final), maxiter = 1 (falls
+    back), maxiter = 2 (exhaustion right after the moved iteration), NaN; always bit-identical to the fused
+    pipeline."""
     sim, st = make_case(1500, 200, 4, 0.10, var_type=var_type)
     a, b = pkg.VgaContext(0), pkg.VgaContext(0)
     try:
-        b.set_option("pipeline", 2)
+        b.set_option("pipeline", pipeline)
+        b.set_option("scored_min_ctas", 0)
         for c in (a, b):
             c.set_y(sp.csc_matrix(sim["Y"]))
         ra = a.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], var_type, 100, 1e-7, return_V=True)
@@ -504,7 +509,9 @@ def test_randomised_configurations(pkg):
             sim = simdata.sim_data_log(n, p, K=K, seed=1000 + trial, pi0=0.9,
                                        log_offset=(simdata.offset_for_density(dens, K=K, pi0=0.9) if dens > 0 else -40.0))
             st = simdata.solver_state(sim, start=["cold", "warm"][int(rng.integers(2))], var_type=vt, seed=trial, noise=0.1)
-            ctx.set_option("pipeline", int(rng.integers(3)))
+            pl = int(rng.integers(3))
+            ctx.set_option("pipeline", 3 if trial % 4 == 3 else pl)
+            ctx.set_option("scored_min_ctas", 0)
             ctx.set_option("delta", float(rng.choice([0.0, 0.0, 1e-14])))
             ctx.set_y(sp.csc_matrix(sim["Y"]) if rng.integers(2) else sim["Y"])
             res = ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], vt, maxiter, tol, return_V=True)
@@ -518,7 +525,7 @@ def test_randomised_configurations(pkg):
         ctx.close()
 
 
-@pytest.mark.parametrize("pipeline", [0, 2])
+@pytest.mark.parametrize("pipeline", [0, 2, 3])
 def test_retry_loop_when_verification_fails(pkg, pipeline):
     """The host's K*+1 retry loop (pass 2 repeated until every unit is below tol) is exercised with a test
     hook: pass 1 finds K* for tol, pass 2 verifies against tol*1e-8, fails, and the loop must walk up to the
@@ -527,6 +534,7 @@ def test_retry_loop_when_verification_fails(pkg, pipeline):
     ctx = pkg.VgaContext(0)
     try:
         ctx.set_option("pipeline", pipeline)
+        ctx.set_option("scored_min_ctas", 0)
         ctx.set_option("debug_verify_scale", 1e-8)
         ctx.set_y(sp.csc_matrix(sim["Y"]))
         res = ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], "by_col", 50, 1e-2, return_V=True)
@@ -543,3 +551,86 @@ def test_retry_loop_when_verification_fails(pkg, pipeline):
         assert not res["converged"] and res["n_updates"] == mi
     finally:
         ctx.close()
+
+
+def test_scored_pipeline_many_tiles(pkg):
+    """pipeline 3 on a matrix with several waves of tiles (device-generated 40 000 x 6 000): bit-identical M,
+    V sums and update count to the fused pipeline, and the top-up pass has (almost) nothing left to do."""
+    n, p, K = 40000, 6000, 10
+    a, b = pkg.VgaContext(0), pkg.VgaContext(0)
+    try:
+        b.set_option("pipeline", 3)
+        for c in (a, b):
+            c.sim_data_log(n, p, K, seed=77, log_offset=-4.644)
+        ia, ib = a.vga_step(10, 1e-5), b.vga_step(10, 1e-5)
+        assert ia.n_updates == ib.n_updates and ia.converged == ib.converged
+        assert ia.sym == ib.sym and ia.ssexp == ib.ssexp and ia.slogv == ib.slogv
+        assert np.array_equal(a.get_v_sum(), b.get_v_sum())
+        for r0 in (0, 17000, n - 999):
+            assert np.array_equal(a.get_rows(r0, 999, "M"), b.get_rows(r0, 999, "M"))
+        da, db = a.last_diag(), b.last_diag()
+        assert db["topup_units"] <= da["topup_units"]
+        if ia.n_updates >= 3:
+            assert db["topup_units"] < 0.1 * ((n + 31) // 32) * ((p + 1) // 2)
+    finally:
+        a.close(); b.close()
+
+
+# ---------------------------------------------------------------------------------------
+# batch_size-faithful host-streamed step (R/ebpmf_log.R:195-203, :254-300)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("var_type", ["by_col", "by_row", "constant"])
+@pytest.mark.parametrize("nslots", [1, 3])
+def test_batched_step_vs_oracle_batched_branch(pkg, var_type, nslots):
+    """Per-batch stop scope: every batch gets ITS OWN update count; sums add up in batch order; by_row v_sum
+    concatenates.  Compared with the oracle's restatement of the batched branch, batches cut as R cuts them."""
+    sim, st = make_case(1500, 211, 4, 0.10, var_type=var_type)
+    n = 1500
+    h = pkg.VgaBatched(0, nslots)
+    try:
+        h.set_y(sp.csc_matrix(sim["Y"]), batch_size=400)
+        assert list(h.batch_row0) == [0, 375, 750, 1125, 1500]
+        batches = vga_numpy.r_cut_batches(n, 4)
+        for maxiter, tol in ((10, 1e-5), (100, 1e-9), (2, 1e-5)):
+            res = h.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], var_type, maxiter, tol, return_V=True)
+            ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], var_type,
+                                               maxiter, tol, batches=batches)
+            assert res["n_updates"] == list(ref["n_updates"]) and res["converged"] == [bool(c) for c in ref["converged"]]
+            assert relM(res["M"], ref["M"]) < RTOL and rel(res["V"], ref["V"]) < RTOL
+            assert rel(res["v_sum"], ref["v_sum"]) < RTOL
+            for k in ("sym", "ssexp", "slogv"):
+                assert abs(res[k] - ref[k]) <= RTOL * max(abs(ref[k]), 1.0), (k, res[k], ref[k])
+        assert abs(h.sum_lfactorial() - vga_numpy.sum_lfactorial_sparseMat(sp.csc_matrix(sim["Y"]))) < 1e-8 * 1e4
+    finally:
+        h.close()
+
+
+def test_batched_equals_one_context_per_batch(pkg):
+    """The batched handle against the plain context run batch by batch on row slices (bit-identical), M_out
+    aliasing M_in, an uneven last batch, and a batch count that is not a multiple of the slot count."""
+    sim, st = make_case(1203, 97, 3, 0.15)
+    Y = sp.csc_matrix(sim["Y"])
+    row0 = np.array([0, 256, 300, 811, 812, 1203], dtype=np.int64)
+    h = pkg.VgaBatched(0, 2)
+    ctx = pkg.VgaContext(0)
+    try:
+        h.set_y(Y, batch_row0=row0)
+        M = np.array(st["M0"], order="F")
+        res = h.vga_step_host(M, st["EL"], st["EF"], st["sigma2"], "by_col", 10, 1e-5, M_out=M)
+        assert res["M"] is M
+        vs = np.zeros(97)
+        for b in range(len(row0) - 1):
+            lo, hi = int(row0[b]), int(row0[b + 1])
+            ctx.set_y(sp.csc_matrix(Y[lo:hi, :]))
+            r = ctx.vga_step_host(st["M0"][lo:hi], st["EL"][lo:hi], st["EF"], st["sigma2"], "by_col", 10, 1e-5)
+            assert r["n_updates"] == res["n_updates"][b]
+            assert np.array_equal(r["M"], M[lo:hi])
+            vs += r["v_sum"]
+        assert np.array_equal(vs, res["v_sum"])
+        # NaN in one batch -> error naming the batch
+        EL = st["EL"].copy(); EL[900, 1] = np.nan
+        with pytest.raises(pkg.EbpmfError) as ei:
+            h.vga_step_host(st["M0"], EL, st["EF"], st["sigma2"], "by_col", 10, 1e-5)
+        assert ei.value.code == 3 and "batch 4" in str(ei.value)
+    finally:
+        h.close(); ctx.close()

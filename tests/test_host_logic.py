@@ -56,6 +56,22 @@ def test_shard_rows(pkg, n, world):
     assert all(r % 256 == 0 for _, r in sh[:-1] if r and _ + r < n)
 
 
+@pytest.mark.parametrize("n,batch_size", [(1000, 300), (1000, 1000), (1000, 5000), (7, 2), (100, 33), (12345, 1000),
+                                          (5, 1), (2, 1), (513, 256), (4097, 64)])
+def test_r_batches_equals_r_cut(pkg, n, batch_size):
+    """Host mirror of `split(1:n, cut(seq_along(1:n), n_batch, labels=FALSE))` (R/ebpmf_log.R:195-197): contiguous
+    ranges whose starts equal the oracle's restatement of base::cut."""
+    row0 = pkg.r_batches(n, batch_size)
+    n_batch = int(np.ceil(n / batch_size))
+    assert row0[0] == 0 and row0[-1] == n and np.all(np.diff(row0) > 0)
+    if n_batch <= 1:
+        assert list(row0) == [0, n]
+        return
+    ref = vga_numpy.r_cut_batches(n, n_batch)
+    assert [int(b[0]) for b in ref] + [n] == list(row0)
+    assert all(np.array_equal(b, np.arange(b[0], b[-1] + 1)) for b in ref)
+
+
 def test_shard_csc_equals_row_slice(pkg):
     rng = np.random.default_rng(1)
     Y = sp.csc_matrix(rng.poisson(0.2, size=(700, 31)).astype(float))
