@@ -150,6 +150,26 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def numa_local_cpus(device):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None.  Pinned host buffers are placed by first
+    touch, so allocating them from a NUMA-local CPU keeps each rank's PCIe traffic on its own socket."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return (node, cpus) if cpus else None
+    except Exception:
+        return None
+
+
 def cpu_sample_inputs(ctx, rows):
     """Rows [0, rows) of the device-generated workload, pulled to the host for the CPU arm."""
     import scipy.sparse as sp
@@ -401,9 +421,17 @@ def main():
         s2 = ctx.get_sigma2()
         cp, ri, x = ctx.get_y_csc()
         scp, sri, sx = pkg.shard_csc(cp, ri, x, 0, er)
+        # pinned buffers are allocated (and first touched) from a CPU of the GPU's own NUMA node
+        all_cpus = os.sched_getaffinity(0)
+        numa = numa_local_cpus(local_rank)
+        if numa:
+            os.sched_setaffinity(0, numa[1])
         M0 = torch.empty((p, er), dtype=torch.float64).pin_memory().numpy().T       # pinned, column-major er x p
         M0[...] = ctx.get_rows(0, er)
         Mo = torch.empty((p, er), dtype=torch.float64).pin_memory().numpy().T       # pinned result buffer
+        Mo[...] = 0.0
+        if numa:
+            os.sched_setaffinity(0, all_cpus)
         ELs = np.asfortranarray(EL[:er])
         ectx = pkg.VgaContext(local_rank)
         ectx.set_y_csc(er, p, scp, sri, sx)
@@ -439,7 +467,8 @@ def main():
                               "previous step's output and is already on the device (R feeds res$M back unchanged, "
                               "R/ebpmf_log.R:309, R/ebpmf_log_flash_update.R:35)",
                       "sample": "rows [0,%d) x %d cols per GPU per step (bounded: the full slab is 30 GB); PCIe-bound"
-                                % (er, p), "n_updates": r["n_updates"], "ms_per_step": 1e3 * e_wall / args.steps}
+                                % (er, p), "n_updates": r["n_updates"], "ms_per_step": 1e3 * e_wall / args.steps,
+                      "pinned_buffers_numa_node": (numa[0] if numa else None)}
         out["e2e_full_roundtrip"] = {"value": er * p * world / (full_wall / args.steps), "unit": "entries/s",
                                      "h2d_bytes_per_step": int(8 * er * p + 8 * (er + p) * (K + 2) + 8 * p),
                                      "d2h_bytes_per_step": int(8 * er * p + 8 * p + 64),

@@ -197,9 +197,9 @@ int cols_per_cta_for(long long p, long long nRB) {
     return (int)c;
 }
 
-template <int KTP, int FORMULA, bool DELTA>
+template <int KTP, int FORMULA, bool DELTA, bool PERM = false>
 int launch_first_ktp2(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
-    auto kern = vga_fused_kernel<KTP, kE, FORMULA, DELTA>;
+    auto kern = vga_fused_kernel<KTP, kE, FORMULA, DELTA, false, PERM>;
     const int smem = (int)sizeof(FusedSmem<KTP>);
     static bool configured[8] = {false, false, false, false, false, false, false, false};   // per device
     if (ctx->device < 8 ? !configured[ctx->device] : true) {
@@ -213,6 +213,9 @@ int launch_first_ktp2(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
 
 template <int KTP, int FORMULA>
 int launch_first_ktp(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
+    if (FORMULA == FORMULA_A1 && a.perm)      // scored pipeline: tiles in score order
+        return a.delta > 0 ? launch_first_ktp2<KTP, FORMULA_A1, true, true>(ctx, a, grid)
+                           : launch_first_ktp2<KTP, FORMULA_A1, false, true>(ctx, a, grid);
     return a.delta > 0 ? launch_first_ktp2<KTP, FORMULA, true>(ctx, a, grid)
                        : launch_first_ktp2<KTP, FORMULA, false>(ctx, a, grid);
 }

@@ -346,7 +346,7 @@ struct FusedSmem {
 // writes M_1 and const0; no finalisation.  The CTA's largest first step max|f_0/f_0'| goes to
 // a.score: it predicts where the slowest entries are (the CTA holding the entry that sets the global
 // count ranks in the first few % by this score on every case tried, cold or warm start).
-template <int KTP, int E, int FORMULA, bool DELTA, bool ITER0_ONLY = false>
+template <int KTP, int E, int FORMULA, bool DELTA, bool ITER0_ONLY = false, bool PERM = false>
 __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const FusedArgs a)
 {
     static_assert(kTileCols % E == 0, "E must divide the tile width");
@@ -358,8 +358,9 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
     const int n = (int)a.n, p = (int)a.p;
     // scored pipeline: the CTAs take the (column span, row block) tiles by decreasing predicted
     // hardness (a.perm, from vga_score_kernel); CTAs are dispatched in linear order, x fastest
+    // (PERM is a template parameter so that the default instantiation keeps its code unchanged)
     int span = blockIdx.x, rb = blockIdx.y;
-    if (!ITER0_ONLY && a.perm) {
+    if (PERM) {
         const int id = a.perm[blockIdx.y * gridDim.x + blockIdx.x];
         rb = id / (int)gridDim.x;
         span = id - rb * (int)gridDim.x;
