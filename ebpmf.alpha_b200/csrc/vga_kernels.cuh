@@ -85,8 +85,8 @@ struct FusedArgs {
     double *colV;                   // [nRW][p]      sum over the warp's 32 rows of V
     double *unitS;                  // [nRW][nJG][2] sum exp(M+V/2), sum(log(V)/2+c) of the unit
     double *rowpart;                // [nJG][n] sum over the unit's columns of V (by_row only), else null
-    float *score;                   // ordered pipeline: per-CTA max |f_0/f_0'| written by the const0 kernel
-    const int *perm;                // ordered pipeline: CTA ids by decreasing score (null: natural order)
+    float *score;                   // ordered / scored pipelines: per-tile max |f_0/f_0'| (stage A or vga_score_kernel)
+    const int *perm;                // ordered / scored pipelines: tile ids by decreasing score (null: natural order)
     int nspans;                     // column spans per row block (grid.x of the natural decomposition)
     Status *status;
     const Status *const *peers;     // the other ranks' Status words, mapped peer memory (NVLink); may be null
@@ -849,12 +849,19 @@ __global__ void __launch_bounds__(kThreads, EBPMF_STREAM_MINB) vga_stream_kernel
     int t0_next = (MODE == MODE_FIRST) ? *kstar_live : 0;
     const double tol_lane = row_ok ? ((MODE == MODE_TOPUP) ? a.tol_verify : a.tol) : INFINITY;
 
-    // first pass: register prefetch of the next unit's (M, const0)
+    // register prefetch of the next unit's (M, const0); the top-up pass also reads the units' counts two
+    // units ahead, so that it knows one unit in advance whether the next unit's operands are needed
     double mnext[E], cnext[E];
-    if (MODE == MODE_FIRST) {
+    int kn1 = 0, kn2 = 0;                            // top-up: k_unit of this unit and of the next one
+    if (MODE == MODE_TOPUP) {
+        kn1 = a.kunit[ku_idx];
+        kn2 = (jc0 + E < jc1) ? a.kunit[ku_idx + (size_t)a.nRW] : kFrozen;
+    }
+    {
+        const bool want = (MODE == MODE_FIRST) || (kn1 < target);
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            const bool okn = row_ok && (jc0 + e < jc1);
+            const bool okn = want && row_ok && (jc0 + e < jc1);
             mnext[e] = okn ? ld_stream(Msrc + off + e * ns) : 0.0;
             cnext[e] = okn ? ld_stream(a.C0 + off + e * ns) : 2.0;
         }
@@ -869,30 +876,34 @@ __global__ void __launch_bounds__(kThreads, EBPMF_STREAM_MINB) vga_stream_kernel
             absorb_peer(a.status, a.epoch, peer_word);           // the word peeked 8 units ago
             peer_word = peek_peer(a, (unsigned)(jb / E) + bx + rb);
         }
+        double m[E], c0[E], w[E], c1[E], c2[E], sc[E], r[E], sexp[E], f[E];
+        bool ok[E];
+        bool want_next = true;
         if (MODE == MODE_TOPUP) {
-            k = a.kunit[ku_idx];
-            if (k >= target) continue;               // at K* already (k > K* cannot happen), or frozen (0xFFFF)
-            ++my_topups;
+            k = kn1;
+            kn1 = kn2;
+            kn2 = (jb + 2 * E < jc1) ? a.kunit[ku_idx + 2 * (size_t)a.nRW] : kFrozen;
+            want_next = kn1 < target;
         } else {
             t0 = t0_next;                            // read one unit ahead: off the critical path, still <= u
             t0_next = *kstar_live;
         }
-        double m[E], c0[E], w[E], c1[E], c2[E], sc[E], r[E], sexp[E], f[E];
-        bool ok[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            m[e] = mnext[e]; c0[e] = cnext[e];
+            const bool okn = want_next && row_ok && (jb + E + e < jc1);
+            mnext[e] = okn ? ld_stream(Msrc + off + (E + e) * ns) : 0.0;
+            cnext[e] = okn ? ld_stream(a.C0 + off + (E + e) * ns) : 2.0;
+        }
+        if (MODE == MODE_TOPUP) {
+            if (k >= target) continue;               // at K* already (k > K* cannot happen), or frozen (0xFFFF)
+            ++my_topups;
+        }
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const bool colok = jb + e < jc1;
             ok[e] = row_ok && colok;
             const int jj = colok ? jb + e : jc0;
-            if (MODE == MODE_FIRST) {
-                m[e] = mnext[e]; c0[e] = cnext[e];
-                const bool okn = row_ok && (jb + E + e < jc1);
-                mnext[e] = okn ? ld_stream(Msrc + off + (E + e) * ns) : 0.0;
-                cnext[e] = okn ? ld_stream(a.C0 + off + (E + e) * ns) : 2.0;
-            } else {
-                m[e] = ok[e] ? ld_stream(Msrc + off + e * ns) : 0.0;
-                c0[e] = ok[e] ? ld_stream(a.C0 + off + e * ns) : 2.0;
-            }
             if (by_col) { c1[e] = __ldg(a.sc1 + jj); c2[e] = __ldg(a.sc2 + jj); }
             else { c1[e] = c1_row; c2[e] = c2_row; }
             const double c0m1 = __dadd_rn(c0[e], -1.0);
