@@ -76,6 +76,7 @@ SIGNATURES = {
     "ebpmf_group_sum_lfactorial": (_int, [_vp, C.POINTER(_dbl)]),
     "ebpmf_group_vga_step_host": (_int, [_vp, _vp, _i64, _vp, _vp, _int, _vp, _int, _dbl, _vp, _vp, _vp, _PI]),
     "ebpmf_batched_create": (_int, [_int, _int, C.POINTER(_vp)]),
+    "ebpmf_batched_create_multi": (_int, [_int, _vp, _int, C.POINTER(_vp)]),
     "ebpmf_batched_destroy": (_int, [_vp]),
     "ebpmf_batched_last_error": (C.c_char_p, [_vp]),
     "ebpmf_batched_set_option": (_int, [_vp, C.c_char_p, _dbl]),

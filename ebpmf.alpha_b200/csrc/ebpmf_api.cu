@@ -1645,8 +1645,7 @@ void swap_y(ebpmf_ctx *c, YState &y) {
 }  // namespace
 
 struct ebpmf_batched {
-    int device = 0;
-    std::vector<ebpmf_ctx *> slot;
+    std::vector<ebpmf_ctx *> slot;      // worker contexts, possibly on several devices; batch b runs on slot b % S
     std::vector<YState> ys;             // one per batch, resident
     std::vector<long long> row0;        // nbatch + 1
     long long n = 0, p = 0;
@@ -1662,8 +1661,12 @@ int bfail(ebpmf_batched *h, int code, const std::string &msg) {
 }
 
 void release_batches(ebpmf_batched *h) {
-    cudaSetDevice(h->device);
-    for (YState &y : h->ys) { release(y.colptr); release(y.rowidx); release(y.yx); release(y.rbptr); }
+    const size_t S = h->slot.size();
+    for (size_t b = 0; b < h->ys.size(); ++b) {
+        YState &y = h->ys[b];
+        cudaSetDevice(h->slot[b % S]->device);       // the slab lives on the device of the slot that runs it
+        release(y.colptr); release(y.rowidx); release(y.yx); release(y.rbptr);
+    }
     h->ys.clear();
 }
 
@@ -1685,15 +1688,17 @@ void detach_batch(ebpmf_ctx *c, YState &y) {
 
 extern "C" {
 
-int ebpmf_batched_create(int device, int nslots, ebpmf_batched **out) {
-    if (!out || nslots < 1 || nslots > 8) return bfail(nullptr, EBPMF_ERR_ARG, "batched_create: nslots must be in 1..8");
+// Batches are independent (their stop tests are separate), so several GPUs need no collective: slot s
+// lives on devices[s % ndev] and batch b always runs on slot b % S, where its Y slab is resident.
+int ebpmf_batched_create_multi(int ndev, const int *devices, int nslots_per_device, ebpmf_batched **out) {
+    if (!out || ndev < 1 || ndev > 64 || nslots_per_device < 1 || nslots_per_device > 8)
+        return bfail(nullptr, EBPMF_ERR_ARG, "batched_create: need 1..64 devices and 1..8 slots per device");
     *out = nullptr;
     ebpmf_batched *h = new (std::nothrow) ebpmf_batched();
     if (!h) return bfail(nullptr, EBPMF_ERR_NOMEM, "out of host memory");
-    h->device = device;
-    for (int s = 0; s < nslots; ++s) {
+    for (int s = 0; s < ndev * nslots_per_device; ++s) {
         ebpmf_ctx *c = nullptr;
-        int rc = ebpmf_ctx_create(device, &c);
+        int rc = ebpmf_ctx_create(devices ? devices[s % ndev] : s % ndev, &c);
         if (rc != EBPMF_OK) {
             for (ebpmf_ctx *q : h->slot) ebpmf_ctx_destroy(q);
             delete h;
@@ -1703,6 +1708,10 @@ int ebpmf_batched_create(int device, int nslots, ebpmf_batched **out) {
     }
     *out = h;
     return EBPMF_OK;
+}
+
+int ebpmf_batched_create(int device, int nslots, ebpmf_batched **out) {
+    return ebpmf_batched_create_multi(1, &device, nslots, out);
 }
 
 int ebpmf_batched_destroy(ebpmf_batched *h) {
@@ -1770,11 +1779,12 @@ int ebpmf_batched_set_y_csc(ebpmf_batched *h, int64_t n, int64_t p, const int32_
     ebpmf_ctx *c0 = h->slot[0];
     h->ys.resize((size_t)nbatch);
     for (int64_t b = 0; b < nbatch; ++b) {
+        ebpmf_ctx *cb = h->slot[(size_t)b % h->slot.size()];       // upload on the device that will run the batch
         const long long nb = batch_row0[b + 1] - batch_row0[b];
-        int rc = ebpmf_ctx_set_y_csc(c0, nb, p, cp[(size_t)b].data(), ri[(size_t)b].data(), xx[(size_t)b].data());
-        if (rc != EBPMF_OK) return bfail(h, rc, c0->err);
-        swap_y(c0, h->ys[(size_t)b]);           // the slab now belongs to the batch store
-        c0->have_y = false;
+        int rc = ebpmf_ctx_set_y_csc(cb, nb, p, cp[(size_t)b].data(), ri[(size_t)b].data(), xx[(size_t)b].data());
+        if (rc != EBPMF_OK) return bfail(h, rc, cb->err);
+        swap_y(cb, h->ys[(size_t)b]);           // the slab now belongs to the batch store
+        cb->have_y = false;
         std::vector<int32_t>().swap(ri[(size_t)b]);
         std::vector<double>().swap(xx[(size_t)b]);
     }

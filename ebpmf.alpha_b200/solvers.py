@@ -398,9 +398,15 @@ class VgaBatched:
     ``nslots`` worker contexts so host<->device copies overlap the solves; M lives on the host."""
 
     def __init__(self, device=0, nslots=3):
+        """``device``: one device index, or a list of them (batches are dealt round-robin over
+        ``len(devices) * nslots`` worker contexts; no collective is needed, batches are independent)."""
         self._lib = _lib.load()
         h = C.c_void_p()
-        _lib.check(self._lib.ebpmf_batched_create(int(device), int(nslots), C.byref(h)))
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*device)
+            _lib.check(self._lib.ebpmf_batched_create_multi(len(device), devs, int(nslots), C.byref(h)))
+        else:
+            _lib.check(self._lib.ebpmf_batched_create(int(device), int(nslots), C.byref(h)))
         self._h = h
         self.n = self.p = self.batch_row0 = None
 

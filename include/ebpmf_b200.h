@@ -211,6 +211,9 @@ int  ebpmf_group_vga_step_host(ebpmf_group *g, const double *M_in, int64_t K, co
  * all over batches; n_updates / converged (length nbatch, may be NULL) give the per-batch values. */
 typedef struct ebpmf_batched ebpmf_batched;
 int  ebpmf_batched_create(int device, int nslots, ebpmf_batched **out);
+/* several GPUs, one process: batches are independent, so there is no collective -- slot s lives on
+ * devices[s % ndev] (NULL: 0..ndev-1) and batch b runs on slot b % (ndev * nslots_per_device) */
+int  ebpmf_batched_create_multi(int ndev, const int *devices, int nslots_per_device, ebpmf_batched **out);
 int  ebpmf_batched_destroy(ebpmf_batched *h);
 const char *ebpmf_batched_last_error(const ebpmf_batched *h);
 int  ebpmf_batched_set_option(ebpmf_batched *h, const char *name, double value);

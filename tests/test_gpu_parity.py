@@ -634,3 +634,24 @@ def test_batched_equals_one_context_per_batch(pkg):
         assert ei.value.code == 3 and "batch 4" in str(ei.value)
     finally:
         h.close(); ctx.close()
+
+
+def test_batched_over_two_gpus_equals_one(pkg):
+    """Batches dealt over two GPUs (no collective: batches are independent) give bit-identical results to one
+    GPU.  Skipped on single-GPU boxes; `scripts/mgpu_batched_check.py` is the same check as a script."""
+    import ctypes
+    cnt = ctypes.c_int()
+    pkg.load().ebpmf_device_count(ctypes.byref(cnt))
+    if cnt.value < 2:
+        pytest.skip("needs 2 GPUs")
+    sim, st = make_case(2100, 150, 4, 0.10)
+    a, b = pkg.VgaBatched(0, 2), pkg.VgaBatched([0, 1], 2)
+    try:
+        for h in (a, b):
+            h.set_y(sp.csc_matrix(sim["Y"]), batch_size=300)
+        ra = a.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], "by_col", 10, 1e-5, return_V=True)
+        rb = b.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], "by_col", 10, 1e-5, return_V=True)
+        assert ra["n_updates"] == rb["n_updates"] and np.array_equal(ra["M"], rb["M"]) and np.array_equal(ra["V"], rb["V"])
+        assert np.array_equal(ra["v_sum"], rb["v_sum"]) and ra["sym"] == rb["sym"] and ra["slogv"] == rb["slogv"]
+    finally:
+        a.close(); b.close()
