@@ -30,3 +30,17 @@ out["lowmem_M"] = lm
 out["lfact"] = np.array([vn.sum_lfactorial_sparseMat(sim["Y"])])
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "vga_golden.npz"), **out)
 print("wrote", len(out), "arrays")
+
+# ---- the batched branch (R/ebpmf_log.R:254-300): general_control$batch_size = 25 -> 4 batches of 24 rows ----
+bout = {}
+batches = vn.r_cut_batches(96, int(np.ceil(96 / 25)))
+bout["batch_row0"] = np.array([int(b[0]) for b in batches] + [96], dtype=np.int64)
+for vt in ("by_col", "by_row", "constant"):
+    st = simdata.solver_state(sim, start="cold", var_type=vt, seed=77)
+    r = vn.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], vt, 10, 1e-5, batches=batches)
+    bout[vt + "_M"] = r["M"]; bout[vt + "_V"] = r["V"]; bout[vt + "_v_sum"] = np.atleast_1d(r["v_sum"])
+    bout[vt + "_scal"] = np.array([r["sym"], r["ssexp"], r["slogv"]])
+    bout[vt + "_n_updates"] = np.array(r["n_updates"], dtype=np.int64)
+    bout[vt + "_converged"] = np.array(r["converged"], dtype=np.int64)
+np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "vga_golden_batched.npz"), **bout)
+print("wrote", len(bout), "batched arrays")
