@@ -4,7 +4,9 @@
  * NOT COMPILED IN THIS REPOSITORY'S CI: R (R.h, Rinternals.h, libR) is not installed in the build
  * image or on the GPU box, so this file is compile-checked only where R exists
  * (R CMD INSTALL with src/Makevars).  It is deliberately tiny: every line of arithmetic lives
- * behind the C ABI, which IS tested (from Python/ctypes, tests/).  No Rinternals.h is faked.
+ * behind the C ABI, which IS tested (from Python/ctypes, tests/).  What is checked here without R:
+ * tests/test_r_glue.py syntax-checks this file against declarations of the R API subset it uses
+ * (tests/r_api_stub, never linked) and checks the .Call arities against R/vga_cuda.R.
  *
  * Conventions
  *   - arguments are never written (R shares them, copy-on-modify); outputs are fresh
