@@ -36,9 +36,9 @@ def test_registered_arity_matches_definitions():
 def call_arg_counts(text):
     """(routine, number of arguments after the routine) for every .Call(...) in an R source"""
     out = []
-    for m in re.finditer(r"\.Call\(", text):
+    for m in re.finditer(r"\.Call\((?=\s*C_\w+\s*,)", text):
         i = m.end(); depth = 1; commas = 0; in_str = None
-        while depth:
+        while depth and i < len(text):
             c = text[i]
             if in_str:
                 in_str = None if c == in_str else in_str
