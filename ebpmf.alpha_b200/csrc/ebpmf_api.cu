@@ -283,14 +283,15 @@ int sort_ctas_by_score(ebpmf_ctx *ctx, int ncta) {
 
 template <int KTP>
 int launch_score_ktp(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
-    auto kern = vga_score_kernel<KTP>;
     const int smem = (int)sizeof(ScoreSmem<KTP>);
     static bool configured[8] = {false, false, false, false, false, false, false, false};   // per device
     if (ctx->device < 8 ? !configured[ctx->device] : true) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(vga_score_kernel<KTP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(vga_score_kernel<KTP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         if (ctx->device < 8) configured[ctx->device] = true;
     }
-    kern<<<grid, dim3(kThreads), smem, ctx->stream>>>(a);
+    if (a.var_type == EBPMF_VAR_BY_COL) vga_score_kernel<KTP, true><<<grid, dim3(kThreads), smem, ctx->stream>>>(a);
+    else vga_score_kernel<KTP, false><<<grid, dim3(kThreads), smem, ctx->stream>>>(a);
     CU(cudaGetLastError());
     return EBPMF_OK;
 }

@@ -577,7 +577,7 @@ template <int KTP>
 struct ScoreSmem {
     float efs[kMaxSpanCols][KTP];       // EF rows of the CTA's whole column span
     float c1s[kMaxSpanCols], c2s[kMaxSpanCols];
-    float ys[kWarps][kTileCols][32];    // per-warp Y image: 32 rows x 16 columns
+    float ys[2][kTileCols][kRowsPerCta];   // double-buffered Y image of a 256-row x 16-column tile
     float wmax[kWarps];
 };
 
@@ -589,10 +589,24 @@ __device__ __forceinline__ float float_from_hi(unsigned hi) {
     return (e < 0x38100000u) ? 0.f : __uint_as_float(bits);
 }
 
-// One barrier per CTA (after the span's EF rows are staged); afterwards every warp walks its own
-// 32 rows x 16 columns tiles with warp-level synchronisation only, so the CSC look-ups of one warp
-// hide behind the arithmetic of the others.  K_tot <= KTP (the host skips scoring otherwise).
-template <int KTP>
+__device__ __forceinline__ float rcp_approx_f32(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ float ex2_approx_f32(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// The Y image is double-buffered: while a tile is scored out of one buffer, the non-zeros of the next
+// tile are loaded (before the arithmetic) and scattered into the other buffer (after it), two columns
+// per warp, so one barrier per tile is enough and the CSC look-ups hide behind the arithmetic.  A
+// thread zeroes each Y element right after reading it (it is the only reader), which leaves the buffer
+// clean for the tile after next.  K_tot <= KTP (the host skips scoring otherwise).
+template <int KTP, bool BYCOL>
 __global__ void __launch_bounds__(kThreads, 3) vga_score_kernel(const FusedArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -606,9 +620,8 @@ __global__ void __launch_bounds__(kThreads, 3) vga_score_kernel(const FusedArgs 
     const int jc0 = (int)a.col0 + blockIdx.x * a.cols_per_cta;
     const int jc1 = min((int)a.col1, jc0 + a.cols_per_cta);
     const size_t ns = (size_t)n;
-    const bool by_col = a.var_type == 2;
     float c1_row = 1.f, c2_row = 0.5f;
-    if (!by_col) {
+    if (!BYCOL) {
         const int si = (a.var_type == 1) ? (row_ok ? i : 0) : 0;
         c1_row = (float)a.sc1[si];
         c2_row = (float)a.sc2[si];
@@ -617,28 +630,38 @@ __global__ void __launch_bounds__(kThreads, 3) vga_score_kernel(const FusedArgs 
         const int c = idx / KTP, k = idx - c * KTP;
         sm.efs[c][k] = (k < a.K) ? (float)__ldg(a.EFt + (size_t)(jc0 + c) * a.ldk + k) : 0.f;
     }
-    for (int c = tid; c < jc1 - jc0; c += kThreads) {
-        sm.c1s[c] = by_col ? (float)a.sc1[jc0 + c] : 1.f;
-        sm.c2s[c] = by_col ? (float)a.sc2[jc0 + c] : 0.5f;
+    if (BYCOL) {
+        for (int c = tid; c < jc1 - jc0; c += kThreads) {
+            sm.c1s[c] = (float)a.sc1[jc0 + c];
+            sm.c2s[c] = (float)a.sc2[jc0 + c];
+        }
     }
+#pragma unroll
+    for (int c = 0; c < kTileCols; ++c) { sm.ys[0][c][tid] = 0.f; sm.ys[1][c][tid] = 0.f; }
     float el[KTP];
 #pragma unroll
     for (int k = 0; k < KTP; ++k) el[k] = (row_ok && k < a.K) ? (float)__ldg(a.EL + i + k * ns) : 0.f;
     __syncthreads();
 
-    float (*yw)[32] = sm.ys[warp];
-    const int wr0 = r0 + warp * 32;                       // this warp's first row
     const int *rpb = a.rbptr + (size_t)rb * p;            // CSC offsets of this row block, per column
-    float best = 0.f;
-    int lo_n = 0, hi_n = 0;                               // lane c: non-zero range of the next tile's column c
-    if (lane < kTileCols && jc0 + lane < jc1) { lo_n = rpb[jc0 + lane]; hi_n = rpb[p + jc0 + lane]; }
-    for (int j0 = jc0; j0 < jc1; j0 += kTileCols) {
-        const int lo_t = lo_n, hi_t = hi_n;
-        lo_n = hi_n = 0;
-        if (lane < kTileCols && j0 + kTileCols + lane < jc1) {
-            lo_n = rpb[j0 + kTileCols + lane];
-            hi_n = rpb[p + j0 + kTileCols + lane];
+    // this warp scatters tile columns `warp` and `warp + 8`
+    auto scatter_range = [&](int j, int &lo, int &hi) {
+        lo = hi = 0;
+        if (j < jc1) { lo = rpb[j]; hi = rpb[p + j]; }
+    };
+    {   // tile 0 -> buffer 0
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int lo, hi;
+            scatter_range(jc0 + warp + 8 * h, lo, hi);
+            for (int q = lo + lane; q < hi; q += 32) sm.ys[0][warp + 8 * h][a.rowidx[q] - r0] = (float)__ldg(a.yx + q);
         }
+    }
+    __syncthreads();
+
+    float best = 0.f;
+    int cur = 0;
+    for (int j0 = jc0; j0 < jc1; j0 += kTileCols, cur ^= 1) {
         unsigned mhi[kTileCols];                          // high words of the tile's M values
         {
             const unsigned *mp = reinterpret_cast<const unsigned *>(a.M_in + (size_t)i + ns * (size_t)j0) + 1;
@@ -646,19 +669,16 @@ __global__ void __launch_bounds__(kThreads, 3) vga_score_kernel(const FusedArgs 
             for (int c = 0; c < kTileCols; ++c)
                 mhi[c] = (row_ok && j0 + c < jc1) ? __ldcs(mp + 2 * ns * (size_t)c) : 0u;
         }
+        // next tile's non-zeros: the first 32 of each of this warp's two columns go through registers
+        int nlo[2], nhi[2], nrow[2];
+        float nval[2];
 #pragma unroll
-        for (int c = 0; c < kTileCols; ++c) yw[c][lane] = 0.f;
-        __syncwarp();
-#pragma unroll 4
-        for (int c = 0; c < kTileCols; ++c) {
-            const int lo = __shfl_sync(0xffffffffu, lo_t, c), hi = __shfl_sync(0xffffffffu, hi_t, c);
-            for (int q = lo + lane; q < hi; q += 32) {
-                const int r = a.rowidx[q] - wr0;
-                const float y = (float)__ldg(a.yx + q);
-                if ((unsigned)r < 32u) yw[c][r] = y;
-            }
+        for (int h = 0; h < 2; ++h) {
+            scatter_range(j0 + kTileCols + warp + 8 * h, nlo[h], nhi[h]);
+            const int q = nlo[h] + lane;
+            nrow[h] = -1; nval[h] = 0.f;
+            if (q < nhi[h]) { nrow[h] = a.rowidx[q] - r0; nval[h] = (float)__ldg(a.yx + q); }
         }
-        __syncwarp();
         const int cs0 = j0 - jc0;
 #pragma unroll
         for (int c = 0; c < kTileCols; ++c) {
@@ -672,20 +692,29 @@ __global__ void __launch_bounds__(kThreads, 3) vga_score_kernel(const FusedArgs 
                 b0 = fmaf(el[4 * k4 + 2], e.z, b0);
                 b1 = fmaf(el[4 * k4 + 3], e.w, b1);
             }
-            const float c1 = by_col ? sm.c1s[cs0 + c] : c1_row, c2 = by_col ? sm.c2s[cs0 + c] : c2_row;
-            const float cap = fmaf(c2 + c2, yw[c][lane], b0 + b1);                 // const0 - 1
+            const float c1 = BYCOL ? sm.c1s[cs0 + c] : c1_row, c2 = BYCOL ? sm.c2s[cs0 + c] : c2_row;
+            const float y = sm.ys[cur][c][tid];
+            sm.ys[cur][c][tid] = 0.f;                                              // clean for the tile after next
+            const float cap = fmaf(c2 + c2, y, b0 + b1);                           // const0 - 1
             const float m = fminf(float_from_hi(mhi[c]), cap);                     // :16
-            const float r = __frcp_rn((cap + 1.f) - m);                            // :22
+            const float r = rcp_approx_f32((cap + 1.f) - m);                       // :22
             const float aa = c2 * r;
-            const float ex = __expf(m + aa);
+            const float ex = ex2_approx_f32((m + aa) * 1.4426950408889634f);
             const float f = fmaf(-m, c1, fmaf(cap, c1, -ex));                      // :25
             const float g = fmaf(-ex, fmaf(aa, r, 1.f), -c1);                      // :31
-            float step = fabsf(__fdividef(f, g));
-            if (!(step <= 3.0e38f)) step = 3.0e38f;                                // Inf/NaN: take this tile early
-            if (row_ok && j0 + c < jc1) best = fmaxf(best, step);
+            float step = fabsf(f * rcp_approx_f32(g));
+            step = (step <= 3.0e38f) ? step : 3.0e38f;                             // Inf/NaN: take this tile early
+            best = fmaxf(best, step);                                              // padding rows/columns score ~0
         }
-        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (nrow[h] >= 0) sm.ys[cur ^ 1][warp + 8 * h][nrow[h]] = nval[h];
+            for (int q = nlo[h] + lane + 32; q < nhi[h]; q += 32)                  // columns with > 32 non-zeros here
+                sm.ys[cur ^ 1][warp + 8 * h][a.rowidx[q] - r0] = (float)__ldg(a.yx + q);
+        }
+        __syncthreads();
     }
+    if (!row_ok) best = 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
     if (lane == 0) sm.wmax[warp] = best;
