@@ -337,6 +337,25 @@ def main():
                   "note": "units whose next Newton update is <= delta (and |f| < tol/16) are frozen; M, V within "
                           "~delta of the exact-count result, n_updates identical; NOT the headline value"}
 
+    # ---- the same step with the scored pipeline (option, not the default) --------
+    # exact mode, bit-identical results: an FP32 tensor-core scoring pass orders the tiles of pass 1
+    ctx.set_option("pipeline", 3)
+    sinfos = []
+    for it in range(1 + args.steps):
+        inf = ctx.vga_step(MAXITER_VGA, VGA_TOL)
+        ctx.rewind_m()
+        if it > 0:
+            sinfos.append(inf)
+    barrier()
+    ctx.set_option("pipeline", 0)
+    s_ms = allmax(sum(i.kernel_ms for i in sinfos)) / args.steps
+    scored_mode = {"value": entries / (s_ms * 1e-3), "unit": "entries/s", "ms_per_step": s_ms,
+                   "n_updates": sinfos[-1].n_updates,
+                   "pass_ms": {"score_and_first": sum(i.pass1_ms for i in sinfos) / args.steps,
+                               "topup": sum(i.pass2_ms for i in sinfos) / args.steps},
+                   "note": "pipeline = 3: tiles of pass 1 taken by decreasing predicted hardness (tf32 scoring pass); "
+                           "same results bit for bit, exact update count; NOT the headline value"}
+
     # ---- roofline (HBM line of the dominant kernel = first pass) --------------------------------
     peak, peak_src = read_peaks()
     alg_bytes_per_entry = 16.0 + 12.0 * density            # read M 8 + write M 8 + CSC (x 8 + i 4) * density
@@ -387,7 +406,7 @@ def main():
         "topup_units_frac": diag["topup_units"] / max(1.0, ((n + 31) // 32) * ((p + 1) // 2)),
         "peer_kstar_sharing": {"peers_mapped": ctx.peer_count() if world > 1 else 0,
                                "how": "pass-1 kernels read the other GPUs' published update count over NVLink peer memory"},
-        "roofline": roofline, "fp64": fp64, "issue_roofline": issue, "delta_mode": delta_mode,
+        "roofline": roofline, "fp64": fp64, "issue_roofline": issue, "delta_mode": delta_mode, "scored_pipeline": scored_mode,
         "gpu_launches": 6 * args.steps, "clocks": clk.summary(),
     }
 

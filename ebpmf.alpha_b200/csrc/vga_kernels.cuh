@@ -573,11 +573,13 @@ __global__ void __launch_bounds__(kThreads, EBPMF_MINB) vga_fused_kernel(const F
 // ---------------------------------------------------------------------------------------
 constexpr int kMaxSpanCols = 256;      // cols_per_cta never exceeds this (cols_per_cta_for in ebpmf_api.cu)
 
+constexpr int kScorePad = 4;            // row padding (floats) that keeps the fragment-shaped smem reads conflict-free
+
 template <int KTP>
 struct ScoreSmem {
-    float efs[kMaxSpanCols][KTP];       // EF rows of the CTA's whole column span
+    float efs[kMaxSpanCols][KTP + kScorePad];   // EF rows of the CTA's whole column span, rounded to tf32
     float c1s[kMaxSpanCols], c2s[kMaxSpanCols];
-    float ys[2][kTileCols][kRowsPerCta];   // double-buffered Y image of a 256-row x 16-column tile
+    float ys[2][kTileCols][kRowsPerCta + kScorePad];   // double-buffered Y image of a 256-row x 16-column tile
     float wmax[kWarps];
 };
 
@@ -601,55 +603,99 @@ __device__ __forceinline__ float ex2_approx_f32(float x) {
     return r;
 }
 
-// The Y image is double-buffered: while a tile is scored out of one buffer, the non-zeros of the next
-// tile are loaded (before the arithmetic) and scattered into the other buffer (after it), two columns
-// per warp, so one barrier per tile is enough and the CSC look-ups hide behind the arithmetic.  A
-// thread zeroes each Y element right after reading it (it is the only reader), which leaves the buffer
-// clean for the tile after next.  K_tot <= KTP (the host skips scoring otherwise).
+__device__ __forceinline__ unsigned to_tf32(float x) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+// D(16x8) += A(16x8, row) * B(8x8, col), tf32 inputs, f32 accumulate.  Fragment layout (g = lane >> 2,
+// t = lane & 3): a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4); b0 (k = t, n = g) b1 (k = t+4, n = g);
+// d0 (g, 2t) d1 (g, 2t+1) d2 (g+8, 2t) d3 (g+8, 2t+1).
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Scoring is a heuristic (it decides an ORDER, never a result), so this is the one place where the
+// factor product runs on the tensor cores: per tile each warp forms Beta for its 32 rows x 16 columns
+// with 2 x 2 x KTP/8 tf32 MMAs (EL fragments live in registers for the whole CTA, EF fragments come from
+// shared memory) instead of 16 x KTP FFMAs per thread.  A lane then owns the 16 entries of the
+// accumulator layout: rows 16*mb + 8*h + g, columns 8*nb + 2*t + w.  The Y image is double-buffered: the
+// next tile's non-zeros are loaded before the arithmetic and scattered after it (two columns per warp),
+// one barrier per tile; a thread zeroes each Y element right after reading it (it is the only reader).
+// K_tot <= KTP (the host skips scoring otherwise).
+#ifndef EBPMF_SCORE_MINB
+#define EBPMF_SCORE_MINB 3     // measured: 2 CTAs/SM with a tile-ahead register prefetch of M is slower (9.6 vs 8.6 ms)
+#endif
 template <int KTP, bool BYCOL>
-__global__ void __launch_bounds__(kThreads, 3) vga_score_kernel(const FusedArgs a)
+__global__ void __launch_bounds__(kThreads, EBPMF_SCORE_MINB) vga_score_kernel(const FusedArgs a)
 {
+    constexpr int KB = KTP / 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScoreSmem<KTP> &sm = *reinterpret_cast<ScoreSmem<KTP> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
     const int n = (int)a.n, p = (int)a.p;
     const int rb = blockIdx.y;
     const int r0 = rb * kRowsPerCta;
-    const int i = r0 + tid;
-    const bool row_ok = i < n;
     const int jc0 = (int)a.col0 + blockIdx.x * a.cols_per_cta;
     const int jc1 = min((int)a.col1, jc0 + a.cols_per_cta);
+    const int span = jc1 - jc0;
+    const int span16 = (span + kTileCols - 1) / kTileCols * kTileCols;
     const size_t ns = (size_t)n;
-    float c1_row = 1.f, c2_row = 0.5f;
-    if (!BYCOL) {
-        const int si = (a.var_type == 1) ? (row_ok ? i : 0) : 0;
-        c1_row = (float)a.sc1[si];
-        c2_row = (float)a.sc2[si];
-    }
-    for (int idx = tid; idx < (jc1 - jc0) * KTP; idx += kThreads) {
+
+    for (int idx = tid; idx < span16 * KTP; idx += kThreads) {
         const int c = idx / KTP, k = idx - c * KTP;
-        sm.efs[c][k] = (k < a.K) ? (float)__ldg(a.EFt + (size_t)(jc0 + c) * a.ldk + k) : 0.f;
+        const float v = (c < span && k < a.K) ? (float)__ldg(a.EFt + (size_t)(jc0 + c) * a.ldk + k) : 0.f;
+        sm.efs[c][k] = __uint_as_float(to_tf32(v));
     }
     if (BYCOL) {
-        for (int c = tid; c < jc1 - jc0; c += kThreads) {
-            sm.c1s[c] = (float)a.sc1[jc0 + c];
-            sm.c2s[c] = (float)a.sc2[jc0 + c];
+        for (int c = tid; c < span16; c += kThreads) {
+            sm.c1s[c] = (c < span) ? (float)a.sc1[jc0 + c] : 1.f;
+            sm.c2s[c] = (c < span) ? (float)a.sc2[jc0 + c] : 0.5f;
         }
     }
 #pragma unroll
     for (int c = 0; c < kTileCols; ++c) { sm.ys[0][c][tid] = 0.f; sm.ys[1][c][tid] = 0.f; }
-    float el[KTP];
+
+    // this lane's four rows: lr[mb][h] = warp*32 + 16*mb + 8*h + g (within the row block)
+    int lrow[2][2];
+    bool rok[2][2];
+    float c1r[2][2], c2r[2][2];
+    unsigned afrag[2][KB][4];
 #pragma unroll
-    for (int k = 0; k < KTP; ++k) el[k] = (row_ok && k < a.K) ? (float)__ldg(a.EL + i + k * ns) : 0.f;
+    for (int mb = 0; mb < 2; ++mb) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            lrow[mb][h] = warp * 32 + 16 * mb + 8 * h + g;
+            rok[mb][h] = r0 + lrow[mb][h] < n;
+            c1r[mb][h] = 1.f; c2r[mb][h] = 0.5f;
+            if (!BYCOL) {
+                const int si = (a.var_type == 1) ? (rok[mb][h] ? r0 + lrow[mb][h] : 0) : 0;
+                c1r[mb][h] = (float)a.sc1[si];
+                c2r[mb][h] = (float)a.sc2[si];
+            }
+        }
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int h = q & 1, k = 8 * kb + t + 4 * (q >> 1);
+                const float v = (rok[mb][h] && k < a.K) ? (float)__ldg(a.EL + (size_t)(r0 + lrow[mb][h]) + (size_t)k * ns) : 0.f;
+                afrag[mb][kb][q] = to_tf32(v);
+            }
+        }
+    }
     __syncthreads();
 
     const int *rpb = a.rbptr + (size_t)rb * p;            // CSC offsets of this row block, per column
-    // this warp scatters tile columns `warp` and `warp + 8`
     auto scatter_range = [&](int j, int &lo, int &hi) {
         lo = hi = 0;
         if (j < jc1) { lo = rpb[j]; hi = rpb[p + j]; }
     };
-    {   // tile 0 -> buffer 0
+    {   // tile 0 -> buffer 0; this warp scatters tile columns `warp` and `warp + 8`
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             int lo, hi;
@@ -659,15 +705,28 @@ __global__ void __launch_bounds__(kThreads, 3) vga_score_kernel(const FusedArgs 
     }
     __syncthreads();
 
+    // high words of M: column (8*nb + 2*t + w) of the tile, rows lrow[mb][h] -> 4 column pointers per tile,
+    // row offsets are compile-time multiples of 8 rows
+    const unsigned *mrow = reinterpret_cast<const unsigned *>(a.M_in + (size_t)r0 + (size_t)(warp * 32 + g)) + 1;
     float best = 0.f;
     int cur = 0;
     for (int j0 = jc0; j0 < jc1; j0 += kTileCols, cur ^= 1) {
-        unsigned mhi[kTileCols];                          // high words of the tile's M values
-        {
-            const unsigned *mp = reinterpret_cast<const unsigned *>(a.M_in + (size_t)i + ns * (size_t)j0) + 1;
+        unsigned mhi[2][2][2][2];                         // [nb][w][mb][h]
+        bool cok[2][2];
 #pragma unroll
-            for (int c = 0; c < kTileCols; ++c)
-                mhi[c] = (row_ok && j0 + c < jc1) ? __ldcs(mp + 2 * ns * (size_t)c) : 0u;
+        for (int nb = 0; nb < 2; ++nb) {
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const int col = j0 + 8 * nb + 2 * t + w;
+                cok[nb][w] = col < jc1;
+                const unsigned *mc = mrow + 2 * ns * (size_t)col;
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        mhi[nb][w][mb][h] = (cok[nb][w] && rok[mb][h]) ? __ldcs(mc + 2 * (16 * mb + 8 * h)) : 0u;
+                }
+            }
         }
         // next tile's non-zeros: the first 32 of each of this warp's two columns go through registers
         int nlo[2], nhi[2], nrow[2];
@@ -681,30 +740,41 @@ __global__ void __launch_bounds__(kThreads, 3) vga_score_kernel(const FusedArgs 
         }
         const int cs0 = j0 - jc0;
 #pragma unroll
-        for (int c = 0; c < kTileCols; ++c) {
-            const float4 *ef4 = reinterpret_cast<const float4 *>(&sm.efs[cs0 + c][0]);
-            float b0 = 0.f, b1 = 0.f;
+        for (int nb = 0; nb < 2; ++nb) {
+            float acc[2][4];
 #pragma unroll
-            for (int k4 = 0; k4 < KTP / 4; ++k4) {
-                const float4 e = ef4[k4];
-                b0 = fmaf(el[4 * k4 + 0], e.x, b0);
-                b1 = fmaf(el[4 * k4 + 1], e.y, b1);
-                b0 = fmaf(el[4 * k4 + 2], e.z, b0);
-                b1 = fmaf(el[4 * k4 + 3], e.w, b1);
+            for (int mb = 0; mb < 2; ++mb) { acc[mb][0] = acc[mb][1] = acc[mb][2] = acc[mb][3] = 0.f; }
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+                const unsigned b0 = __float_as_uint(sm.efs[cs0 + 8 * nb + g][8 * kb + t]);
+                const unsigned b1 = __float_as_uint(sm.efs[cs0 + 8 * nb + g][8 * kb + t + 4]);
+                mma_tf32_16x8x8(acc[0], afrag[0][kb], b0, b1);
+                mma_tf32_16x8x8(acc[1], afrag[1][kb], b0, b1);
             }
-            const float c1 = BYCOL ? sm.c1s[cs0 + c] : c1_row, c2 = BYCOL ? sm.c2s[cs0 + c] : c2_row;
-            const float y = sm.ys[cur][c][tid];
-            sm.ys[cur][c][tid] = 0.f;                                              // clean for the tile after next
-            const float cap = fmaf(c2 + c2, y, b0 + b1);                           // const0 - 1
-            const float m = fminf(float_from_hi(mhi[c]), cap);                     // :16
-            const float r = rcp_approx_f32((cap + 1.f) - m);                       // :22
-            const float aa = c2 * r;
-            const float ex = ex2_approx_f32((m + aa) * 1.4426950408889634f);
-            const float f = fmaf(-m, c1, fmaf(cap, c1, -ex));                      // :25
-            const float g = fmaf(-ex, fmaf(aa, r, 1.f), -c1);                      // :31
-            float step = fabsf(f * rcp_approx_f32(g));
-            step = (step <= 3.0e38f) ? step : 3.0e38f;                             // Inf/NaN: take this tile early
-            best = fmaxf(best, step);                                              // padding rows/columns score ~0
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const int c = 8 * nb + 2 * t + w;                 // column within the tile
+                const float c1c = BYCOL ? sm.c1s[cs0 + c] : 1.f, c2c = BYCOL ? sm.c2s[cs0 + c] : 0.5f;
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float c1 = BYCOL ? c1c : c1r[mb][h], c2 = BYCOL ? c2c : c2r[mb][h];
+                        const float y = sm.ys[cur][c][lrow[mb][h]];
+                        sm.ys[cur][c][lrow[mb][h]] = 0.f;                          // clean for the tile after next
+                        const float cap = fmaf(c2 + c2, y, acc[mb][2 * h + w]);    // const0 - 1
+                        const float m = fminf(float_from_hi(mhi[nb][w][mb][h]), cap);   // :16
+                        const float r = rcp_approx_f32((cap + 1.f) - m);           // :22
+                        const float aa = c2 * r;
+                        const float ex = ex2_approx_f32((m + aa) * 1.4426950408889634f);
+                        const float f = fmaf(-m, c1, fmaf(cap, c1, -ex));          // :25
+                        const float gg = fmaf(-ex, fmaf(aa, r, 1.f), -c1);         // :31
+                        float step = fabsf(f * rcp_approx_f32(gg));
+                        step = (step <= 3.0e38f) ? step : 3.0e38f;                 // Inf/NaN: take this tile early
+                        if (cok[nb][w] && rok[mb][h]) best = fmaxf(best, step);
+                    }
+                }
+            }
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -714,7 +784,6 @@ __global__ void __launch_bounds__(kThreads, 3) vga_score_kernel(const FusedArgs 
         }
         __syncthreads();
     }
-    if (!row_ok) best = 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
     if (lane == 0) sm.wmax[warp] = best;

@@ -275,8 +275,8 @@ int  ebpmf_ctx_sim_data_log(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, int
  *   "pipeline" 0 (default): fused first pass; 1: const0 kernel + streaming Newton kernel; 2: as 1, and the
  *              const0 kernel also performs Newton iteration 0 and scores each CTA by its largest first step,
  *              so that the streaming kernel meets the slowest entries first (same results, bit for bit);
- *              3: an FP32 scoring pass ranks the (column span, row block) tiles by their largest first Newton
- *              step and the fused first pass takes them in that order (same results, bit for bit).
+ *              3: a tf32 tensor-core scoring pass ranks the (column span, row block) tiles by their largest
+ *              first Newton step and the fused first pass takes them in that order (same results, bit for bit).
  *   "scored_min_ctas" (default 888 = two waves): pipeline 3 skips the scoring pass below this many tiles.
  *   "debug_verify_scale" (0,1], default 1: TEST HOOK -- the top-up pass verifies against tol*scale, which
  *              forces the host's K*+1 retry loop to run (tests/test_gpu_parity.py::test_retry_loop_...). */
