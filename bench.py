@@ -15,9 +15,15 @@ partials in every step.  Inputs are generated ON THE DEVICE (ebpmf_ctx_sim_data_
 
   value      entries/s over all ranks, inputs resident in HBM, device time (CUDA events on the
              library's stream), max over ranks
-  e2e        the same metric through the host-buffer C-ABI call ebpmf_vga_step_host (what the R
-             .Call shim does): pinned host M in, H2D, step, D2H of M and v_sum, on a bounded row
-             sample of the same workload (PCIe-bound, independent of the row count)
+  e2e        the same metric through the host-buffer C-ABI call the R .Call shim makes every outer
+             iteration, ebpmf_vga_step_resident_host: factors and sigma2 in from pinned host memory,
+             step, D2H of M and v_sum (the step's input M is the previous step's output and stays on
+             the device, as in R/ebpmf_log.R:309), on a bounded row sample of the same workload
+             (PCIe-bound, independent of the row count).  Next to it: e2e_full_roundtrip
+             (ebpmf_vga_step_host, M in AND out) and e2e_batched (ebpmf_batched_vga_step_host, the
+             batch_size < n branch of R/ebpmf_log.R:254-300, batches pipelined)
+  delta_mode, scored_pipeline   the same step with the two options of DESIGN.md section 3b / 4 (never
+             the headline value)
   roofline   HBM line for the dominant kernel (first pass); the FP64 pipe is the binding unit
              (DESIGN.md §4), so an "fp64" object with the measured DFMA peak sits beside it
   cpu_baseline  the oracle's C transcription of the R code (OpenMP, all host cores) on a bounded
