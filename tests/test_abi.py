@@ -73,3 +73,20 @@ def test_fails_loudly_without_a_gpu(pkg):
     assert ei.value.code == 2 and "no CPU fallback" in str(ei.value)
     with pytest.raises(pkg.EbpmfError):
         pkg.vga_pois_solver_mat_newton(np.zeros((2, 2)), np.zeros((2, 2)), 1, np.zeros((2, 2)), np.ones((2, 2)))
+
+
+def test_plain_c_host_compiles_links_and_fails_loudly_without_a_gpu(pkg, tmp_path):
+    """examples/vga_step_demo.c: the header is valid C99, the library links from plain C with no other
+    dependency, and without a GPU the program stops with the library's message (exit 2) -- no CPU path."""
+    exe = str(tmp_path / "vga_step_demo")
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    cmd = ["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "vga_step_demo.c"), "-L", libdir, "-lebpmf_b200", "-Wl,-rpath," + libdir, "-lm",
+           "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the demo is run by tests/test_gpu_parity.py")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU fallback" in r.stderr

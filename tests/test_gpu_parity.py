@@ -655,3 +655,23 @@ def test_batched_over_two_gpus_equals_one(pkg):
         assert np.array_equal(ra["v_sum"], rb["v_sum"]) and ra["sym"] == rb["sym"] and ra["slogv"] == rb["slogv"]
     finally:
         a.close(); b.close()
+
+
+def test_plain_c_demo_runs(pkg, tmp_path):
+    """examples/vga_step_demo.c built with gcc against the shared library: a non-Python, non-R host."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "vga_step_demo")
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-I", os.path.join(root, "include"),
+                        os.path.join(root, "examples", "vga_step_demo.c"), "-L", libdir, "-lebpmf_b200",
+                        "-Wl,-rpath," + libdir, "-lm", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # the same data replayed through the NumPy oracle (same xorshift stream): u = 5, sym = -9672.454278
+    assert "5 Newton updates (converged 1)" in r.stdout, r.stdout
+    sym = float(re.search(r"sym (-?[0-9.]+)", r.stdout).group(1))
+    assert abs(sym - (-9672.454278)) < 1e-4
