@@ -65,8 +65,10 @@ SIGNATURES = {
     "ebpmf_update_sigma2": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp, _dbl, _dbl, _dbl, _i64, _vp, _vp, _vp]),
     "ebpmf_calc_obj": (_int, [_vp, _i64, _i64, _dbl, _dbl, _dbl, _i64, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl,
                               _dbl, C.POINTER(_dbl)]),
-    "ebpmf_vga_step_host": (_int, [_vp, _vp, _i64, _vp, _vp, _int, _vp, _int, _dbl, _vp, _vp, _vp, _PI]),
-    "ebpmf_vga_step_resident_host": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _int, _dbl, _vp, _vp, _vp, _PI]),
+    "ebpmf_vga_step_host": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _int, _vp, _int, _dbl, _vp, _vp, _vp, _PI]),
+    "ebpmf_vga_step_resident_host": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _int, _vp, _int, _dbl, _vp, _vp, _vp, _PI]),
+    "ebpmf_ctx_m_products": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ebpmf_ctx_counters": (_int, [_vp, _vp, _int]),
     "ebpmf_group_create": (_int, [_int, _vp, C.POINTER(_vp)]),
     "ebpmf_group_destroy": (_int, [_vp]),
     "ebpmf_group_last_error": (C.c_char_p, [_vp]),
@@ -74,7 +76,8 @@ SIGNATURES = {
     "ebpmf_group_set_option": (_int, [_vp, C.c_char_p, _dbl]),
     "ebpmf_group_set_y_csc": (_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "ebpmf_group_sum_lfactorial": (_int, [_vp, C.POINTER(_dbl)]),
-    "ebpmf_group_vga_step_host": (_int, [_vp, _vp, _i64, _vp, _vp, _int, _vp, _int, _dbl, _vp, _vp, _vp, _PI]),
+    "ebpmf_group_set_m": (_int, [_vp, _i64, _i64, _vp]),
+    "ebpmf_group_vga_step_host": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _int, _vp, _int, _dbl, _vp, _vp, _vp, _PI]),
     "ebpmf_batched_create": (_int, [_int, _int, C.POINTER(_vp)]),
     "ebpmf_batched_create_multi": (_int, [_int, _vp, _int, C.POINTER(_vp)]),
     "ebpmf_batched_destroy": (_int, [_vp]),
@@ -82,7 +85,8 @@ SIGNATURES = {
     "ebpmf_batched_set_option": (_int, [_vp, C.c_char_p, _dbl]),
     "ebpmf_batched_set_y_csc": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
     "ebpmf_batched_sum_lfactorial": (_int, [_vp, C.POINTER(_dbl)]),
-    "ebpmf_batched_vga_step_host": (_int, [_vp, _vp, _i64, _vp, _vp, _int, _vp, _int, _dbl, _vp, _vp, _vp, _PI, _vp, _vp]),
+    "ebpmf_batched_vga_step_host": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _int, _vp, _int, _dbl, _vp, _vp, _vp, _PI, _vp,
+                                           _vp]),
     "ebpmf_vga_newton": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _int, _vp, _int, _int,
                                 _dbl, _vp, _vp, _PI]),
     "ebpmf_vga_fixed_iter": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _int, _vp, _int, _vp, _int, _int, _vp, _vp]),

@@ -4,6 +4,8 @@
 #include "../../include/ebpmf_b200.h"
 #include "vga_kernels.cuh"
 #include "simgen.cuh"
+#include "host_pipe.hpp"
+#include "m_products.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -18,6 +20,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -68,8 +72,9 @@ struct DevBuf {
 
 struct ebpmf_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr, ev_p1 = nullptr, ev_p2 = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_p1 = nullptr, ev_p2 = nullptr, ev_p3 = nullptr, ev_setup = nullptr, ev_topup = nullptr;
+    std::vector<cudaEvent_t> ev_chunk, ev_in;    // host-pipelined step: pass 1 of chunk c done / M_in of chunk c on the device
     std::string err;
 
     // shapes
@@ -77,32 +82,48 @@ struct ebpmf_ctx {
     long long nRB = 0, nRW = 0;
     int K = 0, KTP = 0, ldk = 0;
     int var_type = -1;
-    int pipeline = 0;          // 0: fused first pass, 1: split (const0 kernel + streaming Newton), 2: ordered split,
-                               // 3: scored (FP32 scoring pass, then the fused first pass in score order)
+    int freeze = 1;            // 1 (default): periodic fast-forward, bit-identical to iterating on; 0: plain iteration
     double delta = 0.0;        // 0: exact update count (default); > 0: delta mode (ebpmf_ctx_set_option)
-    unsigned scored_min_ctas = 2 * 148 * 3;   // scored pipeline: below two waves of CTAs the order cannot matter
     double debug_verify_scale = 1.0;   // test hook: pass 2 verifies against tol*scale (exercises the retry loop)
+    int use_history = 1;       // order the first pass by the previous step's per-tile counts
+    int speculate = 1;         // host-pipelined step: copy a chunk out as soon as its first pass is done
+    int pipe_chunks = 0;       // host-pipelined step: number of column chunks (0: chosen from the matrix size)
     bool can_rewind = false;
+    int cur_nspans = 0, cur_ntiles = 0, cur_cols = 0;   // tiling of the step in flight (fused_args)
     unsigned long long diag_topups = 0, diag_iters = 0;
+    int diag_topup_tiles = 0;
+    unsigned long long launches = 0;              // kernels launched by this context (bench.py's gpu_launches)
+    double diag_spec_bytes = 0.0, diag_recopy_bytes = 0.0;   // last host-pipelined step: speculative / repeated D2H bytes
     bool have_y = false, have_m = false, have_f = false, have_s2 = false, have_v = false, have_vsum = false;
+
+    // order of the first pass: per-tile counts of the previous step on this shape
+    bool have_hist = false;
+    long long hist_n = 0, hist_p = 0;
+    int hist_cols = 0;
+    int hard_span = 0;         // column span of (one of) the hardest tile(s) of the previous step
+    double spec_waste = 0.0;   // share of the previous pipelined step's speculative copies that had to be repeated
 
     // resident buffers
     DevBuf colptr, rowidx, yx, rbptr;
     DevBuf Mcur, Malt, V;
     DevBuf EL, EF, EFt, sigma2, l0, f0;
-    DevBuf C0;         // const0 of the last first pass (n x p)
     DevBuf sc1, sc2;   // 1/sigma2, sigma2/2
-    DevBuf kunit, colV, unitS, rowpart;
+    DevBuf kunit, colV, tileS, rowpart;
+    DevBuf tile_hard, tile_kmin;
     DevBuf red;        // [4 scalars: sym, ssexp, slogv, sumV][v_sum ...]
-    DevBuf colsums;    // colsym[p] | v_sum scratch[p] | unitsum[nJG][2]
+    DevBuf colsums;    // colsym[p] | v_sum scratch[p]
     DevBuf status;     // Status
     DevBuf tables;     // MathTables
-    DevBuf score, score_sorted, cta_ids, perm, cub_tmp;   // ordered pipeline (pipeline == 2)
+    DevBuf order_keys, order_keys2, order_ids, perm, cub_tmp, span_rank, chunk_dirty, small_out;
     DevBuf misc;       // small scratch (R2, fitmax, obj terms, lfactorial partials)
     DevBuf scratch[6]; // dense-signature operands
+    DevBuf prod;       // ebpmf_ctx_m_products scratch
 
     Status *h_status = nullptr;   // pinned
     double *h_small = nullptr;    // pinned, 64 doubles
+    int *h_ints = nullptr;        // pinned, 4096 ints: hard span, chunk dirty flags
+
+    std::unique_ptr<HostPipe> pipe;   // pinned ring + copy threads, created on the first host-buffer step
 
     // NCCL
     ncclComm_t comm = nullptr;
@@ -197,195 +218,122 @@ int cols_per_cta_for(long long p, long long nRB) {
     return (int)c;
 }
 
-template <int KTP, int FORMULA, bool DELTA, bool PERM = false>
-int launch_first_ktp2(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
-    auto kern = vga_fused_kernel<KTP, kE, FORMULA, DELTA, false, PERM>;
-    const int smem = (int)sizeof(FusedSmem<KTP>);
-    static bool configured[8] = {false, false, false, false, false, false, false, false};   // per device
-    if (ctx->device < 8 ? !configured[ctx->device] : true) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        if (ctx->device < 8) configured[ctx->device] = true;
+// How one step walks the matrix: tiles = (row block, column span); the spans are grouped into column
+// CHUNKS that are launched (and, in the host-buffer step, copied) one after the other.  Chunk 0 is the
+// single span that held the hardest tile of the previous step, so that K* reaches the global count
+// before anything else starts.
+struct StepPlan {
+    int cols_per_cta = 0, nspans = 0, ntiles = 0;
+    int nchunks = 1;
+    std::vector<int> span0, span1;        // chunk c covers the spans [span0[c], span1[c])
+    std::vector<int> tile_begin, tile_count;   // its positions in the launch order
+    std::vector<int> span_rank;           // span -> chunk
+    bool ordered = false;                 // ctx->perm holds the order (else natural order, one chunk)
+};
+
+StepPlan make_plan(ebpmf_ctx *ctx, int want_chunks) {
+    StepPlan pl;
+    pl.cols_per_cta = cols_per_cta_for(ctx->p, ctx->nRB);
+    pl.nspans = (int)((ctx->p + pl.cols_per_cta - 1) / pl.cols_per_cta);
+    pl.ntiles = pl.nspans * (int)ctx->nRB;
+    const bool hist = ctx->use_history && ctx->have_hist && ctx->hist_n == ctx->n && ctx->hist_p == ctx->p &&
+                      ctx->hist_cols == pl.cols_per_cta;
+    want_chunks = std::max(1, std::min(want_chunks, pl.nspans));
+    if (want_chunks == 1) {
+        pl.span0 = {0}; pl.span1 = {pl.nspans};
+    } else {
+        const int hs = hist ? std::min(std::max(ctx->hard_span, 0), pl.nspans - 1) : 0;
+        const int per = (pl.nspans - 1 + (want_chunks - 1) - 1) / (want_chunks - 1);      // spans per ordinary chunk
+        pl.span0.push_back(hs); pl.span1.push_back(hs + 1);
+        for (int s = 0; s < hs; s += per) { pl.span0.push_back(s); pl.span1.push_back(std::min(s + per, hs)); }
+        for (int s = hs + 1; s < pl.nspans; s += per) { pl.span0.push_back(s); pl.span1.push_back(std::min(s + per, pl.nspans)); }
     }
-    kern<<<grid, dim3(kThreads), smem, ctx->stream>>>(a);
-    CU(cudaGetLastError());
-    return EBPMF_OK;
-}
-
-template <int KTP, int FORMULA>
-int launch_first_ktp(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
-    if (FORMULA == FORMULA_A1 && a.perm)      // scored pipeline: tiles in score order
-        return a.delta > 0 ? launch_first_ktp2<KTP, FORMULA_A1, true, true>(ctx, a, grid)
-                           : launch_first_ktp2<KTP, FORMULA_A1, false, true>(ctx, a, grid);
-    return a.delta > 0 ? launch_first_ktp2<KTP, FORMULA, true>(ctx, a, grid)
-                       : launch_first_ktp2<KTP, FORMULA, false>(ctx, a, grid);
-}
-
-template <int KTP, int FORMULA>
-int launch_prep_ktp(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
-    auto kern = vga_prep_kernel<KTP, FORMULA>;
-    const int smem = (int)sizeof(PrepSmem<KTP>);
-    kern<<<grid, dim3(kThreads), smem, ctx->stream>>>(a);
-    CU(cudaGetLastError());
-    return EBPMF_OK;
-}
-
-template <int FORMULA>
-int launch_prep(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
-    switch (ctx->KTP) {
-        case 8: return launch_prep_ktp<8, FORMULA>(ctx, a, grid);
-        case 16: return launch_prep_ktp<16, FORMULA>(ctx, a, grid);
-        case 24: return launch_prep_ktp<24, FORMULA>(ctx, a, grid);
-        case 32: return launch_prep_ktp<32, FORMULA>(ctx, a, grid);
+    pl.nchunks = (int)pl.span0.size();
+    pl.span_rank.assign((size_t)pl.nspans, 0);
+    int pos = 0;
+    for (int c = 0; c < pl.nchunks; ++c) {
+        for (int sp = pl.span0[(size_t)c]; sp < pl.span1[(size_t)c]; ++sp) pl.span_rank[(size_t)sp] = c;
+        pl.tile_begin.push_back(pos);
+        pl.tile_count.push_back((pl.span1[(size_t)c] - pl.span0[(size_t)c]) * (int)ctx->nRB);
+        pos += pl.tile_count.back();
     }
-    return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported", ctx->K);
+    pl.ordered = hist || pl.nchunks > 1;
+    return pl;
 }
 
-template <int KTP>
-int launch_iter0_ktp(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
-    auto kern = vga_fused_kernel<KTP, kE, FORMULA_A1, false, true>;
-    const int smem = (int)sizeof(FusedSmem<KTP>);
-    static bool configured[8] = {false, false, false, false, false, false, false, false};   // per device
-    if (ctx->device < 8 ? !configured[ctx->device] : true) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        if (ctx->device < 8) configured[ctx->device] = true;
-    }
-    kern<<<grid, dim3(kThreads), smem, ctx->stream>>>(a);
-    CU(cudaGetLastError());
-    return EBPMF_OK;
-}
-
-__global__ void iota_kernel(int *ids, int count) {
+__global__ void order_keys_rank_kernel(const unsigned short *tile_hard, const int *span_rank, int ntiles, int nspans,
+                                       int use_hist, unsigned *keys, int *ids) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < count) ids[t] = t;
+    if (t >= ntiles) return;
+    const unsigned hard = use_hist ? (unsigned)tile_hard[t] : 0u;
+    keys[t] = ((unsigned)span_rank[t % nspans] << 16) | (0xFFFFu - hard);
+    ids[t] = t;
 }
 
-int reserve_order_buffers(ebpmf_ctx *ctx, int ncta) {
-    CHECK(reserve(ctx, ctx->score, sizeof(float) * (size_t)ncta));
-    CHECK(reserve(ctx, ctx->score_sorted, sizeof(float) * (size_t)ncta));
-    CHECK(reserve(ctx, ctx->cta_ids, sizeof(int) * (size_t)ncta));
-    CHECK(reserve(ctx, ctx->perm, sizeof(int) * (size_t)ncta));
-    return EBPMF_OK;
-}
-
-// ctx->perm = CTA ids by decreasing ctx->score (cub radix sort, ~60 us for 57 k CTAs)
-int sort_ctas_by_score(ebpmf_ctx *ctx, int ncta) {
-    iota_kernel<<<(ncta + 255) / 256, 256, 0, ctx->stream>>>(as<int>(ctx->cta_ids), ncta);
+// ctx->perm = tile ids in launch order: by chunk, inside a chunk by decreasing hardness of the previous step
+// (stable radix sort: equal keys keep the natural order)
+int build_order(ebpmf_ctx *ctx, const StepPlan &pl) {
+    if (!pl.ordered) return EBPMF_OK;
+    const int nt = pl.ntiles;
+    if (pl.nchunks > 0xFFFF) return fail(ctx, EBPMF_ERR_ARG, "too many column chunks");
+    CHECK(reserve(ctx, ctx->order_keys, sizeof(unsigned) * (size_t)nt));
+    CHECK(reserve(ctx, ctx->order_keys2, sizeof(unsigned) * (size_t)nt));
+    CHECK(reserve(ctx, ctx->order_ids, sizeof(int) * (size_t)nt));
+    CHECK(reserve(ctx, ctx->perm, sizeof(int) * (size_t)nt));
+    CHECK(reserve(ctx, ctx->span_rank, sizeof(int) * (size_t)pl.nspans));
+    CHECK(reserve(ctx, ctx->chunk_dirty, sizeof(int) * (size_t)std::max(pl.nchunks, 1)));
+    CU(cudaMemcpyAsync(ctx->span_rank.ptr, pl.span_rank.data(), sizeof(int) * (size_t)pl.nspans, cudaMemcpyHostToDevice,
+                       ctx->stream));
+    const bool hist = ctx->use_history && ctx->have_hist && ctx->hist_n == ctx->n && ctx->hist_p == ctx->p &&
+                      ctx->hist_cols == pl.cols_per_cta;
+    order_keys_rank_kernel<<<(nt + 255) / 256, 256, 0, ctx->stream>>>(as<unsigned short>(ctx->tile_hard), as<int>(ctx->span_rank),
+                                                                      nt, pl.nspans, hist ? 1 : 0, as<unsigned>(ctx->order_keys),
+                                                                      as<int>(ctx->order_ids));
     CU(cudaGetLastError());
     size_t tmp_bytes = 0;
-    CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, as<float>(ctx->score), as<float>(ctx->score_sorted),
-                                                 as<int>(ctx->cta_ids), as<int>(ctx->perm), ncta, 0, 32, ctx->stream));
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, as<unsigned>(ctx->order_keys), as<unsigned>(ctx->order_keys2),
+                                       as<int>(ctx->order_ids), as<int>(ctx->perm), nt, 0, 32, ctx->stream));
     CHECK(reserve(ctx, ctx->cub_tmp, tmp_bytes));
-    CU(cub::DeviceRadixSort::SortPairsDescending(ctx->cub_tmp.ptr, tmp_bytes, as<float>(ctx->score),
-                                                 as<float>(ctx->score_sorted), as<int>(ctx->cta_ids), as<int>(ctx->perm),
-                                                 ncta, 0, 32, ctx->stream));
+    CU(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.ptr, tmp_bytes, as<unsigned>(ctx->order_keys), as<unsigned>(ctx->order_keys2),
+                                       as<int>(ctx->order_ids), as<int>(ctx->perm), nt, 0, 32, ctx->stream));
+    ctx->launches += 4;
     return EBPMF_OK;
 }
 
-template <int KTP>
-int launch_score_ktp(ebpmf_ctx *ctx, const FusedArgs &a, dim3 grid) {
-    const int smem = (int)sizeof(ScoreSmem<KTP>);
-    static bool configured[8] = {false, false, false, false, false, false, false, false};   // per device
-    if (ctx->device < 8 ? !configured[ctx->device] : true) {
-        CU(cudaFuncSetAttribute(vga_score_kernel<KTP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CU(cudaFuncSetAttribute(vga_score_kernel<KTP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        if (ctx->device < 8) configured[ctx->device] = true;
+template <int KTP, int FORMULA, int MODE, int FREEZE>
+int launch_fused_inst(ebpmf_ctx *ctx, const FusedArgs &a, int count) {
+    auto kern = vga_fused_kernel<KTP, kE, FORMULA, MODE, FREEZE>;
+    const int smem = (int)sizeof(FusedSmem<KTP, FORMULA>);
+    static bool configured[64] = {false};   // per device
+    if (ctx->device < 64 ? !configured[ctx->device] : true) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (ctx->device < 64) configured[ctx->device] = true;
     }
-    if (a.var_type == EBPMF_VAR_BY_COL) vga_score_kernel<KTP, true><<<grid, dim3(kThreads), smem, ctx->stream>>>(a);
-    else vga_score_kernel<KTP, false><<<grid, dim3(kThreads), smem, ctx->stream>>>(a);
+    kern<<<dim3((unsigned)count), dim3(kThreads), smem, ctx->stream>>>(a);
     CU(cudaGetLastError());
+    ++ctx->launches;
     return EBPMF_OK;
 }
 
-// Scored pipeline (pipeline == 3, FORMULA_A1): an FP32 scoring pass ranks the tiles by their largest
-// first Newton step, then the SAME fused kernel takes them in that order.  The slowest entries are
-// met first, K* is published early and (almost) every unit runs to the global count inside pass 1,
-// in registers; the top-up pass finds next to nothing to do.  Results are bit-identical to
-// pipeline 0 (a unit's iterates do not depend on the order the units are taken in).
-int launch_score_and_sort(ebpmf_ctx *ctx, FusedArgs &a, dim3 grid) {
-    const int ncta = (int)(grid.x * grid.y);
-    CHECK(reserve_order_buffers(ctx, ncta));
-    a.score = as<float>(ctx->score);
-    a.perm = nullptr;
+template <int KTP, int FORMULA, int MODE>
+int launch_fused_ktp(ebpmf_ctx *ctx, const FusedArgs &a, int count) {
+    if (a.delta > 0) return launch_fused_inst<KTP, FORMULA, MODE, FREEZE_DELTA>(ctx, a, count);
+    if (ctx->freeze) return launch_fused_inst<KTP, FORMULA, MODE, FREEZE_PERIODIC>(ctx, a, count);
+    return launch_fused_inst<KTP, FORMULA, MODE, FREEZE_NONE>(ctx, a, count);
+}
+
+// one launch of the fused kernel over `count` tiles starting at position `tile_begin` of the order
+template <int FORMULA, int MODE>
+int launch_fused(ebpmf_ctx *ctx, FusedArgs a, int tile_begin, int count) {
+    if (count <= 0) return EBPMF_OK;
+    a.tile_begin = tile_begin;
     switch (ctx->KTP) {
-        case 8: CHECK((launch_score_ktp<8>(ctx, a, grid))); break;
-        case 16: CHECK((launch_score_ktp<16>(ctx, a, grid))); break;
-        case 24: CHECK((launch_score_ktp<24>(ctx, a, grid))); break;
-        case 32: CHECK((launch_score_ktp<32>(ctx, a, grid))); break;
-        default: return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported", ctx->K);
-    }
-    CHECK(sort_ctas_by_score(ctx, ncta));
-    a.perm = as<int>(ctx->perm);
-    return EBPMF_OK;
-}
-
-// Ordered pipeline (pipeline == 2, FORMULA_A1, maxiter >= 2): stage A (the fused kernel's ITER0_ONLY
-// form) performs Newton iteration 0 and scores every CTA by its largest first step; the streaming kernel
-// then walks the CTAs by decreasing score, so the slowest entries -- the ones that set the global update count --
-// are met first and almost no unit finishes below K* (the top-up pass becomes nearly empty).
-template <bool DELTA>
-int launch_first_ordered(ebpmf_ctx *ctx, FusedArgs a, dim3 grid) {
-    const int ncta = (int)(grid.x * grid.y);
-    CHECK(reserve_order_buffers(ctx, ncta));
-    a.score = as<float>(ctx->score);
-    a.perm = nullptr;
-    a.nspans = (int)grid.x;
-    switch (ctx->KTP) {   // stage A: tile staging + Beta + Newton iteration 0 (the fused kernel's ITER0_ONLY form)
-        case 8: CHECK((launch_iter0_ktp<8>(ctx, a, grid))); break;
-        case 16: CHECK((launch_iter0_ktp<16>(ctx, a, grid))); break;
-        case 24: CHECK((launch_iter0_ktp<24>(ctx, a, grid))); break;
-        case 32: CHECK((launch_iter0_ktp<32>(ctx, a, grid))); break;
-        default: return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported", ctx->K);
-    }
-    if (ctx->comm)    // "some entry is not converged at k = 0" is a property of the WHOLE matrix
-        NC(g_nccl.AllReduce(&as<Status>(ctx->status)->notconv0, &as<Status>(ctx->status)->notconv0, 1, ncclInt32,
-                            ncclMax, ctx->comm, ctx->stream));
-    CHECK(sort_ctas_by_score(ctx, ncta));
-    a.perm = as<int>(ctx->perm);
-    vga_stream_kernel<kE, FORMULA_A1, MODE_FIRST, DELTA><<<dim3((unsigned)ncta), dim3(kThreads), 0, ctx->stream>>>(a);
-    CU(cudaGetLastError());
-    return EBPMF_OK;
-}
-
-// pass 1 of the fused path (K1 / K4): either ONE fused kernel (tile staging + Beta rebuild +
-// register-resident Newton), or the split pipeline: const0 kernel, then streaming Newton.
-template <int FORMULA>
-int launch_first(ebpmf_ctx *ctx, const FusedArgs &a) {
-    const long long ncols = a.col1 - a.col0;
-    if (ncols <= 0) return EBPMF_OK;
-    dim3 grid((unsigned)((ncols + a.cols_per_cta - 1) / a.cols_per_cta), (unsigned)ctx->nRB);
-    if (ctx->pipeline == 2 && FORMULA == FORMULA_A1 && a.maxiter >= 2 && a.col0 == 0 && a.col1 == ctx->p)
-        return a.delta > 0 ? launch_first_ordered<true>(ctx, a, grid) : launch_first_ordered<false>(ctx, a, grid);
-    if (ctx->pipeline == 1 || ctx->pipeline == 2) {
-        CHECK((launch_prep<FORMULA>(ctx, a, grid)));
-        if (a.delta > 0) vga_stream_kernel<kE, FORMULA, MODE_FIRST, true><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
-        else vga_stream_kernel<kE, FORMULA, MODE_FIRST, false><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
-        CU(cudaGetLastError());
-        return EBPMF_OK;
-    }
-    FusedArgs b = a;
-    b.perm = nullptr;
-    if (ctx->pipeline == 3 && FORMULA == FORMULA_A1 && a.maxiter >= 2 && ctx->K <= 32 && a.cols_per_cta <= kMaxSpanCols &&
-        grid.x * grid.y >= ctx->scored_min_ctas)
-        CHECK(launch_score_and_sort(ctx, b, grid));
-    switch (ctx->KTP) {
-        case 8: return launch_first_ktp<8, FORMULA>(ctx, b, grid);
-        case 16: return launch_first_ktp<16, FORMULA>(ctx, b, grid);
-        case 24: return launch_first_ktp<24, FORMULA>(ctx, b, grid);
-        case 32: return launch_first_ktp<32, FORMULA>(ctx, b, grid);
+        case 8: return launch_fused_ktp<8, FORMULA, MODE>(ctx, a, count);
+        case 16: return launch_fused_ktp<16, FORMULA, MODE>(ctx, a, count);
+        case 24: return launch_fused_ktp<24, FORMULA, MODE>(ctx, a, count);
+        case 32: return launch_fused_ktp<32, FORMULA, MODE>(ctx, a, count);
     }
     return fail(ctx, EBPMF_ERR_ARG, "K = %d factor columns not supported", ctx->K);
-}
-
-// pass 2 (streaming top-up to the global count)
-template <int FORMULA>
-int launch_topup(ebpmf_ctx *ctx, const FusedArgs &a) {
-    const long long ncols = a.col1 - a.col0;
-    if (ncols <= 0) return EBPMF_OK;
-    dim3 grid((unsigned)((ncols + a.cols_per_cta - 1) / a.cols_per_cta), (unsigned)ctx->nRB);
-    if (a.delta > 0) vga_stream_kernel<kE, FORMULA, MODE_TOPUP, true><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
-    else vga_stream_kernel<kE, FORMULA, MODE_TOPUP, false><<<grid, dim3(kThreads), 0, ctx->stream>>>(a);
-    CU(cudaGetLastError());
-    return EBPMF_OK;
 }
 
 int stride_for(int kind, long long n, long long *rs, long long *cs) {
@@ -435,40 +383,34 @@ int ensure_common(ebpmf_ctx *ctx) {
     return EBPMF_OK;
 }
 
-int alloc_solver_state(ebpmf_ctx *ctx, long long n, long long p) {
-    ctx->nRB = (n + kRowsPerCta - 1) / kRowsPerCta;
-    ctx->nRW = (n + 31) / 32;
-    const long long nJG = (p + kE - 1) / kE;
-    CHECK(reserve(ctx, ctx->kunit, sizeof(unsigned short) * (size_t)nJG * (size_t)ctx->nRW));
-    CHECK(reserve(ctx, ctx->status, sizeof(Status)));
-    return EBPMF_OK;
-}
-
-// reductions of the per-unit partials into red = [sym, ssexp, slogv, sumV][v_sum...]
-// (the final M is in Malt at this point: sum(Y*M) runs over the CSC non-zeros only)
+// reductions of the per-tile partials into red = [sym, ssexp, slogv, sumV][v_sum...]
+// (the final M is in Malt at this point: sum(Y*M) runs over the CSC non-zeros only); also the column
+// span of the hardest tile, where the NEXT step's first pass will start
 int run_reductions(ebpmf_ctx *ctx) {
     const long long n = ctx->n, p = ctx->p;
-    const long long nJG = (p + kE - 1) / kE;
     double *red = as<double>(ctx->red);
     double *colsym = as<double>(ctx->colsums);
     double *colv = (ctx->var_type == EBPMF_VAR_BY_COL) ? red + 4 : colsym + p;
-    double *unitsum = colsym + 2 * p;
     reduce_over_rows_kernel<1><<<(unsigned)((p + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(
-        as<double>(ctx->colV), ctx->nRW, p, colv);
-    CU(cudaGetLastError());
-    reduce_over_rows_kernel<2><<<(unsigned)((nJG + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(
-        as<double>(ctx->unitS), ctx->nRW, nJG, unitsum);
+        as<double>(ctx->colV), ctx->nRB, p, colv);
     CU(cudaGetLastError());
     sym_nnz_kernel<<<(unsigned)((p * 32 + 255) / 256), 256, 0, ctx->stream>>>(
         as<int>(ctx->colptr), as<int>(ctx->rowidx), as<double>(ctx->yx), as<double>(ctx->Malt), n, p, colsym);
     CU(cudaGetLastError());
-    reduce_scalars_kernel<<<1, 1024, 0, ctx->stream>>>(colsym, colv, p, unitsum, nJG, red);
+    reduce_scalars_kernel<<<1, 1024, 0, ctx->stream>>>(colsym, colv, p, as<double>(ctx->tileS), ctx->cur_ntiles, red);
     CU(cudaGetLastError());
+    ctx->launches += 3;
     if (ctx->var_type == EBPMF_VAR_BY_ROW) {
-        reduce_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(as<double>(ctx->rowpart), n, nJG,
+        reduce_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(as<double>(ctx->rowpart), n, ctx->cur_nspans,
                                                                                  red + 4);
         CU(cudaGetLastError());
+        ++ctx->launches;
     }
+    hardest_span_kernel<<<1, 1024, 0, ctx->stream>>>(as<unsigned short>(ctx->tile_hard), ctx->cur_ntiles, ctx->cur_nspans,
+                                                     as<int>(ctx->small_out));
+    CU(cudaGetLastError());
+    ++ctx->launches;
+    CU(cudaMemcpyAsync(ctx->h_ints, ctx->small_out.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (ctx->comm) {
         const size_t count = 4 + (ctx->var_type == EBPMF_VAR_BY_COL ? (size_t)p : 0);
         NC(g_nccl.AllReduce(red, red, count, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
@@ -476,7 +418,7 @@ int run_reductions(ebpmf_ctx *ctx) {
     return EBPMF_OK;
 }
 
-// The pass orchestration shared by the fused step (A1) and low_memory (A10).
+// The pass orchestration shared by the fused step (A1), low_memory (A10) and the dense solver.
 // first / topup are callables that enqueue one pass on ctx->stream.
 template <typename First, typename Topup, typename After>
 int run_global_stop(ebpmf_ctx *ctx, int maxiter, First first, Topup topup, After after, ebpmf_solve_info *info) {
@@ -503,13 +445,14 @@ int run_global_stop(ebpmf_ctx *ctx, int maxiter, First first, Topup topup, After
             ++passes;
             continue;
         }
+        ctx->diag_topups = s.topup_units;
+        ctx->diag_iters = s.unit_iters;
+        ctx->diag_topup_tiles = s.topup_tiles;
         if (info) {
             info->n_updates = s.kstar;
             info->converged = (s.kstar < maxiter) ? 1 : 0;
             info->passes = passes;
             info->reserved = 0;
-            ctx->diag_topups = s.topup_units;
-            ctx->diag_iters = s.unit_iters;
             float ms = 0.f;
             CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
             info->kernel_ms = ms;
@@ -524,35 +467,58 @@ int run_global_stop(ebpmf_ctx *ctx, int maxiter, First first, Topup topup, After
     }
 }
 
-FusedArgs fused_args(ebpmf_ctx *ctx, int maxiter, double tol, bool want_v) {
+FusedArgs fused_args(ebpmf_ctx *ctx, const StepPlan &pl, int maxiter, double tol, bool want_v) {
     FusedArgs a;
     memset(&a, 0, sizeof a);
     a.n = ctx->n; a.p = ctx->p; a.K = ctx->K; a.var_type = ctx->var_type;
     a.M_in = as<double>(ctx->Mcur); a.M_out = as<double>(ctx->Malt);
     a.V_out = want_v ? as<double>(ctx->V) : nullptr;
-    a.C0 = as<double>(ctx->C0);
-    a.EL = as<double>(ctx->EL); a.EFt = as<double>(ctx->EFt); a.ldk = ctx->ldk; a.sigma2 = as<double>(ctx->sigma2);
+    a.EL = as<double>(ctx->EL); a.EFt = as<double>(ctx->EFt); a.ldk = ctx->ldk;
     a.sc1 = as<double>(ctx->sc1); a.sc2 = as<double>(ctx->sc2);
     a.l0 = as<double>(ctx->l0); a.f0 = as<double>(ctx->f0);
     a.rowidx = as<int>(ctx->rowidx); a.yx = as<double>(ctx->yx); a.rbptr = as<int>(ctx->rbptr);
     a.kunit = as<unsigned short>(ctx->kunit); a.nRW = ctx->nRW; a.nJG = (ctx->p + kE - 1) / kE;
-    a.colV = as<double>(ctx->colV); a.unitS = as<double>(ctx->unitS);
+    a.colV = as<double>(ctx->colV); a.tileS = as<double>(ctx->tileS);
     a.rowpart = (ctx->var_type == EBPMF_VAR_BY_ROW) ? as<double>(ctx->rowpart) : nullptr;
+    a.tile_hard = as<unsigned short>(ctx->tile_hard); a.tile_kmin = as<unsigned short>(ctx->tile_kmin);
+    a.perm = pl.ordered ? as<int>(ctx->perm) : nullptr;
+    a.tile_begin = 0;
+    a.nspans = pl.nspans; a.cols_per_cta = pl.cols_per_cta;
+    a.chunk_dirty = (pl.nchunks > 1) ? as<int>(ctx->chunk_dirty) : nullptr;
+    a.span_rank = (pl.nchunks > 1) ? as<int>(ctx->span_rank) : nullptr;
+    a.bulk = (ctx->n % 2 == 0 && !getenv("EBPMF_B200_NO_BULK")) ? 1 : 0;
     a.status = as<Status>(ctx->status);
     a.peers = reinterpret_cast<const Status *const *>(ctx->peer_ptrs.ptr);
     a.npeers = ctx->npeers;
     a.epoch = ctx->epoch + 1;      // run_global_stop increments the counter before the first launch
     a.tables = as<MathTables>(ctx->tables);
     a.maxiter = maxiter; a.tol = tol; a.delta = ctx->delta; a.tol_verify = tol * ctx->debug_verify_scale;
-    a.col0 = 0; a.col1 = ctx->p;
-    a.cols_per_cta = cols_per_cta_for(ctx->p, ctx->nRB);
+    ctx->cur_nspans = pl.nspans; ctx->cur_ntiles = pl.ntiles; ctx->cur_cols = pl.cols_per_cta;
     return a;
+}
+
+// one O(nnz) pass over the dgCMatrix slots before they are trusted by the kernels (the row indices
+// address shared memory and the offset table is built by binary search)
+int validate_csc(ebpmf_ctx *ctx, long long n, long long p, const int32_t *colptr, const int32_t *rowidx) {
+    if (colptr[0] != 0) return fail(ctx, EBPMF_ERR_ARG, "bad dgCMatrix @p slot: p[0] != 0");
+    for (long long j = 0; j < p; ++j) {
+        const int lo = colptr[j], hi = colptr[j + 1];
+        if (hi < lo) return fail(ctx, EBPMF_ERR_ARG, "bad dgCMatrix @p slot: not non-decreasing at column %lld", j);
+        int prev = -1;
+        for (int q = lo; q < hi; ++q) {
+            const int r = rowidx[q];
+            if (r <= prev || r >= n)
+                return fail(ctx, EBPMF_ERR_ARG, "bad dgCMatrix @i slot: column %lld holds row index %d (rows must be increasing, < %lld)", j, r, n);
+            prev = r;
+        }
+    }
+    return EBPMF_OK;
 }
 
 int upload_csc(ebpmf_ctx *ctx, long long n, long long p, const int32_t *colptr, const int32_t *rowidx,
                const double *x) {
+    CHECK(validate_csc(ctx, n, p, colptr, rowidx));
     const long long nnz = colptr[p];
-    if (nnz < 0 || colptr[0] != 0) return fail(ctx, EBPMF_ERR_ARG, "bad dgCMatrix @p slot");
     CHECK(reserve(ctx, ctx->colptr, sizeof(int) * (size_t)(p + 1)));
     CHECK(reserve(ctx, ctx->rowidx, sizeof(int) * (size_t)std::max(1LL, nnz)));
     CHECK(reserve(ctx, ctx->yx, sizeof(double) * (size_t)std::max(1LL, nnz)));
@@ -562,19 +528,28 @@ int upload_csc(ebpmf_ctx *ctx, long long n, long long p, const int32_t *colptr, 
         CU(cudaMemcpyAsync(ctx->yx.ptr, x, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
     }
     ctx->nnz = nnz;
-    (void)n;
     return EBPMF_OK;
 }
 
-// after colptr/rowidx/yx are resident: shapes, row-block offset table, partial buffers
 // shape-dependent scratch of the fused step (grow-only), and nRB / nRW
 int reserve_shape_buffers(ebpmf_ctx *ctx, long long n, long long p) {
+    if (n != ctx->n || p != ctx->p) ctx->have_hist = false;
     ctx->n = n; ctx->p = p;
-    CHECK(alloc_solver_state(ctx, n, p));
+    ctx->nRB = (n + kRowsPerCta - 1) / kRowsPerCta;
+    ctx->nRW = (n + 31) / 32;
     const long long nJG = (p + kE - 1) / kE;
-    CHECK(reserve(ctx, ctx->colV, sizeof(double) * (size_t)ctx->nRW * (size_t)p));
-    CHECK(reserve(ctx, ctx->unitS, sizeof(double) * 2 * (size_t)ctx->nRW * (size_t)nJG));
-    CHECK(reserve(ctx, ctx->colsums, sizeof(double) * (2 * (size_t)p + 2 * (size_t)nJG)));
+    const int cols = cols_per_cta_for(p, ctx->nRB);
+    const long long nspans = (p + cols - 1) / cols;
+    const long long ntiles = nspans * ctx->nRB;
+    if (ntiles > 0x7fffffffLL) return fail(ctx, EBPMF_ERR_ARG, "matrix too large for one shard");
+    CHECK(reserve(ctx, ctx->kunit, sizeof(unsigned short) * (size_t)nJG * (size_t)ctx->nRW));
+    CHECK(reserve(ctx, ctx->status, sizeof(Status)));
+    CHECK(reserve(ctx, ctx->colV, sizeof(double) * (size_t)ctx->nRB * (size_t)p));
+    CHECK(reserve(ctx, ctx->tileS, sizeof(double) * 2 * (size_t)ntiles));
+    CHECK(reserve(ctx, ctx->tile_hard, sizeof(unsigned short) * (size_t)ntiles));
+    CHECK(reserve(ctx, ctx->tile_kmin, sizeof(unsigned short) * (size_t)ntiles));
+    CHECK(reserve(ctx, ctx->small_out, sizeof(int) * 16));
+    CHECK(reserve(ctx, ctx->colsums, sizeof(double) * 2 * (size_t)p));
     CHECK(reserve(ctx, ctx->sc1, sizeof(double) * (size_t)std::max(n, p)));
     CHECK(reserve(ctx, ctx->sc2, sizeof(double) * (size_t)std::max(n, p)));
     CHECK(reserve(ctx, ctx->red, sizeof(double) * (4 + (size_t)std::max(n, p))));
@@ -582,24 +557,17 @@ int reserve_shape_buffers(ebpmf_ctx *ctx, long long n, long long p) {
     return EBPMF_OK;
 }
 
+// after colptr/rowidx/yx are resident: shapes, row-block offset table, partial buffers
 int finish_set_y(ebpmf_ctx *ctx, long long n, long long p) {
-    ctx->n = n; ctx->p = p;
-    CHECK(alloc_solver_state(ctx, n, p));
+    CHECK(reserve_shape_buffers(ctx, n, p));
     const long long cells = (ctx->nRB + 1) * p;
     CHECK(reserve(ctx, ctx->rbptr, sizeof(int) * (size_t)cells));
     build_rbptr_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(
         as<int>(ctx->colptr), as<int>(ctx->rowidx), p, ctx->nRB, as<int>(ctx->rbptr));
     CU(cudaGetLastError());
-    const long long nJG = (p + kE - 1) / kE;
-    CHECK(reserve(ctx, ctx->colV, sizeof(double) * (size_t)ctx->nRW * (size_t)p));
-    CHECK(reserve(ctx, ctx->unitS, sizeof(double) * 2 * (size_t)ctx->nRW * (size_t)nJG));
-    CHECK(reserve(ctx, ctx->colsums, sizeof(double) * (2 * (size_t)p + 2 * (size_t)nJG)));
-    CHECK(reserve(ctx, ctx->sc1, sizeof(double) * (size_t)std::max(n, p)));
-    CHECK(reserve(ctx, ctx->sc2, sizeof(double) * (size_t)std::max(n, p)));
-    CHECK(reserve(ctx, ctx->red, sizeof(double) * (4 + (size_t)std::max(n, p))));
-    CHECK(reserve(ctx, ctx->misc, sizeof(double) * (size_t)(3 * std::max(n, p) + 4096)));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->have_y = true;
+    ctx->have_hist = false;
     ctx->have_m = ctx->have_f = ctx->have_s2 = ctx->have_v = ctx->have_vsum = false;
     return EBPMF_OK;
 }
@@ -663,6 +631,68 @@ int copy_out_ld(ebpmf_ctx *ctx, double *dst, const void *src, long long rows, lo
     return EBPMF_OK;
 }
 
+// pinned ring + copy threads for caller-owned (possibly pageable) host matrices; created on first use
+int ensure_pipe(ebpmf_ctx *ctx) {
+    if (ctx->pipe && ctx->pipe->ready()) return EBPMF_OK;
+    auto env_int = [](const char *name, long dflt, long lo, long hi) {
+        const char *v = getenv(name);
+        if (!v) return dflt;
+        const long x = atol(v);
+        return std::min(hi, std::max(lo, x));
+    };
+    long cores = sysconf(_SC_NPROCESSORS_ONLN);
+    if (cores < 1) cores = 1;
+    const long slot_mb = env_int("EBPMF_B200_PIPE_SLOT_MB", 32, 1, 1024);
+    const long nslots = env_int("EBPMF_B200_PIPE_SLOTS", 12, 2, 256);
+    const long nthreads = env_int("EBPMF_B200_PIPE_THREADS", std::min(8L, std::max(2L, cores / 2)), 1, 64);
+    ctx->pipe.reset(new (std::nothrow) HostPipe());
+    if (!ctx->pipe) return fail(ctx, EBPMF_ERR_NOMEM, "out of host memory");
+    std::string err;
+    if (ctx->pipe->init(ctx->device, (size_t)slot_mb << 20, (int)nslots, (int)nthreads, err)) {
+        ctx->pipe.reset();
+        return fail(ctx, EBPMF_ERR_CUDA, "%s", err.c_str());
+    }
+    return EBPMF_OK;
+}
+
+int pipe_wait(ebpmf_ctx *ctx, const HostPipe::JobRef &j) {
+    std::string err;
+    if (ctx->pipe->wait(j, err)) return fail(ctx, EBPMF_ERR_CUDA, "%s", err.c_str());
+    return EBPMF_OK;
+}
+
+constexpr size_t kPipeMinBytes = (size_t)32 << 20;   // below this a plain cudaMemcpy is as good
+
+// whole-matrix host -> device (packed) on the compute stream's timeline; returns when the data is on the device
+int matrix_in(ebpmf_ctx *ctx, void *dst, const double *src, long long rows, long long cols, long long ld) {
+    const size_t bytes = sizeof(double) * (size_t)rows * (size_t)cols;
+    if (bytes < kPipeMinBytes) {
+        CHECK(copy_in_ld(ctx, dst, src, rows, cols, ld));
+        CU(cudaStreamSynchronize(ctx->stream));
+        return EBPMF_OK;
+    }
+    CHECK(ensure_pipe(ctx));
+    CU(cudaStreamSynchronize(ctx->stream));             // nothing on the compute stream still uses dst
+    auto j = ctx->pipe->h2d((double *)dst, src, (size_t)rows, (size_t)cols, (size_t)ld, ctx->ev_setup);
+    CHECK(pipe_wait(ctx, j));
+    CU(cudaEventSynchronize(ctx->ev_setup));
+    return EBPMF_OK;
+}
+
+// whole-matrix device (packed) -> host; the compute stream must have produced src already (callers synchronise)
+int matrix_out(ebpmf_ctx *ctx, double *dst, const void *src, long long rows, long long cols, long long ld) {
+    const size_t bytes = sizeof(double) * (size_t)rows * (size_t)cols;
+    if (bytes < kPipeMinBytes) {
+        CHECK(copy_out_ld(ctx, dst, src, rows, cols, ld));
+        CU(cudaStreamSynchronize(ctx->stream));
+        return EBPMF_OK;
+    }
+    CHECK(ensure_pipe(ctx));
+    CU(cudaStreamSynchronize(ctx->stream));
+    auto j = ctx->pipe->d2h((const double *)src, dst, (size_t)rows, (size_t)cols, (size_t)ld, nullptr);
+    return pipe_wait(ctx, j);
+}
+
 int set_m_ld(ebpmf_ctx *ctx, const double *M, long long ld) {
     if (!ctx || !M) return fail(ctx, EBPMF_ERR_ARG, "set_m: bad arguments");
     if (!ctx->have_y) return fail(ctx, EBPMF_ERR_STATE, "set_m: Y not set");
@@ -670,13 +700,12 @@ int set_m_ld(ebpmf_ctx *ctx, const double *M, long long ld) {
     const size_t bytes = sizeof(double) * (size_t)ctx->n * (size_t)ctx->p;
     CHECK(reserve(ctx, ctx->Mcur, bytes));
     CHECK(reserve(ctx, ctx->Malt, bytes));
-    CHECK(copy_in_ld(ctx, ctx->Mcur.ptr, M, ctx->n, ctx->p, ld));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CHECK(matrix_in(ctx, ctx->Mcur.ptr, M, ctx->n, ctx->p, ld));
     ctx->have_m = true; ctx->can_rewind = false;
     return EBPMF_OK;
 }
 
-int set_factors_ld(ebpmf_ctx *ctx, int64_t K, const double *EL, long long ldl, const double *EF) {
+int set_factors_ld(ebpmf_ctx *ctx, int64_t K, const double *EL, long long ldl, const double *EF, bool sync = true) {
     if (!ctx || !EL || !EF || K < 1) return fail(ctx, EBPMF_ERR_ARG, "set_factors: bad arguments");
     if (!ctx->have_y) return fail(ctx, EBPMF_ERR_STATE, "set_factors: Y not set");
     const int ktp = ktp_for((int)K);
@@ -692,7 +721,8 @@ int set_factors_ld(ebpmf_ctx *ctx, int64_t K, const double *EL, long long ldl, c
     transpose_ef_kernel<<<(unsigned)((p * ldk + 255) / 256), 256, 0, ctx->stream>>>(as<double>(ctx->EF), p, (int)K, ldk,
                                                                                    as<double>(ctx->EFt));
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(ctx->stream));
+    ++ctx->launches;
+    if (sync) CU(cudaStreamSynchronize(ctx->stream));
     ctx->K = (int)K; ctx->KTP = ktp; ctx->ldk = ldk; ctx->have_f = true;
     return EBPMF_OK;
 }
@@ -701,9 +731,7 @@ int get_matrix_ld(ebpmf_ctx *ctx, bool want_v, double *out, long long ld) {
     if (!ctx || !out) return fail(ctx, EBPMF_ERR_ARG, "get: bad arguments");
     if (want_v ? !ctx->have_v : !ctx->have_m) return fail(ctx, EBPMF_ERR_STATE, want_v ? "get_v: the last step did not materialise V (want_v = 0)" : "get_m: M not set");
     CHECK(ensure_common(ctx));
-    CHECK(copy_out_ld(ctx, out, want_v ? ctx->V.ptr : ctx->Mcur.ptr, ctx->n, ctx->p, ld));
-    CU(cudaStreamSynchronize(ctx->stream));
-    return EBPMF_OK;
+    return matrix_out(ctx, out, want_v ? ctx->V.ptr : ctx->Mcur.ptr, ctx->n, ctx->p, ld);
 }
 
 
@@ -802,9 +830,17 @@ int ebpmf_ctx_create(int device, ebpmf_ctx **out) {
     ctx = new (std::nothrow) ebpmf_ctx();
     if (!ctx) return fail(nullptr, EBPMF_ERR_NOMEM, "out of host memory");
     ctx->device = device;
-    if (const char *pl = getenv("EBPMF_B200_PIPELINE"))
-        ctx->pipeline = !strcmp(pl, "scored") ? 3 : !strcmp(pl, "ordered") ? 2 : !strcmp(pl, "split") ? 1 : 0;
-    if (const char *dl = getenv("EBPMF_B200_DELTA")) ctx->delta = atof(dl);
+    if (const char *dl = getenv("EBPMF_B200_DELTA")) {          // same range check as ebpmf_ctx_set_option
+        const double d = atof(dl);
+        if (!(d >= 0.0) || d > 1e-10) {
+            delete ctx;
+            return fail(nullptr, EBPMF_ERR_ARG, "EBPMF_B200_DELTA must be in [0, 1e-10]");
+        }
+        ctx->delta = d;
+    }
+    if (const char *fz = getenv("EBPMF_B200_FREEZE")) ctx->freeze = atoi(fz) ? 1 : 0;
+    if (const char *hs = getenv("EBPMF_B200_HISTORY")) ctx->use_history = atoi(hs) ? 1 : 0;
+    if (const char *sp = getenv("EBPMF_B200_SPECULATE")) ctx->speculate = atoi(sp) ? 1 : 0;
     cudaError_t ce;
 #define CREATE_STEP(call)                                                                                        \
     ce = (call);                                                                                                 \
@@ -815,14 +851,16 @@ int ebpmf_ctx_create(int device, ebpmf_ctx **out) {
     }
     CREATE_STEP(cudaSetDevice(device));
     CREATE_STEP(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CREATE_STEP(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CREATE_STEP(cudaEventCreate(&ctx->ev0));
     CREATE_STEP(cudaEventCreate(&ctx->ev1));
     CREATE_STEP(cudaEventCreate(&ctx->ev_p1));
     CREATE_STEP(cudaEventCreate(&ctx->ev_p2));
-    CREATE_STEP(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+    CREATE_STEP(cudaEventCreate(&ctx->ev_p3));
+    CREATE_STEP(cudaEventCreateWithFlags(&ctx->ev_setup, cudaEventDisableTiming));
+    CREATE_STEP(cudaEventCreateWithFlags(&ctx->ev_topup, cudaEventDisableTiming));
     CREATE_STEP(cudaMallocHost((void **)&ctx->h_status, sizeof(Status)));
     CREATE_STEP(cudaMallocHost((void **)&ctx->h_small, sizeof(double) * 64));
+    CREATE_STEP(cudaMallocHost((void **)&ctx->h_ints, sizeof(int) * 4096));
     CREATE_STEP(cudaMalloc(&ctx->tables.ptr, sizeof(MathTables)));
     ctx->tables.cap = sizeof(MathTables);
     CREATE_STEP(cudaMalloc(&ctx->status.ptr, sizeof(Status)));
@@ -853,22 +891,23 @@ int ebpmf_ctx_destroy(ebpmf_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (void *q : ctx->ipc_opened) cudaIpcCloseMemHandle(q);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    ctx->pipe.reset();                     // joins the copy threads, frees the pinned rings
     DevBuf *bufs[] = {&ctx->colptr, &ctx->rowidx, &ctx->yx, &ctx->rbptr, &ctx->Mcur, &ctx->Malt, &ctx->V,
                       &ctx->EL, &ctx->EF, &ctx->EFt, &ctx->sigma2, &ctx->l0, &ctx->f0, &ctx->kunit,
-                      &ctx->colV, &ctx->unitS, &ctx->rowpart, &ctx->red, &ctx->colsums, &ctx->status, &ctx->misc,
-                      &ctx->C0, &ctx->sc1, &ctx->sc2, &ctx->tables, &ctx->peer_ptrs,
-                      &ctx->score, &ctx->score_sorted, &ctx->cta_ids, &ctx->perm, &ctx->cub_tmp};
+                      &ctx->colV, &ctx->tileS, &ctx->rowpart, &ctx->tile_hard, &ctx->tile_kmin, &ctx->red, &ctx->colsums,
+                      &ctx->status, &ctx->misc, &ctx->sc1, &ctx->sc2, &ctx->tables, &ctx->peer_ptrs,
+                      &ctx->order_keys, &ctx->order_keys2, &ctx->order_ids, &ctx->perm, &ctx->cub_tmp, &ctx->span_rank,
+                      &ctx->chunk_dirty, &ctx->small_out, &ctx->prod};
     for (DevBuf *b : bufs) release(*b);
     for (DevBuf &b : ctx->scratch) release(b);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->ev_p1) cudaEventDestroy(ctx->ev_p1);
-    if (ctx->ev_p2) cudaEventDestroy(ctx->ev_p2);
-    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    if (ctx->h_ints) cudaFreeHost(ctx->h_ints);
+    cudaEvent_t evs[] = {ctx->ev0, ctx->ev1, ctx->ev_p1, ctx->ev_p2, ctx->ev_p3, ctx->ev_setup, ctx->ev_topup};
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_in) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
     return EBPMF_OK;
 }
@@ -938,7 +977,11 @@ int ebpmf_ctx_set_factors(ebpmf_ctx *ctx, int64_t K, const double *EL, const dou
     return set_factors_ld(ctx, K, EL, ctx ? ctx->n : 0, EF);
 }
 
-int ebpmf_ctx_set_sigma2(ebpmf_ctx *ctx, int var_type, const double *sigma2) {
+}  // extern "C"
+
+namespace {
+
+int set_sigma2_impl(ebpmf_ctx *ctx, int var_type, const double *sigma2, bool sync) {
     if (!ctx || !sigma2) return fail(ctx, EBPMF_ERR_ARG, "set_sigma2: bad arguments");
     if (var_type < 0 || var_type > 2) return fail(ctx, EBPMF_ERR_VAR_TYPE, "Non-supported var type");
     if (!ctx->have_y) return fail(ctx, EBPMF_ERR_STATE, "set_sigma2: Y not set");
@@ -947,37 +990,230 @@ int ebpmf_ctx_set_sigma2(ebpmf_ctx *ctx, int var_type, const double *sigma2) {
     CHECK(reserve(ctx, ctx->sigma2, sizeof(double) * std::max((size_t)ctx->p, (size_t)ctx->n)));
     CU(cudaMemcpyAsync(ctx->sigma2.ptr, sigma2, sizeof(double) * len, cudaMemcpyHostToDevice, ctx->stream));
     if (var_type == EBPMF_VAR_BY_ROW) {
-        const long long nJG = (ctx->p + kE - 1) / kE;
-        CHECK(reserve(ctx, ctx->rowpart, sizeof(double) * (size_t)nJG * (size_t)ctx->n));
+        const int cols = cols_per_cta_for(ctx->p, ctx->nRB);
+        const long long nspans = (ctx->p + cols - 1) / cols;
+        CHECK(reserve(ctx, ctx->rowpart, sizeof(double) * (size_t)nspans * (size_t)ctx->n));
     }
     sigma_consts_kernel<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(as<double>(ctx->sigma2), (long long)len,
                                                                                 as<double>(ctx->sc1), as<double>(ctx->sc2));
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(ctx->stream));
+    ++ctx->launches;
+    if (sync) CU(cudaStreamSynchronize(ctx->stream));
     ctx->var_type = var_type; ctx->have_s2 = true;
     return EBPMF_OK;
 }
 
-int ebpmf_ctx_vga_step(ebpmf_ctx *ctx, int maxiter, double tol, int want_v, ebpmf_solve_info *info) {
-    if (!ctx) return fail(ctx, EBPMF_ERR_ARG, "vga_step: ctx is NULL");
-    if (maxiter < 1 || maxiter > 65535) return fail(ctx, EBPMF_ERR_ARG, "vga_step: maxiter must be in [1, 65535]");
+// Multi-GPU: every rank says whether its preparation (allocations, uploads, argument checks) succeeded
+// BEFORE the first collective of the solve, so that one failing rank makes all ranks return an error
+// instead of leaving the others blocked in ncclAllReduce.
+int ranks_agree(ebpmf_ctx *ctx, int rc) {
+    if (!ctx->comm) return rc;
+    int *flag = as<int>(ctx->small_out) + 8;
+    ctx->h_ints[8] = (rc == EBPMF_OK) ? 1 : 0;
+    if (cudaMemcpyAsync(flag, ctx->h_ints + 8, sizeof(int), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+        g_nccl.AllReduce(flag, flag, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream) != ncclSuccess ||
+        cudaMemcpyAsync(ctx->h_ints + 8, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return rc != EBPMF_OK ? rc : fail(ctx, EBPMF_ERR_NCCL, "the ranks could not agree on the state of the solve");
+    }
+    if (rc != EBPMF_OK) return rc;
+    if (ctx->h_ints[8] != 1) return fail(ctx, EBPMF_ERR_STATE, "another rank failed while preparing this solve");
+    return EBPMF_OK;
+}
+
+// everything a fused A1 step needs before its first collective
+int prepare_step(ebpmf_ctx *ctx, const char *who, int maxiter, bool want_v, int want_chunks, StepPlan &pl) {
+    if (maxiter < 1 || maxiter > 65534) return fail(ctx, EBPMF_ERR_ARG, "%s: maxiter must be in [1, 65534]", who);
     if (!ctx->have_y || !ctx->have_m || !ctx->have_f || !ctx->have_s2)
-        return fail(ctx, EBPMF_ERR_STATE, "vga_step: Y, M, factors and sigma2 must be set first");
+        return fail(ctx, EBPMF_ERR_STATE, "%s: Y, M, factors and sigma2 must be set first", who);
     CHECK(ensure_common(ctx));
     if (want_v) CHECK(reserve(ctx, ctx->V, sizeof(double) * (size_t)ctx->n * (size_t)ctx->p));
-    CHECK(reserve(ctx, ctx->C0, sizeof(double) * (size_t)ctx->n * (size_t)ctx->p));
-    const FusedArgs a = fused_args(ctx, maxiter, tol, want_v != 0);
-    ctx->have_v = false; ctx->have_vsum = false;
-    int rc = run_global_stop(
-        ctx, maxiter, [&] { return launch_first<FORMULA_A1>(ctx, a); },
-        [&] { return launch_topup<FORMULA_A1>(ctx, a); }, [&] { return run_reductions(ctx); }, info);
-    if (rc != EBPMF_OK) return rc;
+    pl = make_plan(ctx, want_chunks);
+    CHECK(build_order(ctx, pl));
+    return EBPMF_OK;
+}
+
+// bookkeeping after a successful fused step: sums to the host, the resident M is now res$M, order history
+int finish_step(ebpmf_ctx *ctx, const StepPlan &pl, bool want_v, ebpmf_solve_info *info) {
     CU(cudaMemcpyAsync(ctx->h_small, ctx->red.ptr, sizeof(double) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if (info) { info->sym = ctx->h_small[0]; info->ssexp = ctx->h_small[1]; info->slogv = ctx->h_small[2]; }
     std::swap(ctx->Mcur, ctx->Malt);      // the resident M is now res$M
-    ctx->have_v = want_v != 0; ctx->have_vsum = true; ctx->can_rewind = true;
+    ctx->have_v = want_v; ctx->have_vsum = true; ctx->can_rewind = true;
+    ctx->have_hist = true; ctx->hist_n = ctx->n; ctx->hist_p = ctx->p; ctx->hist_cols = pl.cols_per_cta;
+    ctx->hard_span = ctx->h_ints[0];
     return EBPMF_OK;
+}
+
+int vga_step_impl(ebpmf_ctx *ctx, int maxiter, double tol, int want_v, ebpmf_solve_info *info) {
+    if (!ctx) return fail(ctx, EBPMF_ERR_ARG, "vga_step: ctx is NULL");
+    StepPlan pl;
+    int rc = prepare_step(ctx, "vga_step", maxiter, want_v != 0, 1, pl);
+    CHECK(ranks_agree(ctx, rc));
+    const FusedArgs a = fused_args(ctx, pl, maxiter, tol, want_v != 0);
+    ctx->have_v = false; ctx->have_vsum = false;
+    rc = run_global_stop(
+        ctx, maxiter, [&] { return launch_fused<FORMULA_A1, MODE_FIRST>(ctx, a, 0, pl.ntiles); },
+        [&] { return launch_fused<FORMULA_A1, MODE_TOPUP>(ctx, a, 0, pl.ntiles); }, [&] { return run_reductions(ctx); }, info);
+    if (rc != EBPMF_OK) return rc;
+    return finish_step(ctx, pl, want_v != 0, info);
+}
+
+int get_v_sum_impl(ebpmf_ctx *ctx, double *v_sum) {
+    if (!ctx || !v_sum) return fail(ctx, EBPMF_ERR_ARG, "get_v_sum: bad arguments");
+    if (!ctx->have_vsum) return fail(ctx, EBPMF_ERR_STATE, "get_v_sum: no VGA step has run");
+    CHECK(ensure_common(ctx));
+    const double *red = as<double>(ctx->red);
+    if (ctx->var_type == EBPMF_VAR_CONSTANT) {
+        CU(cudaMemcpyAsync(v_sum, red + 3, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        const size_t len = ctx->var_type == EBPMF_VAR_BY_COL ? (size_t)ctx->p : (size_t)ctx->n;
+        CU(cudaMemcpyAsync(v_sum, red + 4, sizeof(double) * len, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return EBPMF_OK;
+}
+
+// The whole step with CALLER-OWNED host buffers (pageable is fine), pipelined by column chunks:
+//   M_in (optional: NULL = the resident M is the input) goes up chunk by chunk through the pinned ring while the
+//   first pass already runs on the chunks that have arrived; every chunk's result is copied out as soon as its
+//   first pass is done (speculatively: with the tiles taken hardest-first, only the first chunk still changes
+//   in the top-up pass) and the chunks the top-up pass touched are copied again.  ld_* are leading dimensions
+//   of the host matrices (>= n; a row shard of a larger matrix has ld = its row count).
+int step_host_impl(ebpmf_ctx *ctx, const double *M_in, long long ld_in, int64_t K, const double *EL, long long ldl,
+                   const double *EF, int var_type, const double *sigma2, int maxiter, double tol, double *M_out,
+                   long long ld_out, double *V_out, double *v_sum, ebpmf_solve_info *info) {
+    if (!ctx || !M_out) return fail(ctx, EBPMF_ERR_ARG, "vga_step_host: bad arguments");
+    StepPlan pl;
+    const long long n = ctx->n, p = ctx->p;
+    const size_t bytes = sizeof(double) * (size_t)n * (size_t)p;
+    const bool piped = bytes >= kPipeMinBytes;
+    int rc = EBPMF_OK;
+    do {
+        if (!ctx->have_y) { rc = fail(ctx, EBPMF_ERR_STATE, "vga_step_host: Y not set"); break; }
+        if (!M_in && !ctx->have_m) { rc = fail(ctx, EBPMF_ERR_STATE, "vga_step_resident_host: upload M once with ebpmf_ctx_set_m"); break; }
+        if ((rc = set_factors_ld(ctx, K, EL, ldl, EF, false)) != EBPMF_OK) break;
+        if ((rc = set_sigma2_impl(ctx, var_type, sigma2, false)) != EBPMF_OK) break;
+        if (M_in) {
+            if ((rc = reserve(ctx, ctx->Mcur, bytes)) != EBPMF_OK) break;
+            if ((rc = reserve(ctx, ctx->Malt, bytes)) != EBPMF_OK) break;
+            if (!piped) { if ((rc = set_m_ld(ctx, M_in, ld_in)) != EBPMF_OK) break; }
+            ctx->have_m = true; ctx->can_rewind = false;
+        }
+        if (piped && (rc = ensure_pipe(ctx)) != EBPMF_OK) break;
+        int want_chunks = 1;
+        if (piped) {
+            want_chunks = ctx->pipe_chunks > 0 ? ctx->pipe_chunks
+                                               : (int)std::min<size_t>(32, std::max<size_t>(4, bytes / ((size_t)1280 << 20)));
+        }
+        rc = prepare_step(ctx, "vga_step_host", maxiter, V_out != nullptr, want_chunks, pl);
+        if (rc == EBPMF_OK) {
+            while ((int)ctx->ev_chunk.size() < pl.nchunks) {
+                cudaEvent_t e1 = nullptr, e2 = nullptr;
+                if (cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) != cudaSuccess) {
+                    rc = fail(ctx, EBPMF_ERR_CUDA, "cudaEventCreate failed");
+                    break;
+                }
+                ctx->ev_chunk.push_back(e1); ctx->ev_in.push_back(e2);
+            }
+        }
+    } while (0);
+    CHECK(ranks_agree(ctx, rc));
+
+    const FusedArgs a = fused_args(ctx, pl, maxiter, tol, V_out != nullptr);
+    ctx->have_v = false; ctx->have_vsum = false;
+    auto col0 = [&](int c) { return (long long)pl.span0[(size_t)c] * pl.cols_per_cta; };
+    auto col1 = [&](int c) { return std::min(p, (long long)pl.span1[(size_t)c] * pl.cols_per_cta); };
+    const bool hist = pl.ordered && ctx->use_history && ctx->have_hist;     // make_plan checked the shape
+    const bool spec = piped && ctx->speculate && hist && pl.nchunks > 1 && ctx->spec_waste < 0.5;
+    std::vector<HostPipe::JobRef> in_jobs, out_jobs((size_t)pl.nchunks);
+    if (pl.nchunks > 1) CU(cudaMemsetAsync(ctx->chunk_dirty.ptr, 0, sizeof(int) * (size_t)pl.nchunks, ctx->stream));
+    if (piped && M_in) {
+        CU(cudaStreamSynchronize(ctx->stream));         // nothing queued earlier may still read the buffer M arrives in
+        for (int c = 0; c < pl.nchunks; ++c)
+            in_jobs.push_back(ctx->pipe->h2d(as<double>(ctx->Mcur) + (size_t)col0(c) * (size_t)n, M_in + (size_t)col0(c) * (size_t)ld_in,
+                                             (size_t)n, (size_t)(col1(c) - col0(c)), (size_t)ld_in, ctx->ev_in[(size_t)c]));
+    }
+    double spec_bytes = 0.0, recopy_bytes = 0.0;
+    ebpmf_solve_info local;
+    memset(&local, 0, sizeof local);
+    rc = run_global_stop(
+        ctx, maxiter,
+        [&] {
+            for (int c = 0; c < pl.nchunks; ++c) {
+                if (piped && M_in) {
+                    CHECK(pipe_wait(ctx, in_jobs[(size_t)c]));                   // its last piece has been issued
+                    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[(size_t)c], 0));
+                }
+                CHECK((launch_fused<FORMULA_A1, MODE_FIRST>(ctx, a, pl.tile_begin[(size_t)c], pl.tile_count[(size_t)c])));
+                if (spec) {
+                    CU(cudaEventRecord(ctx->ev_chunk[(size_t)c], ctx->stream));
+                    out_jobs[(size_t)c] = ctx->pipe->d2h(as<double>(ctx->Malt) + (size_t)col0(c) * (size_t)n,
+                                                         M_out + (size_t)col0(c) * (size_t)ld_out, (size_t)n,
+                                                         (size_t)(col1(c) - col0(c)), (size_t)ld_out, ctx->ev_chunk[(size_t)c]);
+                    spec_bytes += 8.0 * (double)n * (double)(col1(c) - col0(c));
+                }
+            }
+            return (int)EBPMF_OK;
+        },
+        [&] { return launch_fused<FORMULA_A1, MODE_TOPUP>(ctx, a, 0, pl.ntiles); },
+        [&] {
+            CHECK(run_reductions(ctx));
+            if (pl.nchunks > 1)
+                CU(cudaMemcpyAsync(ctx->h_ints + 16, ctx->chunk_dirty.ptr, sizeof(int) * (size_t)pl.nchunks, cudaMemcpyDeviceToHost,
+                                   ctx->stream));
+            return (int)EBPMF_OK;
+        },
+        &local);
+    if (rc != EBPMF_OK) {
+        if (piped) {                                    // let every queued transfer finish before the caller's buffers go away
+            for (auto &j : in_jobs) if (j) (void)pipe_wait(ctx, j);
+            for (auto &j : out_jobs) if (j) (void)pipe_wait(ctx, j);
+        }
+        return rc;
+    }
+    CHECK(finish_step(ctx, pl, V_out != nullptr, &local));        // synchronises the compute stream; Mcur is the result
+    if (info) *info = local;
+    if (!piped) {
+        CHECK(copy_out_ld(ctx, M_out, ctx->Mcur.ptr, n, p, ld_out));
+        if (V_out) CHECK(copy_out_ld(ctx, V_out, ctx->V.ptr, n, p, ld_out));
+        CU(cudaStreamSynchronize(ctx->stream));
+    } else {
+        // chunks whose speculative copy is stale (the top-up pass rewrote them, or a K*+1 retry ran), or all of them
+        for (int c = 0; c < pl.nchunks; ++c) {
+            const bool stale = !spec || local.passes > 2 || (pl.nchunks > 1 && ctx->h_ints[16 + c] != 0);
+            if (!stale) continue;
+            if (out_jobs[(size_t)c]) {
+                CHECK(pipe_wait(ctx, out_jobs[(size_t)c]));       // never two writers on the same host columns
+                recopy_bytes += 8.0 * (double)n * (double)(col1(c) - col0(c));
+            }
+            out_jobs[(size_t)c] = ctx->pipe->d2h(as<double>(ctx->Mcur) + (size_t)col0(c) * (size_t)n,
+                                                 M_out + (size_t)col0(c) * (size_t)ld_out, (size_t)n, (size_t)(col1(c) - col0(c)),
+                                                 (size_t)ld_out, nullptr);
+        }
+        HostPipe::JobRef vjob;
+        if (V_out) vjob = ctx->pipe->d2h(as<double>(ctx->V), V_out, (size_t)n, (size_t)p, (size_t)ld_out, nullptr);
+        for (auto &j : out_jobs) if (j) CHECK(pipe_wait(ctx, j));
+        if (vjob) CHECK(pipe_wait(ctx, vjob));
+        ctx->spec_waste = spec_bytes > 0 ? recopy_bytes / spec_bytes : 0.0;
+    }
+    ctx->diag_spec_bytes = spec_bytes; ctx->diag_recopy_bytes = recopy_bytes;
+    if (v_sum) CHECK(get_v_sum_impl(ctx, v_sum));
+    return EBPMF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ebpmf_ctx_set_sigma2(ebpmf_ctx *ctx, int var_type, const double *sigma2) {
+    return set_sigma2_impl(ctx, var_type, sigma2, true);
+}
+
+int ebpmf_ctx_vga_step(ebpmf_ctx *ctx, int maxiter, double tol, int want_v, ebpmf_solve_info *info) {
+    return vga_step_impl(ctx, maxiter, tol, want_v, info);
 }
 
 int ebpmf_ctx_rewind_m(ebpmf_ctx *ctx) {
@@ -992,20 +1228,7 @@ int ebpmf_ctx_get_m(ebpmf_ctx *ctx, double *M) { return get_matrix_ld(ctx, false
 
 int ebpmf_ctx_get_v(ebpmf_ctx *ctx, double *V) { return get_matrix_ld(ctx, true, V, ctx ? ctx->n : 0); }
 
-int ebpmf_ctx_get_v_sum(ebpmf_ctx *ctx, double *v_sum) {
-    if (!ctx || !v_sum) return fail(ctx, EBPMF_ERR_ARG, "get_v_sum: bad arguments");
-    if (!ctx->have_vsum) return fail(ctx, EBPMF_ERR_STATE, "get_v_sum: no VGA step has run");
-    CHECK(ensure_common(ctx));
-    const double *red = as<double>(ctx->red);
-    if (ctx->var_type == EBPMF_VAR_CONSTANT) {
-        CU(cudaMemcpyAsync(v_sum, red + 3, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    } else {
-        const size_t len = ctx->var_type == EBPMF_VAR_BY_COL ? (size_t)ctx->p : (size_t)ctx->n;
-        CU(cudaMemcpyAsync(v_sum, red + 4, sizeof(double) * len, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    CU(cudaStreamSynchronize(ctx->stream));
-    return EBPMF_OK;
-}
+int ebpmf_ctx_get_v_sum(ebpmf_ctx *ctx, double *v_sum) { return get_v_sum_impl(ctx, v_sum); }
 
 int ebpmf_ctx_update_sigma2(ebpmf_ctx *ctx, const double *R2, double a0, double b0, double cap_var_mean_ratio,
                             int64_t n_total, int64_t p_total, double *sigma2_out) {
@@ -1112,35 +1335,164 @@ int ebpmf_calc_obj(ebpmf_ctx *ctx, int64_t n, int64_t p, double sym, double ssex
     return EBPMF_OK;
 }
 
-int ebpmf_vga_step_host(ebpmf_ctx *ctx, const double *M_in, int64_t K, const double *EL, const double *EF,
-                        int var_type, const double *sigma2, int maxiter, double tol, double *M_out, double *V_out,
-                        double *v_sum, ebpmf_solve_info *info) {
-    if (!ctx || !M_in || !M_out) return fail(ctx, EBPMF_ERR_ARG, "vga_step_host: bad arguments");
-    CHECK(ebpmf_ctx_set_factors(ctx, K, EL, EF));
-    CHECK(ebpmf_ctx_set_sigma2(ctx, var_type, sigma2));
-    CHECK(ebpmf_ctx_set_m(ctx, M_in));
-    CHECK(ebpmf_ctx_vga_step(ctx, maxiter, tol, V_out != nullptr, info));
-    CHECK(ebpmf_ctx_get_m(ctx, M_out));
-    if (V_out) CHECK(ebpmf_ctx_get_v(ctx, V_out));
-    if (v_sum) CHECK(ebpmf_ctx_get_v_sum(ctx, v_sum));
+}  // extern "C"
+namespace {
+// the host matrices of a *_step_host call must have the shape of the resident Y (R: "non-conformable arrays")
+int check_shape(ebpmf_ctx *ctx, const char *who, int64_t n, int64_t p) {
+    if (!ctx->have_y) return fail(ctx, EBPMF_ERR_STATE, "%s: Y not set", who);
+    if (n != ctx->n || p != ctx->p)
+        return fail(ctx, EBPMF_ERR_ARG, "%s: non-conformable arrays: M is %lld x %lld but the resident Y is %lld x %lld", who,
+                    (long long)n, (long long)p, ctx->n, ctx->p);
     return EBPMF_OK;
+}
+}  // namespace
+extern "C" {
+
+int ebpmf_vga_step_host(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *M_in, int64_t K, const double *EL,
+                        const double *EF, int var_type, const double *sigma2, int maxiter, double tol, double *M_out,
+                        double *V_out, double *v_sum, ebpmf_solve_info *info) {
+    if (!ctx || !M_in || !M_out) return fail(ctx, EBPMF_ERR_ARG, "vga_step_host: bad arguments");
+    CHECK(check_shape(ctx, "vga_step_host", n, p));
+    return step_host_impl(ctx, M_in, n, K, EL, n, EF, var_type, sigma2, maxiter, tol, M_out, n, V_out, v_sum, info);
 }
 
 // The per-iteration call of ebpmf_log's outer loop once M lives on the device: R feeds res$M back
 // unchanged (fit_flash$flash_fit$Y = res$M, R/ebpmf_log.R:309; flash_init(fit_flash$flash_fit$Y, ..),
 // R/ebpmf_log_flash_update.R:35), so the step's input M IS the resident M left by the previous step
 // and only the factors and sigma2 cross PCIe on the way in.
-int ebpmf_vga_step_resident_host(ebpmf_ctx *ctx, int64_t K, const double *EL, const double *EF, int var_type,
-                                 const double *sigma2, int maxiter, double tol, double *M_out, double *V_out,
-                                 double *v_sum, ebpmf_solve_info *info) {
+int ebpmf_vga_step_resident_host(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, const double *EL, const double *EF,
+                                 int var_type, const double *sigma2, int maxiter, double tol, double *M_out,
+                                 double *V_out, double *v_sum, ebpmf_solve_info *info) {
     if (!ctx || !M_out) return fail(ctx, EBPMF_ERR_ARG, "vga_step_resident_host: bad arguments");
-    if (!ctx->have_m) return fail(ctx, EBPMF_ERR_STATE, "vga_step_resident_host: upload M once with ebpmf_ctx_set_m");
-    CHECK(ebpmf_ctx_set_factors(ctx, K, EL, EF));
-    CHECK(ebpmf_ctx_set_sigma2(ctx, var_type, sigma2));
-    CHECK(ebpmf_ctx_vga_step(ctx, maxiter, tol, V_out != nullptr, info));
-    CHECK(ebpmf_ctx_get_m(ctx, M_out));
-    if (V_out) CHECK(ebpmf_ctx_get_v(ctx, V_out));
-    if (v_sum) CHECK(ebpmf_ctx_get_v_sum(ctx, v_sum));
+    CHECK(check_shape(ctx, "vga_step_resident_host", n, p));
+    return step_host_impl(ctx, nullptr, 0, K, EL, n, EF, var_type, sigma2, maxiter, tol, M_out, n, V_out, v_sum, info);
+}
+
+// ---- N1: products of the resident M with the factors, and the residual sums of squares -----------
+}  // extern "C"
+namespace {
+template <int KP>
+int launch_products(ebpmf_ctx *ctx, const ProdArgs &a, cudaEvent_t mid) {
+    const long long nRB = (a.n + kRowsPerCta - 1) / kRowsPerCta;
+    m_ef_kernel<KP><<<dim3((unsigned)a.nsplit, (unsigned)nRB), kThreads, 0, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(mid, ctx->stream));
+    const int smem = (int)sizeof(MtElSmem<KP>);
+    static bool configured[64] = {false};
+    if (ctx->device < 64 ? !configured[ctx->device] : true) {
+        CU(cudaFuncSetAttribute(mt_el_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (ctx->device < 64) configured[ctx->device] = true;
+    }
+    mt_el_kernel<KP><<<dim3((unsigned)((a.p + kTileCols - 1) / kTileCols), (unsigned)a.nrange), kThreads, smem, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    return EBPMF_OK;
+}
+}  // namespace
+extern "C" {
+
+int ebpmf_ctx_m_products(ebpmf_ctx *ctx, int64_t Kw, const double *EL_w, const double *EF_w, double *MF, double *MtL,
+                         double *r2_col, double *r2_row, double *kernel_ms) {
+    if (!ctx || !EL_w || !EF_w || !MF || !MtL || Kw < 1 || Kw > 256)
+        return fail(ctx, EBPMF_ERR_ARG, "m_products: bad arguments (1 <= Kw <= 256)");
+    if (!ctx->have_y || !ctx->have_m) return fail(ctx, EBPMF_ERR_STATE, "m_products: no resident M");
+    CHECK(ensure_common(ctx));
+    const long long n = ctx->n, p = ctx->p;
+    const int K = (int)Kw;
+    const int KPmax = ktp_for(std::min(K, 32));
+    const long long nRB = (n + kRowsPerCta - 1) / kRowsPerCta;
+    // splits: enough CTAs for a few waves, partials stay small
+    const int nsplit = (int)std::max(1LL, std::min<long long>((p + kTileCols - 1) / kTileCols, (148LL * 2 * 6 + nRB - 1) / nRB));
+    int cols_per_split = (int)((p + nsplit - 1) / nsplit);
+    cols_per_split = ((cols_per_split + kTileCols - 1) / kTileCols) * kTileCols;
+    const long long ngroups = (p + kTileCols - 1) / kTileCols;
+    const int nrange = (int)std::max(1LL, std::min<long long>(nRB, (148LL * 2 * 6 + ngroups - 1) / ngroups));
+    long long rows_per_range = (nRB + nrange - 1) / nrange * kRowsPerCta;
+    // device scratch, carved out of one buffer
+    size_t off = 0;
+    auto carve = [&](size_t doubles) { const size_t o = off; off += (doubles + 1) & ~(size_t)1; return o; };
+    const size_t oEL = carve((size_t)n * K), oEF = carve((size_t)p * K), oEFt = carve((size_t)p * KPmax);
+    const size_t oMFp = carve((size_t)nsplit * KPmax * n), oRsq = carve((size_t)nsplit * n);
+    const size_t oMtLp = carve((size_t)nrange * p * KPmax), oCsq = carve((size_t)nrange * p);
+    const size_t oMF = carve((size_t)n * K), oMtL = carve((size_t)p * K), oGL = carve((size_t)K * K), oGF = carve((size_t)K * K);
+    const size_t oSqR = carve((size_t)n), oSqC = carve((size_t)p), oR2r = carve((size_t)n), oR2c = carve((size_t)p);
+    int rc = reserve(ctx, ctx->prod, sizeof(double) * off);
+    CHECK(ranks_agree(ctx, rc));
+    double *base = as<double>(ctx->prod);
+    CU(cudaMemcpyAsync(base + oEL, EL_w, sizeof(double) * (size_t)n * K, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(base + oEF, EF_w, sizeof(double) * (size_t)p * K, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    float ms_a = 0.f, ms_b = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 32) {             // factor columns in chunks of at most 32 (one pass over M each)
+        const int Kc = std::min(32, K - k0);
+        const int KP = ktp_for(Kc);
+        transpose_ef_kernel<<<(unsigned)((p * KP + 255) / 256), 256, 0, ctx->stream>>>(base + oEF + (size_t)p * k0, p, Kc, KP, base + oEFt);
+        CU(cudaGetLastError());
+        ProdArgs a;
+        memset(&a, 0, sizeof a);
+        a.n = n; a.p = p; a.K = Kc; a.M = as<double>(ctx->Mcur); a.EL = base + oEL + (size_t)n * k0; a.EFt = base + oEFt;
+        a.MFpart = base + oMFp; a.rowsq = base + oRsq; a.MtLpart = base + oMtLp; a.colsq = base + oCsq;
+        a.nsplit = nsplit; a.cols_per_split = cols_per_split; a.nrange = nrange; a.rows_per_range = (int)rows_per_range;
+        a.bulk = (n % 2 == 0 && !getenv("EBPMF_B200_NO_BULK")) ? 1 : 0;
+        CU(cudaEventRecord(ctx->ev_p1, ctx->stream));
+        switch (KP) {
+            case 8: CHECK((launch_products<8>(ctx, a, ctx->ev_p2))); break;
+            case 16: CHECK((launch_products<16>(ctx, a, ctx->ev_p2))); break;
+            case 24: CHECK((launch_products<24>(ctx, a, ctx->ev_p2))); break;
+            default: CHECK((launch_products<32>(ctx, a, ctx->ev_p2))); break;
+        }
+        CU(cudaEventRecord(ctx->ev_p3, ctx->stream));
+        sum_splits_kernel<<<(unsigned)(((long long)Kc * n + 255) / 256), 256, 0, ctx->stream>>>(base + oMFp, (long long)KP * n, (long long)Kc * n, nsplit,
+                                                                                             base + oMF + (size_t)n * k0);
+        mtl_gather_kernel<<<(unsigned)((p * Kc + 255) / 256), 256, 0, ctx->stream>>>(base + oMtLp, nrange, p, KP, Kc, base + oMtL + (size_t)p * k0);
+        CU(cudaGetLastError());
+        if (k0 == 0) {                               // sums of squares of M: any chunk's pass gives them
+            sum_splits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(base + oRsq, n, n, nsplit, base + oSqR);
+            sum_splits_kernel<<<(unsigned)((p + 255) / 256), 256, 0, ctx->stream>>>(base + oCsq, p, p, nrange, base + oSqC);
+            CU(cudaGetLastError());
+        }
+        ctx->launches += 5;
+        if (kernel_ms) {                             // per-kernel times of the chunk (events are reused: read them now)
+            CU(cudaEventSynchronize(ctx->ev_p3));
+            float t = 0.f;
+            CU(cudaEventElapsedTime(&t, ctx->ev_p1, ctx->ev_p2)); ms_a += t;
+            CU(cudaEventElapsedTime(&t, ctx->ev_p2, ctx->ev_p3)); ms_b += t;
+        }
+    }
+    if (r2_col || r2_row) {
+        gram_kernel<<<(unsigned)(K * K), 256, 0, ctx->stream>>>(base + oEL, n, K, base + oGL);
+        gram_kernel<<<(unsigned)(K * K), 256, 0, ctx->stream>>>(base + oEF, p, K, base + oGF);
+        CU(cudaGetLastError());
+        ctx->launches += 2;
+    }
+    if (ctx->comm) {                                 // rows are sharded: t(M) EL, the column sums and EL'EL span all ranks
+        NC(g_nccl.AllReduce(base + oMtL, base + oMtL, (size_t)p * K, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
+        NC(g_nccl.AllReduce(base + oSqC, base + oSqC, (size_t)p, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
+        if (r2_col) NC(g_nccl.AllReduce(base + oGL, base + oGL, (size_t)K * K, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
+    }
+    if (r2_col) {
+        r2_from_products_kernel<<<(unsigned)((p + 255) / 256), 256, 0, ctx->stream>>>(base + oSqC, base + oEF, base + oMtL, p, K, p, 0,
+                                                                                     base + oGL, base + oR2c);
+        CU(cudaGetLastError());
+        ++ctx->launches;
+    }
+    if (r2_row) {
+        r2_from_products_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(base + oSqR, base + oEL, base + oMF, n, K, n, 0,
+                                                                                     base + oGF, base + oR2r);
+        CU(cudaGetLastError());
+        ++ctx->launches;
+    }
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaMemcpyAsync(MF, base + oMF, sizeof(double) * (size_t)n * K, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(MtL, base + oMtL, sizeof(double) * (size_t)p * K, cudaMemcpyDeviceToHost, ctx->stream));
+    if (r2_col) CU(cudaMemcpyAsync(r2_col, base + oR2c, sizeof(double) * (size_t)p, cudaMemcpyDeviceToHost, ctx->stream));
+    if (r2_row) CU(cudaMemcpyAsync(r2_row, base + oR2r, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (kernel_ms) {
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, ctx->ev0, ctx->ev1));
+        kernel_ms[0] = t; kernel_ms[1] = ms_a; kernel_ms[2] = ms_b;
+    }
     return EBPMF_OK;
 }
 
@@ -1154,7 +1506,7 @@ int ebpmf_vga_newton(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *M, cons
         return fail(ctx, EBPMF_ERR_ARG, "vga_newton: bad arguments");
     if (!X && !(X_colptr && (X_colptr[p] == 0 || (X_rowidx && X_x))))
         return fail(ctx, EBPMF_ERR_ARG, "vga_newton: X must be dense or dgCMatrix slots");
-    if (maxiter < 1 || maxiter > 65535) return fail(ctx, EBPMF_ERR_ARG, "vga_newton: maxiter must be in [1, 65535]");
+    if (maxiter < 1 || maxiter > 65534) return fail(ctx, EBPMF_ERR_ARG, "vga_newton: maxiter must be in [1, 65534]");
     CHECK(ensure_common(ctx));
     DenseArgs a;
     memset(&a, 0, sizeof a);
@@ -1266,12 +1618,18 @@ int ebpmf_vga_low_memory(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, const 
                          int maxiter, double tol, double *M_out, ebpmf_solve_info *info) {
     if (!ctx || !M || !l0 || !f0 || !EL || !EF || !sigma2 || !M_out || n < 1 || p < 1 || K < 1)
         return fail(ctx, EBPMF_ERR_ARG, "vga_low_memory: bad arguments");
-    if (maxiter < 1 || maxiter > 65535) return fail(ctx, EBPMF_ERR_ARG, "vga_low_memory: maxiter must be in [1, 65535]");
+    if (maxiter < 1 || maxiter > 65534) return fail(ctx, EBPMF_ERR_ARG, "vga_low_memory: maxiter must be in [1, 65534]");
     // R falls through both `if(var_type==...)` blocks for an unknown var_type and returns the
     // clamped M (:78,:108); the clamp needs the kernels too, so run zero iterations of by_col
     // semantics is NOT the same thing -- report the unsupported type instead of guessing.
     if (var_type < 0 || var_type > 2) return fail(ctx, EBPMF_ERR_VAR_TYPE, "Non-supported var type");
-    // this entry point owns the context's resident state for the duration of the call
+    // This entry point takes over the context's resident state (Y, M, factors, sigma2) and does NOT give it
+    // back: whatever happens, the resident state is invalidated on return, so that a later resident step on
+    // the same context fails with EBPMF_ERR_STATE instead of silently running on this call's matrices.
+    struct Invalidate {
+        ebpmf_ctx *c;
+        ~Invalidate() { c->have_y = c->have_m = c->have_f = c->have_s2 = c->have_v = c->have_vsum = c->have_hist = false; c->can_rewind = false; }
+    } invalidate{ctx};
     if (Y) CHECK(ebpmf_ctx_set_y_dense(ctx, n, p, Y));
     else CHECK(ebpmf_ctx_set_y_csc(ctx, n, p, Y_colptr, Y_rowidx, Y_x));
     CHECK(ebpmf_ctx_set_factors(ctx, K, EL, EF));
@@ -1281,15 +1639,15 @@ int ebpmf_vga_low_memory(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, const 
     CHECK(reserve(ctx, ctx->f0, sizeof(double) * (size_t)p));
     CU(cudaMemcpyAsync(ctx->l0.ptr, l0, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->f0.ptr, f0, sizeof(double) * (size_t)p, cudaMemcpyHostToDevice, ctx->stream));
-    CHECK(reserve(ctx, ctx->C0, sizeof(double) * (size_t)n * (size_t)p));
-    const FusedArgs a = fused_args(ctx, maxiter, tol, false);
+    StepPlan pl = make_plan(ctx, 1);
+    CHECK(build_order(ctx, pl));
+    const FusedArgs a = fused_args(ctx, pl, maxiter, tol, false);
     int rc = run_global_stop(
-        ctx, maxiter, [&] { return launch_first<FORMULA_A10>(ctx, a); },
-        [&] { return launch_topup<FORMULA_A10>(ctx, a); }, [&] { return EBPMF_OK; }, info);
+        ctx, maxiter, [&] { return launch_fused<FORMULA_A10, MODE_FIRST>(ctx, a, 0, pl.ntiles); },
+        [&] { return launch_fused<FORMULA_A10, MODE_TOPUP>(ctx, a, 0, pl.ntiles); }, [&] { return (int)EBPMF_OK; }, info);
     if (rc != EBPMF_OK) return rc;
     if (info) { info->sym = info->ssexp = info->slogv = 0.0; }
     std::swap(ctx->Mcur, ctx->Malt);
-    ctx->have_vsum = false; ctx->have_v = false;
     return ebpmf_ctx_get_m(ctx, M_out);
 }
 
@@ -1416,15 +1774,18 @@ int ebpmf_ctx_set_option(ebpmf_ctx *ctx, const char *name, double value) {
         ctx->debug_verify_scale = value;
         return EBPMF_OK;
     }
-    if (!strcmp(name, "pipeline")) {
-        if (value != 0.0 && value != 1.0 && value != 2.0 && value != 3.0)
-            return fail(ctx, EBPMF_ERR_ARG, "set_option: pipeline is 0, 1, 2 or 3");
-        ctx->pipeline = (int)value;
+    if (!strcmp(name, "freeze") || !strcmp(name, "history") || !strcmp(name, "speculate")) {
+        if (value != 0.0 && value != 1.0) return fail(ctx, EBPMF_ERR_ARG, "set_option: %s is 0 or 1", name);
+        (name[0] == 'f' ? ctx->freeze : name[0] == 'h' ? ctx->use_history : ctx->speculate) = (int)value;
         return EBPMF_OK;
     }
-    if (!strcmp(name, "scored_min_ctas")) {
-        if (!(value >= 0.0) || value > 1e9) return fail(ctx, EBPMF_ERR_ARG, "set_option: scored_min_ctas must be in [0, 1e9]");
-        ctx->scored_min_ctas = (unsigned)value;
+    if (!strcmp(name, "pipe_chunks")) {
+        if (!(value >= 0.0) || value > 4096.0) return fail(ctx, EBPMF_ERR_ARG, "set_option: pipe_chunks must be in [0, 4096]");
+        ctx->pipe_chunks = (int)value;
+        return EBPMF_OK;
+    }
+    if (!strcmp(name, "forget_history")) {
+        ctx->have_hist = false; ctx->spec_waste = 0.0;
         return EBPMF_OK;
     }
     return fail(ctx, EBPMF_ERR_ARG, "set_option: unknown option '%s'", name);
@@ -1440,6 +1801,15 @@ int ebpmf_ctx_last_diag(ebpmf_ctx *ctx, uint64_t *topup_units, uint64_t *unit_ev
     if (!ctx) return fail(ctx, EBPMF_ERR_ARG, "last_diag: ctx is NULL");
     if (topup_units) *topup_units = ctx->diag_topups;
     if (unit_evals) *unit_evals = ctx->diag_iters;
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_counters(ebpmf_ctx *ctx, double *out, int count) {
+    if (!ctx || !out || count < 1) return fail(ctx, EBPMF_ERR_ARG, "counters: bad arguments");
+    const double v[8] = {(double)ctx->diag_topups, (double)ctx->diag_iters, (double)ctx->diag_topup_tiles,
+                         (double)ctx->launches, ctx->diag_spec_bytes, ctx->diag_recopy_bytes, (double)ctx->cur_ntiles,
+                         ctx->have_hist ? 1.0 : 0.0};
+    for (int q = 0; q < count && q < 8; ++q) out[q] = v[q];
     return EBPMF_OK;
 }
 
@@ -1469,6 +1839,7 @@ struct ebpmf_group {
     std::vector<ebpmf_ctx *> ctx;
     std::vector<long long> row0, nrows;
     long long n = 0, p = 0;
+    bool have_m = false;
     std::string err;
 };
 
@@ -1543,6 +1914,8 @@ int ebpmf_group_set_y_csc(ebpmf_group *g, int64_t n, int64_t p, const int32_t *c
                           const double *x) {
     if (!g || n < 1 || p < 1 || !colptr) return gfail(g, EBPMF_ERR_ARG, "group_set_y_csc: bad arguments");
     const int N = (int)g->ctx.size();
+    if (colptr[p] > 0 && (!rowidx || !x)) return gfail(g, EBPMF_ERR_ARG, "group_set_y_csc: @i / @x missing");
+    if (validate_csc(g->ctx[0], n, p, colptr, rowidx) != EBPMF_OK) return gfail(g, EBPMF_ERR_ARG, g->ctx[0]->err);
     const long long nblk = (n + kRowsPerCta - 1) / kRowsPerCta;
     if (nblk < N) return gfail(g, EBPMF_ERR_ARG, "group_set_y_csc: fewer 256-row blocks than GPUs; use a smaller group");
     g->row0.assign(N, 0); g->nrows.assign(N, 0);
@@ -1552,7 +1925,7 @@ int ebpmf_group_set_y_csc(ebpmf_group *g, int64_t n, int64_t p, const int32_t *c
         rows = std::max(0LL, std::min(rows, (long long)n - r0));
         g->row0[r] = r0; g->nrows[r] = rows; r0 += rows;
     }
-    g->n = n; g->p = p;
+    g->n = n; g->p = p; g->have_m = false;
     return run_ranks(g, [&](int r) {
         // the row slice Y[row0:row0+nrows, ] as its own dgCMatrix (what `Y[b,]` does in R/ebpmf_log.R:199)
         const long long lo = g->row0[r], hi = lo + g->nrows[r];
@@ -1585,35 +1958,43 @@ int ebpmf_group_set_option(ebpmf_group *g, const char *name, double value) {
 // The whole VGA step on the FULL host matrices; each GPU works on its row shard (strided copies out
 // of / into the column-major host arrays), the shards meet in the NCCL combine.  v_sum has length
 // p ('by_col'), n ('by_row', written shard by shard) or 1.
-int ebpmf_group_vga_step_host(ebpmf_group *g, const double *M_in, int64_t K, const double *EL, const double *EF,
-                              int var_type, const double *sigma2, int maxiter, double tol, double *M_out,
-                              double *V_out, double *v_sum, ebpmf_solve_info *info) {
-    if (!g || !M_in || !M_out || !EL || !EF || !sigma2) return gfail(g, EBPMF_ERR_ARG, "group_vga_step_host: bad arguments");
+int ebpmf_group_vga_step_host(ebpmf_group *g, int64_t n_in, int64_t p_in, const double *M_in, int64_t K, const double *EL,
+                              const double *EF, int var_type, const double *sigma2, int maxiter, double tol,
+                              double *M_out, double *V_out, double *v_sum, ebpmf_solve_info *info) {
+    if (!g || !M_out || !EL || !EF || !sigma2) return gfail(g, EBPMF_ERR_ARG, "group_vga_step_host: bad arguments");
     if (g->n < 1) return gfail(g, EBPMF_ERR_STATE, "group_vga_step_host: Y not set");
+    if (n_in != g->n || p_in != g->p) return gfail(g, EBPMF_ERR_ARG, "group_vga_step_host: non-conformable arrays (M does not have the shape of the resident Y)");
+    if (!M_in && !g->have_m) return gfail(g, EBPMF_ERR_STATE, "group_vga_step_host: M_in is NULL and no M is resident (ebpmf_group_set_m)");
     const int N = (int)g->ctx.size();
     std::vector<ebpmf_solve_info> infos((size_t)N);
     const long long n = g->n;
     int rc = run_ranks(g, [&](int r) {
         ebpmf_ctx *c = g->ctx[r];
         const long long lo = g->row0[r];
-        CHECK(set_factors_ld(c, K, EL + lo, n, EF));
-        CHECK(ebpmf_ctx_set_sigma2(c, var_type, var_type == EBPMF_VAR_BY_ROW ? sigma2 + lo : sigma2));
-        CHECK(set_m_ld(c, M_in + lo, n));
-        CHECK(ebpmf_ctx_vga_step(c, maxiter, tol, V_out != nullptr, &infos[(size_t)r]));
-        CHECK(get_matrix_ld(c, false, M_out + lo, n));
-        if (V_out) CHECK(get_matrix_ld(c, true, V_out + lo, n));
-        if (v_sum) {
-            if (var_type == EBPMF_VAR_BY_ROW) CHECK(ebpmf_ctx_get_v_sum(c, v_sum + lo));
-            else if (r == 0) CHECK(ebpmf_ctx_get_v_sum(c, v_sum));
-        }
-        return (int)EBPMF_OK;
+        double *vs = nullptr;
+        if (v_sum) vs = (var_type == EBPMF_VAR_BY_ROW) ? v_sum + lo : (r == 0 ? v_sum : nullptr);
+        return step_host_impl(c, M_in ? M_in + lo : nullptr, n, K, EL + lo, n, EF, var_type,
+                              var_type == EBPMF_VAR_BY_ROW ? sigma2 + lo : sigma2, maxiter, tol, M_out + lo, n,
+                              V_out ? V_out + lo : nullptr, vs, &infos[(size_t)r]);
     });
-    if (rc != EBPMF_OK) return rc;
+    if (rc != EBPMF_OK) { g->have_m = false; return rc; }
+    g->have_m = true;                       // every shard now holds its rows of res$M
     if (info) {
         *info = infos[0];                       // sums and the update count are global after the combine
         for (int r = 1; r < N; ++r) info->kernel_ms = std::max(info->kernel_ms, infos[(size_t)r].kernel_ms);
     }
     return EBPMF_OK;
+}
+
+// M_init -> the shards, once per ebpmf_log() call; afterwards ebpmf_group_vga_step_host(.., M_in = NULL, ..)
+int ebpmf_group_set_m(ebpmf_group *g, int64_t n_in, int64_t p_in, const double *M) {
+    if (!g || !M) return gfail(g, EBPMF_ERR_ARG, "group_set_m: bad arguments");
+    if (g->n < 1) return gfail(g, EBPMF_ERR_STATE, "group_set_m: Y not set");
+    if (n_in != g->n || p_in != g->p) return gfail(g, EBPMF_ERR_ARG, "group_set_m: non-conformable arrays");
+    const long long n = g->n;
+    int rc = run_ranks(g, [&](int r) { return set_m_ld(g->ctx[r], M + g->row0[r], n); });
+    g->have_m = (rc == EBPMF_OK);
+    return rc;
 }
 
 // sum(lfactorial(Y@x)) over all shards
@@ -1807,12 +2188,13 @@ int ebpmf_batched_sum_lfactorial(ebpmf_batched *h, double *out) {
     return EBPMF_OK;
 }
 
-int ebpmf_batched_vga_step_host(ebpmf_batched *h, const double *M_in, int64_t K, const double *EL, const double *EF,
-                                int var_type, const double *sigma2, int maxiter, double tol, double *M_out,
-                                double *V_out, double *v_sum, ebpmf_solve_info *info, int32_t *n_updates,
-                                int32_t *converged) {
+int ebpmf_batched_vga_step_host(ebpmf_batched *h, int64_t n_in, int64_t p_in, const double *M_in, int64_t K,
+                                const double *EL, const double *EF, int var_type, const double *sigma2, int maxiter,
+                                double tol, double *M_out, double *V_out, double *v_sum, ebpmf_solve_info *info,
+                                int32_t *n_updates, int32_t *converged) {
     if (!h || !M_in || !M_out || !EL || !EF || !sigma2) return bfail(h, EBPMF_ERR_ARG, "batched_vga_step_host: bad arguments");
     if (h->n < 1 || h->ys.empty()) return bfail(h, EBPMF_ERR_STATE, "batched_vga_step_host: Y not set");
+    if (n_in != h->n || p_in != h->p) return bfail(h, EBPMF_ERR_ARG, "batched_vga_step_host: non-conformable arrays (M does not have the shape of the resident Y)");
     const int S = (int)h->slot.size();
     const long long n = h->n, p = h->p;
     const int nb = (int)h->ys.size();

@@ -152,7 +152,7 @@ SEXP C_ebpmf_vga_step(SEXP xp, SEXP M, SEXP EL, SEXP EF, SEXP sigma2, SEXP var_t
     SEXP Vo = PROTECT(wv ? alloc_like(M) : R_NilValue);
     SEXP vs = PROTECT(Rf_allocVector(REALSXP, want));
     ebpmf_solve_info info;
-    int rc = ebpmf_vga_step_host(ctx, REAL(M), Rf_ncols(EL), REAL(EL), REAL(EF), vt, REAL(sigma2),
+    int rc = ebpmf_vga_step_host(ctx, (int64_t)n, (int64_t)p, REAL(M), Rf_ncols(EL), REAL(EL), REAL(EF), vt, REAL(sigma2),
                                  Rf_asInteger(maxiter), Rf_asReal(tol), REAL(Mo), wv ? REAL(Vo) : NULL, REAL(vs), &info);
     if (rc != EBPMF_OK) { UNPROTECT(3); check(ctx, rc); }
     SEXP out = info_list(&info, Mo, Vo, vs);
@@ -187,7 +187,7 @@ SEXP C_ebpmf_vga_step_resident(SEXP xp, SEXP dims, SEXP EL, SEXP EF, SEXP sigma2
     SEXP Vo = PROTECT(wv ? Rf_allocMatrix(REALSXP, n, p) : R_NilValue);
     SEXP vs = PROTECT(Rf_allocVector(REALSXP, want));
     ebpmf_solve_info info;
-    int rc = ebpmf_vga_step_resident_host(ctx, Rf_ncols(EL), REAL(EL), REAL(EF), vt, REAL(sigma2), Rf_asInteger(maxiter),
+    int rc = ebpmf_vga_step_resident_host(ctx, (int64_t)n, (int64_t)p, Rf_ncols(EL), REAL(EL), REAL(EF), vt, REAL(sigma2), Rf_asInteger(maxiter),
                                           Rf_asReal(tol), REAL(Mo), wv ? REAL(Vo) : NULL, REAL(vs), &info);
     if (rc != EBPMF_OK) { UNPROTECT(3); check(ctx, rc); }
     SEXP out = info_list(&info, Mo, Vo, vs);
@@ -375,7 +375,7 @@ SEXP C_ebpmf_batched_vga_step(SEXP xp, SEXP M, SEXP EL, SEXP EF, SEXP sigma2, SE
     SEXP vs = PROTECT(Rf_allocVector(REALSXP, want));
     SEXP nu = PROTECT(Rf_allocVector(INTSXP, Rf_asInteger(nbatch)));
     ebpmf_solve_info info;
-    int rc = ebpmf_batched_vga_step_host(h, REAL(M), Rf_ncols(EL), REAL(EL), REAL(EF), vt, REAL(sigma2),
+    int rc = ebpmf_batched_vga_step_host(h, (int64_t)n, (int64_t)p, REAL(M), Rf_ncols(EL), REAL(EL), REAL(EF), vt, REAL(sigma2),
                                          Rf_asInteger(maxiter), Rf_asReal(tol), REAL(Mo), wv ? REAL(Vo) : NULL, REAL(vs),
                                          &info, INTEGER(nu), NULL);
     if (rc != EBPMF_OK) { UNPROTECT(4); check_batched(h, rc); }

@@ -248,17 +248,18 @@ class VgaContext:
         if var_type not in VAR_TYPE:
             raise EbpmfError(4, "Non-supported var type")
         M = _f(M)
-        EL = _f(np.asarray(EL, dtype=np.float64).reshape(self.n, -1))
-        EF = _f(np.asarray(EF, dtype=np.float64).reshape(self.p, -1))
+        n, p = M.shape                                  # the library checks them against the resident Y
+        EL = _f(np.asarray(EL, dtype=np.float64).reshape(n, -1))
+        EF = _f(np.asarray(EF, dtype=np.float64).reshape(p, -1))
         s2 = _vec(sigma2)
-        ln = {"by_col": self.p, "by_row": self.n, "constant": 1}[var_type]
-        Mo = np.empty((self.n, self.p), order="F") if M_out is None else M_out     # e.g. a pinned buffer
-        if Mo.shape != (self.n, self.p) or not Mo.flags.f_contiguous or Mo.dtype != np.float64:
+        ln = {"by_col": p, "by_row": n, "constant": 1}[var_type]
+        Mo = np.empty((n, p), order="F") if M_out is None else M_out     # any host memory, pageable included
+        if Mo.shape != (n, p) or not Mo.flags.f_contiguous or Mo.dtype != np.float64:
             raise ValueError("M_out must be an n x p column-major float64 array")
-        Vo = np.empty((self.n, self.p), order="F") if return_V else None
+        Vo = np.empty((n, p), order="F") if return_V else None
         vs = np.empty(ln)
         info = SolveInfo()
-        self._ck(self._lib.ebpmf_vga_step_host(self._h, _ptr(M), EL.shape[1], _ptr(EL), _ptr(EF), VAR_TYPE[var_type],
+        self._ck(self._lib.ebpmf_vga_step_host(self._h, n, p, _ptr(M), EL.shape[1], _ptr(EL), _ptr(EF), VAR_TYPE[var_type],
                                                _ptr(s2), int(maxiter), float(tol), _ptr(Mo), _ptr(Vo), _ptr(vs),
                                                C.byref(info)))
         self.var_type = var_type
@@ -279,7 +280,10 @@ class VgaContext:
         Vo = np.empty((self.n, self.p), order="F") if return_V else None
         vs = np.empty(ln)
         info = SolveInfo()
-        self._ck(self._lib.ebpmf_vga_step_resident_host(self._h, EL.shape[1], _ptr(EL), _ptr(EF), VAR_TYPE[var_type],
+        if Mo.shape != (self.n, self.p) or not Mo.flags.f_contiguous or Mo.dtype != np.float64:
+            raise ValueError("M_out must be an n x p column-major float64 array")
+        self._ck(self._lib.ebpmf_vga_step_resident_host(self._h, Mo.shape[0], Mo.shape[1], EL.shape[1], _ptr(EL), _ptr(EF),
+                                                        VAR_TYPE[var_type],
                                                         _ptr(s2), int(maxiter), float(tol), _ptr(Mo), _ptr(Vo),
                                                         _ptr(vs), C.byref(info)))
         self.var_type = var_type
@@ -297,8 +301,30 @@ class VgaContext:
         return nnz.value
 
     def set_option(self, name, value):
-        """'delta' (0 = exact update count, the default), 'pipeline' (0 fused / 1 split / 2 ordered / 3 scored), ...: see include/ebpmf_b200.h."""
+        """'delta' (0 = exact update count, the default), 'freeze', 'history', 'speculate', 'pipe_chunks', ...: see
+        include/ebpmf_b200.h."""
         self._ck(self._lib.ebpmf_ctx_set_option(self._h, name.encode(), float(value)))
+
+    def counters(self):
+        out = np.zeros(8)
+        self._ck(self._lib.ebpmf_ctx_counters(self._h, _ptr(out), 8))
+        keys = ("topup_units", "unit_evals", "topup_tiles", "launches", "spec_bytes", "recopy_bytes", "tiles", "have_history")
+        return dict(zip(keys, (float(v) for v in out)))
+
+    def m_products(self, EL_w, EF_w, want_r2_col=True, want_r2_row=True):
+        """What flashier needs from the resident M, computed on the device (N1): M %*% EF_w, t(M) %*% EL_w and the
+        column / row sums of (M - EL_w %*% t(EF_w))^2 (R/ebpmf_log_flash_update.R:35,55-64)."""
+        EL_w = _f(np.asarray(EL_w, dtype=np.float64).reshape(self.n, -1))
+        EF_w = _f(np.asarray(EF_w, dtype=np.float64).reshape(self.p, -1))
+        if EL_w.shape[1] != EF_w.shape[1]:
+            raise ValueError("non-conformable arguments")
+        Kw = EL_w.shape[1]
+        MF = np.empty((self.n, Kw), order="F"); MtL = np.empty((self.p, Kw), order="F")
+        rc = np.empty(self.p) if want_r2_col else None
+        rr = np.empty(self.n) if want_r2_row else None
+        ms = (C.c_double * 3)()
+        self._ck(self._lib.ebpmf_ctx_m_products(self._h, Kw, _ptr(EL_w), _ptr(EF_w), _ptr(MF), _ptr(MtL), _ptr(rc), _ptr(rr), ms))
+        return dict(MF=MF, MtL=MtL, r2_col=rc, r2_row=rr, kernel_ms=ms[0], m_ef_ms=ms[1], mt_el_ms=ms[2])
 
     def last_diag(self):
         a, b = C.c_uint64(), C.c_uint64()
@@ -351,10 +377,19 @@ class VgaGroup:
         self._ck(self._lib.ebpmf_group_sum_lfactorial(self._h, C.byref(out)))
         return out.value
 
+    def set_m(self, M):
+        M = _f(M)
+        if M.shape != (self.n, self.p):
+            raise ValueError("non-conformable arrays")
+        self._ck(self._lib.ebpmf_group_set_m(self._h, self.n, self.p, _ptr(M)))
+
     def vga_step_host(self, M, EL, EF, sigma2, var_type, maxiter=10, tol=1e-5, return_V=False, M_out=None):
+        """``M`` None: the shards' resident M (``set_m`` once, then every step's output) is the input."""
         if var_type not in VAR_TYPE:
             raise EbpmfError(4, "Non-supported var type")
-        M = _f(M)
+        M = None if M is None else _f(M)
+        if M is not None and M.shape != (self.n, self.p):
+            raise ValueError("non-conformable arrays")
         EL = _f(np.asarray(EL, dtype=np.float64).reshape(self.n, -1))
         EF = _f(np.asarray(EF, dtype=np.float64).reshape(self.p, -1))
         s2 = _vec(sigma2)
@@ -365,7 +400,7 @@ class VgaGroup:
         Vo = np.empty((self.n, self.p), order="F") if return_V else None
         vs = np.empty(ln)
         info = SolveInfo()
-        self._ck(self._lib.ebpmf_group_vga_step_host(self._h, _ptr(M), EL.shape[1], _ptr(EL), _ptr(EF),
+        self._ck(self._lib.ebpmf_group_vga_step_host(self._h, self.n, self.p, _ptr(M), EL.shape[1], _ptr(EL), _ptr(EF),
                                                      VAR_TYPE[var_type], _ptr(s2), int(maxiter), float(tol), _ptr(Mo),
                                                      _ptr(Vo), _ptr(vs), C.byref(info)))
         return dict(M=Mo, V=Vo, v_sum=(vs if var_type != "constant" else float(vs[0])), sym=info.sym,
@@ -453,7 +488,7 @@ class VgaBatched:
         nu = np.zeros(nb, dtype=np.int32)
         cv = np.zeros(nb, dtype=np.int32)
         info = SolveInfo()
-        self._ck(self._lib.ebpmf_batched_vga_step_host(self._h, _ptr(M), EL.shape[1], _ptr(EL), _ptr(EF),
+        self._ck(self._lib.ebpmf_batched_vga_step_host(self._h, M.shape[0], M.shape[1], _ptr(M), EL.shape[1], _ptr(EL), _ptr(EF),
                                                        VAR_TYPE[var_type], _ptr(s2), int(maxiter), float(tol),
                                                        _ptr(Mo), _ptr(Vo), _ptr(vs), C.byref(info), _ptr(nu), _ptr(cv)))
         return dict(M=Mo, V=Vo, v_sum=(vs if var_type != "constant" else float(vs[0])), sym=info.sym,

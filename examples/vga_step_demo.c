@@ -55,7 +55,7 @@ int main(void)
     ebpmf_solve_info info;
     int rc = ebpmf_ctx_set_y_csc(ctx, n, p, colptr, rowidx, x);
     if (rc == EBPMF_OK)
-        rc = ebpmf_vga_step_host(ctx, M, K, EL, EF, EBPMF_VAR_BY_COL, sigma2, 10, 1e-5, Mo, NULL, v_sum, &info);
+        rc = ebpmf_vga_step_host(ctx, n, p, M, K, EL, EF, EBPMF_VAR_BY_COL, sigma2, 10, 1e-5, Mo, NULL, v_sum, &info);
     if (rc != EBPMF_OK) {
         fprintf(stderr, "ebpmf_b200: %s\n", ebpmf_last_error(ctx));
         ebpmf_ctx_destroy(ctx);

@@ -35,7 +35,7 @@ extern "C" {
 #endif
 
 #define EBPMF_OK            0
-#define EBPMF_ERR_ARG       1   /* bad argument (NULL, maxiter outside [1,65535], shapes that do not conform) */
+#define EBPMF_ERR_ARG       1   /* bad argument (NULL, maxiter outside [1,65534], shapes that do not conform) */
 #define EBPMF_ERR_CUDA      2   /* CUDA runtime failure / no usable GPU */
 #define EBPMF_ERR_NAN       3   /* a NaN reached the stop test: R stops with "missing value where
                                    TRUE/FALSE needed" at R/vga_solver_mat.R:26,85,100 */
@@ -160,10 +160,17 @@ int  ebpmf_calc_obj(ebpmf_ctx *ctx, int64_t n, int64_t p, double sym, double sse
                     int64_t len, const double *sv, const double *sigma2, const double *R2,
                     double KL_LF, double const_, double ss, double a0, double b0, double *obj);
 
-/* The whole step with HOST buffers in one call (what the .Call shim uses each outer iteration):
- * set_m + set_factors + set_sigma2 + vga_step + get_m [+ get_v] + get_v_sum, with the H2D / D2H
- * copies of M pipelined by column chunks against the kernels.  V_out may be NULL. */
-int  ebpmf_vga_step_host(ebpmf_ctx *ctx, const double *M_in, int64_t K, const double *EL,
+/* The whole step with CALLER-OWNED HOST buffers in one call (what the .Call shim uses each outer iteration):
+ * factors + sigma2 + M in, step, M [+ V] + v_sum out.  n, p are the dims of the host matrices and must equal
+ * those of the resident Y (else EBPMF_ERR_ARG, R's "non-conformable arrays").  The host matrices may be
+ * pageable (REAL() of an R matrix): for matrices >= 32 MB the library moves them through an internal ring of
+ * pinned slots drained / filled by a few host threads, by COLUMN CHUNKS that overlap the kernels -- the M
+ * input of chunk c+1 goes up while the first pass runs on chunk c, and the result of a chunk comes down as
+ * soon as its first pass is done (speculatively: the tiles are taken hardest-first by the previous step's
+ * per-tile counts, so normally only the first chunk is still changed by the top-up pass; chunks the top-up
+ * pass did touch are copied again).  Results are bit-identical to set_m + vga_step + get_m.  V_out may be NULL.
+ * Measured rates and the probe behind the design: profiles/r02_probe_host_copy.txt, DESIGN.md section 7b. */
+int  ebpmf_vga_step_host(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *M_in, int64_t K, const double *EL,
                          const double *EF, int var_type, const double *sigma2,
                          int maxiter, double tol,
                          double *M_out, double *V_out, double *v_sum, ebpmf_solve_info *info);
@@ -172,9 +179,23 @@ int  ebpmf_vga_step_host(ebpmf_ctx *ctx, const double *M_in, int64_t K, const do
  * (fit_flash$flash_fit$Y = res$M, R/ebpmf_log.R:309; flash_init(fit_flash$flash_fit$Y, ...),
  * R/ebpmf_log_flash_update.R:35), so after one ebpmf_ctx_set_m(M_init) the input of every later step is
  * the resident M left by the previous one.  In: factors and sigma2.  Out: M [, V], v_sum, info. */
-int  ebpmf_vga_step_resident_host(ebpmf_ctx *ctx, int64_t K, const double *EL, const double *EF,
+int  ebpmf_vga_step_resident_host(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, const double *EL, const double *EF,
                                   int var_type, const double *sigma2, int maxiter, double tol,
                                   double *M_out, double *V_out, double *v_sum, ebpmf_solve_info *info);
+
+/* ---- N1: what flashier needs FROM M, computed where M lives -----------------------------------
+ * flashier treats the latent M as its data matrix (fit_flash$flash_fit$Y = res$M, R/ebpmf_log.R:270,309;
+ * flash_init(fit_flash$flash_fit$Y, ...), R/ebpmf_log_flash_update.R:35) and touches it only through
+ * products with the current loadings / factors and through the residual sums of squares R2
+ * (R/ebpmf_log_flash_update.R:55-64).  One streaming pass over the RESIDENT M (8 B per entry, nothing
+ * crosses PCIe but the small results):
+ *   MF  (n x Kw) = M %*% EF_w                      MtL (p x Kw) = t(M) %*% EL_w
+ *   r2_col (p)   = colSums((M - EL_w %*% t(EF_w))^2)    r2_row (n) = rowSums(...)     (either may be NULL)
+ * EL_w is n x Kw, EF_w is p x Kw (column-major host pointers; this rank's rows of EL_w).  With a
+ * communicator MtL and r2_col are summed over the ranks (rows are sharded); MF and r2_row stay sharded. */
+int  ebpmf_ctx_m_products(ebpmf_ctx *ctx, int64_t Kw, const double *EL_w, const double *EF_w,
+                          double *MF, double *MtL, double *r2_col, double *r2_row,
+                          double *kernel_ms /* NULL or 3 doubles: whole call, M %*% EF kernel(s), t(M) %*% EL kernel(s) */);
 
 /* ---- one process, several GPUs (an R session is one process) -------------------------------
  * A group owns one context per GPU and one NCCL communicator over them; every group call runs one
@@ -190,7 +211,10 @@ int  ebpmf_group_set_option(ebpmf_group *g, const char *name, double value);
 int  ebpmf_group_set_y_csc(ebpmf_group *g, int64_t n, int64_t p,
                            const int32_t *colptr, const int32_t *rowidx, const double *x);
 int  ebpmf_group_sum_lfactorial(ebpmf_group *g, double *out);
-int  ebpmf_group_vga_step_host(ebpmf_group *g, const double *M_in, int64_t K, const double *EL,
+/* n, p: dims of the host matrices (must equal the resident Y's).  M_in == NULL: the input is the M the shards
+ * already hold (ebpmf_group_set_m once, then every step's output), as in ebpmf_vga_step_resident_host. */
+int  ebpmf_group_set_m(ebpmf_group *g, int64_t n, int64_t p, const double *M);
+int  ebpmf_group_vga_step_host(ebpmf_group *g, int64_t n, int64_t p, const double *M_in, int64_t K, const double *EL,
                                const double *EF, int var_type, const double *sigma2,
                                int maxiter, double tol,
                                double *M_out, double *V_out, double *v_sum, ebpmf_solve_info *info);
@@ -221,7 +245,7 @@ int  ebpmf_batched_set_y_csc(ebpmf_batched *h, int64_t n, int64_t p, const int32
                              const int32_t *rowidx, const double *x,
                              int64_t nbatch, const int64_t *batch_row0);
 int  ebpmf_batched_sum_lfactorial(ebpmf_batched *h, double *out);
-int  ebpmf_batched_vga_step_host(ebpmf_batched *h, const double *M_in, int64_t K, const double *EL,
+int  ebpmf_batched_vga_step_host(ebpmf_batched *h, int64_t n, int64_t p, const double *M_in, int64_t K, const double *EL,
                                  const double *EF, int var_type, const double *sigma2,
                                  int maxiter, double tol,
                                  double *M_out, double *V_out, double *v_sum, ebpmf_solve_info *info,
@@ -272,12 +296,15 @@ int  ebpmf_ctx_sim_data_log(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, int
  *              satisfy |f| < tol/16 and whose next Newton update |f/f'| <= d is frozen: its remaining
  *              updates are numerical no-ops and are skipped, so M and V differ from exact mode by at
  *              most ~d (absolute); the global update count n_updates is still R's.  DESIGN.md §3b.
- *   "pipeline" 0 (default): fused first pass; 1: const0 kernel + streaming Newton kernel; 2: as 1, and the
- *              const0 kernel also performs Newton iteration 0 and scores each CTA by its largest first step,
- *              so that the streaming kernel meets the slowest entries first (same results, bit for bit);
- *              3: a tf32 tensor-core scoring pass ranks the (column span, row block) tiles by their largest
- *              first Newton step and the fused first pass takes them in that order (same results, bit for bit).
- *   "scored_min_ctas" (default 888 = two waves): pipeline 3 skips the scoring pass below this many tiles.
+ *   "freeze"   1 (default): once a converged unit's iterates repeat with period <= 2 (a floating-point fixed
+ *              point or a 2-cycle of adjacent doubles) its update count is advanced by an even number at once;
+ *              results are BIT-IDENTICAL to "freeze" 0, which performs every update (tests).
+ *   "history"  1 (default): the first pass takes the tiles hardest-first by the previous step's per-tile counts
+ *              (kept per context and shape), so K* is known within the first wave and the top-up pass is
+ *              nearly empty; 0: natural order.  Results are bit-identical either way.
+ *   "forget_history" (any value): drop the kept per-tile counts (the next step runs in natural order).
+ *   "speculate" 1 (default) / 0, "pipe_chunks" (0 = automatic): the chunked host-buffer step described at
+ *              ebpmf_vga_step_host.
  *   "debug_verify_scale" (0,1], default 1: TEST HOOK -- the top-up pass verifies against tol*scale, which
  *              forces the host's K*+1 retry loop to run (tests/test_gpu_parity.py::test_retry_loop_...). */
 int  ebpmf_ctx_set_option(ebpmf_ctx *ctx, const char *name, double value);
@@ -285,6 +312,12 @@ int  ebpmf_ctx_set_option(ebpmf_ctx *ctx, const char *name, double value);
 /* diagnostics of the last fused solve: units (warp x 2 columns) that needed second-pass work and
  * the total number of unit evaluations (each = 64 entry evaluations of f) */
 int  ebpmf_ctx_last_diag(ebpmf_ctx *ctx, uint64_t *topup_units, uint64_t *unit_evals);
+
+/* counters of the context / its last fused solve: out[0] units that needed second-pass work, [1] unit
+ * evaluations, [2] tiles the second pass restaged, [3] kernels launched by this context so far, [4] bytes the
+ * last host-buffer step copied out speculatively, [5] bytes it had to copy again, [6] tiles per pass,
+ * [7] 1 if per-tile counts of a previous step are kept.  count <= 8. */
+int  ebpmf_ctx_counters(ebpmf_ctx *ctx, double *out, int count);
 
 /* device-time micro-probe of the FP64 pipe (DFMA chains), used by bench.py for the FP64 line */
 int  ebpmf_probe_fp64_tflops(ebpmf_ctx *ctx, double *tflops);

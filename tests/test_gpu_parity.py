@@ -265,32 +265,37 @@ def test_device_sim_data_matches_oracle(gpu_ctx):
 
 
 # ---------------------------------------------------------------------------------------
-# options: delta mode (frozen units) and the split pipeline
+# options: delta mode (frozen units), periodic fast-forward ("freeze"), history order of the first pass
 # ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize("pipeline", [0, 1, 2, 3])
+@pytest.mark.parametrize("freeze,history", [(0, 0), (1, 0), (0, 1), (1, 1)])
 @pytest.mark.parametrize("delta", [0.0, 1e-14])
 @pytest.mark.parametrize("var_type,maxiter,tol", [("by_col", 10, 1e-5), ("by_row", 1000, 1e-8), ("constant", 3, 1e-5)])
-def test_options_delta_and_pipeline(pkg, pipeline, delta, var_type, maxiter, tol):
-    """Both options keep the 1e-8 parity and R's update count; delta mode stays within ~delta of exact mode."""
+def test_options_delta_freeze_history(pkg, freeze, history, delta, var_type, maxiter, tol):
+    """Every option keeps the 1e-8 parity and R's update count; "freeze" (skipping the repeats of a period-2
+    iterate sequence) and "history" (hardest tiles first) are BIT-identical to plain iteration in natural
+    order; delta mode stays within ~delta of exact mode.  The second call runs with the first call's per-tile
+    counts as order."""
     sim, st = make_case(1300, 301, 5, 0.10, var_type=var_type)
-    ctx = pkg.VgaContext(0)
+    ctx, plain = pkg.VgaContext(0), pkg.VgaContext(0)
     try:
-        ctx.set_option("pipeline", pipeline)
-        ctx.set_option("scored_min_ctas", 0)
-        ctx.set_option("delta", delta)
-        ctx.set_y(sp.csc_matrix(sim["Y"]))
-        res = ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], var_type, maxiter, tol, return_V=True)
+        ctx.set_option("freeze", freeze); ctx.set_option("history", history); ctx.set_option("delta", delta)
+        plain.set_option("freeze", 0); plain.set_option("history", 0)
+        for c in (ctx, plain):
+            c.set_y(sp.csc_matrix(sim["Y"]))
         ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], var_type, maxiter, tol)
-        check_step(res, ref, var_type)
-        ctx.set_option("pipeline", 0)
-        ctx.set_option("delta", 0.0)
-        exact = ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], var_type, maxiter, tol, return_V=True)
-        if delta == 0.0:
-            assert np.array_equal(res["M"], exact["M"]) and np.array_equal(res["V"], exact["V"])   # bit-identical
-        else:
-            assert np.max(np.abs(res["M"] - exact["M"])) < 1e-12 and rel(res["V"], exact["V"]) < 1e-12
+        exact = plain.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], var_type, maxiter, tol, return_V=True)
+        for call in range(2):
+            res = ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], var_type, maxiter, tol, return_V=True)
+            check_step(res, ref, var_type)
+            assert ctx.counters()["have_history"] == 1.0
+            if delta == 0.0:
+                assert np.array_equal(res["M"], exact["M"]) and np.array_equal(res["V"], exact["V"])   # bit-identical
+                assert np.array_equal(np.atleast_1d(res["v_sum"]), np.atleast_1d(exact["v_sum"]))
+                assert (res["sym"], res["ssexp"], res["slogv"]) == (exact["sym"], exact["ssexp"], exact["slogv"])
+            else:
+                assert np.max(np.abs(res["M"] - exact["M"])) < 1e-12 and rel(res["V"], exact["V"]) < 1e-12
     finally:
-        ctx.close()
+        ctx.close(); plain.close()
 
 
 def test_option_validation(pkg):
@@ -371,8 +376,8 @@ def test_maxiter_one(gpu_ctx):
     assert res["n_updates"] == 1 and not res["converged"]
 
 
-@pytest.mark.parametrize("K,pipeline", [(31, 0), (45, 0), (45, 1), (70, 0), (45, 2), (45, 3), (70, 3)])
-def test_many_factors(pkg, K, pipeline):
+@pytest.mark.parametrize("K,freeze", [(31, 1), (45, 1), (45, 0), (70, 1), (70, 0)])
+def test_many_factors(pkg, K, freeze):
     """K_tot = K + 2 above the 32-column register tile: Beta is accumulated over chunks of 32 factor columns
     (flash_control$Kmax defaults to 30, R/ebpmf_log_controls.R:74, but greedy additions can exceed it)."""
     c = simdata.offset_for_density(0.10, K=4)
@@ -383,12 +388,12 @@ def test_many_factors(pkg, K, pipeline):
     EF = np.hstack([st["EF"], 0.05 * rng.normal(size=(150, K - 4))])
     ctx = pkg.VgaContext(0)
     try:
-        ctx.set_option("pipeline", pipeline)
-        ctx.set_option("scored_min_ctas", 0)
+        ctx.set_option("freeze", freeze)
         ctx.set_y(sp.csc_matrix(sim["Y"]))
-        res = ctx.vga_step_host(st["M0"], EL, EF, st["sigma2"], "by_col", 100, 1e-8, return_V=True)
         ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], EL, EF, st["sigma2"], "by_col", 100, 1e-8)
-        check_step(res, ref, "by_col")
+        for call in range(2):                      # the second call takes the tiles in the first call's hardness order
+            res = ctx.vga_step_host(st["M0"], EL, EF, st["sigma2"], "by_col", 100, 1e-8, return_V=True)
+            check_step(res, ref, "by_col")
     finally:
         ctx.close()
 
@@ -431,24 +436,22 @@ def test_resident_m_loop_equals_full_roundtrip(gpu_ctx):
         assert np.array_equal(r["v_sum"], rf["v_sum"]) and r["sym"] == rf["sym"]
 
 
-@pytest.mark.parametrize("pipeline", [2, 3])
 @pytest.mark.parametrize("var_type", ["by_col", "by_row"])
-def test_ordered_pipeline_edge_cases(pkg, var_type, pipeline):
-    """pipeline 2 (iteration 0 inside the const0 kernel, CTAs by decreasing first step) and pipeline 3 (FP32
-    scoring pass, fused kernel in score order): u = 0 (R breaks at i = 1, M_0 final), maxiter = 1 (falls
-    back), maxiter = 2 (exhaustion right after the moved iteration), NaN; always bit-identical to the fused
-    pipeline."""
+def test_freeze_and_history_edge_cases(pkg, var_type):
+    """Periodic fast-forward + history order against plain iteration in natural order: u = 0 (R breaks at
+    i = 1, M_0 final), maxiter = 1, maxiter = 2 (exhaustion: the last update is performed by the top-up pass
+    for every unit), an exhausted tight tolerance, NaN; always bit-identical, always the oracle's count."""
     sim, st = make_case(1500, 200, 4, 0.10, var_type=var_type)
     a, b = pkg.VgaContext(0), pkg.VgaContext(0)
     try:
-        b.set_option("pipeline", pipeline)
-        b.set_option("scored_min_ctas", 0)
+        a.set_option("freeze", 0); a.set_option("history", 0)
         for c in (a, b):
             c.set_y(sp.csc_matrix(sim["Y"]))
         ra = a.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], var_type, 100, 1e-7, return_V=True)
         rb = b.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], var_type, 100, 1e-7, return_V=True)
         assert ra["n_updates"] == rb["n_updates"] and np.array_equal(ra["M"], rb["M"]) and np.array_equal(ra["V"], rb["V"])
-        for mi, tol, M0 in ((100, 1e-7, ra["M"]), (1, 1e-5, st["M0"]), (2, 1e-5, st["M0"]), (3, 1e-12, st["M0"])):
+        for mi, tol, M0 in ((100, 1e-7, ra["M"]), (1, 1e-5, st["M0"]), (2, 1e-5, st["M0"]), (3, 1e-12, st["M0"]),
+                            (7, 1e-13, st["M0"]), (40, 1e-13, st["M0"])):
             xa = a.vga_step_host(M0, st["EL"], st["EF"], st["sigma2"], var_type, mi, tol, return_V=True)
             xb = b.vga_step_host(M0, st["EL"], st["EF"], st["sigma2"], var_type, mi, tol, return_V=True)
             ref = vga_numpy.ebpmf_log_vga_step(M0, sim["Y"], st["EL"], st["EF"], st["sigma2"], var_type, mi, tol)
@@ -456,6 +459,7 @@ def test_ordered_pipeline_edge_cases(pkg, var_type, pipeline):
             assert xa["n_updates"] == xb["n_updates"] and xa["converged"] == xb["converged"]
             assert np.array_equal(xa["M"], xb["M"]) and np.array_equal(xa["V"], xb["V"])
             assert np.array_equal(np.atleast_1d(xa["v_sum"]), np.atleast_1d(xb["v_sum"]))
+            assert (xa["sym"], xa["ssexp"], xa["slogv"]) == (xb["sym"], xb["ssexp"], xb["slogv"])
         EL = st["EL"].copy(); EL[5, 1] = np.nan
         with pytest.raises(pkg.EbpmfError) as ei:
             b.vga_step_host(st["M0"], EL, st["EF"], st["sigma2"], var_type, 10, 1e-5)
@@ -496,7 +500,7 @@ def test_config5_variants_medium_size(gpu_ctx, pkg):
 
 
 def test_randomised_configurations(pkg):
-    """40 random small configurations (shape, K, density, var_type, maxiter, tol, start, pipeline, delta):
+    """40 random small configurations (shape, K, density, var_type, maxiter, tol, start, freeze, history, delta):
     every one must match the oracle to 1e-8 with the same update count."""
     rng = np.random.default_rng(20261019)
     ctx = pkg.VgaContext(0)
@@ -509,9 +513,8 @@ def test_randomised_configurations(pkg):
             sim = simdata.sim_data_log(n, p, K=K, seed=1000 + trial, pi0=0.9,
                                        log_offset=(simdata.offset_for_density(dens, K=K, pi0=0.9) if dens > 0 else -40.0))
             st = simdata.solver_state(sim, start=["cold", "warm"][int(rng.integers(2))], var_type=vt, seed=trial, noise=0.1)
-            pl = int(rng.integers(3))
-            ctx.set_option("pipeline", 3 if trial % 4 == 3 else pl)
-            ctx.set_option("scored_min_ctas", 0)
+            ctx.set_option("freeze", int(rng.integers(2)))
+            ctx.set_option("history", int(rng.integers(2)))
             ctx.set_option("delta", float(rng.choice([0.0, 0.0, 1e-14])))
             ctx.set_y(sp.csc_matrix(sim["Y"]) if rng.integers(2) else sim["Y"])
             res = ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], vt, maxiter, tol, return_V=True)
@@ -525,16 +528,15 @@ def test_randomised_configurations(pkg):
         ctx.close()
 
 
-@pytest.mark.parametrize("pipeline", [0, 2, 3])
-def test_retry_loop_when_verification_fails(pkg, pipeline):
+@pytest.mark.parametrize("freeze", [0, 1])
+def test_retry_loop_when_verification_fails(pkg, freeze):
     """The host's K*+1 retry loop (pass 2 repeated until every unit is below tol) is exercised with a test
     hook: pass 1 finds K* for tol, pass 2 verifies against tol*1e-8, fails, and the loop must walk up to the
     count R would reach with tol*1e-8 -- results equal the oracle's for that tolerance."""
     sim, st = make_case(1800, 220, 4, 0.10)
     ctx = pkg.VgaContext(0)
     try:
-        ctx.set_option("pipeline", pipeline)
-        ctx.set_option("scored_min_ctas", 0)
+        ctx.set_option("freeze", freeze)
         ctx.set_option("debug_verify_scale", 1e-8)
         ctx.set_y(sp.csc_matrix(sim["Y"]))
         res = ctx.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], "by_col", 50, 1e-2, return_V=True)
@@ -553,27 +555,147 @@ def test_retry_loop_when_verification_fails(pkg, pipeline):
         ctx.close()
 
 
-def test_scored_pipeline_many_tiles(pkg):
-    """pipeline 3 on a matrix with several waves of tiles (device-generated 40 000 x 6 000): bit-identical M,
-    V sums and update count to the fused pipeline, and the top-up pass has (almost) nothing left to do."""
+def test_history_order_many_tiles(pkg):
+    """Several waves of tiles (device-generated 40 000 x 6 000): with the previous step's per-tile counts as the
+    order of the first pass (and the periodic fast-forward) the results are bit-identical to plain iteration in
+    natural order, and the top-up pass has (almost) nothing left to do -- also when the factors moved in between."""
     n, p, K = 40000, 6000, 10
     a, b = pkg.VgaContext(0), pkg.VgaContext(0)
     try:
-        b.set_option("pipeline", 3)
+        a.set_option("freeze", 0); a.set_option("history", 0)
         for c in (a, b):
             c.sim_data_log(n, p, K, seed=77, log_offset=-4.644)
-        ia, ib = a.vga_step(10, 1e-5), b.vga_step(10, 1e-5)
-        assert ia.n_updates == ib.n_updates and ia.converged == ib.converged
-        assert ia.sym == ib.sym and ia.ssexp == ib.ssexp and ia.slogv == ib.slogv
-        assert np.array_equal(a.get_v_sum(), b.get_v_sum())
-        for r0 in (0, 17000, n - 999):
-            assert np.array_equal(a.get_rows(r0, 999, "M"), b.get_rows(r0, 999, "M"))
-        da, db = a.last_diag(), b.last_diag()
-        assert db["topup_units"] <= da["topup_units"]
-        if ia.n_updates >= 3:
-            assert db["topup_units"] < 0.1 * ((n + 31) // 32) * ((p + 1) // 2)
+        units = ((n + 31) // 32) * ((p + 1) // 2)
+        for step in range(3):
+            ia, ib = a.vga_step(10, 1e-5), b.vga_step(10, 1e-5)
+            assert ia.n_updates == ib.n_updates and ia.converged == ib.converged
+            assert ia.sym == ib.sym and ia.ssexp == ib.ssexp and ia.slogv == ib.slogv
+            assert np.array_equal(a.get_v_sum(), b.get_v_sum())
+            for r0 in (0, 17000, n - 999):
+                assert np.array_equal(a.get_rows(r0, 999, "M"), b.get_rows(r0, 999, "M"))
+            ca, cb = a.counters(), b.counters()
+            if step > 0 and ia.n_updates >= 3:
+                assert cb["topup_units"] < 0.05 * units, (step, cb)
+                assert cb["topup_units"] <= ca["topup_units"]
+            if step > 0:
+                assert cb["unit_evals"] < ca["unit_evals"]              # the fast-forward skips repeated iterates
+            for c in (a, b):
+                c.rewind_m()
+            if step == 1:                      # move the factors: the kept order is now only a prediction
+                EL, EF = a.get_factors()
+                rng = np.random.default_rng(5)
+                EL[:, 2:] += 0.05 * rng.normal(size=EL[:, 2:].shape); EF[:, 2:] += 0.05 * rng.normal(size=EF[:, 2:].shape)
+                for c in (a, b):
+                    c.set_factors(EL, EF)
     finally:
         a.close(); b.close()
+
+
+def test_host_step_chunked_pipeline(pkg):
+    """The host-buffer step above the pipelining threshold (6 000 x 1 100 = 53 MB; odd and even row counts, so both
+    the bulk-copy and the per-thread slab paths run) with plain pageable NumPy arrays: column chunks, speculative
+    copies, repeated copies of the chunks the top-up pass touched -- bit-identical to set_m + vga_step + get_m, with
+    and without speculation, M in and resident."""
+    for n in (6000, 6001):
+        p, K = 1100, 6
+        c = simdata.offset_for_density(0.08, K=K)
+        sim = simdata.sim_data_log(n, p, K=K, seed=11, log_offset=c)
+        st = simdata.solver_state(sim, start="cold")
+        plain, piped = pkg.VgaContext(0), pkg.VgaContext(0)
+        try:
+            plain.set_option("freeze", 0); plain.set_option("history", 0)
+            piped.set_option("pipe_chunks", 7)
+            for cx in (plain, piped):
+                cx.set_y(sp.csc_matrix(sim["Y"]))
+            plain.set_factors(st["EL"], st["EF"]); plain.set_sigma2(st["sigma2"], "by_col")
+            M = st["M0"]
+            piped.set_m(M)
+            for it in range(4):
+                plain.set_m(M)
+                info = plain.vga_step(10, 1e-5, want_v=True)
+                Mref, Vref, vref = plain.get_m(), plain.get_v(), plain.get_v_sum()
+                piped.set_option("speculate", 0 if it == 3 else 1)
+                if it % 2 == 0:
+                    r = piped.vga_step_host(M, st["EL"], st["EF"], st["sigma2"], "by_col", 10, 1e-5, return_V=(it == 2))
+                else:
+                    r = piped.vga_step_resident_host(st["EL"], st["EF"], st["sigma2"], "by_col", 10, 1e-5)
+                assert r["n_updates"] == info.n_updates and r["converged"] == bool(info.converged)
+                assert np.array_equal(r["M"], Mref), (n, it)
+                assert np.array_equal(r["v_sum"], vref) and r["sym"] == info.sym and r["ssexp"] == info.ssexp
+                if r["V"] is not None:
+                    assert np.array_equal(r["V"], Vref)
+                cnt = piped.counters()
+                if it in (1, 2):
+                    assert cnt["spec_bytes"] == 8.0 * n * p         # history exists: everything went out speculatively
+                    assert cnt["recopy_bytes"] < cnt["spec_bytes"]
+                M = Mref
+        finally:
+            plain.close(); piped.close()
+    with pytest.raises(pkg.EbpmfError) as ei:        # host matrices must have the shape of the resident Y
+        ctx = pkg.VgaContext(0)
+        ctx.set_y(sp.csc_matrix(sim["Y"]))
+        ctx.vga_step_host(st["M0"][:100], st["EL"][:100], st["EF"], st["sigma2"], "by_col", 10, 1e-5)
+    assert ei.value.code == 1
+    ctx.close()
+
+
+@pytest.mark.parametrize("n,p,Kw", [(3000, 700, 5), (4097, 333, 22), (2048, 64, 32), (1500, 90, 41)])
+def test_m_products_vs_numpy(pkg, n, p, Kw):
+    """N1: M %*% EF, t(M) %*% EL and the column / row sums of (M - EL EF')^2 on the resident M against NumPy,
+    to 1e-10 relative (even and odd row counts: bulk-copy and per-thread tile paths; Kw > 32: two passes)."""
+    rng = np.random.default_rng(n + Kw)
+    sim, st = make_case(n, p, 3, 0.10)
+    M = np.asfortranarray(st["M0"] + 0.1 * rng.normal(size=(n, p)))
+    EL = np.asfortranarray(rng.normal(size=(n, Kw))); EF = np.asfortranarray(rng.normal(size=(p, Kw)) * 0.3)
+    ctx = pkg.VgaContext(0)
+    try:
+        ctx.set_y(sp.csc_matrix(sim["Y"])); ctx.set_m(M)
+        r = ctx.m_products(EL, EF)
+        R = M - EL @ EF.T
+        for got, want in ((r["MF"], M @ EF), (r["MtL"], M.T @ EL), (r["r2_col"], np.sum(R * R, axis=0)),
+                          (r["r2_row"], np.sum(R * R, axis=1))):
+            assert np.max(np.abs(got - want)) <= 1e-10 * max(1.0, np.max(np.abs(want)))
+        assert r["kernel_ms"] > 0
+        r2 = ctx.m_products(EL, EF)                     # run-to-run bit-reproducible
+        assert np.array_equal(r["MF"], r2["MF"]) and np.array_equal(r["MtL"], r2["MtL"]) and np.array_equal(r["r2_col"], r2["r2_col"])
+    finally:
+        ctx.close()
+
+
+def test_malformed_dgcmatrix_is_refused(pkg):
+    """@p not non-decreasing, a row index out of range or unsorted within a column: EBPMF_ERR_ARG, not device memory
+    corruption (the kernels scatter through these indices)."""
+    ctx = pkg.VgaContext(0)
+    try:
+        cp = np.array([0, 2, 4], dtype=np.int32); x = np.ones(4)
+        for bad_cp, bad_ri in ((np.array([0, 3, 2], dtype=np.int32), np.array([0, 1, 0, 1], dtype=np.int32)),
+                               (cp, np.array([0, 5, 0, 1], dtype=np.int32)),
+                               (cp, np.array([1, 0, 0, 1], dtype=np.int32)),
+                               (cp, np.array([0, -1, 0, 1], dtype=np.int32))):
+            with pytest.raises(pkg.EbpmfError) as ei:
+                ctx.set_y_csc(3, 2, bad_cp, bad_ri, x)
+            assert ei.value.code == 1
+        ctx.set_y_csc(3, 2, cp, np.array([0, 2, 1, 2], dtype=np.int32), x)
+    finally:
+        ctx.close()
+
+
+def test_low_memory_does_not_leave_foreign_state(pkg):
+    """vga_pois_solver_mat_newton_low_memory takes over the context's resident Y / M: afterwards a resident step on
+    the same context must fail with EBPMF_ERR_STATE instead of running on the wrong matrices."""
+    sim, st = make_case(400, 60, 3, 0.10)
+    ctx = pkg.VgaContext(0)
+    try:
+        ctx.set_y(sp.csc_matrix(sim["Y"])); ctx.set_m(st["M0"]); ctx.set_factors(st["EL"], st["EF"])
+        ctx.set_sigma2(st["sigma2"], "by_col")
+        ctx.vga_step(10, 1e-5)
+        pkg.vga_pois_solver_mat_newton_low_memory(st["M0"][:100, :20], sim["Y"][:100, :20], np.ones(100), np.ones(20),
+                                                  st["EL"][:100], st["EF"][:20], st["sigma2"][:20], "by_col", 50, 1e-6, ctx=ctx)
+        with pytest.raises(pkg.EbpmfError) as ei:
+            ctx.vga_step(10, 1e-5)
+        assert ei.value.code == 5
+    finally:
+        ctx.close()
 
 
 # ---------------------------------------------------------------------------------------
