@@ -61,6 +61,7 @@ SIGNATURES = {
     "ebpmf_ctx_get_factors": (_int, [_vp, _vp, _vp]),
     "ebpmf_ctx_get_sigma2": (_int, [_vp, _vp]),
     "ebpmf_ctx_get_rows": (_int, [_vp, _int, _i64, _i64, _vp]),
+    "ebpmf_ctx_get_block": (_int, [_vp, _int, _i64, _i64, _i64, _i64, _vp]),
     "ebpmf_ctx_update_sigma2": (_int, [_vp, _vp, _dbl, _dbl, _dbl, _i64, _i64, _vp]),
     "ebpmf_update_sigma2": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp, _dbl, _dbl, _dbl, _i64, _vp, _vp, _vp]),
     "ebpmf_calc_obj": (_int, [_vp, _i64, _i64, _dbl, _dbl, _dbl, _i64, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl,

@@ -92,6 +92,7 @@ struct ebpmf_ctx {
     int cur_nspans = 0, cur_ntiles = 0, cur_cols = 0;   // tiling of the step in flight (fused_args)
     unsigned long long diag_topups = 0, diag_iters = 0;
     int diag_topup_tiles = 0;
+    double last_kernel_ms = 0.0;                  // device time of the last call that has no ebpmf_solve_info (fixed_iter)
     unsigned long long launches = 0;              // kernels launched by this context (bench.py's gpu_launches)
     double diag_spec_bytes = 0.0, diag_recopy_bytes = 0.0;   // last host-pipelined step: speculative / repeated D2H bytes
     bool have_y = false, have_m = false, have_f = false, have_s2 = false, have_v = false, have_vsum = false;
@@ -1604,11 +1605,17 @@ int ebpmf_vga_fixed_iter(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *M, 
     a.maxiter = maxiter;
     const long long nRB = (n + kRowsPerCta - 1) / kRowsPerCta;
     dim3 grid((unsigned)std::min<long long>(p, 4096), (unsigned)nRB);
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
     vga_fixed_iter_kernel<<<grid, kThreads, 0, ctx->stream>>>(a);
     CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    ++ctx->launches;
     CU(cudaMemcpyAsync(M_out, ctx->scratch[1].ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(V_out, ctx->scratch[3].ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_kernel_ms = ms;
     return EBPMF_OK;
 }
 
@@ -1702,6 +1709,19 @@ int ebpmf_ctx_get_rows(ebpmf_ctx *ctx, int which, int64_t row0, int64_t nrows, d
     const double *src = (which ? as<double>(ctx->V) : as<double>(ctx->Mcur)) + row0;
     CU(cudaMemcpy2DAsync(out, sizeof(double) * (size_t)nrows, src, sizeof(double) * (size_t)ctx->n,
                          sizeof(double) * (size_t)nrows, (size_t)ctx->p, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return EBPMF_OK;
+}
+
+int ebpmf_ctx_get_block(ebpmf_ctx *ctx, int which, int64_t row0, int64_t nrows, int64_t col0, int64_t ncols, double *out) {
+    if (!ctx || !out || row0 < 0 || nrows < 1 || col0 < 0 || ncols < 1) return fail(ctx, EBPMF_ERR_ARG, "get_block: bad arguments");
+    if (!ctx->have_m || row0 + nrows > ctx->n || col0 + ncols > ctx->p)
+        return fail(ctx, EBPMF_ERR_STATE, "get_block: M not set or block out of range");
+    if (which != 0 && !ctx->have_v) return fail(ctx, EBPMF_ERR_STATE, "get_block: V was not materialised");
+    CHECK(ensure_common(ctx));
+    const double *src = (which ? as<double>(ctx->V) : as<double>(ctx->Mcur)) + row0 + (size_t)ctx->n * (size_t)col0;
+    CU(cudaMemcpy2DAsync(out, sizeof(double) * (size_t)nrows, src, sizeof(double) * (size_t)ctx->n,
+                         sizeof(double) * (size_t)nrows, (size_t)ncols, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return EBPMF_OK;
 }
@@ -1806,10 +1826,10 @@ int ebpmf_ctx_last_diag(ebpmf_ctx *ctx, uint64_t *topup_units, uint64_t *unit_ev
 
 int ebpmf_ctx_counters(ebpmf_ctx *ctx, double *out, int count) {
     if (!ctx || !out || count < 1) return fail(ctx, EBPMF_ERR_ARG, "counters: bad arguments");
-    const double v[8] = {(double)ctx->diag_topups, (double)ctx->diag_iters, (double)ctx->diag_topup_tiles,
+    const double v[9] = {(double)ctx->diag_topups, (double)ctx->diag_iters, (double)ctx->diag_topup_tiles,
                          (double)ctx->launches, ctx->diag_spec_bytes, ctx->diag_recopy_bytes, (double)ctx->cur_ntiles,
-                         ctx->have_hist ? 1.0 : 0.0};
-    for (int q = 0; q < count && q < 8; ++q) out[q] = v[q];
+                         ctx->have_hist ? 1.0 : 0.0, ctx->last_kernel_ms};
+    for (int q = 0; q < count && q < 9; ++q) out[q] = v[q];
     return EBPMF_OK;
 }
 

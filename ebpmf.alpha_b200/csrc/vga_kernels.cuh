@@ -201,6 +201,60 @@ __device__ __forceinline__ double rcp_step(double x) {
 
 __device__ __forceinline__ bool same_bits(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
 
+// reciprocal of temp = const0 - M (:22).  MUFU seed + one quadratic correction (rel. error ~2^-40 = 9e-13): V =
+// Sigma2/temp and the exp argument const2/temp inherit it, four orders inside the 1e-8 parity budget.
+// -DEBPMF_RCP_CUBIC=1 restores the cubic step (~1.5 ulp) for A/B runs.
+#ifndef EBPMF_RCP_CUBIC
+#define EBPMF_RCP_CUBIC 0
+#endif
+__device__ __forceinline__ double rcp_temp(double x) {
+#if EBPMF_RCP_CUBIC
+    return rcp_fast(x);
+#else
+    return rcp_step(x);
+#endif
+}
+
+// one evaluation of f at m (R/vga_solver_mat.R:22-25); returns "every entry of the unit has |f| < tol"
+template <int E, bool SCALED>
+__device__ __forceinline__ bool newton_eval(const double (&m)[E], const double (&c0)[E], const double (&w)[E],
+                                            const double (&c1)[E], const double (&c2)[E], const double (&sc)[E],
+                                            double tol_lane, unsigned exptab, double (&r)[E], double (&a)[E],
+                                            double (&sexp)[E], double (&f)[E])
+{
+    bool lane_conv = true;
+    double xx[E], ex[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const double temp = __dadd_rn(c0[e], -m[e]);                       // :22
+        r[e] = rcp_temp(temp);
+        a[e] = __dmul_rn(c2[e], r[e]);                                     // const2/temp
+        xx[e] = __dadd_rn(m[e], a[e]);
+    }
+    exp_fast_n<E>(xx, ex, exptab);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        sexp[e] = SCALED ? __dmul_rn(sc[e], ex[e]) : ex[e];                // :23
+        f[e] = __fma_rn(-m[e], c1[e], __dadd_rn(w[e], -sexp[e]));          // :25 | :84,:98
+        lane_conv = lane_conv && (fabs(f[e]) < tol_lane);                  // :26 (strict <)
+    }
+    return __all_sync(0xffffffffu, lane_conv);
+}
+
+// the Newton update (R/vga_solver_mat.R:31 | :90,:105) from the last evaluation
+template <int E, int FORMULA>
+__device__ __forceinline__ void newton_step(const double (&m)[E], const double (&c1)[E], const double (&r)[E],
+                                            const double (&a)[E], const double (&sexp)[E], const double (&f)[E],
+                                            double (&mn)[E])
+{
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const double q = (FORMULA == FORMULA_A1) ? a[e] : __dmul_rn(0.5, r[e]);   // const2/temp^2 | 0.5*temp^-2
+        const double g = __fma_rn(-sexp[e], __fma_rn(q, r[e], 1.0), -c1[e]);
+        mn[e] = __fma_rn(-f[e], rcp_step(g), m[e]);
+    }
+}
+
 template <int E, int FORMULA, int MODE, bool SCALED, int FREEZE>
 __device__ __forceinline__ int newton_unit(double (&m)[E], const double (&c0)[E], double (&w)[E],
                                            const double (&c1)[E], const double (&c2)[E], const double (&sc)[E],
@@ -216,87 +270,96 @@ __device__ __forceinline__ int newton_unit(double (&m)[E], const double (&c0)[E]
     for (int e = 0; e < E; ++e) asm volatile("" : "+d"(w[e]));
     asm volatile("" : "+d"(tol_lane));
     asm volatile("" : "+r"(exptab));        // likewise the table's shared-window address
-    double mprev[E];                        // FREEZE_PERIODIC: the iterate before m (valid while prev_conv)
-#pragma unroll
-    for (int e = 0; e < E; ++e) mprev[e] = m[e];
-    bool prev_conv = false;
+    const int k_in = k;
+    int not_evaluated = 0;                  // counts skipped by the fast-forward, and the exhausted exit's last update
+    double a[E];
+    if constexpr (FREEZE != FREEZE_DELTA) {
+        int klast = maxiter - 1;            // at k == klast the next update is number maxiter
+        asm volatile("" : "+r"(klast));
+        bool conv;
+        // ---- phase 1: plain iteration until the unit is converged for the first time (nothing else to track)
 #pragma unroll 1
-    for (;;) {
-        bool lane_conv = true;
-        double a[E], xx[E], ex[E];
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const double temp = __dadd_rn(c0[e], -m[e]);                       // :22
-            r[e] = rcp_fast(temp);
-            a[e] = __dmul_rn(c2[e], r[e]);                                     // const2/temp
-            xx[e] = __dadd_rn(m[e], a[e]);
+        for (;;) {
+            conv = newton_eval<E, SCALED>(m, c0, w, c1, c2, sc, tol_lane, exptab, r, a, sexp, f);
+            if (conv || k >= klast || (MODE == MODE_TOPUP && k == target)) break;
+            newton_step<E, FORMULA>(m, c1, r, a, sexp, f, m);
+            ++k;
         }
-        exp_fast_n<E>(xx, ex, exptab);
-        ++evals;
+        if (conv) kb = k;
+        // ---- phase 2: the unit has been converged; run on to the target count, fast-forwarding once the
+        // iterates repeat.  Entering an iteration, (r, a, sexp, f, conv) belong to m at index k.
+        double mprev[E];
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            sexp[e] = SCALED ? __dmul_rn(sc[e], ex[e]) : ex[e];                // :23
-            f[e] = __fma_rn(-m[e], c1[e], __dadd_rn(w[e], -sexp[e]));          // :25 | :84,:98
-            lane_conv = lane_conv && (fabs(f[e]) < tol_lane);                  // :26 (strict <)
-        }
-        const bool conv = __all_sync(0xffffffffu, lane_conv);
-        if (conv && kb < 0) kb = k;
-        const bool stop = (MODE == MODE_FIRST) ? (conv && (k >= target)) : (k == target);
-        if (FREEZE != FREEZE_DELTA || !conv) {
+        for (int e = 0; e < E; ++e) mprev[e] = m[e];
+        bool prev_conv = false;
+#pragma unroll 1
+        for (;;) {
+            const bool stop = (MODE == MODE_FIRST) ? (conv && (k >= target)) : (k == target);
             if (stop) { if (conv) flags |= 1; break; }
-            if (MODE == MODE_FIRST && k >= maxiter - 1) { flags |= 4; break; }   // update no. maxiter: top-up pass
-            double mn[E];
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const double q = (FORMULA == FORMULA_A1) ? a[e] : __dmul_rn(0.5, r[e]);   // const2/temp^2 | 0.5*temp^-2
-                const double g = __fma_rn(-sexp[e], __fma_rn(q, r[e], 1.0), -c1[e]);      // :31 | :90,:105
-                mn[e] = __fma_rn(-f[e], rcp_step(g), m[e]);
+            if (k >= klast) {               // update number maxiter: the top-up pass performs it, stale V and all (F6)
+                if (MODE == MODE_FIRST) { flags |= 4; }
+                else { newton_step<E, FORMULA>(m, c1, r, a, sexp, f, m); ++k; ++not_evaluated; flags |= 2; }
+                break;
             }
-            if (FREEZE == FREEZE_PERIODIC && conv) {
+            double mn[E];
+            newton_step<E, FORMULA>(m, c1, r, a, sexp, f, mn);
+            if (FREEZE == FREEZE_PERIODIC && conv && prev_conv) {
                 // converged now and one iteration ago, and every entry's next iterate is m itself or the
                 // previous iterate: from here on the sequence has period (at most) 2 and every state is
                 // converged, so k may advance by any EVEN amount without changing (m, mn).
-                if (prev_conv) {
-                    bool lane_per = true;
+                bool lane_per = true;
 #pragma unroll
-                    for (int e = 0; e < E; ++e) lane_per = lane_per && (same_bits(mn[e], m[e]) || same_bits(mn[e], mprev[e]));
-                    if (__all_sync(0xffffffffu, lane_per)) {
-                        // land so that the NEXT iteration index (k + 1 after the update below) is lim - 1 or
-                        // lim: the stop tests then run on real evaluations, exactly as without the jump
-                        const int lim = min(target, maxiter - 1);
-                        if (k + 1 < lim) k += (lim - 1 - k) & ~1;
-                    }
+                for (int e = 0; e < E; ++e) lane_per = lane_per && (same_bits(mn[e], m[e]) || same_bits(mn[e], mprev[e]));
+                if (__all_sync(0xffffffffu, lane_per)) {
+                    // land so that the NEXT iteration index (k + 1 after the update below) is lim - 1 or
+                    // lim: the stop tests then run on real evaluations, exactly as without the jump
+                    const int lim = min(target, klast);
+                    if (k + 1 < lim) { const int d = (lim - 1 - k) & ~1; k += d; not_evaluated += d; }
                 }
-#pragma unroll
-                for (int e = 0; e < E; ++e) mprev[e] = m[e];
             }
+#pragma unroll
+            for (int e = 0; e < E; ++e) { mprev[e] = m[e]; m[e] = mn[e]; }
             prev_conv = conv;
-#pragma unroll
-            for (int e = 0; e < E; ++e) m[e] = mn[e];
-        } else {
-            // delta mode, unit converged: form the update and FREEZE the unit if every entry's update
-            // is a numerical no-op (|f/g| <= delta, |f| < tol/16): all later iterates equal this one
-            // to within delta, so the unit is final for any global count.
-            double mn[E];
-            bool lane_small = true;
-            const double tol16 = tol_lane * 0.0625;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const double q = (FORMULA == FORMULA_A1) ? a[e] : __dmul_rn(0.5, r[e]);
-                const double g = __fma_rn(-sexp[e], __fma_rn(q, r[e], 1.0), -c1[e]);
-                const double rg = rcp_step(g);
-                mn[e] = __fma_rn(-f[e], rg, m[e]);
-                lane_small = lane_small && (fabs(__dmul_rn(f[e], rg)) <= delta) && (fabs(f[e]) < tol16);
-            }
-            if (__all_sync(0xffffffffu, lane_small)) { flags |= 1 | 8; break; }
-            if (stop) { flags |= 1; break; }
-            if (MODE == MODE_FIRST && k >= maxiter - 1) { flags |= 4; break; }
-#pragma unroll
-            for (int e = 0; e < E; ++e) m[e] = mn[e];
+            ++k;
+            conv = newton_eval<E, SCALED>(m, c0, w, c1, c2, sc, tol_lane, exptab, r, a, sexp, f);
+            if (conv && kb < 0) kb = k;
         }
-        ++k;
-        if (k >= maxiter) { flags |= 2; break; }
+    } else {
+        // delta mode: a converged unit FREEZES as soon as every entry's update is a numerical no-op
+        // (|f/g| <= delta, |f| < tol/16): all later iterates equal this one to within delta, so the unit is
+        // final for any global count.
+#pragma unroll 1
+        for (;;) {
+            const bool conv = newton_eval<E, SCALED>(m, c0, w, c1, c2, sc, tol_lane, exptab, r, a, sexp, f);
+            if (conv && kb < 0) kb = k;
+            const bool stop = (MODE == MODE_FIRST) ? (conv && (k >= target)) : (k == target);
+            if (!conv) {
+                if (stop) break;
+                if (MODE == MODE_FIRST && k >= maxiter - 1) { flags |= 4; break; }
+                newton_step<E, FORMULA>(m, c1, r, a, sexp, f, m);
+            } else {
+                double mn[E];
+                bool lane_small = true;
+                const double tol16 = tol_lane * 0.0625;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const double q = (FORMULA == FORMULA_A1) ? a[e] : __dmul_rn(0.5, r[e]);
+                    const double g = __fma_rn(-sexp[e], __fma_rn(q, r[e], 1.0), -c1[e]);
+                    const double rg = rcp_step(g);
+                    mn[e] = __fma_rn(-f[e], rg, m[e]);
+                    lane_small = lane_small && (fabs(__dmul_rn(f[e], rg)) <= delta) && (fabs(f[e]) < tol16);
+                }
+                if (__all_sync(0xffffffffu, lane_small)) { flags |= 1 | 8; break; }
+                if (stop) { flags |= 1; break; }
+                if (MODE == MODE_FIRST && k >= maxiter - 1) { flags |= 4; break; }
+#pragma unroll
+                for (int e = 0; e < E; ++e) m[e] = mn[e];
+            }
+            ++k;
+            if (k >= maxiter) { flags |= 2; ++not_evaluated; break; }
+        }
     }
+    evals += (unsigned)(k - k_in + 1 - not_evaluated);
     return flags;
 }
 

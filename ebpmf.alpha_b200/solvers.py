@@ -203,6 +203,12 @@ class VgaContext:
         self._ck(self._lib.ebpmf_ctx_get_rows(self._h, 0 if which == "M" else 1, int(row0), int(nrows), _ptr(out)))
         return out
 
+    def get_block(self, row0, nrows, col0, ncols, which="M"):
+        out = np.empty((nrows, ncols), order="F")
+        self._ck(self._lib.ebpmf_ctx_get_block(self._h, 0 if which == "M" else 1, int(row0), int(nrows), int(col0), int(ncols),
+                                               _ptr(out)))
+        return out
+
     def shape(self):
         n, p, K, nnz = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
         self._ck(self._lib.ebpmf_ctx_get_shape(self._h, C.byref(n), C.byref(p), C.byref(K), C.byref(nnz)))
@@ -306,9 +312,10 @@ class VgaContext:
         self._ck(self._lib.ebpmf_ctx_set_option(self._h, name.encode(), float(value)))
 
     def counters(self):
-        out = np.zeros(8)
-        self._ck(self._lib.ebpmf_ctx_counters(self._h, _ptr(out), 8))
-        keys = ("topup_units", "unit_evals", "topup_tiles", "launches", "spec_bytes", "recopy_bytes", "tiles", "have_history")
+        out = np.zeros(9)
+        self._ck(self._lib.ebpmf_ctx_counters(self._h, _ptr(out), 9))
+        keys = ("topup_units", "unit_evals", "topup_tiles", "launches", "spec_bytes", "recopy_bytes", "tiles", "have_history",
+                "last_kernel_ms")
         return dict(zip(keys, (float(v) for v in out)))
 
     def m_products(self, EL_w, EF_w, want_r2_col=True, want_r2_row=True):

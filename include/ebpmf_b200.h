@@ -136,6 +136,8 @@ int  ebpmf_ctx_get_factors(ebpmf_ctx *ctx, double *EL, double *EF);
 int  ebpmf_ctx_get_sigma2(ebpmf_ctx *ctx, double *sigma2);
 /* rows [row0, row0+nrows) of the resident M (or of V when which != 0) as an nrows x p matrix */
 int  ebpmf_ctx_get_rows(ebpmf_ctx *ctx, int which, int64_t row0, int64_t nrows, double *out);
+/* the block rows [row0, row0+nrows) x columns [col0, col0+ncols) of the resident M (or V), packed nrows x ncols */
+int  ebpmf_ctx_get_block(ebpmf_ctx *ctx, int which, int64_t row0, int64_t nrows, int64_t col0, int64_t ncols, double *out);
 
 /* ebpmf_log_update_sigma2, R/ebpmf_log.R:413-447, on the device from the v_sum of the last step.
  * R2 = fit_flash$flash_fit$R2 (length 1|n|p; for 'constant' the caller passes sum(R2)).
@@ -316,7 +318,8 @@ int  ebpmf_ctx_last_diag(ebpmf_ctx *ctx, uint64_t *topup_units, uint64_t *unit_e
 /* counters of the context / its last fused solve: out[0] units that needed second-pass work, [1] unit
  * evaluations, [2] tiles the second pass restaged, [3] kernels launched by this context so far, [4] bytes the
  * last host-buffer step copied out speculatively, [5] bytes it had to copy again, [6] tiles per pass,
- * [7] 1 if per-tile counts of a previous step are kept.  count <= 8. */
+ * [7] 1 if per-tile counts of a previous step are kept, [8] device ms of the last ebpmf_vga_fixed_iter kernel.
+ * count <= 9. */
 int  ebpmf_ctx_counters(ebpmf_ctx *ctx, double *out, int count);
 
 /* device-time micro-probe of the FP64 pipe (DFMA chains), used by bench.py for the FP64 line */
