@@ -207,6 +207,9 @@ __device__ __forceinline__ bool same_bits(double a, double b) { return __double_
 #ifndef EBPMF_RCP_CUBIC
 #define EBPMF_RCP_CUBIC 0
 #endif
+#ifndef EBPMF_PIN_A
+#define EBPMF_PIN_A 1
+#endif
 __device__ __forceinline__ double rcp_temp(double x) {
 #if EBPMF_RCP_CUBIC
     return rcp_fast(x);
@@ -230,6 +233,12 @@ __device__ __forceinline__ bool newton_eval(const double (&m)[E], const double (
         r[e] = rcp_temp(temp);
         a[e] = __dmul_rn(c2[e], r[e]);                                     // const2/temp
         xx[e] = __dadd_rn(m[e], a[e]);
+#if EBPMF_PIN_A
+        // keep a and the exp argument in registers: otherwise the compiler recomputes both (2 FP64-pipe
+        // instructions each) in the exp fast path and again in the update
+        asm volatile("" : "+d"(a[e]));
+        asm volatile("" : "+d"(xx[e]));
+#endif
     }
     exp_fast_n<E>(xx, ex, exptab);
 #pragma unroll
@@ -306,15 +315,28 @@ __device__ __forceinline__ int newton_unit(double (&m)[E], const double (&c0)[E]
             if (FREEZE == FREEZE_PERIODIC && conv && prev_conv) {
                 // converged now and one iteration ago, and every entry's next iterate is m itself or the
                 // previous iterate: from here on the sequence has period (at most) 2 and every state is
-                // converged, so k may advance by any EVEN amount without changing (m, mn).
-                bool lane_per = true;
+                // converged.  The state at index k + d (iterate, and everything an evaluation of it would
+                // produce: r, a, sexp, f, conv) is therefore THIS state for every even d -- and for every d
+                // when all entries sit on a true fixed point (mn == m bit for bit).
+                bool lane_per = true, lane_fix = true;
 #pragma unroll
-                for (int e = 0; e < E; ++e) lane_per = lane_per && (same_bits(mn[e], m[e]) || same_bits(mn[e], mprev[e]));
+                for (int e = 0; e < E; ++e) {
+                    const bool fx = same_bits(mn[e], m[e]);
+                    lane_fix = lane_fix && fx;
+                    lane_per = lane_per && (fx || same_bits(mn[e], mprev[e]));
+                }
                 if (__all_sync(0xffffffffu, lane_per)) {
-                    // land so that the NEXT iteration index (k + 1 after the update below) is lim - 1 or
-                    // lim: the stop tests then run on real evaluations, exactly as without the jump
-                    const int lim = min(target, klast);
-                    if (k + 1 < lim) { const int d = (lim - 1 - k) & ~1; k += d; not_evaluated += d; }
+                    const int lim = min(target, klast);      // where the stop / exhaustion tests next fire
+                    const int d = lim - k;
+                    if (d > 0) {
+                        if (!(d & 1) || __all_sync(0xffffffffu, lane_fix)) {
+                            // index lim carries the current state: no evaluation left to do
+                            k = lim; not_evaluated += d;
+                            continue;
+                        }
+                        // odd distance on a 2-cycle: jump an even amount, the update below lands on lim
+                        k += d - 1; not_evaluated += d - 1;
+                    }
                 }
             }
 #pragma unroll
