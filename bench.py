@@ -14,22 +14,27 @@ partials in every step.  Inputs are generated ON THE DEVICE (ebpmf_ctx_sim_data_
 30 GB per GPU, far larger than L2, so no L2 flush is needed between steps.
 
   value      entries/s over all ranks, inputs resident in HBM, device time (CUDA events on the
-             library's stream), max over ranks
+             library's stream), max over ranks.  Steady state of ebpmf_log's loop: the tiles of the
+             first pass are taken in the order of the previous step's per-tile counts (kept by the
+             library).  `first_step` is the same step without that history, `perturbed_history` a
+             step whose history comes from DIFFERENT factors (the bench rewinds M between steps, so
+             the plain history is a perfect predictor; the perturbed one is not)
   e2e        the same metric through the host-buffer C-ABI call the R .Call shim makes every outer
-             iteration, ebpmf_vga_step_resident_host: factors and sigma2 in from pinned host memory,
-             step, D2H of M and v_sum (the step's input M is the previous step's output and stays on
-             the device, as in R/ebpmf_log.R:309), on a bounded row sample of the same workload
-             (PCIe-bound, independent of the row count).  Next to it: e2e_full_roundtrip
-             (ebpmf_vga_step_host, M in AND out) and e2e_batched (ebpmf_batched_vga_step_host, the
-             batch_size < n branch of R/ebpmf_log.R:254-300, batches pipelined)
-  delta_mode, scored_pipeline   the same step with the two options of DESIGN.md section 3b / 4 (never
-             the headline value)
-  roofline   HBM line for the dominant kernel (first pass); the FP64 pipe is the binding unit
-             (DESIGN.md §4), so an "fp64" object with the measured DFMA peak sits beside it
+             iteration, ebpmf_vga_step_resident_host, with PLAIN PAGEABLE host arrays (what R hands
+             the shim) and a FRESHLY ALLOCATED result matrix per call (what Rf_allocMatrix gives):
+             factors and sigma2 in, step, M and v_sum out; the full slab at N = 1.  Next to it:
+             e2e_reused_buffer (result buffer kept between calls), e2e_full_roundtrip (M in AND out),
+             e2e_batched (the batch_size < n branch), and m_products (N1: what flashier needs from M
+             computed on the device, so that M need not leave it at all)
+  roofline   HBM line of the dominant kernel (first pass).  The FP64 pipe / issue port binds it
+             (DESIGN.md section 4), so `fp64` (measured DFMA peak) and `issue_roofline` sit beside it; the
+             instruction counts and DRAM traffic come from the committed ncu capture
+             profiles/r02_ncu_metrics.json (written by scripts/ncu_summary.py), the times are live
   cpu_baseline  the oracle's C transcription of the R code (OpenMP, all host cores) on a bounded
              row sample -- a restatement of the R code, NOT the R code (R is not installed)
 
-`--impl reference` times that CPU restatement alone (the reference cannot run here).
+`--workload c5` times the solver VARIANTS of BASELINE config 5 (dense drop-in signature, _fixed_iter,
+_low_memory) on a row slab of 200k x 20k.  `--impl reference` times the CPU restatement alone.
 """
 from __future__ import annotations
 
@@ -67,10 +72,16 @@ WORKLOADS = {
                label="BASELINE config 3: 100000 x 20000, K=10 (+2 offset cols)"),
     "c2": dict(n=10000, p=2000, K=5, log_offset=-3.4256, density_target=0.10,
                label="BASELINE config 2: 10000 x 2000, K=5 (+2 offset cols)"),
+    # config 5 (200k x 20k, K=10): the dense signatures need 4-6 n x p operands on the host AND the device
+    # (6 x 32 GB at full size), so the variants run on a row slab of it
+    "c5": dict(n=50000, p=20000, K=10, log_offset=-4.6440, density_target=0.05,
+               label="BASELINE config 5 row slab: 50000 x 20000 of 200000 x 20000, K=10 (+2 offset cols); solver variants"),
 }
 MAXITER_VGA, VGA_TOL = 10, 1e-5
+C5_MAXITER, C5_TOL = 10, 1e-5
 DELTA = 1e-14
 SEED = 12345
+NCU_METRICS = os.path.join(ROOT, "profiles", "r02_ncu_metrics.json")
 
 
 def read_peaks():
@@ -79,6 +90,24 @@ def read_peaks():
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def read_ncu_metrics():
+    """Counters of the committed ncu capture of the first-pass kernel (scripts/ncu_summary.py --json)."""
+    try:
+        return json.load(open(NCU_METRICS))
+    except Exception:
+        return None
+
+
+def mem_available_bytes():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    return 64 << 30
 
 
 class ClockSampler:
@@ -156,24 +185,10 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def numa_local_cpus(device):
-    """CPUs of the NUMA node the GPU hangs off (sysfs), or None.  Pinned host buffers are placed by first
-    touch, so allocating them from a NUMA-local CPU keeps each rank's PCIe traffic on its own socket."""
-    try:
-        import torch
-        pr = torch.cuda.get_device_properties(device)
-        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
-        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
-        return (node, cpus) if cpus else None
-    except Exception:
-        return None
+def pageable_f(rows, cols):
+    """A fresh rows x cols column-major float64 matrix in plain pageable memory (np.empty -> malloc -> mmap),
+    untouched: what Rf_allocMatrix hands the .Call shim."""
+    return np.empty((cols, rows), dtype=np.float64).T
 
 
 def cpu_sample_inputs(ctx, rows):
@@ -183,7 +198,8 @@ def cpu_sample_inputs(ctx, rows):
     cp, ri, x = ctx.get_y_csc()
     Y = sp.csc_matrix((x, ri, cp), shape=(n, p))[:rows].toarray(order="F")
     EL, EF = ctx.get_factors()
-    return dict(Y=Y, EL=np.asfortranarray(EL[:rows]), EF=EF, sigma2=ctx.get_sigma2(), M0=ctx.get_rows(0, rows))
+    return dict(Y=Y, EL=np.asfortranarray(EL[:rows]), EF=EF, sigma2=ctx.get_sigma2(), M0=ctx.get_rows(0, rows),
+                csc=(cp, ri, x))
 
 
 def cpu_baseline(sample, reps=2):
@@ -210,6 +226,30 @@ def cpu_baseline(sample, reps=2):
                        "C transcription of the R code, OpenMP; R itself is not installed" % (rows, p, out["n_updates"]),
                 rstyle_1thread_entries_per_s=r2 * p / t_r,
                 rstyle_sample="rows [0,%d), operator-by-operator with temporaries, 1 thread (a1 only)" % r2), out
+
+
+def oracle_forced(M0, Y, EL, EF, sigma2, u, converged, want_trace=False):
+    """The oracle's result for a block of entries when the GLOBAL update count is u (decided by entries outside
+    the block): exactly u updates (C transcription with tol = 0), then what R/vga_solver_mat.R:35-36 returns --
+    V from the temp of the final M when the loop broke, from the temp before the last update when it did not.
+    want_trace: also max|f| over the block at the iterates 0..u (what R's stop test looked at)."""
+    from oracle import c_oracle
+    Beta = np.asfortranarray(EL @ EF.T)
+    S2 = np.asfortranarray(np.repeat(np.asarray(sigma2)[None, :], M0.shape[0], axis=0))
+    trace = []
+    if u > 0:
+        r = c_oracle.vga_newton(M0, Y, 1.0, Beta, S2, u, 0.0)
+        M, Vstale = r["M"], r["V"]
+        trace = list(r["maxabs_f"][:u])
+    else:
+        M, Vstale = np.minimum(M0, S2 * Y + Beta), None
+    temp = S2 * Y + Beta + 1 - M
+    V = S2 / temp if (converged or Vstale is None) else Vstale
+    if want_trace:
+        f = Y - np.exp(M + (S2 / 2) / temp) - M * (1 / S2) + Beta / S2           # R/vga_solver_mat.R:22-25 at the final M
+        trace.append(float(np.max(np.abs(f))))
+        return M, V, np.asarray(trace)
+    return M, V
 
 
 def run_reference(args, wl, rank, world):
@@ -245,6 +285,114 @@ def run_reference(args, wl, rank, world):
     }))
 
 
+def step_summary(infos, ctx, n, p):
+    k = len(infos)
+    c = ctx.counters()
+    units = ((n + 31) // 32) * ((p + 1) // 2)
+    return {"ms_per_step": sum(i.kernel_ms for i in infos) / k, "n_updates": infos[-1].n_updates, "passes": infos[-1].passes,
+            "pass_ms": {"first": sum(i.pass1_ms for i in infos) / k, "topup": sum(i.pass2_ms for i in infos) / k,
+                        "reduce": sum(i.reduce_ms for i in infos) / k},
+            "topup_units_frac": c["topup_units"] / units, "evaluations_per_unit": c["unit_evals"] / units}
+
+
+# ------------------------------------------------------------------------------------------------
+# --workload c5: the solver variants (K2 dense drop-in, K3 _fixed_iter, K4 _low_memory)
+# ------------------------------------------------------------------------------------------------
+def run_variants(args, wl, pkg, torch, local_rank):
+    import scipy.sparse as sp
+    from oracle import c_oracle
+    n, p, K = wl["n"], wl["p"], wl["K"]
+    ctx = pkg.VgaContext(local_rank)
+    nnz = ctx.sim_data_log(n, p, K, row0=0, seed=SEED, log_offset=wl["log_offset"], warm_start=False)
+    peak, peak_src = read_peaks()
+    cp, ri, x = ctx.get_y_csc()
+    Ysp = sp.csc_matrix((x, ri, cp), shape=(n, p))
+    EL, EF = ctx.get_factors()
+    s2 = ctx.get_sigma2()
+    M0 = ctx.get_m()
+    srows = min(args.cpu_rows, n)
+    Ys = Ysp[:srows].toarray(order="F")
+    out = {"metric": "VGA Newton entries/sec (fp64, N x p)", "unit": "entries/s", "n_gpus": 1, "steps": args.steps,
+           "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic",
+           "config": {"workload": wl["label"], "rows": n, "cols": p, "K_tot": K + 2, "density": nnz / (n * p),
+                      "maxiter": C5_MAXITER, "tol": C5_TOL,
+                      "note": "maxiter / tol as ebpmf_log calls the solver (R/ebpmf_log_controls.R:33-36); with the signature "
+                              "defaults (1000, 1e-8) a handful of extreme counts (> 1e7) whose rounding floor of f is above "
+                              "1e-8 keep the GLOBAL stop test from ever passing and the solve runs all 1000 updates -- see "
+                              "`signature_defaults`"}}
+    variants = {}
+
+    def rel(a, b):
+        return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0)))
+
+    # --- K4: vga_pois_solver_mat_newton_low_memory (sparse Y, l0/f0 scales, F8 derivative) -------------
+    rng = np.random.default_rng(5)
+    l0 = np.exp(rng.normal(0, 0.1, n)); f0 = np.exp(rng.normal(0, 0.1, p))
+    infos = []
+    for it in range(1 + args.steps):
+        info = {}
+        Mo = pkg.vga_pois_solver_mat_newton_low_memory(M0, Ysp, l0, f0, EL, EF, s2, "by_col", C5_MAXITER, C5_TOL, ctx=ctx, info=info)
+        if it > 0:
+            infos.append(info)
+    ms = sum(i["kernel_ms"] for i in infos) / len(infos)
+    ref = c_oracle.vga_low_memory(M0[:srows], Ys, l0[:srows], f0, EL[:srows], EF, s2, "by_col", infos[-1]["n_updates"], 0.0)
+    alg = (16.0 + 12.0 * nnz / (n * p)) * n * p
+    variants["low_memory"] = {"value": n * p / (ms * 1e-3), "ms_per_step": ms, "n_updates": infos[-1]["n_updates"],
+                              "algorithmic_bytes_per_entry": alg / (n * p), "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak,
+                              "parity_max_rel_err_M_rows": rel(Mo[:srows], ref["M"]),
+                              "parity_how": "C oracle on rows [0,%d) with the global update count forced" % srows}
+    info = {}
+    pkg.vga_pois_solver_mat_newton_low_memory(M0, Ysp, l0, f0, EL, EF, s2, "by_col", 1000, 1e-8, ctx=ctx, info=info)
+    variants["low_memory"]["signature_defaults"] = {"maxiter": 1000, "tol": 1e-8, "n_updates": info["n_updates"],
+                                                    "converged": info["converged"], "ms_per_step": info["kernel_ms"],
+                                                    "max_count_in_Y": float(x.max())}
+    del Mo
+    # --- K2: vga_pois_solver_mat_newton, dense operands (M, X, Beta, Sigma2 in; M, V out = 48 B/entry) -----
+    Beta = np.asfortranarray(EL @ EF.T)
+    S2 = np.asfortranarray(np.repeat(s2[None, :], n, axis=0))
+    Yd = Ysp.toarray(order="F")
+    infos = []
+    for it in range(1 + args.steps):
+        info = {}
+        r = pkg.vga_pois_solver_mat_newton(M0, Yd, 1.0, Beta, S2, C5_MAXITER, C5_TOL, return_V=True, info=info, ctx=ctx)
+        if it > 0:
+            infos.append(info)
+    ms = sum(i["kernel_ms"] for i in infos) / len(infos)
+    u = infos[-1]["n_updates"]
+    ref = c_oracle.vga_newton(M0[:srows], Ys, 1.0, Beta[:srows], S2[:srows], u, 0.0)
+    Vref = S2[:srows] / (S2[:srows] * Ys + Beta[:srows] + 1 - ref["M"]) if infos[-1]["converged"] else ref["V"]
+    variants["dense_signature"] = {"value": n * p / (ms * 1e-3), "ms_per_step": ms, "n_updates": u,
+                                   "algorithmic_bytes_per_entry": 48.0, "hbm_frac": 48.0 * n * p / (ms * 1e-3) / 1e9 / peak,
+                                   "parity_max_rel_err_M_rows": rel(r["M"][:srows], ref["M"]),
+                                   "parity_max_rel_err_V_rows": rel(r["V"][:srows], Vref),
+                                   "parity_how": "C oracle on rows [0,%d) with the global update count forced" % srows}
+    # --- K3: vga_pois_solver_mat_newton_fixed_iter (maxiter = 1: the only call site, inst/code/Poisson_MF_splitting.R:212) ----
+    fi = {}
+    for mi in (1, 10):
+        ts = []
+        for it in range(1 + min(args.steps, 3)):
+            r = pkg.vga_pois_solver_mat_newton_fixed_iter(M0, None, Yd, 1.0, Beta, S2, mi, ctx=ctx)
+            if it > 0:
+                ts.append(ctx.counters()["last_kernel_ms"])
+        ms = sum(ts) / len(ts)
+        ref = c_oracle.vga_fixed_iter(M0[:srows], None, Ys, 1.0, Beta[:srows], S2[:srows], mi)
+        fi["maxiter_%d" % mi] = {"value": n * p / (ms * 1e-3), "ms_per_step": ms, "algorithmic_bytes_per_entry": 48.0,
+                                 "hbm_frac": 48.0 * n * p / (ms * 1e-3) / 1e9 / peak,
+                                 "parity_max_rel_err_M_rows": rel(r["M"][:srows], ref["M"]),
+                                 "parity_max_rel_err_V_rows": rel(r["V"][:srows], ref["V"])}
+    variants["fixed_iter"] = fi
+    out["variants"] = variants
+    out["value"] = variants["dense_signature"]["value"]
+    out["ms_per_step"] = variants["dense_signature"]["ms_per_step"]
+    out["roofline"] = {"bound": "hbm", "kernel": "vga_dense_kernel<MODE_FIRST>", "achieved": 48.0 * n * p / (out["ms_per_step"] * 1e-3) / 1e9,
+                       "peak": peak, "unit": "GB/s", "frac": variants["dense_signature"]["hbm_frac"], "traffic": None,
+                       "peak_source": peak_src, "note": "whole solve (both passes) against 48 B/entry"}
+    out["gpu_launches"] = int(ctx.counters()["launches"])
+    emit(json.dumps(out))
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -252,10 +400,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4slab", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-rows", type=int, default=2048, help="rows of the bounded CPU-baseline sample")
-    ap.add_argument("--e2e-rows", type=int, default=16384, help="rows of the bounded host-buffer (e2e) sample")
+    ap.add_argument("--cpu-rows", type=int, default=2048, help="rows of the bounded CPU-baseline / parity sample")
+    ap.add_argument("--e2e-rows", type=int, default=0, help="rows of the host-buffer (e2e) run; 0 = the whole slab if host memory allows")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--full-parity", action="store_true", help="check M, V and the three ELBO sums of the WHOLE slab against the oracle (minutes)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -272,6 +421,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    if args.workload == "c5":
+        if rank == 0:
+            run_variants(args, wl, pkg, torch, local_rank)
+        return
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -289,23 +442,34 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    ctx = pkg.VgaContext(local_rank)
-    if world > 1:   # the library's own NCCL communicator; torch.distributed only ships the id
-        uid = [pkg.VgaContext.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(rank, world, uid[0])
+    def allmin(x):
+        return -allmax(-x)
 
+    def new_comm_ctx():
+        c = pkg.VgaContext(local_rank)
+        if world > 1:   # the library's own NCCL communicator; torch.distributed only ships the id
+            uid = [pkg.VgaContext.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            c.comm_init(rank, world, uid[0])
+        return c
+
+    ctx = new_comm_ctx()
     n, p, K = wl["n"], wl["p"], wl["K"]
     nnz = ctx.sim_data_log(n, p, K, row0=rank * n, seed=SEED, log_offset=wl["log_offset"], warm_start=False)
     density = nnz / (n * p)
     fp64_tf = max(ctx.probe_fp64_tflops() for _ in range(3))
+    entries = n * p * world
 
     # ---- resident-state steps -----------------------------------------------------------------
-    infos = []
-    for _ in range(args.warmup):
+    first = ctx.vga_step(MAXITER_VGA, VGA_TOL)          # no history yet: natural tile order
+    ctx.rewind_m()
+    first_step = step_summary([first], ctx, n, p)
+    for _ in range(max(0, args.warmup - 1)):
         ctx.vga_step(MAXITER_VGA, VGA_TOL)
         ctx.rewind_m()
     barrier()
+    infos = []
+    launches0 = ctx.counters()["launches"]
     with ClockSampler(local_rank) as clk:
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -313,17 +477,31 @@ def main():
             ctx.rewind_m()
         barrier()
         wall = time.perf_counter() - t0
-    dev_ms = sum(i.kernel_ms for i in infos)
-    dev_ms = allmax(dev_ms)
+    launches = int(ctx.counters()["launches"] - launches0)
+    steady = step_summary(infos, ctx, n, p)
+    dev_ms = allmax(sum(i.kernel_ms for i in infos))
     wall = allmax(wall)
     ms_per_step = dev_ms / args.steps
-    entries = n * p * world
     value = entries / (ms_per_step * 1e-3)
     u = infos[-1].n_updates
-    diag = ctx.last_diag()
-    p1 = sum(i.pass1_ms for i in infos) / args.steps
-    p2 = sum(i.pass2_ms for i in infos) / args.steps
-    rd = sum(i.reduce_ms for i in infos) / args.steps
+    p1 = steady["pass_ms"]["first"]
+
+    # ---- a step whose tile order comes from a DIFFERENT problem: factors perturbed after the history was taken -----
+    EL0, EF0 = ctx.get_factors()
+    rng = np.random.default_rng(1 + rank)
+    ELp, EFp = EL0.copy(), EF0.copy()
+    ELp[:, 2:] += 0.05 * rng.normal(size=ELp[:, 2:].shape)
+    EFp[:, 2:] += 0.05 * np.random.default_rng(1).normal(size=EFp[:, 2:].shape)      # EF is replicated: same on every rank
+    ctx.set_factors(ELp, EFp)
+    pinfo = ctx.vga_step(MAXITER_VGA, VGA_TOL)          # history = the unperturbed step's counts
+    ctx.rewind_m()
+    perturbed = step_summary([pinfo], ctx, n, p)
+    perturbed["ms_per_step"] = allmax(perturbed["ms_per_step"])
+    perturbed["value"] = entries / (perturbed["ms_per_step"] * 1e-3)
+    perturbed["note"] = "factor columns 3.. perturbed by N(0, 0.05^2) AFTER the per-tile history was recorded"
+    ctx.set_factors(EL0, EF0)
+    ctx.vga_step(MAXITER_VGA, VGA_TOL); ctx.rewind_m()  # restore the matching history
+    del ELp, EFp
 
     # ---- the same step in delta mode (option, not the default) ----------------
     ctx.set_option("delta", DELTA)
@@ -338,66 +516,59 @@ def main():
     d_ms = allmax(sum(i.kernel_ms for i in dinfos)) / args.steps
     delta_mode = {"delta": DELTA, "value": entries / (d_ms * 1e-3), "unit": "entries/s", "ms_per_step": d_ms,
                   "n_updates": dinfos[-1].n_updates,
-                  "pass_ms": {"first": sum(i.pass1_ms for i in dinfos) / args.steps,
-                              "topup": sum(i.pass2_ms for i in dinfos) / args.steps},
                   "note": "units whose next Newton update is <= delta (and |f| < tol/16) are frozen; M, V within "
                           "~delta of the exact-count result, n_updates identical; NOT the headline value"}
+    ctx.vga_step(MAXITER_VGA, VGA_TOL); ctx.rewind_m()
 
-    # ---- the same step with the scored pipeline (option, not the default) --------
-    # exact mode, bit-identical results: an FP32 tensor-core scoring pass orders the tiles of pass 1
-    ctx.set_option("pipeline", 3)
-    sinfos = []
-    for it in range(1 + args.steps):
-        inf = ctx.vga_step(MAXITER_VGA, VGA_TOL)
-        ctx.rewind_m()
-        if it > 0:
-            sinfos.append(inf)
+    # ---- N1: what flashier needs from M, computed on the device (M never leaves it) -------------------
+    peak, peak_src = read_peaks()
+    mp = None
+    for _ in range(2):
+        mp = ctx.m_products(EL0, EF0)
     barrier()
-    ctx.set_option("pipeline", 0)
-    s_ms = allmax(sum(i.kernel_ms for i in sinfos)) / args.steps
-    scored_mode = {"value": entries / (s_ms * 1e-3), "unit": "entries/s", "ms_per_step": s_ms,
-                   "n_updates": sinfos[-1].n_updates,
-                   "pass_ms": {"score_and_first": sum(i.pass1_ms for i in sinfos) / args.steps,
-                               "topup": sum(i.pass2_ms for i in sinfos) / args.steps},
-                   "note": "pipeline = 3: tiles of pass 1 taken by decreasing predicted hardness (tf32 scoring pass); "
-                           "same results bit for bit, exact update count; NOT the headline value"}
+    mp_ms = allmax(mp["kernel_ms"])
+    m_products = {"ms": mp_ms, "m_ef_ms": mp["m_ef_ms"], "mt_el_ms": mp["mt_el_ms"], "K": K + 2,
+                  "value": entries / (mp_ms * 1e-3), "unit": "entries/s",
+                  "algorithmic_bytes_per_entry": 8.0,
+                  "hbm_frac_of_8B_per_entry": 8.0 * n * p / (mp_ms * 1e-3) / 1e9 / peak,
+                  "hbm_frac_per_kernel": {"m_ef": 8.0 * n * p / (mp["m_ef_ms"] * 1e-3) / 1e9 / peak,
+                                          "mt_el": 8.0 * n * p / (mp["mt_el_ms"] * 1e-3) / 1e9 / peak},
+                  "d2h_bytes": int(8 * (n + p) * (K + 2) + 8 * (n + p)),
+                  "what": "ebpmf_ctx_m_products: M %*% EF, t(M) %*% EL, column/row sums of (M - EL EF')^2 (flashier's R2) from the "
+                          "resident M (R/ebpmf_log_flash_update.R:35,55-64); two streaming kernels, each reads M once"}
 
     # ---- roofline (HBM line of the dominant kernel = first pass) --------------------------------
-    peak, peak_src = read_peaks()
+    ncu = read_ncu_metrics() if args.workload == "c4slab" else None
     alg_bytes_per_entry = 16.0 + 12.0 * density            # read M 8 + write M 8 + CSC (x 8 + i 4) * density
     alg_bytes = alg_bytes_per_entry * n * p                 # per launch of the first-pass kernel (one slab)
     achieved = alg_bytes / (p1 * 1e-3) / 1e9
-    # DRAM bytes of that kernel from the committed ncu capture (profiles/r01_ncu_summary.md), this workload only
-    traffic = 95.81 if (args.workload == "c4slab" and os.environ.get("EBPMF_B200_PIPELINE", "fused") == "fused") else None
     roofline = {"bound": "hbm", "kernel": "vga_fused_kernel<MODE_FIRST>", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write)",
+                "unit": "GB/s", "frac": achieved / peak,
+                "traffic": (ncu["dram_gb_per_launch"] if ncu else None), "traffic_unit": "GB per launch (ncu dram read+write)",
+                "traffic_source": (os.path.relpath(NCU_METRICS, ROOT) if ncu else None),
                 "algorithmic_gb_per_launch": alg_bytes / 1e9, "peak_source": peak_src,
                 "algorithmic_bytes_per_entry": alg_bytes_per_entry,
-                "note": "the FP64 pipe, not HBM, binds this kernel for u > 0 (see fp64)"}
-    # FP64 line: FP64-pipe instructions per entry, counted in the SASS of the Newton loop:
-    # 18 per evaluation of f (u+1 of them, +1 for the 58 % of units redone in pass 2), 6.5 per update,
-    # K_tot FMAs for Beta, ~20 in the epilogue
-    dp_instr = 18.0 * (u + 1.6) + 6.5 * u + 1.0 * (K + 2) + 20.0
-    fp64 = {"dfma_tflops_measured": fp64_tf, "dp_instr_per_entry_model": dp_instr,
-            "line_entries_per_s": (fp64_tf * 1e12 / 2.0) / dp_instr,
-            "frac_of_fp64_line": (value / world) / ((fp64_tf * 1e12 / 2.0) / dp_instr)}
-
-    # Issue-port line (what binds pass 1): FP64 instructions hold a sub-partition's
-    # issue port for 2 cycles (3 with three distinct register sources), everything else 1 cycle.  The
-    # instruction counts per 32 entries come from the committed ncu capture of this workload
-    # (profiles/r01_ncu_summary.md); the cycles are measured live.
+                "step_level_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                "note": "the FP64 pipe / issue port, not HBM, binds this kernel for u > 0 (see fp64, issue_roofline)"}
+    # FP64 line: FP64-pipe warp-instructions per 32 entries from the ncu capture x the live launch time,
+    # against the DFMA rate measured live (ebpmf_probe_fp64_tflops: one DFMA warp-instruction = 64 flop)
+    fp64 = {"dfma_tflops_measured": fp64_tf}
     issue = None
-    if args.workload == "c4slab" and os.environ.get("EBPMF_B200_PIPELINE", "fused") == "fused":
-        clk_mhz = 1965.0
+    if ncu:
+        dfma_per_s = fp64_tf * 1e12 / 64.0                  # warp-level DFMA instructions per second, whole chip
+        fp64_inst = ncu["fp64_inst_per_32_entries"] * (n * p / 32.0)
+        fp64.update({"fp64_inst_per_32_entries": ncu["fp64_inst_per_32_entries"],
+                     "frac_of_fp64_line": fp64_inst / (p1 * 1e-3) / dfma_per_s,
+                     "line_entries_per_s": dfma_per_s * 32.0 / ncu["fp64_inst_per_32_entries"],
+                     "source": os.path.relpath(NCU_METRICS, ROOT), "kernel": ncu.get("kernel"), "git": ncu.get("git")})
+        # issue-port line: an FP64 instruction holds a sub-partition's issue port for 2 cycles
+        clk_mhz = clk.summary().get("sm_mhz") or 1965.0
         cycles_per_32 = p1 * 1e-3 * clk_mhz * 1e6 * 148 * 4 / (n * p / 32.0)
-        slots = 651.5 + 263.1
+        slots = ncu["inst_per_32_entries"] + ncu["fp64_inst_per_32_entries"]
         issue = {"bound": "issue port (FP64 = 2 slots)", "slots_per_32_entries": slots,
-                 "inst_per_32_entries": 651.5, "fp64_inst_per_32_entries": 263.1,
-                 "three_register_dfma_per_32_entries": 59.4,
-                 "three_register_note": "not added to slots: with them the model (974) exceeds the measured cycles, "
-                                        "so their third cycle is at least partly hidden behind other warps",
-                 "cycles_per_32_entries_measured": cycles_per_32, "frac": slots / cycles_per_32,
-                 "sm_mhz_assumed": clk_mhz, "source": "profiles/r01_ncu_summary.md + scripts/probes"}
+                 "inst_per_32_entries": ncu["inst_per_32_entries"], "fp64_inst_per_32_entries": ncu["fp64_inst_per_32_entries"],
+                 "cycles_per_32_entries_measured": cycles_per_32, "frac": slots / cycles_per_32, "sm_mhz": clk_mhz,
+                 "note": "the builder's own model, not a hardware roofline"}
 
     out = {
         "metric": "VGA Newton entries/sec (fp64, N x p)", "value": value, "unit": "entries/s",
@@ -406,123 +577,235 @@ def main():
         "config": {"workload": wl["label"], "rows_per_gpu": n, "cols": p, "K_tot": K + 2, "density": density,
                    "nnz_per_gpu": nnz, "maxiter_vga": MAXITER_VGA, "vga_tol": VGA_TOL, "var_type": "by_col",
                    "start": "M0 = log(Y + 0.5)", "l2": "inputs (%.1f GB per GPU) are larger than L2; no flush"
-                   % (16.0 * n * p / 1e9), "parallelism": "row-sharded x%d, NCCL MAX(u) + SUM(v_sum[p]+3)" % world},
+                   % (16.0 * n * p / 1e9), "parallelism": "row-sharded x%d, NCCL MAX(u) + SUM(v_sum[p]+3)" % world,
+                   "tile_order": "previous step's per-tile update counts (kept by the library across steps)"},
         "n_updates": u, "converged": bool(infos[-1].converged), "passes": infos[-1].passes,
-        "pass_ms": {"first": p1, "topup": p2, "reduce": rd}, "wall_ms_per_step": 1e3 * wall / args.steps,
-        "topup_units_frac": diag["topup_units"] / max(1.0, ((n + 31) // 32) * ((p + 1) // 2)),
+        "pass_ms": steady["pass_ms"], "wall_ms_per_step": 1e3 * wall / args.steps,
+        "topup_units_frac": steady["topup_units_frac"], "evaluations_per_unit": steady["evaluations_per_unit"],
+        "first_step": first_step, "perturbed_history": perturbed,
         "peer_kstar_sharing": {"peers_mapped": ctx.peer_count() if world > 1 else 0,
                                "how": "pass-1 kernels read the other GPUs' published update count over NVLink peer memory"},
-        "roofline": roofline, "fp64": fp64, "issue_roofline": issue, "delta_mode": delta_mode, "scored_pipeline": scored_mode,
-        "gpu_launches": 6 * args.steps, "clocks": clk.summary(),
+        "roofline": roofline, "fp64": fp64, "issue_roofline": issue, "delta_mode": delta_mode, "m_products": m_products,
+        "gpu_launches": launches, "gpu_launches_how": "kernel launches counted by the library inside the timed region",
+        "clocks": clk.summary(),
     }
 
-    # ---- parity gate + CPU baseline on a bounded row sample (rank 0) -----------------------------
-    if rank == 0 and not args.no_cpu:
-        sample = cpu_sample_inputs(ctx, args.cpu_rows)
-        cb, ref = cpu_baseline(sample)
-        out["cpu_baseline"] = cb
-        # parity: the oracle on the sample with the GLOBAL update count forced (tol = 0 => exactly u updates)
-        from oracle import vga_numpy
-        Beta = sample["EL"] @ sample["EF"].T
-        S2 = np.repeat(sample["sigma2"][None, :], args.cpu_rows, axis=0)
-        if u > 0:
-            Mref = vga_numpy.vga_pois_solver_mat_newton(sample["M0"], sample["Y"], 1, Beta, S2, u, 0.0)["M"]
-        else:
-            Mref = np.minimum(sample["M0"], S2 * sample["Y"] + Beta)
-        ctx.vga_step(MAXITER_VGA, VGA_TOL)
-        Mgpu = ctx.get_rows(0, args.cpu_rows)
-        ctx.rewind_m()
-        err = float(np.max(np.abs(Mgpu - Mref) / np.maximum(np.abs(Mref), 1.0)))
-        out["parity"] = {"max_rel_err_M_sample": err, "tol": 1e-8, "ok": bool(err < 1e-8),
-                         "how": "oracle on rows [0,%d) with the global u forced" % args.cpu_rows}
-    elif not args.no_cpu and dist is not None:
-        ctx.vga_step(MAXITER_VGA, VGA_TOL)      # keep the collectives of rank 0's extra step matched
-        ctx.rewind_m()
-
-    # ---- e2e: host buffers through ebpmf_vga_step_host --------------------------------------------
+    # ---- e2e: PAGEABLE host buffers through the host-buffer C ABI -----------------------------------------
     if not args.no_e2e:
-        er = min(args.e2e_rows, n)
-        EL, EF = ctx.get_factors()
+        budget = int(0.40 * allmin(float(mem_available_bytes())) / max(1, min(world, 8)))
+        er = args.e2e_rows if args.e2e_rows > 0 else n
+        if 2 * 8 * er * p > budget:                      # result + M0 copies on the host
+            er = max(2048, (budget // (2 * 8 * p)) // 256 * 256)
+        er = min(er, n)
         s2 = ctx.get_sigma2()
-        cp, ri, x = ctx.get_y_csc()
-        scp, sri, sx = pkg.shard_csc(cp, ri, x, 0, er)
-        # pinned buffers are allocated (and first touched) from a CPU of the GPU's own NUMA node
-        all_cpus = os.sched_getaffinity(0)
-        numa = numa_local_cpus(local_rank)
-        if numa:
-            os.sched_setaffinity(0, numa[1])
-        M0 = torch.empty((p, er), dtype=torch.float64).pin_memory().numpy().T       # pinned, column-major er x p
-        M0[...] = ctx.get_rows(0, er)
-        Mo = torch.empty((p, er), dtype=torch.float64).pin_memory().numpy().T       # pinned result buffer
-        Mo[...] = 0.0
-        if numa:
-            os.sched_setaffinity(0, all_cpus)
-        ELs = np.asfortranarray(EL[:er])
-        ectx = pkg.VgaContext(local_rank)
-        ectx.set_y_csc(er, p, scp, sri, sx)
-        # (a) the drop-in signature: M in, M out, every step
-        for _ in range(2):
-            r = ectx.vga_step_host(M0, ELs, EF, s2, "by_col", MAXITER_VGA, VGA_TOL, M_out=Mo)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            r = ectx.vga_step_host(M0, ELs, EF, s2, "by_col", MAXITER_VGA, VGA_TOL, M_out=Mo)
-        torch.cuda.synchronize()
-        full_wall = allmax(time.perf_counter() - t0)
-        # (b) ebpmf_log's loop: M is the previous step's output and stays resident (R/ebpmf_log.R:309);
-        #     per step the factors and sigma2 go in from pinned host memory, M and v_sum come out
-        ELp = torch.empty((K + 2, er), dtype=torch.float64).pin_memory().numpy().T; ELp[...] = ELs
-        EFp = torch.empty((K + 2, p), dtype=torch.float64).pin_memory().numpy().T; EFp[...] = EF
-        ectx.set_m(M0)
-        for _ in range(2):
-            r = ectx.vga_step_resident_host(ELp, EFp, s2, "by_col", MAXITER_VGA, VGA_TOL, M_out=Mo)
-            ectx.rewind_m()                          # pointer swap: every timed step starts from the same M
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            r = ectx.vga_step_resident_host(ELp, EFp, s2, "by_col", MAXITER_VGA, VGA_TOL, M_out=Mo)
-            ectx.rewind_m()
-        torch.cuda.synchronize()
-        e_wall = allmax(time.perf_counter() - t0)
-        out["e2e"] = {"value": er * p * world / (e_wall / args.steps), "unit": "entries/s",
+        if er == n:
+            ectx, ELs = ctx, EL0
+        else:                                           # bounded row sample in its own context (no communicator)
+            cp, ri, x = ctx.get_y_csc()
+            scp, sri, sx = pkg.shard_csc(cp, ri, x, 0, er)
+            ELs = np.asfortranarray(EL0[:er])
+            ectx = pkg.VgaContext(local_rank)
+            ectx.set_y_csc(er, p, scp, sri, sx)
+            ectx.set_m(ctx.get_rows(0, er))
+            del cp, ri, x
+        # (b) ebpmf_log's loop: M is the previous step's output and stays resident (R/ebpmf_log.R:309); per step the
+        #     factors and sigma2 go in (pageable NumPy arrays), M and v_sum come out.  The result matrix is a NEW
+        #     matrix every call, allocated the way the .Call glue allocates it (allocVector3 with the library's
+        #     allocator = ebpmf_host_alloc: a block of the warm host pool); the previous result stays alive during
+        #     the call (fit_flash holds it) and goes back to the pool afterwards, as under R's garbage collector.
+        def timed_resident(alloc, warm, steps):
+            prev = None
+            for it in range(warm + steps):
+                if it == warm:
+                    barrier()
+                    t0 = time.perf_counter()
+                cur = alloc(er, p)
+                r = ectx.vga_step_resident_host(ELs, EF0, s2, "by_col", MAXITER_VGA, VGA_TOL, M_out=cur)
+                ectx.rewind_m()
+                prev = cur
+                del cur
+            torch.cuda.synchronize()
+            w = allmax(time.perf_counter() - t0)
+            del prev
+            return w / steps, r["n_updates"]
+
+        ks = max(1, min(args.steps, 3))
+        per, nu = timed_resident(pkg.host_matrix, 3, ks)
+        cnt = ectx.counters()
+        out["e2e"] = {"value": er * p * world / per, "unit": "entries/s",
                       "h2d_bytes_per_step": int(8 * (er + p) * (K + 2) + 8 * p),
                       "d2h_bytes_per_step": int(8 * er * p + 8 * p + 64),
-                      "call": "ebpmf_vga_step_resident_host: the per-iteration call of ebpmf_log's outer loop -- factors "
-                              "and sigma2 in from pinned host memory, M and v_sum out; the step's input M is the "
-                              "previous step's output and is already on the device (R feeds res$M back unchanged, "
-                              "R/ebpmf_log.R:309, R/ebpmf_log_flash_update.R:35)",
-                      "sample": "rows [0,%d) x %d cols per GPU per step (bounded: the full slab is 30 GB); PCIe-bound"
-                                % (er, p), "n_updates": r["n_updates"], "ms_per_step": 1e3 * e_wall / args.steps,
-                      "pinned_buffers_numa_node": (numa[0] if numa else None)}
-        out["e2e_full_roundtrip"] = {"value": er * p * world / (full_wall / args.steps), "unit": "entries/s",
-                                     "h2d_bytes_per_step": int(8 * er * p + 8 * (er + p) * (K + 2) + 8 * p),
-                                     "d2h_bytes_per_step": int(8 * er * p + 8 * p + 64),
-                                     "call": "ebpmf_vga_step_host: M in AND out every step (the stand-alone drop-in signature)",
-                                     "ms_per_step": 1e3 * full_wall / args.steps}
-        ectx.close()
-        # (c) ebpmf_log's batched branch (general_control$batch_size < n, R/ebpmf_log.R:254-300): one solve per row
-        #     batch with the stop test scoped to the batch, M in and out from pinned host memory, the batches
-        #     pipelined through 3 worker contexts so H2D, solve and D2H of different batches overlap
-        import scipy.sparse as sp
-        bs = max(256, er // 8)
-        bh = pkg.VgaBatched(local_rank, 3)
-        bh.set_y(sp.csc_matrix((sx, sri, scp), shape=(er, p)), batch_size=bs)
-        for _ in range(2):
-            rb_ = bh.vga_step_host(M0, ELp, EFp, s2, "by_col", MAXITER_VGA, VGA_TOL, M_out=Mo)
+                      "call": "ebpmf_vga_step_resident_host: the per-iteration call of ebpmf_log's outer loop -- factors and "
+                              "sigma2 in from PAGEABLE host memory (plain NumPy arrays, as R's REAL() pointers are), M and "
+                              "v_sum out; every call gets a NEW result matrix, allocated as the .Call glue allocates it "
+                              "(allocVector3 + the library's allocator ebpmf_host_alloc: pageable blocks of a warm pool, "
+                              "returned by R's gc); the step's input M is the previous step's output and is already on "
+                              "the device (R feeds res$M back unchanged, R/ebpmf_log.R:309, R/ebpmf_log_flash_update.R:35)",
+                      "sample": "rows [0,%d) of %d x %d cols per GPU per step%s" % (er, n, p, "" if er == n else " (bounded by host memory)"),
+                      "steps": ks, "n_updates": nu, "ms_per_step": 1e3 * per,
+                      "d2h_gb_per_s_per_gpu": 8.0 * er * p / per / 1e9,
+                      "speculative_copy_bytes": cnt["spec_bytes"], "recopied_bytes": cnt["recopy_bytes"],
+                      "host_pool": pkg.host_pool_stats()}
+        pkg.host_pool_trim()
+        # (b') the same with a plain Rf_allocMatrix-style result: fresh, never-touched pageable pages every call
+        per, _ = timed_resident(pageable_f, 1, ks)
+        out["e2e_fresh_pages"] = {"value": er * p * world / per, "unit": "entries/s", "ms_per_step": 1e3 * per,
+                                  "d2h_gb_per_s_per_gpu": 8.0 * er * p / per / 1e9,
+                                  "call": "as e2e, but the result is a freshly mmap'ed matrix every call (np.empty = what "
+                                          "Rf_allocMatrix gives without the allocator): first-touch page faults included"}
+        # (b'') the pool with page-locked blocks (EBPMF_B200_POOL_PIN=1): the copy engine writes the result directly
+        os.environ["EBPMF_B200_POOL_PIN"] = "1"
+        t0 = time.perf_counter()
+        per, _ = timed_resident(pkg.host_matrix, 3, ks)
+        out["e2e_pool_pinned"] = {"value": er * p * world / per, "unit": "entries/s", "ms_per_step": 1e3 * per,
+                                  "d2h_gb_per_s_per_gpu": 8.0 * er * p / per / 1e9,
+                                  "one_time_setup_s": time.perf_counter() - t0 - per * ks,
+                                  "call": "as e2e with EBPMF_B200_POOL_PIN=1 (pool blocks are cudaHostRegister'ed once)"}
+        del os.environ["EBPMF_B200_POOL_PIN"]
+        pkg.host_pool_trim()
+        Mo = pageable_f(er, p)
+        # (a) the stand-alone drop-in signature: M in AND out every step (pageable both ways)
+        Mi = ectx.get_m()                               # the resident M is the bench's M0 (every step above was rewound)
+        kf = max(1, min(args.steps, 2))
+        ectx.vga_step_host(Mi, ELs, EF0, s2, "by_col", MAXITER_VGA, VGA_TOL, M_out=Mo)       # also touches Mo's pages
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            rb_ = bh.vga_step_host(M0, ELp, EFp, s2, "by_col", MAXITER_VGA, VGA_TOL, M_out=Mo)
+        for _ in range(kf):
+            ectx.vga_step_host(Mi, ELs, EF0, s2, "by_col", MAXITER_VGA, VGA_TOL, M_out=Mo)
+        torch.cuda.synchronize()
+        w = allmax(time.perf_counter() - t0)
+        out["e2e_full_roundtrip"] = {"value": er * p * world / (w / kf), "unit": "entries/s", "ms_per_step": 1e3 * w / kf,
+                                     "h2d_bytes_per_step": int(8 * er * p + 8 * (er + p) * (K + 2) + 8 * p),
+                                     "d2h_bytes_per_step": int(8 * er * p + 8 * p + 64),
+                                     "call": "ebpmf_vga_step_host: M in AND out every step, pageable (the stand-alone drop-in signature)"}
+        if er == n:
+            ctx.rewind_m()                              # leave ctx with the bench's M0 again
+        else:
+            ectx.close()
+        del Mi, Mo
+        # (c) ebpmf_log's batched branch (general_control$batch_size < n, R/ebpmf_log.R:254-300) on a bounded sample:
+        #     one solve per row batch, stop test scoped to the batch, M in and out (pageable), 3 pipelined worker contexts
+        import scipy.sparse as sp
+        br = min(16384, n)
+        cp, ri, x = ctx.get_y_csc()
+        scp, sri, sx = pkg.shard_csc(cp, ri, x, 0, br)
+        del cp, ri, x
+        Mb = ctx.get_rows(0, br)
+        Mbo = pageable_f(br, p)
+        bs = max(256, br // 8)
+        bh = pkg.VgaBatched(local_rank, 3)
+        bh.set_y(sp.csc_matrix((sx, sri, scp), shape=(br, p)), batch_size=bs)
+        ELb = np.asfortranarray(EL0[:br])
+        for _ in range(2):
+            rb_ = bh.vga_step_host(Mb, ELb, EF0, s2, "by_col", MAXITER_VGA, VGA_TOL, M_out=Mbo)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ks):
+            rb_ = bh.vga_step_host(Mb, ELb, EF0, s2, "by_col", MAXITER_VGA, VGA_TOL, M_out=Mbo)
         torch.cuda.synchronize()
         b_wall = allmax(time.perf_counter() - t0)
-        out["e2e_batched"] = {"value": er * p * world / (b_wall / args.steps), "unit": "entries/s",
-                              "h2d_bytes_per_step": int(8 * er * p + 8 * (er + p * (len(bh.batch_row0) - 1)) * (K + 2) + 8 * p),
-                              "d2h_bytes_per_step": int(8 * er * p + 8 * p * (len(bh.batch_row0) - 1) + 64),
+        out["e2e_batched"] = {"value": br * p * world / (b_wall / ks), "unit": "entries/s",
                               "call": "ebpmf_batched_vga_step_host: ebpmf_log's batched branch (batch_size = %d rows, %d "
-                                      "batches, per-batch stop as in R/ebpmf_log.R:259-268), M in AND out, 3 pipelined "
-                                      "worker contexts" % (bs, len(bh.batch_row0) - 1),
-                              "n_updates_per_batch": rb_["n_updates"], "ms_per_step": 1e3 * b_wall / args.steps}
+                                      "batches, per-batch stop as in R/ebpmf_log.R:259-268), M in AND out (pageable), 3 pipelined "
+                                      "worker contexts; %d-row sample" % (bs, len(bh.batch_row0) - 1, br),
+                              "n_updates_per_batch": rb_["n_updates"], "ms_per_step": 1e3 * b_wall / ks}
         bh.close()
+        del Mb, Mbo
+
+    # ---- parity gate at slab scale + CPU baseline (rank 0 checks; every rank runs the step: collectives) ----------
+    if not args.no_cpu:
+        pinfo = ctx.vga_step(MAXITER_VGA, VGA_TOL, want_v=True)
+        if rank == 0:
+            from oracle import c_oracle
+            import scipy.sparse as sp
+            rows = min(args.cpu_rows, n)
+            vs_gpu = ctx.get_v_sum()
+            cols = sorted(set(int(c) for c in (0, 1, p // 7, p // 2, p // 2 + 1, (3 * p) // 4, p - 2, p - 1)))
+            take = lambda which: np.column_stack([ctx.get_block(0, n, c, 1, which)[:, 0] for c in cols])
+            sample = cpu_sample_inputs(ctx, rows)
+            sample["M0"] = ctx.get_rows(0, rows, "M_in")     # the M the step started from (still on the device)
+            rel = lambda a, b: float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0)))
+            relv = lambda a, b: float(np.max(np.abs(a - b) / np.abs(b)))
+            uu, cv = pinfo.n_updates, bool(pinfo.converged)
+            Mref, Vref = oracle_forced(sample["M0"], sample["Y"], sample["EL"], sample["EF"], sample["sigma2"], uu, cv)
+            # whole columns: all rows of the slab for a handful of columns
+            cp, ri, x = sample["csc"]
+            Ysp = sp.csc_matrix((x, ri, cp), shape=(n, p))
+            Yc = np.asfortranarray(Ysp[:, cols].toarray())
+            Mcr, Vcr = oracle_forced(take("M_in"), Yc, EL0, EF0[cols], sample["sigma2"][cols], uu, cv)
+            errs = {"M_rows": rel(ctx.get_rows(0, rows, "M"), Mref), "V_rows": relv(ctx.get_rows(0, rows, "V"), Vref),
+                    "M_cols": rel(take("M"), Mcr), "V_cols": relv(take("V"), Vcr)}
+            if world == 1:                              # v_sum[j] = sum over ALL rows of V[, j]: exact for whole columns
+                errs["v_sum_cols"] = relv(vs_gpu[cols], Vcr.sum(axis=0))
+            par = {"max_rel_err": errs, "tol": 1e-8, "n_updates": uu,
+                   "how": "oracle (C transcription, global u forced) on rows [0,%d) x all columns and on all %d rows x columns %s: "
+                          "M, V%s" % (rows, n, cols, ", and v_sum of those columns" if world == 1 else "")}
+            if args.full_parity and world == 1:
+                Ycsr = Ysp.tocsr()
+                worst = {"M": 0.0, "V": 0.0}
+                sums = np.zeros(3)
+                vsum = np.zeros(p)
+                gtrace = np.zeros(uu + 1)
+                blk = 4096
+                for r0 in range(0, n, blk):
+                    nr = min(blk, n - r0)
+                    Y_b = np.asfortranarray(Ycsr[r0:r0 + nr].toarray())
+                    Mr, Vr, tr = oracle_forced(ctx.get_rows(r0, nr, "M_in"), Y_b, EL0[r0:r0 + nr], EF0, sample["sigma2"], uu, cv,
+                                               want_trace=True)
+                    gtrace = np.maximum(gtrace, tr)
+                    worst["M"] = max(worst["M"], rel(ctx.get_rows(r0, nr, "M"), Mr))
+                    worst["V"] = max(worst["V"], relv(ctx.get_rows(r0, nr, "V"), Vr))
+                    pr = c_oracle.partials(Y_b, Mr, Vr)
+                    sums += [pr["sym"], pr["ssexp"], pr["slogv"]]
+                    vsum += pr["col_v"]
+                gp = [pinfo.sym, pinfo.ssexp, pinfo.slogv]
+                # R's loop: test at iterate k (k = 0, 1, ...), break at the first max|f| < tol; u = that k, or maxiter
+                below = [k for k in range(min(uu, MAXITER_VGA - 1) + 1) if gtrace[k] < VGA_TOL]
+                u_oracle = below[0] if below else (MAXITER_VGA if uu == MAXITER_VGA else -1)    # -1: the oracle would run on
+                par["full_slab"] = {"max_rel_err_M": worst["M"], "max_rel_err_V": worst["V"],
+                                    "rel_err_sym_ssexp_slogv": [abs(a - b) / abs(b) for a, b in zip(gp, sums)],
+                                    "max_rel_err_v_sum": relv(vs_gpu, vsum),
+                                    "oracle_max_abs_f_by_iterate": [float(v) for v in gtrace],
+                                    "n_updates_oracle": int(u_oracle), "n_updates_gpu": int(uu),
+                                    "n_updates_equal": bool(u_oracle == uu),
+                                    "how": "every entry of the slab against the oracle in %d-row blocks; sums accumulated over the "
+                                           "blocks; the oracle's global max|f| per iterate gives R's update count" % blk}
+                errs["full_slab"] = max([worst["M"], worst["V"], par["full_slab"]["max_rel_err_v_sum"], 0.0 if u_oracle == uu else 1.0]
+                                        + par["full_slab"]["rel_err_sym_ssexp_slogv"])
+            ctx.rewind_m()
+            par["ok"] = bool(max(errs.values()) < 1e-8)
+            out["parity"] = par
+            cb, _ = cpu_baseline(sample)
+            out["cpu_baseline"] = cb
+        else:
+            ctx.rewind_m()
+
+        # ---- parity of the row-sharded path against the oracle on the WHOLE matrix (config 2) -------------
+        from oracle import simdata, c_oracle
+        import scipy.sparse as sp
+        n2, p2, K2 = 10000, 2000, 5
+        sim = simdata.sim_data_log(n2, p2, K=K2, seed=SEED, log_offset=WORKLOADS["c2"]["log_offset"])
+        st = simdata.solver_state(sim, start="cold")
+        row0, nrows = pkg.shard_rows(n2, world)[rank]
+        sl = slice(row0, row0 + nrows)
+        Yc = sp.csc_matrix(sim["Y"]); Yc.sort_indices()
+        cp, ri, x = pkg.shard_csc(Yc.indptr, Yc.indices, Yc.data, row0, nrows)
+        c2 = new_comm_ctx()
+        c2.set_y_csc(nrows, p2, cp, ri, x)
+        res = c2.vga_step_host(st["M0"][sl], st["EL"][sl], st["EF"], st["sigma2"], "by_col", MAXITER_VGA, VGA_TOL, return_V=True)
+        ref = c_oracle.vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], "by_col", MAXITER_VGA, VGA_TOL)
+        e = [float(np.max(np.abs(res["M"] - ref["M"][sl]) / np.maximum(np.abs(ref["M"][sl]), 1.0))),
+             float(np.max(np.abs(res["V"] - ref["V"][sl]) / np.abs(ref["V"][sl]))),
+             float(np.max(np.abs(res["v_sum"] - ref["v_sum"]) / np.abs(ref["v_sum"]))),
+             max(abs(res[k] - ref[k]) / abs(ref[k]) for k in ("sym", "ssexp", "slogv")),
+             0.0 if res["n_updates"] == ref["n_updates"] else 1.0]
+        e = [allmax(v) for v in e]
+        c2.close()
+        out["parity_multi"] = {"workload": "BASELINE config 2 (10000 x 2000, K=5) row-sharded over %d GPU(s), oracle on the whole matrix" % world,
+                               "max_rel_err_over_ranks": {"M_shard": e[0], "V_shard": e[1], "v_sum_allreduced": e[2], "sym_ssexp_slogv": e[3]},
+                               "n_updates": res["n_updates"], "n_updates_equal_on_every_rank": e[4] == 0.0, "tol": 1e-8,
+                               "ok": bool(max(e[:4]) < 1e-8 and e[4] == 0.0)}
+
     if rank == 0:
         emit(json.dumps(out))
     ctx.close()

@@ -37,6 +37,10 @@ _PI = C.POINTER(SolveInfo)
 # name -> (restype, argtypes): one row per declaration in include/ebpmf_b200.h
 SIGNATURES = {
     "ebpmf_version": (C.c_char_p, []),
+    "ebpmf_host_alloc": (_vp, [C.c_size_t]),
+    "ebpmf_host_free": (_int, [_vp]),
+    "ebpmf_host_pool_trim": (None, []),
+    "ebpmf_host_pool_stats": (None, [_vp]),
     "ebpmf_device_count": (_int, [C.POINTER(_int)]),
     "ebpmf_ctx_create": (_int, [_int, C.POINTER(_vp)]),
     "ebpmf_ctx_destroy": (_int, [_vp]),
@@ -64,7 +68,7 @@ SIGNATURES = {
     "ebpmf_ctx_get_block": (_int, [_vp, _int, _i64, _i64, _i64, _i64, _vp]),
     "ebpmf_ctx_update_sigma2": (_int, [_vp, _vp, _dbl, _dbl, _dbl, _i64, _i64, _vp]),
     "ebpmf_update_sigma2": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp, _dbl, _dbl, _dbl, _i64, _vp, _vp, _vp]),
-    "ebpmf_calc_obj": (_int, [_vp, _i64, _i64, _dbl, _dbl, _dbl, _i64, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl,
+    "ebpmf_calc_obj": (_int, [_vp, _i64, _i64, _dbl, _dbl, _dbl, _i64, _vp, _i64, _vp, _i64, _vp, _dbl, _dbl, _dbl, _dbl,
                               _dbl, C.POINTER(_dbl)]),
     "ebpmf_vga_step_host": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _int, _vp, _int, _dbl, _vp, _vp, _vp, _PI]),
     "ebpmf_vga_step_resident_host": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _int, _vp, _int, _dbl, _vp, _vp, _vp, _PI]),

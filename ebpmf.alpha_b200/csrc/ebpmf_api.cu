@@ -694,6 +694,47 @@ int matrix_out(ebpmf_ctx *ctx, double *dst, const void *src, long long rows, lon
     return pipe_wait(ctx, j);
 }
 
+// several packed n x p host matrices (NULL entries skipped) -> device, queued together so that the staging threads
+// and the copy engine stay busy across matrix boundaries; returns when all of them are on the device
+int matrices_in(ebpmf_ctx *ctx, void *const *dst, const double *const *src, int count, long long rows, long long cols) {
+    const size_t bytes = sizeof(double) * (size_t)rows * (size_t)cols;
+    if (bytes < kPipeMinBytes) {
+        for (int q = 0; q < count; ++q)
+            if (src[q]) CU(cudaMemcpyAsync(dst[q], src[q], bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        return EBPMF_OK;
+    }
+    CHECK(ensure_pipe(ctx));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::vector<HostPipe::JobRef> jobs;
+    for (int q = 0; q < count; ++q)
+        if (src[q]) jobs.push_back(ctx->pipe->h2d((double *)dst[q], src[q], (size_t)rows, (size_t)cols, (size_t)rows, ctx->ev_setup));
+    int rc = EBPMF_OK;
+    for (auto &j : jobs) { const int r = pipe_wait(ctx, j); if (rc == EBPMF_OK) rc = r; }
+    CHECK(rc);
+    CU(cudaEventSynchronize(ctx->ev_setup));           // recorded after the LAST job's last piece (one in-order copy stream)
+    return EBPMF_OK;
+}
+
+// up to two packed n x p device matrices -> host (the second pair may be NULL); the compute stream is synchronised first
+int matrices_out(ebpmf_ctx *ctx, double *dst0, const void *src0, double *dst1, const void *src1, long long rows, long long cols) {
+    const size_t bytes = sizeof(double) * (size_t)rows * (size_t)cols;
+    if (bytes < kPipeMinBytes) {
+        CU(cudaMemcpyAsync(dst0, src0, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (dst1) CU(cudaMemcpyAsync(dst1, src1, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        return EBPMF_OK;
+    }
+    CHECK(ensure_pipe(ctx));
+    CU(cudaStreamSynchronize(ctx->stream));
+    auto j0 = ctx->pipe->d2h((const double *)src0, dst0, (size_t)rows, (size_t)cols, (size_t)rows, nullptr);
+    HostPipe::JobRef j1;
+    if (dst1) j1 = ctx->pipe->d2h((const double *)src1, dst1, (size_t)rows, (size_t)cols, (size_t)rows, nullptr);
+    int rc = pipe_wait(ctx, j0);
+    if (j1) { const int r = pipe_wait(ctx, j1); if (rc == EBPMF_OK) rc = r; }
+    return rc;
+}
+
 int set_m_ld(ebpmf_ctx *ctx, const double *M, long long ld) {
     if (!ctx || !M) return fail(ctx, EBPMF_ERR_ARG, "set_m: bad arguments");
     if (!ctx->have_y) return fail(ctx, EBPMF_ERR_STATE, "set_m: Y not set");
@@ -796,6 +837,12 @@ int setup_peers(ebpmf_ctx *ctx) {
 // exported C ABI
 // =========================================================================================
 extern "C" {
+
+// ---- warm host blocks for result matrices (HostPool, host_pipe.hpp) ------------------------------
+void *ebpmf_host_alloc(size_t bytes) { return HostPool::instance().alloc(bytes); }
+int ebpmf_host_free(void *ptr) { return HostPool::instance().release(ptr) ? EBPMF_OK : EBPMF_ERR_ARG; }
+void ebpmf_host_pool_trim(void) { HostPool::instance().trim(); }
+void ebpmf_host_pool_stats(double *out4) { if (out4) HostPool::instance().stats(out4); }
 
 const char *ebpmf_version(void) { return "ebpmf_b200 0.1.0 (sm_100a)"; }
 
@@ -1316,19 +1363,22 @@ int ebpmf_update_sigma2(ebpmf_ctx *ctx, int var_type, int64_t n, int64_t p, cons
     return EBPMF_OK;
 }
 
-int ebpmf_calc_obj(ebpmf_ctx *ctx, int64_t n, int64_t p, double sym, double ssexp, double slogv, int64_t len,
-                   const double *sv, const double *sigma2, const double *R2, double KL_LF, double const_, double ss,
-                   double a0, double b0, double *obj) {
-    if (!ctx || !sv || !sigma2 || !R2 || !obj || len < 1) return fail(ctx, EBPMF_ERR_ARG, "calc_obj: bad arguments");
+int ebpmf_calc_obj(ebpmf_ctx *ctx, int64_t n, int64_t p, double sym, double ssexp, double slogv, int64_t len_sv,
+                   const double *sv, int64_t len_sigma2, const double *sigma2, int64_t len_r2, const double *R2,
+                   double KL_LF, double const_, double ss, double a0, double b0, double *obj) {
+    if (!ctx || !sv || !sigma2 || !R2 || !obj || len_sv < 1 || len_sigma2 < 1 || len_r2 < 1)
+        return fail(ctx, EBPMF_ERR_ARG, "calc_obj: bad arguments");
     CHECK(ensure_common(ctx));
-    CHECK(reserve(ctx, ctx->scratch[0], sizeof(double) * (3 * (size_t)len + 8)));
+    CHECK(reserve(ctx, ctx->scratch[0], sizeof(double) * ((size_t)len_sv + (size_t)len_sigma2 + (size_t)len_r2 + 8)));
     double *d = as<double>(ctx->scratch[0]);
-    CU(cudaMemcpyAsync(d, sv, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(d + len, sigma2, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(d + 2 * len, R2, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
-    obj_terms_kernel<<<1, 1024, 0, ctx->stream>>>(d, d + len, d + 2 * len, len, ss, a0, b0, d + 3 * len);
+    double *dS = d + len_sv, *dR = dS + len_sigma2, *dT = dR + len_r2;
+    CU(cudaMemcpyAsync(d, sv, sizeof(double) * (size_t)len_sv, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dS, sigma2, sizeof(double) * (size_t)len_sigma2, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dR, R2, sizeof(double) * (size_t)len_r2, cudaMemcpyHostToDevice, ctx->stream));
+    obj_terms_kernel<<<1, 1024, 0, ctx->stream>>>(d, len_sv, dS, len_sigma2, dR, len_r2, ss, a0, b0, dT);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(ctx->h_small, d + 3 * len, sizeof(double) * 5, cudaMemcpyDeviceToHost, ctx->stream));
+    ++ctx->launches;
+    CU(cudaMemcpyAsync(ctx->h_small, dT, sizeof(double) * 5, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     const double *t = ctx->h_small;
     // R/ebpmf_log.R:407, left to right
@@ -1523,13 +1573,15 @@ int ebpmf_vga_newton(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *M, cons
     const size_t lS = operand_len(S_kind, n, p), lB = operand_len(Beta_kind, n, p), lV = operand_len(Sigma2_kind, n, p);
     CHECK(reserve(ctx, ctx->scratch[4], sizeof(double) * (lS + lB + lV)));
     double *dS = as<double>(ctx->scratch[4]), *dB = dS + lS, *dV = dB + lB;
-    CU(cudaMemcpyAsync(ctx->scratch[0].ptr, M, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(dS, S, sizeof(double) * lS, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(dB, Beta, sizeof(double) * lB, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(dV, Sigma2, sizeof(double) * lV, cudaMemcpyHostToDevice, ctx->stream));
-    if (X) {
-        CU(cudaMemcpyAsync(ctx->scratch[2].ptr, X, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    } else {
+    {   // n x p operands go through the pinned ring (pageable R memory at close to pinned speed), the rest directly
+        void *dsts[5] = {ctx->scratch[0].ptr, ctx->scratch[2].ptr, dS, dB, dV};
+        const double *srcs[5] = {M, X, lS == NP ? S : nullptr, lB == NP ? Beta : nullptr, lV == NP ? Sigma2 : nullptr};
+        CHECK(matrices_in(ctx, dsts, srcs, 5, n, p));
+    }
+    if (lS != NP) CU(cudaMemcpyAsync(dS, S, sizeof(double) * lS, cudaMemcpyHostToDevice, ctx->stream));
+    if (lB != NP) CU(cudaMemcpyAsync(dB, Beta, sizeof(double) * lB, cudaMemcpyHostToDevice, ctx->stream));
+    if (lV != NP) CU(cudaMemcpyAsync(dV, Sigma2, sizeof(double) * lV, cudaMemcpyHostToDevice, ctx->stream));
+    if (!X) {
         const long long nnz = X_colptr[p];
         CHECK(reserve(ctx, ctx->scratch[5], (sizeof(int) + sizeof(double)) * (size_t)std::max(1LL, nnz) + sizeof(int) * (size_t)(p + 1) + 16));
         double *dx = as<double>(ctx->scratch[5]);
@@ -1566,9 +1618,7 @@ int ebpmf_vga_newton(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *M, cons
         [&] { return EBPMF_OK; }, info);
     if (rc != EBPMF_OK) return rc;
     if (info) { info->sym = info->ssexp = info->slogv = 0.0; }
-    CU(cudaMemcpyAsync(M_out, ctx->scratch[1].ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    if (V_out) CU(cudaMemcpyAsync(V_out, ctx->scratch[3].ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CHECK(matrices_out(ctx, M_out, ctx->scratch[1].ptr, V_out, V_out ? ctx->scratch[3].ptr : nullptr, n, p));
     return EBPMF_OK;
 }
 
@@ -1590,12 +1640,14 @@ int ebpmf_vga_fixed_iter(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *M, 
     const size_t lS = operand_len(S_kind, n, p), lB = operand_len(Beta_kind, n, p), lV = operand_len(Sigma2_kind, n, p);
     CHECK(reserve(ctx, ctx->scratch[4], sizeof(double) * (lS + lB + lV)));
     double *dS = as<double>(ctx->scratch[4]), *dB = dS + lS, *dV = dB + lB;
-    CU(cudaMemcpyAsync(ctx->scratch[0].ptr, M, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->scratch[2].ptr, Y, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    if (V) CU(cudaMemcpyAsync(ctx->scratch[5].ptr, V, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(dS, S, sizeof(double) * lS, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(dB, Beta, sizeof(double) * lB, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(dV, Sigma2, sizeof(double) * lV, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        void *dsts[6] = {ctx->scratch[0].ptr, ctx->scratch[2].ptr, V ? ctx->scratch[5].ptr : nullptr, dS, dB, dV};
+        const double *srcs[6] = {M, Y, V, lS == NP ? S : nullptr, lB == NP ? Beta : nullptr, lV == NP ? Sigma2 : nullptr};
+        CHECK(matrices_in(ctx, dsts, srcs, 6, n, p));
+    }
+    if (lS != NP) CU(cudaMemcpyAsync(dS, S, sizeof(double) * lS, cudaMemcpyHostToDevice, ctx->stream));
+    if (lB != NP) CU(cudaMemcpyAsync(dB, Beta, sizeof(double) * lB, cudaMemcpyHostToDevice, ctx->stream));
+    if (lV != NP) CU(cudaMemcpyAsync(dV, Sigma2, sizeof(double) * lV, cudaMemcpyHostToDevice, ctx->stream));
     a.n = n; a.p = p;
     a.M_in = as<double>(ctx->scratch[0]); a.V_in = V ? as<double>(ctx->scratch[5]) : nullptr;
     a.Y = as<double>(ctx->scratch[2]);
@@ -1610,9 +1662,8 @@ int ebpmf_vga_fixed_iter(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *M, 
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     ++ctx->launches;
-    CU(cudaMemcpyAsync(M_out, ctx->scratch[1].ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(V_out, ctx->scratch[3].ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    CHECK(matrices_out(ctx, M_out, ctx->scratch[1].ptr, V_out, ctx->scratch[3].ptr, n, p));
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_kernel_ms = ms;
@@ -1701,29 +1752,26 @@ int ebpmf_ctx_get_sigma2(ebpmf_ctx *ctx, double *sigma2) {
     return EBPMF_OK;
 }
 
-int ebpmf_ctx_get_rows(ebpmf_ctx *ctx, int which, int64_t row0, int64_t nrows, double *out) {
-    if (!ctx || !out || row0 < 0 || nrows < 1) return fail(ctx, EBPMF_ERR_ARG, "get_rows: bad arguments");
-    if (!ctx->have_m || row0 + nrows > ctx->n) return fail(ctx, EBPMF_ERR_STATE, "get_rows: M not set or rows out of range");
-    if (which != 0 && !ctx->have_v) return fail(ctx, EBPMF_ERR_STATE, "get_rows: V was not materialised");
-    CHECK(ensure_common(ctx));
-    const double *src = (which ? as<double>(ctx->V) : as<double>(ctx->Mcur)) + row0;
-    CU(cudaMemcpy2DAsync(out, sizeof(double) * (size_t)nrows, src, sizeof(double) * (size_t)ctx->n,
-                         sizeof(double) * (size_t)nrows, (size_t)ctx->p, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    return EBPMF_OK;
-}
-
 int ebpmf_ctx_get_block(ebpmf_ctx *ctx, int which, int64_t row0, int64_t nrows, int64_t col0, int64_t ncols, double *out) {
-    if (!ctx || !out || row0 < 0 || nrows < 1 || col0 < 0 || ncols < 1) return fail(ctx, EBPMF_ERR_ARG, "get_block: bad arguments");
+    if (!ctx || !out || row0 < 0 || nrows < 1 || col0 < 0 || ncols < 1 || which < 0 || which > 2)
+        return fail(ctx, EBPMF_ERR_ARG, "get_block: bad arguments");
     if (!ctx->have_m || row0 + nrows > ctx->n || col0 + ncols > ctx->p)
         return fail(ctx, EBPMF_ERR_STATE, "get_block: M not set or block out of range");
-    if (which != 0 && !ctx->have_v) return fail(ctx, EBPMF_ERR_STATE, "get_block: V was not materialised");
+    if (which == 1 && !ctx->have_v) return fail(ctx, EBPMF_ERR_STATE, "get_block: V was not materialised");
+    if (which == 2 && !ctx->can_rewind) return fail(ctx, EBPMF_ERR_STATE, "get_block: no step to look behind");
     CHECK(ensure_common(ctx));
-    const double *src = (which ? as<double>(ctx->V) : as<double>(ctx->Mcur)) + row0 + (size_t)ctx->n * (size_t)col0;
+    // a step never writes its input: after it the result is in Mcur and the input still in Malt
+    const double *base = which == 1 ? as<double>(ctx->V) : which == 2 ? as<double>(ctx->Malt) : as<double>(ctx->Mcur);
+    const double *src = base + row0 + (size_t)ctx->n * (size_t)col0;
     CU(cudaMemcpy2DAsync(out, sizeof(double) * (size_t)nrows, src, sizeof(double) * (size_t)ctx->n,
                          sizeof(double) * (size_t)nrows, (size_t)ncols, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return EBPMF_OK;
+}
+
+int ebpmf_ctx_get_rows(ebpmf_ctx *ctx, int which, int64_t row0, int64_t nrows, double *out) {
+    if (!ctx || !ctx->have_m) return fail(ctx, EBPMF_ERR_STATE, "get_rows: M not set or rows out of range");
+    return ebpmf_ctx_get_block(ctx, which, row0, nrows, 0, ctx->p, out);
 }
 
 int ebpmf_ctx_sim_data_log(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K, int64_t row0, uint64_t seed,

@@ -20,6 +20,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <memory>
@@ -342,6 +343,116 @@ class HostPipe {
     bool stop_ = true;
     std::atomic<bool> failed_{false};
     std::string err_;
+};
+
+// HostPool: warm host blocks for RESULT matrices.  R allocates a fresh n x p matrix for every result
+// (Rf_allocMatrix); at 30 GB that is 7 million first-touch page faults per call and halves the copy-out
+// rate (profiles/r02_probe_host_copy.txt: 17-29 GB/s into fresh pages against 53 GB/s into touched ones).
+// R lets a package supply the memory of a vector (allocVector3 with an R_allocator_t); the .Call glue hands
+// it blocks from this pool and the pool takes them back when R's garbage collector frees the matrix, so from
+// the second outer iteration on every result lands in pages that are already mapped (and, with
+// EBPMF_B200_POOL_PIN=1, page-locked: the copy engine then writes them directly, no staging memcpy).
+class HostPool {
+   public:
+    static HostPool &instance() { static HostPool p; return p; }
+
+    void *alloc(size_t bytes) {
+        const size_t kHuge = (size_t)2 << 20;
+        bytes = (std::max<size_t>(bytes, 1) + kHuge - 1) / kHuge * kHuge;      // whole huge pages
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            size_t best = free_.size();
+            for (size_t q = 0; q < free_.size(); ++q)
+                if (free_[q].bytes >= bytes && free_[q].bytes - bytes <= free_[q].bytes / 4 &&
+                    (best == free_.size() || free_[q].bytes < free_[best].bytes)) best = q;
+            if (best != free_.size()) {
+                Block b = free_[best];
+                free_.erase(free_.begin() + (long)best);
+                kept_bytes_ -= b.bytes;
+                live_.push_back(b);
+                ++reused_;
+                return b.ptr;
+            }
+        }
+        const size_t len = bytes;
+        void *ptr = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (ptr == MAP_FAILED) return nullptr;
+        (void)madvise(ptr, len, MADV_HUGEPAGE);
+        Block b;
+        b.ptr = ptr; b.bytes = len; b.pinned = false;
+        const char *pin = getenv("EBPMF_B200_POOL_PIN");
+        if (pin && atoi(pin) > 0 && len >= ((size_t)64 << 20)) {
+            populate(ptr, len);
+            b.pinned = (cudaHostRegister(ptr, len, cudaHostRegisterPortable) == cudaSuccess);
+            if (!b.pinned) (void)cudaGetLastError();
+        }
+        std::lock_guard<std::mutex> lk(mu_);
+        live_.push_back(b);
+        ++fresh_;
+        return ptr;
+    }
+
+    // back to the pool (kept warm up to the keep limit); returns false when ptr is not one of ours
+    bool release(void *ptr) {
+        Block b;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            size_t q = 0;
+            for (; q < live_.size(); ++q) if (live_[q].ptr == ptr) break;
+            if (q == live_.size()) return false;
+            b = live_[q];
+            live_.erase(live_.begin() + (long)q);
+            if (kept_bytes_ + b.bytes <= keep_limit()) {
+                free_.push_back(b);
+                kept_bytes_ += b.bytes;
+                return true;
+            }
+        }
+        unmap(b);
+        return true;
+    }
+
+    void trim() {
+        std::vector<Block> drop;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            drop.swap(free_);
+            kept_bytes_ = 0;
+        }
+        for (auto &b : drop) unmap(b);
+    }
+
+    void stats(double *out4) {
+        std::lock_guard<std::mutex> lk(mu_);
+        out4[0] = (double)fresh_; out4[1] = (double)reused_; out4[2] = (double)kept_bytes_; out4[3] = (double)live_.size();
+    }
+
+   private:
+    struct Block { void *ptr = nullptr; size_t bytes = 0; bool pinned = false; };
+    static size_t keep_limit() {
+        const char *v = getenv("EBPMF_B200_POOL_KEEP_GB");
+        const double gb = v ? atof(v) : 96.0;
+        return (size_t)(std::max(0.0, gb) * 1073741824.0);
+    }
+    static void populate(void *ptr, size_t len) {      // touch every page from a few threads (first-touch zeroing)
+        const int nt = 8;
+        std::vector<std::thread> th;
+        const size_t per = (len / nt + 4095) & ~(size_t)4095;
+        for (int t = 0; t < nt; ++t)
+            th.emplace_back([=] {
+                const size_t lo = (size_t)t * per, hi = std::min(len, lo + per);
+                for (size_t o = lo; o < hi; o += 4096) ((volatile char *)ptr)[o] = 0;
+            });
+        for (auto &t : th) t.join();
+    }
+    static void unmap(const Block &b) {
+        if (b.pinned) (void)cudaHostUnregister(b.ptr);
+        (void)munmap(b.ptr, b.bytes);
+    }
+    std::mutex mu_;
+    std::vector<Block> live_, free_;
+    size_t kept_bytes_ = 0;
+    unsigned long long fresh_ = 0, reused_ = 0;
 };
 
 }  // namespace ebpmf

@@ -1162,22 +1162,25 @@ __global__ void __launch_bounds__(1024) max_reduce_kernel(const double *in, long
 // a7: calc_ebpmf_log_obj  R/ebpmf_log.R:406-410 -- the O(len) sums; one block, fixed order.
 // terms[0] = sum(ss*log(2*pi*sigma2)/2), [1] = sum(sv/2/sigma2), [2] = sum(R2/2/sigma2),
 // terms[3] = sum((a0+1)*log(sigma2)),   [4] = sum(b0/sigma2)
+// Every sum() is taken at ITS OWN length, as R does: the sigma2-only terms over length(sigma2), the two
+// mixed terms over the longer of their operands with the shorter one recycled.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) obj_terms_kernel(const double *sv, const double *sigma2, const double *R2,
-                                                         long long len, double ss, double a0, double b0,
+__global__ void __launch_bounds__(1024) obj_terms_kernel(const double *sv, long long lsv, const double *sigma2, long long ls2,
+                                                         const double *R2, long long lr2, double ss, double a0, double b0,
                                                          double *terms)
 {
     __shared__ double sm[5][1024];
     double acc[5] = {0, 0, 0, 0, 0};
     const double two_pi = 6.283185307179586;
-    for (long long q = threadIdx.x; q < len; q += 1024) {
+    for (long long q = threadIdx.x; q < ls2; q += 1024) {
         const double s2 = sigma2[q];
         acc[0] += ss * log(two_pi * s2) / 2;
-        acc[1] += sv[q] / 2 / s2;
-        acc[2] += R2[q] / 2 / s2;
         acc[3] += (a0 + 1) * log(s2);
         acc[4] += b0 / s2;
     }
+    const long long l1 = max(lsv, ls2), l2 = max(lr2, ls2);
+    for (long long q = threadIdx.x; q < l1; q += 1024) acc[1] += sv[q % lsv] / 2 / sigma2[q % ls2];
+    for (long long q = threadIdx.x; q < l2; q += 1024) acc[2] += R2[q % lr2] / 2 / sigma2[q % ls2];
     for (int q = 0; q < 5; ++q) sm[q][threadIdx.x] = acc[q];
     __syncthreads();
     for (int s = 512; s > 0; s >>= 1) {

@@ -49,10 +49,10 @@ vga_pois_solver_mat_newton_low_memory = function(M,Y,l0,f0,EL,EF,
 }
 
 #'@title Calc elbo   (R/ebpmf_log.R:406)
+#' sv, sigma2 and R2 go down with their own lengths: each sum() of R/ebpmf_log.R:407 is taken at its own length
 calc_ebpmf_log_obj = function(n,p,sym,ssexp,slogv,sv,sigma2,R2,KL_LF,const,ss,a0,b0){
-  len = max(length(sv),length(sigma2),length(R2))
-  .Call(C_calc_ebpmf_log_obj, ebpmf_b200_ctx(), n, p, sym, ssexp, slogv, rep_len(as.double(sv),len),
-        rep_len(as.double(sigma2),len), rep_len(as.double(R2),len), KL_LF, const, ss, a0, b0)
+  .Call(C_calc_ebpmf_log_obj, ebpmf_b200_ctx(), n, p, sym, ssexp, slogv, as.double(sv),
+        as.double(sigma2), as.double(R2), KL_LF, const, ss, a0, b0)
 }
 
 #'@title update sigma2   (R/ebpmf_log.R:413)
@@ -100,4 +100,43 @@ ebpmf_b200_batched_vga_step = function(h,M,EL,EF,sigma2,var_type,maxiter,tol,wan
   storage.mode(M) = 'double'
   .Call(C_ebpmf_batched_vga_step, h, M, EL + 0, EF + 0, as.double(sigma2), var_type,
         as.integer(maxiter), as.double(tol), as.logical(want_V), as.integer(attr(h,'n_batch')))
+}
+
+#' N1: what flashier needs from the RESIDENT M, computed on the GPU (M need not come back to the host):
+#' list(MF = M %*% EF_w, MtL = t(M) %*% EL_w, r2_col, r2_row) with r2 = col/row sums of (M - EL_w EF_w')^2,
+#' i.e. flash_fit$R2 for var_type by_col / by_row (R/ebpmf_log_flash_update.R:35,55-64).
+ebpmf_b200_m_products = function(n,p,EL_w,EF_w){
+  .Call(C_ebpmf_m_products, ebpmf_b200_ctx(), as.integer(c(n,p)), EL_w + 0, EF_w + 0)
+}
+
+#' N4: sim_data_log (R/simulate_poisson_matrix.R:9-61) generated on the GPU, straight into the context's
+#' resident state; returns the dgCMatrix Y and the solver state (the start M stays on the device).
+ebpmf_b200_sim_data_log = function(n,p,K,seed=12345,log_offset=0,background_unif_range=c(1,2),pi0=0.8,noise=0.2,
+                                   warm_start=FALSE){
+  r = .Call(C_ebpmf_sim_data_log, ebpmf_b200_ctx(), n, p, K, seed, as.double(log_offset),
+            as.double(background_unif_range), as.double(pi0), as.double(noise), as.logical(warm_start))
+  nnz = r$nnz
+  list(Y = new('dgCMatrix', i = r$i[seq_len(nnz)], p = r$p, x = r$x[seq_len(nnz)], Dim = r$Dim),
+       EL = r$EL, EF = r$EF, sigma2 = r$sigma2)
+}
+
+#' Several GPUs from ONE R session (EBPMF_B200_NGPU > 1): rows sharded over the devices, the update count and
+#' v_sum / ELBO partials combined over NCCL inside the library.  Same calls, same results as the single-GPU
+#' wrappers above; `ebpmf_b200_use_group()` tells ebpmf_log's loop which set to call (INTEGRATION.md section 3).
+ebpmf_b200_ngpu = function() as.integer(Sys.getenv("EBPMF_B200_NGPU", "1"))
+ebpmf_b200_use_group = function() ebpmf_b200_ngpu() > 1L
+ebpmf_b200_group = function(devices = seq_len(ebpmf_b200_ngpu()) - 1L){
+  if(is.null(.ebpmf_b200_env$group)){
+    .ebpmf_b200_env$group = .Call(C_ebpmf_group_new, as.integer(devices))
+  }
+  .ebpmf_b200_env$group
+}
+ebpmf_b200_group_set_y = function(Y){ invisible(.Call(C_ebpmf_group_set_y, ebpmf_b200_group(), as(Y,'dgCMatrix'))) }
+ebpmf_b200_group_sum_lfactorial = function(){ .Call(C_ebpmf_group_sum_lfactorial, ebpmf_b200_group()) }
+ebpmf_b200_group_set_m = function(M){ storage.mode(M) = 'double'; invisible(.Call(C_ebpmf_group_set_m, ebpmf_b200_group(), M)) }
+#' M = NULL: the shards already hold the input (set_m once, then every step's output, R/ebpmf_log.R:309)
+ebpmf_b200_group_vga_step = function(M,n,p,EL,EF,sigma2,var_type,maxiter,tol,want_V=FALSE){
+  if(!is.null(M)) storage.mode(M) = 'double'
+  .Call(C_ebpmf_group_vga_step, ebpmf_b200_group(), M, as.integer(c(n,p)), EL + 0, EF + 0, as.double(sigma2), var_type,
+        as.integer(maxiter), as.double(tol), as.logical(want_V))
 }

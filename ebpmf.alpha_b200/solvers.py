@@ -74,7 +74,49 @@ def _operand(a, n, p, what):
     raise ValueError("%s: non-conformable arrays" % what)
 
 
+class _PoolBlock:
+    """Owner of one block of the library's host pool; gives it back when the last view dies (what R's garbage
+    collector does through the R_allocator_t of the .Call glue)."""
+
+    def __init__(self, nbytes):
+        lib = _lib.load()
+        self._lib = lib
+        self.ptr = lib.ebpmf_host_alloc(C.c_size_t(max(1, int(nbytes))))
+        if not self.ptr:
+            raise MemoryError("ebpmf_host_alloc(%d) failed" % nbytes)
+
+    def __del__(self):  # pragma: no cover
+        try:
+            if self.ptr:
+                self._lib.ebpmf_host_free(C.c_void_p(self.ptr))
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def host_matrix(n, p):
+    """A column-major n x p float64 result matrix in the library's warm host pool (ebpmf_host_alloc): the Python
+    stand-in for the R glue's ``allocVector3(REALSXP, n*p, &ebpmf_allocator)``.  The block returns to the pool when
+    the array (and every view of it) is garbage collected."""
+    blk = _PoolBlock(8 * int(n) * int(p))
+    buf = (C.c_double * (int(n) * int(p))).from_address(blk.ptr)
+    buf._ebpmf_owner = blk                       # the ctypes array keeps the block alive; NumPy keeps the ctypes array
+    a = np.frombuffer(buf, dtype=np.float64, count=int(n) * int(p)).reshape((int(p), int(n))).T
+    return a
+
+
+def host_pool_stats():
+    out = np.zeros(4)
+    _lib.load().ebpmf_host_pool_stats(_ptr(out))
+    return dict(fresh=int(out[0]), reused=int(out[1]), kept_bytes=float(out[2]), live_blocks=int(out[3]))
+
+
+def host_pool_trim():
+    _lib.load().ebpmf_host_pool_trim()
+
+
 _DEFAULT_CTX = {}
+_WHICH = {"M": 0, "V": 1, "M_in": 2}     # get_rows / get_block: result M, V, the M the last step started from
 
 
 def default_context(device=0):
@@ -200,12 +242,12 @@ class VgaContext:
 
     def get_rows(self, row0, nrows, which="M"):
         out = np.empty((nrows, self.p), order="F")
-        self._ck(self._lib.ebpmf_ctx_get_rows(self._h, 0 if which == "M" else 1, int(row0), int(nrows), _ptr(out)))
+        self._ck(self._lib.ebpmf_ctx_get_rows(self._h, _WHICH[which], int(row0), int(nrows), _ptr(out)))
         return out
 
     def get_block(self, row0, nrows, col0, ncols, which="M"):
         out = np.empty((nrows, ncols), order="F")
-        self._ck(self._lib.ebpmf_ctx_get_block(self._h, 0 if which == "M" else 1, int(row0), int(nrows), int(col0), int(ncols),
+        self._ck(self._lib.ebpmf_ctx_get_block(self._h, _WHICH[which], int(row0), int(nrows), int(col0), int(ncols),
                                                _ptr(out)))
         return out
 
@@ -259,7 +301,7 @@ class VgaContext:
         EF = _f(np.asarray(EF, dtype=np.float64).reshape(p, -1))
         s2 = _vec(sigma2)
         ln = {"by_col": p, "by_row": n, "constant": 1}[var_type]
-        Mo = np.empty((n, p), order="F") if M_out is None else M_out     # any host memory, pageable included
+        Mo = host_matrix(n, p) if M_out is None else M_out     # any host memory works; the default is the warm pool
         if Mo.shape != (n, p) or not Mo.flags.f_contiguous or Mo.dtype != np.float64:
             raise ValueError("M_out must be an n x p column-major float64 array")
         Vo = np.empty((n, p), order="F") if return_V else None
@@ -282,8 +324,8 @@ class VgaContext:
         EF = _f(np.asarray(EF, dtype=np.float64).reshape(self.p, -1))
         s2 = _vec(sigma2)
         ln = {"by_col": self.p, "by_row": self.n, "constant": 1}[var_type]
-        Mo = np.empty((self.n, self.p), order="F") if M_out is None else M_out
-        Vo = np.empty((self.n, self.p), order="F") if return_V else None
+        Mo = host_matrix(self.n, self.p) if M_out is None else M_out
+        Vo = host_matrix(self.n, self.p) if return_V else None
         vs = np.empty(ln)
         info = SolveInfo()
         if Mo.shape != (self.n, self.p) or not Mo.flags.f_contiguous or Mo.dtype != np.float64:
@@ -609,13 +651,11 @@ def ebpmf_log_update_sigma2(fit_flash, sigma2, v_sum, var_type, cap_var_mean_rat
 def calc_ebpmf_log_obj(n, p, sym, ssexp, slogv, sv, sigma2, R2, KL_LF, const, ss, a0, b0, ctx=None):
     """R/ebpmf_log.R:406-410."""
     ctx = ctx or default_context()
-    sv = _vec(sv); s2 = _vec(sigma2); R2 = _vec(R2)
-    ln = max(sv.size, s2.size, R2.size)
-    sv, s2, R2 = (np.ascontiguousarray(np.broadcast_to(a, (ln,))) for a in (sv, s2, R2))   # R recycling
+    sv = _vec(sv); s2 = _vec(sigma2); R2 = _vec(R2)     # each keeps its own length: R sums every term at its own length
     out = C.c_double()
-    ctx._ck(ctx._lib.ebpmf_calc_obj(ctx._h, n, p, float(sym), float(ssexp), float(slogv), ln, _ptr(sv), _ptr(s2),
-                                    _ptr(R2), float(KL_LF), float(const), float(ss), float(a0), float(b0),
-                                    C.byref(out)))
+    ctx._ck(ctx._lib.ebpmf_calc_obj(ctx._h, n, p, float(sym), float(ssexp), float(slogv), sv.size, _ptr(sv), s2.size,
+                                    _ptr(s2), R2.size, _ptr(R2), float(KL_LF), float(const), float(ss), float(a0),
+                                    float(b0), C.byref(out)))
     return out.value
 
 

@@ -25,6 +25,7 @@
 #ifndef EBPMF_B200_H
 #define EBPMF_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -72,6 +73,20 @@ typedef struct ebpmf_solve_info {
     double  pass2_ms;       /* top-up pass(es) to the global count                    */
     double  reduce_ms;      /* partial-sum reductions (+ NCCL combine when sharded)   */
 } ebpmf_solve_info;
+
+/* ---- host memory for RESULT matrices ------------------------------------------------------
+ * R allocates a fresh n x p matrix for every result (Rf_allocMatrix).  At the sizes of this path that is
+ * millions of first-touch page faults per call, which halves the device->host rate.  The .Call glue instead
+ * allocates result matrices with allocVector3() and an R_allocator_t whose mem_alloc / mem_free are these
+ * two functions: blocks come from a process-wide pool and return to it when R's garbage collector frees the
+ * matrix, so from the second outer iteration on a result lands in pages that are already mapped
+ * (EBPMF_B200_POOL_PIN=1 also page-locks them: the copy engine then writes them directly;
+ * EBPMF_B200_POOL_KEEP_GB, default 96, bounds what the pool keeps).  Any host pointer remains valid as an
+ * output argument of every entry point; the pool is an optimisation, not a requirement. */
+void *ebpmf_host_alloc(size_t bytes);          /* NULL when the system is out of memory */
+int   ebpmf_host_free(void *ptr);              /* EBPMF_ERR_ARG when ptr did not come from ebpmf_host_alloc */
+void  ebpmf_host_pool_trim(void);              /* give the kept blocks back to the system */
+void  ebpmf_host_pool_stats(double *out4);     /* fresh allocations, reuses, bytes kept, blocks handed out */
 
 /* ---- library / context ---------------------------------------------------------------- */
 const char *ebpmf_version(void);
@@ -134,7 +149,8 @@ int  ebpmf_ctx_get_shape(ebpmf_ctx *ctx, int64_t *n, int64_t *p, int64_t *K, int
 int  ebpmf_ctx_get_y_csc(ebpmf_ctx *ctx, int32_t *colptr, int32_t *rowidx, double *x);
 int  ebpmf_ctx_get_factors(ebpmf_ctx *ctx, double *EL, double *EF);
 int  ebpmf_ctx_get_sigma2(ebpmf_ctx *ctx, double *sigma2);
-/* rows [row0, row0+nrows) of the resident M (or of V when which != 0) as an nrows x p matrix */
+/* rows [row0, row0+nrows) of the resident M (which = 0), of V (1), or of the M the last step started from (2:
+ * what ebpmf_ctx_rewind_m would restore; a step never writes its input) as an nrows x p matrix */
 int  ebpmf_ctx_get_rows(ebpmf_ctx *ctx, int which, int64_t row0, int64_t nrows, double *out);
 /* the block rows [row0, row0+nrows) x columns [col0, col0+ncols) of the resident M (or V), packed nrows x ncols */
 int  ebpmf_ctx_get_block(ebpmf_ctx *ctx, int which, int64_t row0, int64_t nrows, int64_t col0, int64_t ncols, double *out);
@@ -157,9 +173,13 @@ int  ebpmf_update_sigma2(ebpmf_ctx *ctx, int var_type, int64_t n, int64_t p, con
                          double cap_var_mean_ratio, int64_t K, const double *EL, const double *EF,
                          double *sigma2_out);
 
-/* calc_ebpmf_log_obj, R/ebpmf_log.R:406-410.  len = length(sigma2) (= length(sv) = length(R2)). */
+/* calc_ebpmf_log_obj, R/ebpmf_log.R:406-410.  sv, sigma2 and R2 come with their OWN lengths: R takes each
+ * sum() of :407 at the length of its own operands (the sigma2-only terms over length(sigma2); sum(sv/2/sigma2)
+ * and sum(R2/2/sigma2) over the longer operand, the shorter one recycled), e.g. var_type 'constant' has a
+ * scalar sigma2 and may be handed the vector fit_flash$flash_fit$R2. */
 int  ebpmf_calc_obj(ebpmf_ctx *ctx, int64_t n, int64_t p, double sym, double ssexp, double slogv,
-                    int64_t len, const double *sv, const double *sigma2, const double *R2,
+                    int64_t len_sv, const double *sv, int64_t len_sigma2, const double *sigma2,
+                    int64_t len_r2, const double *R2,
                     double KL_LF, double const_, double ss, double a0, double b0, double *obj);
 
 /* The whole step with CALLER-OWNED HOST buffers in one call (what the .Call shim uses each outer iteration):

@@ -62,6 +62,7 @@ def main():
     ap.add_argument("--entries", type=float, required=True, help="matrix entries one launch processes")
     ap.add_argument("--min-region", type=int, default=8)
     ap.add_argument("--sms", type=int, default=148)
+    ap.add_argument("--json", default=None, help="also write the counters bench.py quotes (profiles/r02_ncu_metrics.json)")
     a = ap.parse_args()
 
     raw = ncu_csv(a.report, "raw")
@@ -111,6 +112,25 @@ def main():
     print(f"Issue-slot model: {inst / w32:.1f} + {fp64_inst / w32:.1f} + {three / w32:.1f} = {slots:.1f} slots "
           f"vs {cyc / w32:.1f} cycles measured -> {slots / (cyc / w32):.3f}.")
 
+    if a.json:
+        import json, os
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        try:
+            git = subprocess.run(["git", "-C", root, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+        except Exception:
+            git = None
+        gb = lambda k: float(val(k)) * {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9}[u[col[k]]]
+        json.dump({"kernel": val("Kernel Name"), "git": git, "report": os.path.basename(a.report), "entries_per_launch": a.entries,
+                   "gpu_time_ms": float(val("gpu__time_duration.sum")) * {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}[u[col["gpu__time_duration.sum"]]],
+                   "dram_read_gb": gb("dram__bytes_read.sum"), "dram_write_gb": gb("dram__bytes_write.sum"),
+                   "dram_gb_per_launch": gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum"),
+                   "inst_per_32_entries": inst / w32, "fp64_inst_per_32_entries": fp64_inst / w32,
+                   "three_register_dfma_per_32_entries": three / w32, "cycles_per_32_entries": cyc / w32,
+                   "fp64_pipe_pct_of_peak": fp64_pct, "issue_active_pct": float(val("smsp__issue_active.avg.pct_of_peak_sustained_active")),
+                   "registers_per_thread": int(float(val("launch__registers_per_thread"))),
+                   "note": "one `ncu --set full --clock-control none` capture of the first-pass kernel of a steady-state step "
+                           "(scripts/ab_run.py c4slab); per-launch times under ncu are serialised, bench.py measures its own"},
+                  open(a.json, "w"), indent=1)
     print("\n| SASS range | static instr | executions per 32 entries (each) | instr per 32 entries | FP64 instr per 32 entries | share of stall samples |")
     print("|---|---|---|---|---|---|")
     i = 0

@@ -1,0 +1,14 @@
+/* see R.h in this directory: syntax-check stub, not R (declarations of R_ext/Rallocators.h, R >= 3.1) */
+#ifndef EBPMF_TEST_R_STUB_RALLOCATORS_H
+#define EBPMF_TEST_R_STUB_RALLOCATORS_H
+#include <stddef.h>
+typedef struct R_allocator R_allocator_t;
+typedef void *(*custom_alloc_t)(R_allocator_t *allocator, size_t);
+typedef void (*custom_free_t)(R_allocator_t *allocator, void *);
+struct R_allocator {
+    custom_alloc_t mem_alloc; /* malloc equivalent */
+    custom_free_t mem_free;   /* free equivalent */
+    void *res;                /* reserved (maybe for copy) - must be NULL */
+    void *data;               /* custom data for the allocator implementation */
+};
+#endif

@@ -37,6 +37,8 @@ SEXP Rf_install(const char *name);
 SEXP R_do_slot(SEXP obj, SEXP name);
 SEXP Rf_allocVector(SEXPTYPE type, R_xlen_t len);
 SEXP Rf_allocMatrix(SEXPTYPE type, int nrow, int ncol);
+typedef struct R_allocator R_allocator_t;
+SEXP Rf_allocVector3(SEXPTYPE type, R_xlen_t len, R_allocator_t *allocator);
 SEXP Rf_ScalarReal(double x);
 SEXP Rf_ScalarInteger(int x);
 SEXP Rf_ScalarLogical(int x);

@@ -90,3 +90,34 @@ def test_plain_c_host_compiles_links_and_fails_loudly_without_a_gpu(pkg, tmp_pat
         pytest.skip("a GPU is present: the demo is run by tests/test_gpu_parity.py")
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+def test_host_pool_hands_out_and_reuses_warm_blocks(pkg):
+    """ebpmf_host_alloc / ebpmf_host_free (the R_allocator_t behind the glue's result matrices): no GPU needed
+    for pageable blocks.  A freed block comes back for the next request of a similar size; a pointer that is
+    not ours is refused; host_matrix() views are column-major and return their block when they die."""
+    import gc
+    pkg.host_pool_trim()
+    s0 = pkg.host_pool_stats()
+    a = pkg.host_matrix(300, 70)
+    assert a.shape == (300, 70) and a.flags.f_contiguous and a.dtype == np.float64
+    a[...] = np.arange(300 * 70, dtype=np.float64).reshape(70, 300).T
+    assert a[5, 3] == 3 * 300 + 5
+    addr = a.ctypes.data
+    s1 = pkg.host_pool_stats()
+    assert s1["fresh"] == s0["fresh"] + 1 and s1["live_blocks"] == s0["live_blocks"] + 1
+    del a
+    gc.collect()
+    s2 = pkg.host_pool_stats()
+    assert s2["live_blocks"] == s0["live_blocks"] and s2["kept_bytes"] >= 300 * 70 * 8
+    b = pkg.host_matrix(300, 70)                    # same size: the warm block comes back
+    assert b.ctypes.data == addr and pkg.host_pool_stats()["reused"] == s2["reused"] + 1
+    c = pkg.host_matrix(300, 70)                    # second live matrix: a second block (the previous result stays alive)
+    assert c.ctypes.data != addr
+    del b, c
+    gc.collect()
+    lib = pkg.load()
+    junk = np.zeros(4)
+    assert lib.ebpmf_host_free(ctypes.c_void_p(junk.ctypes.data)) == 1          # EBPMF_ERR_ARG: not a pool block
+    pkg.host_pool_trim()
+    assert pkg.host_pool_stats()["kept_bytes"] == 0

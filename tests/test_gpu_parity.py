@@ -797,3 +797,34 @@ def test_plain_c_demo_runs(pkg, tmp_path):
     assert "5 Newton updates (converged 1)" in r.stdout, r.stdout
     sym = float(re.search(r"sym (-?[0-9.]+)", r.stdout).group(1))
     assert abs(sym - (-9672.454278)) < 1e-4
+
+
+@pytest.mark.gpu
+def test_calc_obj_takes_every_sum_at_its_own_length(gpu_ctx, pkg):
+    """R/ebpmf_log.R:407: each sum() runs over its own operands.  With var_type 'constant' sigma2 is a scalar
+    while R2 (fit_flash$flash_fit$R2) and sv may be vectors; the sigma2-only terms must be counted once."""
+    rng = np.random.default_rng(3)
+    n, p = 40, 17
+    for ls2, lsv, lr2 in [(1, 1, p), (1, p, p), (p, p, p), (p, 1, 1), (n, n, 1)]:
+        s2 = rng.uniform(0.1, 2.0, ls2); sv = rng.uniform(0.0, 5.0, lsv); R2 = rng.uniform(0.0, 30.0, lr2)
+        ref = vga_numpy.calc_ebpmf_log_obj(n, p, 1.5, 2.5, -3.5, sv, s2, R2, -7.0, -11.0, float(n), 1.0, 1.0)
+        got = pkg.calc_ebpmf_log_obj(n, p, 1.5, 2.5, -3.5, sv, s2, R2, -7.0, -11.0, float(n), 1.0, 1.0, ctx=gpu_ctx)
+        assert abs(got - ref) <= 1e-12 * max(1.0, abs(ref)), (ls2, lsv, lr2, got, ref)
+
+
+@pytest.mark.gpu
+def test_step_input_stays_readable_after_the_step(gpu_ctx):
+    """get_rows / get_block with which = 'M_in': a step never writes its input, so the matrix it started from can
+    be read back next to the result (what the slab-scale parity check of bench.py uses)."""
+    sim, st = make_case(700, 90, 3, 0.1, seed=21)
+    gpu_ctx.set_y(sp.csc_matrix(sim["Y"]))
+    gpu_ctx.set_m(st["M0"]); gpu_ctx.set_factors(st["EL"], st["EF"]); gpu_ctx.set_sigma2(st["sigma2"], "by_col")
+    with pytest.raises(Exception):
+        gpu_ctx.get_rows(0, 10, "M_in")                 # no step yet
+    gpu_ctx.vga_step(10, 1e-5, want_v=True)
+    assert np.array_equal(gpu_ctx.get_rows(100, 300, "M_in"), st["M0"][100:400])
+    assert np.array_equal(gpu_ctx.get_block(5, 600, 7, 11, "M_in"), st["M0"][5:605, 7:18])
+    assert np.array_equal(gpu_ctx.get_block(5, 600, 7, 11, "M"), gpu_ctx.get_m()[5:605, 7:18])
+    assert np.array_equal(gpu_ctx.get_block(0, 700, 89, 1, "V"), gpu_ctx.get_v()[:, 89:90])
+    gpu_ctx.rewind_m()
+    assert np.array_equal(gpu_ctx.get_m(), st["M0"])
