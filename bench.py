@@ -647,6 +647,13 @@ def main():
                       "speculative_copy_bytes": cnt["spec_bytes"], "recopied_bytes": cnt["recopy_bytes"],
                       "host_pool": pkg.host_pool_stats()}
         pkg.host_pool_trim()
+        # (b0) diagnostic: ONE plain pageable result buffer reused by every call
+        Mr = pageable_f(er, p)
+        per, _ = timed_resident(lambda a, b: Mr, 2, ks)
+        out["e2e_reused_buffer"] = {"value": er * p * world / per, "unit": "entries/s", "ms_per_step": 1e3 * per,
+                                    "d2h_gb_per_s_per_gpu": 8.0 * er * p / per / 1e9,
+                                    "call": "as e2e, one np.empty result matrix allocated once and reused by every call"}
+        del Mr
         # (b') the same with a plain Rf_allocMatrix-style result: fresh, never-touched pageable pages every call
         per, _ = timed_resident(pageable_f, 1, ks)
         out["e2e_fresh_pages"] = {"value": er * p * world / per, "unit": "entries/s", "ms_per_step": 1e3 * per,
