@@ -527,15 +527,17 @@ def main():
         mp = ctx.m_products(EL0, EF0)
     barrier()
     mp_ms = allmax(mp["kernel_ms"])
-    m_products = {"ms": mp_ms, "m_ef_ms": mp["m_ef_ms"], "mt_el_ms": mp["mt_el_ms"], "K": K + 2,
+    flops = 4.0 * (K + 2) * n * p                      # two products, K_tot multiply-adds per entry each
+    m_products = {"ms": mp_ms, "products_kernel_ms": mp["products_ms"], "partial_sums_ms": mp["partial_sums_ms"], "K": K + 2,
                   "value": entries / (mp_ms * 1e-3), "unit": "entries/s",
                   "algorithmic_bytes_per_entry": 8.0,
-                  "hbm_frac_of_8B_per_entry": 8.0 * n * p / (mp_ms * 1e-3) / 1e9 / peak,
-                  "hbm_frac_per_kernel": {"m_ef": 8.0 * n * p / (mp["m_ef_ms"] * 1e-3) / 1e9 / peak,
-                                          "mt_el": 8.0 * n * p / (mp["mt_el_ms"] * 1e-3) / 1e9 / peak},
+                  "hbm_frac_of_8B_per_entry": 8.0 * n * p / (mp["products_ms"] * 1e-3) / 1e9 / peak,
+                  "fp64_tflops": flops / (mp["products_ms"] * 1e-3) / 1e12,
+                  "fp64_frac_of_measured_dfma_peak": flops / (mp["products_ms"] * 1e-3) / 1e12 / fp64_tf,
+                  "bound": "FP64 pipe for K_tot > ~12 (4 K_tot flop per entry on the FP64 tensor path, mma.sync.m8n8k4.f64), HBM below",
                   "d2h_bytes": int(8 * (n + p) * (K + 2) + 8 * (n + p)),
                   "what": "ebpmf_ctx_m_products: M %*% EF, t(M) %*% EL, column/row sums of (M - EL EF')^2 (flashier's R2) from the "
-                          "resident M (R/ebpmf_log_flash_update.R:35,55-64); two streaming kernels, each reads M once"}
+                          "resident M (R/ebpmf_log_flash_update.R:35,55-64); ONE streaming kernel reads M once"}
 
     # ---- roofline (HBM line of the dominant kernel = first pass) --------------------------------
     ncu = read_ncu_metrics() if args.workload == "c4slab" else None

@@ -1422,21 +1422,23 @@ int ebpmf_vga_step_resident_host(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K
 // ---- N1: products of the resident M with the factors, and the residual sums of squares -----------
 }  // extern "C"
 namespace {
+#ifndef EBPMF_PROD_NW
+#define EBPMF_PROD_NW 8       // warps (32-row groups) per CTA of the products kernel
+#endif
+constexpr int kProdRows = 32 * EBPMF_PROD_NW;
+
 template <int KP>
-int launch_products(ebpmf_ctx *ctx, const ProdArgs &a, cudaEvent_t mid) {
-    const long long nRB = (a.n + kRowsPerCta - 1) / kRowsPerCta;
-    m_ef_kernel<KP><<<dim3((unsigned)a.nsplit, (unsigned)nRB), kThreads, 0, ctx->stream>>>(a);
-    CU(cudaGetLastError());
-    CU(cudaEventRecord(mid, ctx->stream));
-    const int smem = (int)sizeof(MtElSmem<KP>);
+int launch_products(ebpmf_ctx *ctx, const ProdArgs &a) {
+    const long long nRBp = (a.n + kProdRows - 1) / kProdRows;
+    const int smem = (int)sizeof(ProdSmem<KP, EBPMF_PROD_NW>);
     static bool configured[64] = {false};
     if (ctx->device < 64 ? !configured[ctx->device] : true) {
-        CU(cudaFuncSetAttribute(mt_el_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(m_products_kernel<KP, EBPMF_PROD_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         if (ctx->device < 64) configured[ctx->device] = true;
     }
-    mt_el_kernel<KP><<<dim3((unsigned)((a.p + kTileCols - 1) / kTileCols), (unsigned)a.nrange), kThreads, smem, ctx->stream>>>(a);
+    m_products_kernel<KP, EBPMF_PROD_NW><<<dim3((unsigned)a.nsplit, (unsigned)nRBp), 32 * EBPMF_PROD_NW, smem, ctx->stream>>>(a);
     CU(cudaGetLastError());
-    ctx->launches += 2;
+    ++ctx->launches;
     return EBPMF_OK;
 }
 }  // namespace
@@ -1451,14 +1453,12 @@ int ebpmf_ctx_m_products(ebpmf_ctx *ctx, int64_t Kw, const double *EL_w, const d
     const long long n = ctx->n, p = ctx->p;
     const int K = (int)Kw;
     const int KPmax = ktp_for(std::min(K, 32));
-    const long long nRB = (n + kRowsPerCta - 1) / kRowsPerCta;
-    // splits: enough CTAs for a few waves, partials stay small
-    const int nsplit = (int)std::max(1LL, std::min<long long>((p + kTileCols - 1) / kTileCols, (148LL * 2 * 6 + nRB - 1) / nRB));
+    const long long nRB = (n + kProdRows - 1) / kProdRows;
+    // column spans: enough CTAs (one per SM at a time) for a dozen waves, few enough that the M %*% EF partials stay small
+    const int nsplit = (int)std::max(1LL, std::min<long long>((p + kTileCols - 1) / kTileCols, (148LL * 12 + nRB - 1) / nRB));
     int cols_per_split = (int)((p + nsplit - 1) / nsplit);
     cols_per_split = ((cols_per_split + kTileCols - 1) / kTileCols) * kTileCols;
-    const long long ngroups = (p + kTileCols - 1) / kTileCols;
-    const int nrange = (int)std::max(1LL, std::min<long long>(nRB, (148LL * 2 * 6 + ngroups - 1) / ngroups));
-    long long rows_per_range = (nRB + nrange - 1) / nrange * kRowsPerCta;
+    const long long nrange = nRB;                   // t(M) %*% EL: one partial per row block of the kernel
     // device scratch, carved out of one buffer
     size_t off = 0;
     auto carve = [&](size_t doubles) { const size_t o = off; off += (doubles + 1) & ~(size_t)1; return o; };
@@ -1483,26 +1483,27 @@ int ebpmf_ctx_m_products(ebpmf_ctx *ctx, int64_t Kw, const double *EL_w, const d
         memset(&a, 0, sizeof a);
         a.n = n; a.p = p; a.K = Kc; a.M = as<double>(ctx->Mcur); a.EL = base + oEL + (size_t)n * k0; a.EFt = base + oEFt;
         a.MFpart = base + oMFp; a.rowsq = base + oRsq; a.MtLpart = base + oMtLp; a.colsq = base + oCsq;
-        a.nsplit = nsplit; a.cols_per_split = cols_per_split; a.nrange = nrange; a.rows_per_range = (int)rows_per_range;
+        a.nsplit = nsplit; a.cols_per_split = cols_per_split;
         a.bulk = (n % 2 == 0 && !getenv("EBPMF_B200_NO_BULK")) ? 1 : 0;
         CU(cudaEventRecord(ctx->ev_p1, ctx->stream));
         switch (KP) {
-            case 8: CHECK((launch_products<8>(ctx, a, ctx->ev_p2))); break;
-            case 16: CHECK((launch_products<16>(ctx, a, ctx->ev_p2))); break;
-            case 24: CHECK((launch_products<24>(ctx, a, ctx->ev_p2))); break;
-            default: CHECK((launch_products<32>(ctx, a, ctx->ev_p2))); break;
+            case 8: CHECK((launch_products<8>(ctx, a))); break;
+            case 16: CHECK((launch_products<16>(ctx, a))); break;
+            case 24: CHECK((launch_products<24>(ctx, a))); break;
+            default: CHECK((launch_products<32>(ctx, a))); break;
         }
-        CU(cudaEventRecord(ctx->ev_p3, ctx->stream));
+        CU(cudaEventRecord(ctx->ev_p2, ctx->stream));
         sum_splits_kernel<<<(unsigned)(((long long)Kc * n + 255) / 256), 256, 0, ctx->stream>>>(base + oMFp, (long long)KP * n, (long long)Kc * n, nsplit,
                                                                                              base + oMF + (size_t)n * k0);
-        mtl_gather_kernel<<<(unsigned)((p * Kc + 255) / 256), 256, 0, ctx->stream>>>(base + oMtLp, nrange, p, KP, Kc, base + oMtL + (size_t)p * k0);
+        mtl_gather_kernel<<<(unsigned)((p * KP + 255) / 256), 256, 0, ctx->stream>>>(base + oMtLp, (int)nrange, p, KP, Kc, base + oMtL + (size_t)p * k0);
         CU(cudaGetLastError());
         if (k0 == 0) {                               // sums of squares of M: any chunk's pass gives them
             sum_splits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(base + oRsq, n, n, nsplit, base + oSqR);
-            sum_splits_kernel<<<(unsigned)((p + 255) / 256), 256, 0, ctx->stream>>>(base + oCsq, p, p, nrange, base + oSqC);
+            sum_splits_kernel<<<(unsigned)((p + 255) / 256), 256, 0, ctx->stream>>>(base + oCsq, p, p, (int)nrange, base + oSqC);
             CU(cudaGetLastError());
         }
-        ctx->launches += 5;
+        CU(cudaEventRecord(ctx->ev_p3, ctx->stream));
+        ctx->launches += 3 + (k0 == 0 ? 2 : 0);
         if (kernel_ms) {                             // per-kernel times of the chunk (events are reused: read them now)
             CU(cudaEventSynchronize(ctx->ev_p3));
             float t = 0.f;

@@ -9,15 +9,21 @@
 // the latter from sum M^2 - 2 <M, EL EF'> + <EL EF', EL EF'>, i.e. from the products themselves and the two
 // K x K Gram matrices (how flashier forms R2 as well): no third pass over M.
 //
-// Two streaming kernels, one per product, each reads M exactly once (8 B per entry; the bound is HBM for
-// small K and the FP64 pipe beyond K ~ 24: 1 DFMA per entry per factor column):
-//   m_ef_kernel   thread = row: coalesced column walks, K accumulators per thread in registers, EF rows of the
-//                 current 16-column slab broadcast from shared memory (double-buffered, one barrier per slab);
-//   mt_el_kernel  CTA = 16 columns x a range of rows; per 256-row tile the M slab (16 x 2 KB column segments)
-//                 and the EL tile (K x 2 KB) arrive by bulk async copies on one mbarrier; every thread owns
-//                 2 columns x K/8 factor columns of the result for a quarter of the tile's rows, accumulators
-//                 live in registers across the whole row range.
-// Both write small per-split partials that are summed in a fixed order (run-to-run reproducible).
+// ONE streaming kernel reads M exactly once (8 B per entry) and forms both products on the FP64 TENSOR path
+// (mma.sync.m8n8k4.f64 = DMMA).  Measured on B200 (scripts/probes/dmma_probe.cu, profiles/r02_probe_dmma.txt):
+// DMMA and DFMA share the FP64 pipe and the same peak (36.7 vs 34.4 TFLOP/s), but an accumulating DFMA
+// (three distinct register sources) issues in 3 cycles instead of 2, so a DFMA GEMM tops out at ~2/3 of that
+// peak while DMMA can reach it, and it frees issue slots for the loads.  4 K flop per entry make the pass
+// FP64-bound beyond K ~ 12 (HBM-bound below): K = 22 costs >= 9 ms on the 125 000 x 30 000 slab, HBM alone 4.6 ms.
+//   CTA = NW warps = 32 NW rows x a span of columns, walked in slabs of 16 columns; warp w owns rows [32w, 32w+32).
+//   M slab: 16 column segments by bulk async copies, double-buffered (the next slab lands while this one is
+//   multiplied); the slab's EF rows ride on the same mbarrier.
+//   M %*% EF : A = M (8 rows x 4 columns per DMMA), B = EF rows of the slab (shared memory), accumulators
+//              (32 rows x KP) stay in registers across the whole span;
+//   t(M)%*%EL: A = t(M) (the same shared image read transposed), B = this warp's EL rows, held in registers
+//              for the whole span; the slab's 16 x KP result is summed over the warps through shared memory
+//              (fixed order) and written as this row block's partial, one slab behind the multiplication.
+// Partials are summed by the small kernels below in a fixed order (run-to-run reproducible).
 #pragma once
 #include "vga_kernels.cuh"
 
@@ -31,164 +37,187 @@ struct ProdArgs {
     const double *EFt;           // p x KP row-major, zero padded
     double *MFpart;              // [nsplit][KP][n]
     double *rowsq;               // [nsplit][n]
-    double *MtLpart;             // [nrange][p][KP]
-    double *colsq;               // [nrange][p]
-    int nsplit, cols_per_split;  // m_ef_kernel: column ranges (multiples of 16 columns)
-    int nrange, rows_per_range;  // mt_el_kernel: row ranges (multiples of 256 rows)
+    double *MtLpart;             // [row blocks][p][KP]
+    double *colsq;               // [row blocks][p]
+    int nsplit, cols_per_split;  // column spans (multiples of 16 columns)
     int bulk;
 };
 
-// ---- MF = M %*% EF, row sums of M^2 ---------------------------------------------------------
-template <int KP>
-__global__ void __launch_bounds__(kThreads, 2) m_ef_kernel(const ProdArgs a)
+template <int KP, int NW>
+struct ProdSmem {
+    // column stride rows + 4: the fragment loads of both products (8 rows x 4 columns, and 4 rows x 8 columns)
+    // hit 16 distinct bank pairs per half warp; same argument for the EF rows (KP + 4)
+    double ms[2][kTileCols][32 * NW + 4];         // M slab, double-buffered
+    double efs[2][kTileCols][KP + 4];             // EF rows of the slab
+    double red[2][NW][kTileCols][KP];             // per-warp t(M) EL of the slab, double-buffered
+    unsigned long long mbar[2];
+};
+
+// D(8x8) += A(8x4) * B(4x8); lane holds A[lane/4][lane%4], B[lane%4][lane/4], D[lane/4][2*(lane%4) + {0,1}]
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int KP, int NW>
+__global__ void __launch_bounds__(32 * NW, NW <= 4 ? 3 : 1) m_products_kernel(const ProdArgs a)
 {
-    __shared__ __align__(16) double efs[2][kTileCols][KP];
-    const int tid = threadIdx.x;
+    constexpr int NT = KP / 8;                    // 8-wide tiles of factor columns
+    constexpr int ROWS = 32 * NW, NTH = 32 * NW;
+    constexpr int TPC = NTH / kTileCols;          // threads per column for the column sums of squares
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ProdSmem<KP, NW> &sm = *reinterpret_cast<ProdSmem<KP, NW> *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int l4 = lane & 3, l8 = lane >> 2;
     const int n = (int)a.n, p = (int)a.p;
-    const int i = blockIdx.y * kRowsPerCta + tid;
-    const bool row_ok = i < n;
+    const int rb = blockIdx.y, r0 = rb * ROWS;
+    const int rows_valid = min(ROWS, n - r0);
     const int jc0 = blockIdx.x * a.cols_per_split;
     const int jc1 = min(p, jc0 + a.cols_per_split);
     const size_t ns = (size_t)n;
-    double acc[KP];
-#pragma unroll
-    for (int k = 0; k < KP; ++k) acc[k] = 0.0;
-    double sq = 0.0;
-    auto stage = [&](int buf, int j0) {
-        for (int idx = tid; idx < kTileCols * KP; idx += kThreads) {
-            const int c = idx / KP, k = idx - c * KP;
-            efs[buf][c][k] = (j0 + c < jc1) ? __ldg(a.EFt + (size_t)(j0 + c) * KP + k) : 0.0;
-        }
-    };
-    if (jc0 < jc1) stage(0, jc0);
-    __syncthreads();
-    int buf = 0;
-    for (int j0 = jc0; j0 < jc1; j0 += kTileCols, buf ^= 1) {
-        double m[kTileCols];
-        const double *mp = a.M + (size_t)i + ns * (size_t)j0;
-#pragma unroll
-        for (int c = 0; c < kTileCols; ++c) m[c] = (row_ok && j0 + c < jc1) ? ld_stream(mp + c * ns) : 0.0;
-        if (j0 + kTileCols < jc1) stage(buf ^ 1, j0 + kTileCols);          // next slab's EF rows, other buffer
-#pragma unroll
-        for (int c = 0; c < kTileCols; ++c) {
-            sq = fma(m[c], m[c], sq);
-#pragma unroll
-            for (int k = 0; k < KP; ++k) acc[k] = fma(m[c], efs[buf][c][k], acc[k]);
-        }
-        __syncthreads();
-    }
-    if (row_ok) {
-        double *out = a.MFpart + (size_t)blockIdx.x * KP * ns + i;
-#pragma unroll
-        for (int k = 0; k < KP; ++k) out[(size_t)k * ns] = acc[k];
-        a.rowsq[(size_t)blockIdx.x * ns + i] = sq;
-    }
-}
-
-// ---- MtL = t(M) %*% EL, column sums of M^2 -----------------------------------------------------
-constexpr int kProdStride = kRowsPerCta + 2;      // column stride (doubles) of the padded smem images: 16-byte
-                                                  // aligned rows, and 8 consecutive columns hit 8 distinct bank pairs
-template <int KP>
-struct MtElSmem {
-    double ms[kTileCols][kProdStride];
-    double els[KP][kProdStride];      // after the row loop its storage is reused for the cross-group reduction
-    unsigned long long mbar;
-};
-
-template <int KP>
-__global__ void __launch_bounds__(kThreads, 2) mt_el_kernel(const ProdArgs a)
-{
-    constexpr int KT = KP / 8;                    // factor columns per thread: kt, kt+8, ...
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    MtElSmem<KP> &sm = *reinterpret_cast<MtElSmem<KP> *>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = (int)a.n, p = (int)a.p;
-    const int j0 = blockIdx.x * kTileCols;
-    const int ncv = min(kTileCols, p - j0);
-    const int ra = blockIdx.y * a.rows_per_range;
-    const int rb = min(n, ra + a.rows_per_range);
-    const size_t ns = (size_t)n;
     const bool bulk = a.bulk != 0;
-    const unsigned mbar_s = smem_addr(&sm.mbar);
+    if (jc0 >= jc1) return;
+    const unsigned mbar_s[2] = {smem_addr(&sm.mbar[0]), smem_addr(&sm.mbar[1])};
     if (tid == 0) {
-        mbar_init(mbar_s, 1);
+        mbar_init(mbar_s[0], 1); mbar_init(mbar_s[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
     }
-    // thread roles: rg = quarter of the tile's rows, cp = column pair, kt = first factor column
-    const int rg = tid >> 6, u = tid & 63, cp = u >> 3, kt = u & 7;
-    const int sc = tid >> 4, sp = tid & 15;        // column / row phase for the sums of squares
-    double acc[2][KT];
+    // rows the copies never write (ragged last row block): zero once, both buffers
+    if (rows_valid < ROWS)
+        for (int idx = tid; idx < 2 * kTileCols * ROWS; idx += NTH) {
+            const int r = idx % ROWS, c = (idx / ROWS) % kTileCols, b = idx / (ROWS * kTileCols);
+            if (r >= rows_valid) sm.ms[b][c][r] = 0.0;
+        }
+    // this warp's EL rows as B fragments of t(M) %*% EL: el[ks][nt] = EL[r0 + 32w + 4ks + l4][8nt + l8]
+    double el[8][NT];
 #pragma unroll
-    for (int q = 0; q < KT; ++q) { acc[0][q] = 0.0; acc[1][q] = 0.0; }
-    double sq = 0.0;
-    unsigned phase = 0;
-    // what the copies never write: columns past p, factor columns past K (zeroed once)
-    for (int idx = tid; idx < (kTileCols + KP) * kRowsPerCta; idx += kThreads) {
-        const int c = idx >> 8, r = idx & 255;
-        if (c < kTileCols) { if (c >= ncv) sm.ms[c][r] = 0.0; }
-        else if (c - kTileCols >= a.K) sm.els[c - kTileCols][r] = 0.0;
+    for (int ks = 0; ks < 8; ++ks) {
+        const int i = r0 + 32 * warp + 4 * ks + l4;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int k = 8 * nt + l8;
+            el[ks][nt] = (i < n && k < a.K) ? __ldg(a.EL + (size_t)i + ns * (size_t)k) : 0.0;
+        }
     }
-    for (int r0 = ra; r0 < rb; r0 += kRowsPerCta) {
-        const int rows_valid = min(kRowsPerCta, rb - r0);
-        __syncthreads();                             // previous tile consumed (and the mbarrier initialised)
+    double accF[4][NT][2];                         // M %*% EF: rows 32w + 8rt + l8, factor columns 8nt + 2*l4 + {0,1}
+#pragma unroll
+    for (int rt = 0; rt < 4; ++rt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { accF[rt][nt][0] = 0.0; accF[rt][nt][1] = 0.0; }
+    double rsq = 0.0;                              // sum over the span of M[r0 + tid, j]^2
+    const int sc = tid / TPC, sp = tid % TPC;      // column / row phase for the column sums of squares
+
+    auto issue = [&](int buf, int j0) {            // bring the slab [j0, j0+16) and its EF rows into buffer `buf`
+        const int ncv = min(kTileCols, jc1 - j0);
+        if (ncv < kTileCols) {                     // columns past the span: zero (no copy writes them)
+            for (int idx = tid; idx < (kTileCols - ncv) * ROWS; idx += NTH) sm.ms[buf][ncv + idx / ROWS][idx % ROWS] = 0.0;
+            for (int idx = tid; idx < (kTileCols - ncv) * KP; idx += NTH) sm.efs[buf][ncv + idx / KP][idx % KP] = 0.0;
+        }
         if (bulk) {
             if (warp == 0) {
-                if (lane == 0) mbar_expect_tx(mbar_s, (unsigned)((ncv + a.K) * rows_valid * 8));
+                if (lane == 0) mbar_expect_tx(mbar_s[buf], (unsigned)(ncv * rows_valid * 8 + ncv * KP * 8));
                 __syncwarp();
-                if (lane < ncv) bulk_load(smem_addr(&sm.ms[lane][0]), a.M + (size_t)r0 + ns * (size_t)(j0 + lane), (unsigned)(rows_valid * 8), mbar_s);
-                for (int k = lane; k < a.K; k += 32)
-                    bulk_load(smem_addr(&sm.els[k][0]), a.EL + (size_t)r0 + ns * (size_t)k, (unsigned)(rows_valid * 8), mbar_s);
+                if (lane < ncv)
+                    bulk_load(smem_addr(&sm.ms[buf][lane][0]), a.M + (size_t)r0 + ns * (size_t)(j0 + lane), (unsigned)(rows_valid * 8),
+                              mbar_s[buf]);
+                else if (lane >= 16 && lane - 16 < ncv)       // EF rows: KP doubles each (a multiple of 64 bytes)
+                    bulk_load(smem_addr(&sm.efs[buf][lane - 16][0]), a.EFt + (size_t)(j0 + lane - 16) * KP, (unsigned)(KP * 8), mbar_s[buf]);
             }
-            if (rows_valid < kRowsPerCta) {          // ragged last tile: rows the copies do not write
-                for (int idx = tid; idx < (kTileCols + KP) * kRowsPerCta; idx += kThreads) {
-                    const int c = idx >> 8, r = idx & 255;
-                    if (r >= rows_valid) { if (c < kTileCols) sm.ms[c][r] = 0.0; else sm.els[c - kTileCols][r] = 0.0; }
-                }
-            }
-            mbar_wait(mbar_s, phase);
-            phase ^= 1u;
         } else {
-            for (int idx = tid; idx < (kTileCols + KP) * kRowsPerCta; idx += kThreads) {
-                const int c = idx >> 8, r = idx & 255;
-                if (c < kTileCols) sm.ms[c][r] = (c < ncv && r < rows_valid) ? ld_stream(a.M + (size_t)(r0 + r) + ns * (size_t)(j0 + c)) : 0.0;
-                else sm.els[c - kTileCols][r] = (c - kTileCols < a.K && r < rows_valid) ? __ldg(a.EL + (size_t)(r0 + r) + ns * (size_t)(c - kTileCols)) : 0.0;
+            for (int idx = tid; idx < ncv * ROWS; idx += NTH) {
+                const int c = idx / ROWS, r = idx % ROWS;
+                if (r < rows_valid) sm.ms[buf][c][r] = ld_stream(a.M + (size_t)(r0 + r) + ns * (size_t)(j0 + c));
+            }
+            for (int idx = tid; idx < ncv * KP; idx += NTH) sm.efs[buf][idx / KP][idx % KP] = __ldg(a.EFt + (size_t)j0 * KP + idx);
+        }
+    };
+    // sum the warps' t(M) EL of a finished slab (fixed order) into this row block's partial
+    auto flush = [&](int buf, int j0) {
+        const int ncv = min(kTileCols, jc1 - j0);
+        for (int idx = tid; idx < kTileCols * KP; idx += NTH) {
+            const int c = idx / KP, k = idx - c * KP;
+            if (c < ncv) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) s += sm.red[buf][w][c][k];
+                a.MtLpart[((size_t)rb * p + j0 + c) * KP + k] = s;
             }
         }
+    };
+
+    __syncthreads();                               // mbarriers initialised, ragged rows zeroed
+    issue(0, jc0);
+    unsigned phase[2] = {0u, 0u};
+    int buf = 0;
+    for (int j0 = jc0; j0 < jc1; j0 += kTileCols, buf ^= 1) {
+        const int ncv = min(kTileCols, jc1 - j0);
+        if (bulk) { mbar_wait(mbar_s[buf], phase[buf]); phase[buf] ^= 1u; }
+        // ONE barrier per slab: every warp is done with slab s-1 (its M image and EF rows may be overwritten, its
+        // red[] is complete), and -- without bulk copies -- this slab's staged data is visible
         __syncthreads();
-        const double *m0 = &sm.ms[2 * cp][64 * rg], *m1 = &sm.ms[2 * cp + 1][64 * rg];
-        const double *e0 = &sm.els[kt][64 * rg];
-#pragma unroll 8
-        for (int r = 0; r < 64; ++r) {
-            const double x0 = m0[r], x1 = m1[r];
+        if (j0 + kTileCols < jc1) issue(buf ^ 1, j0 + kTileCols);
+        if (j0 > jc0) flush(buf ^ 1, j0 - kTileCols);
+        const double (*ms)[ROWS + 4] = sm.ms[buf];
+        // ---- M %*% EF ---------------------------------------------------------------------------------
 #pragma unroll
-            for (int q = 0; q < KT; ++q) {
-                const double e = e0[(size_t)q * 8 * kProdStride + r];
-                acc[0][q] = fma(x0, e, acc[0][q]);
-                acc[1][q] = fma(x1, e, acc[1][q]);
+        for (int ks = 0; ks < 4; ++ks) {
+            double bf[NT];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) bf[nt] = sm.efs[buf][4 * ks + l4][8 * nt + l8];
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) {
+                const double af = ms[4 * ks + l4][32 * warp + 8 * rt + l8];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) dmma884(accF[rt][nt][0], accF[rt][nt][1], af, bf[nt]);
+            }
+        }
+        // ---- t(M) %*% EL over this warp's 32 rows -------------------------------------------------------
+        double accT[2][NT][2];
+#pragma unroll
+        for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) { accT[ct][nt][0] = 0.0; accT[ct][nt][1] = 0.0; }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct) {
+                const double af = ms[8 * ct + l8][32 * warp + 4 * ks + l4];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) dmma884(accT[ct][nt][0], accT[ct][nt][1], af, el[ks][nt]);
             }
         }
 #pragma unroll
-        for (int q = 0; q < kRowsPerCta / 16; ++q) { const double x = sm.ms[sc][sp + 16 * q]; sq = fma(x, x, sq); }
-    }
-    // combine the four row groups (fixed order), write this range's partial
-    __syncthreads();
-    static_assert(sizeof(double) * 4 * kTileCols * (KP + 1) <= sizeof(double) * KP * kProdStride, "reduction scratch fits the EL tile");
-    struct Red { double red[4][kTileCols][KP + 1]; };
-    Red &smr = *reinterpret_cast<Red *>(&sm.els[0][0]);
+        for (int ct = 0; ct < 2; ++ct)
 #pragma unroll
-    for (int q = 0; q < KT; ++q) { smr.red[rg][2 * cp][kt + 8 * q] = acc[0][q]; smr.red[rg][2 * cp + 1][kt + 8 * q] = acc[1][q]; }
-    sq += __shfl_xor_sync(0xffffffffu, sq, 8);
-    sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-    __syncthreads();
-    for (int idx = tid; idx < kTileCols * KP; idx += kThreads) {
-        const int c = idx / KP, k = idx - c * KP;
-        if (c < ncv)
-            a.MtLpart[((size_t)blockIdx.y * p + j0 + c) * KP + k] = ((smr.red[0][c][k] + smr.red[1][c][k]) + smr.red[2][c][k]) + smr.red[3][c][k];
+            for (int nt = 0; nt < NT; ++nt)
+                *reinterpret_cast<double2 *>(&sm.red[buf][warp][8 * ct + l8][8 * nt + 2 * l4]) = make_double2(accT[ct][nt][0], accT[ct][nt][1]);
+        // ---- sums of squares: this row over the slab's columns; each column over the tile's rows ----------
+        double csq = 0.0;
+#pragma unroll
+        for (int c = 0; c < kTileCols; ++c) { const double x = ms[c][tid]; rsq = fma(x, x, rsq); }
+#pragma unroll
+        for (int q = 0; q < ROWS / TPC; ++q) { const double x = ms[sc][sp + TPC * q]; csq = fma(x, x, csq); }
+#pragma unroll
+        for (int o = TPC / 2; o > 0; o >>= 1) csq += __shfl_xor_sync(0xffffffffu, csq, o);
+        if (sp == 0 && sc < ncv) a.colsq[(size_t)rb * p + j0 + sc] = csq;
     }
-    if (sp == 0 && sc < ncv) a.colsq[(size_t)blockIdx.y * p + j0 + sc] = sq;
+    __syncthreads();
+    flush(buf ^ 1, jc0 + ((jc1 - jc0 - 1) / kTileCols) * kTileCols);       // the last slab
+    // ---- this span's M %*% EF partial and row sums of squares ---------------------------------------------
+    double *out = a.MFpart + (size_t)blockIdx.x * KP * ns;
+#pragma unroll
+    for (int rt = 0; rt < 4; ++rt) {
+        const int i = r0 + 32 * warp + 8 * rt + l8;
+        if (i < n) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                out[(size_t)(8 * nt + 2 * l4) * ns + i] = accF[rt][nt][0];
+                out[(size_t)(8 * nt + 2 * l4 + 1) * ns + i] = accF[rt][nt][1];
+            }
+        }
+    }
+    if (r0 + tid < n) a.rowsq[(size_t)blockIdx.x * ns + r0 + tid] = rsq;
 }
 
 // out[t] = sum_s part[s*stride + t], t < len  (fixed order)
@@ -201,15 +230,16 @@ __global__ void sum_splits_kernel(const double *part, long long stride, long lon
     out[t] = s;
 }
 
-// MtL (p x Kc, column-major, leading dimension p) from the row-major partials [nrange][p][KP]
+// MtL (p x Kc, column-major, leading dimension p) from the row-major partials [nrange][p][KP]: one thread per
+// (j, k) of the partial layout, so the nrange reads of a warp are contiguous; fixed summation order
 __global__ void mtl_gather_kernel(const double *part, int nrange, long long p, int KP, int Kc, double *out)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= p * Kc) return;
-    const long long j = t % p; const int k = (int)(t / p);
+    if (t >= p * KP) return;
+    const long long j = t / KP; const int k = (int)(t - j * KP);
     double s = 0.0;
-    for (int q = 0; q < nrange; ++q) s += part[((size_t)q * p + j) * KP + k];
-    out[t] = s;
+    for (int q = 0; q < nrange; ++q) s += part[(size_t)q * (size_t)p * KP + t];
+    if (k < Kc) out[j + p * k] = s;
 }
 
 // G[k][l] = sum_i A[i + ld*k] * A[i + ld*l]  (K x K Gram matrix of an ld x K column-major matrix), one block per (k,l)

@@ -373,7 +373,7 @@ class VgaContext:
         rr = np.empty(self.n) if want_r2_row else None
         ms = (C.c_double * 3)()
         self._ck(self._lib.ebpmf_ctx_m_products(self._h, Kw, _ptr(EL_w), _ptr(EF_w), _ptr(MF), _ptr(MtL), _ptr(rc), _ptr(rr), ms))
-        return dict(MF=MF, MtL=MtL, r2_col=rc, r2_row=rr, kernel_ms=ms[0], m_ef_ms=ms[1], mt_el_ms=ms[2])
+        return dict(MF=MF, MtL=MtL, r2_col=rc, r2_row=rr, kernel_ms=ms[0], products_ms=ms[1], partial_sums_ms=ms[2])
 
     def last_diag(self):
         a, b = C.c_uint64(), C.c_uint64()

@@ -209,15 +209,15 @@ int  ebpmf_vga_step_resident_host(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t 
  * flashier treats the latent M as its data matrix (fit_flash$flash_fit$Y = res$M, R/ebpmf_log.R:270,309;
  * flash_init(fit_flash$flash_fit$Y, ...), R/ebpmf_log_flash_update.R:35) and touches it only through
  * products with the current loadings / factors and through the residual sums of squares R2
- * (R/ebpmf_log_flash_update.R:55-64).  One streaming pass over the RESIDENT M (8 B per entry, nothing
- * crosses PCIe but the small results):
+ * (R/ebpmf_log_flash_update.R:55-64).  One streaming pass over the RESIDENT M (8 B per entry, both products on
+ * the FP64 tensor path -- mma.sync.m8n8k4.f64 --; nothing crosses PCIe but the small results):
  *   MF  (n x Kw) = M %*% EF_w                      MtL (p x Kw) = t(M) %*% EL_w
  *   r2_col (p)   = colSums((M - EL_w %*% t(EF_w))^2)    r2_row (n) = rowSums(...)     (either may be NULL)
  * EL_w is n x Kw, EF_w is p x Kw (column-major host pointers; this rank's rows of EL_w).  With a
  * communicator MtL and r2_col are summed over the ranks (rows are sharded); MF and r2_row stay sharded. */
 int  ebpmf_ctx_m_products(ebpmf_ctx *ctx, int64_t Kw, const double *EL_w, const double *EF_w,
                           double *MF, double *MtL, double *r2_col, double *r2_row,
-                          double *kernel_ms /* NULL or 3 doubles: whole call, M %*% EF kernel(s), t(M) %*% EL kernel(s) */);
+                          double *kernel_ms /* NULL or 3 doubles: whole call, the streaming products kernel(s), the partial-sum kernels */);
 
 /* ---- one process, several GPUs (an R session is one process) -------------------------------
  * A group owns one context per GPU and one NCCL communicator over them; every group call runs one
