@@ -1462,7 +1462,7 @@ int ebpmf_ctx_m_products(ebpmf_ctx *ctx, int64_t Kw, const double *EL_w, const d
     // device scratch, carved out of one buffer
     size_t off = 0;
     auto carve = [&](size_t doubles) { const size_t o = off; off += (doubles + 1) & ~(size_t)1; return o; };
-    const size_t oEL = carve((size_t)n * K), oEF = carve((size_t)p * K), oEFt = carve((size_t)p * KPmax);
+    const size_t oEL = carve((size_t)n * K), oEF = carve((size_t)p * K), oEFt = carve((size_t)p * (KPmax + 4));
     const size_t oMFp = carve((size_t)nsplit * KPmax * n), oRsq = carve((size_t)nsplit * n);
     const size_t oMtLp = carve((size_t)nrange * p * KPmax), oCsq = carve((size_t)nrange * p);
     const size_t oMF = carve((size_t)n * K), oMtL = carve((size_t)p * K), oGL = carve((size_t)K * K), oGF = carve((size_t)K * K);
@@ -1477,7 +1477,7 @@ int ebpmf_ctx_m_products(ebpmf_ctx *ctx, int64_t Kw, const double *EL_w, const d
     for (int k0 = 0; k0 < K; k0 += 32) {             // factor columns in chunks of at most 32 (one pass over M each)
         const int Kc = std::min(32, K - k0);
         const int KP = ktp_for(Kc);
-        transpose_ef_kernel<<<(unsigned)((p * KP + 255) / 256), 256, 0, ctx->stream>>>(base + oEF + (size_t)p * k0, p, Kc, KP, base + oEFt);
+        transpose_ef_kernel<<<(unsigned)((p * (KP + 4) + 255) / 256), 256, 0, ctx->stream>>>(base + oEF + (size_t)p * k0, p, Kc, KP + 4, base + oEFt);
         CU(cudaGetLastError());
         ProdArgs a;
         memset(&a, 0, sizeof a);

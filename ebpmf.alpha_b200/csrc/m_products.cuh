@@ -34,7 +34,7 @@ struct ProdArgs {
     int K;                       // factor columns (<= KP)
     const double *M;             // n x p column-major, resident
     const double *EL;            // n x K column-major
-    const double *EFt;           // p x KP row-major, zero padded
+    const double *EFt;           // p x (KP + 4) row-major, zero padded
     double *MFpart;              // [nsplit][KP][n]
     double *rowsq;               // [nsplit][n]
     double *MtLpart;             // [row blocks][p][KP]
@@ -115,21 +115,23 @@ __global__ void __launch_bounds__(32 * NW, NW <= 4 ? 3 : 1) m_products_kernel(co
             for (int idx = tid; idx < (kTileCols - ncv) * KP; idx += NTH) sm.efs[buf][ncv + idx / KP][idx % KP] = 0.0;
         }
         if (bulk) {
-            if (warp == 0) {
-                if (lane == 0) mbar_expect_tx(mbar_s[buf], (unsigned)(ncv * rows_valid * 8 + ncv * KP * 8));
-                __syncwarp();
-                if (lane < ncv)
-                    bulk_load(smem_addr(&sm.ms[buf][lane][0]), a.M + (size_t)r0 + ns * (size_t)(j0 + lane), (unsigned)(rows_valid * 8),
-                              mbar_s[buf]);
-                else if (lane >= 16 && lane - 16 < ncv)       // EF rows: KP doubles each (a multiple of 64 bytes)
-                    bulk_load(smem_addr(&sm.efs[buf][lane - 16][0]), a.EFt + (size_t)(j0 + lane - 16) * KP, (unsigned)(KP * 8), mbar_s[buf]);
+            // one bulk copy per M column, spread over the warps, plus ONE copy for the slab's EF rows (EFt rows are
+            // padded to KP + 4 doubles in global memory exactly as in shared memory)
+            if (tid == 0) mbar_expect_tx(mbar_s[buf], (unsigned)(ncv * rows_valid * 8 + ncv * (KP + 4) * 8));
+            constexpr int CPW = (kTileCols + NW - 1) / NW;      // columns per warp
+            if (lane < CPW) {
+                const int c = warp * CPW + lane;
+                if (c < ncv)
+                    bulk_load(smem_addr(&sm.ms[buf][c][0]), a.M + (size_t)r0 + ns * (size_t)(j0 + c), (unsigned)(rows_valid * 8), mbar_s[buf]);
             }
+            if (warp == NW - 1 && lane == CPW)
+                bulk_load(smem_addr(&sm.efs[buf][0][0]), a.EFt + (size_t)j0 * (KP + 4), (unsigned)(ncv * (KP + 4) * 8), mbar_s[buf]);
         } else {
             for (int idx = tid; idx < ncv * ROWS; idx += NTH) {
                 const int c = idx / ROWS, r = idx % ROWS;
                 if (r < rows_valid) sm.ms[buf][c][r] = ld_stream(a.M + (size_t)(r0 + r) + ns * (size_t)(j0 + c));
             }
-            for (int idx = tid; idx < ncv * KP; idx += NTH) sm.efs[buf][idx / KP][idx % KP] = __ldg(a.EFt + (size_t)j0 * KP + idx);
+            for (int idx = tid; idx < ncv * (KP + 4); idx += NTH) (&sm.efs[buf][0][0])[idx] = __ldg(a.EFt + (size_t)j0 * (KP + 4) + idx);
         }
     };
     // sum the warps' t(M) EL of a finished slab (fixed order) into this row block's partial
@@ -157,7 +159,6 @@ __global__ void __launch_bounds__(32 * NW, NW <= 4 ? 3 : 1) m_products_kernel(co
         // red[] is complete), and -- without bulk copies -- this slab's staged data is visible
         __syncthreads();
         if (j0 + kTileCols < jc1) issue(buf ^ 1, j0 + kTileCols);
-        if (j0 > jc0) flush(buf ^ 1, j0 - kTileCols);
         const double (*ms)[ROWS + 4] = sm.ms[buf];
         // ---- M %*% EF ---------------------------------------------------------------------------------
 #pragma unroll
@@ -172,6 +173,8 @@ __global__ void __launch_bounds__(32 * NW, NW <= 4 ? 3 : 1) m_products_kernel(co
                 for (int nt = 0; nt < NT; ++nt) dmma884(accF[rt][nt][0], accF[rt][nt][1], af, bf[nt]);
             }
         }
+        // the previous slab's t(M) EL leaves while the FP64 pipe works through the DMMAs issued above
+        if (j0 > jc0) flush(buf ^ 1, j0 - kTileCols);
         // ---- t(M) %*% EL over this warp's 32 rows -------------------------------------------------------
         double accT[2][NT][2];
 #pragma unroll

@@ -9,6 +9,37 @@ __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// DISTINCT A / B fragments per DMMA (what a real GEMM tile loop has): MODE 0 = 8 distinct A and B registers,
+// 1 = one A shared by groups of 3 DMMAs (the M %*% EF loop: af reused over nt), B distinct
+template <int ND, int MODE>
+__global__ void kd(double *out, const double *in, long long *cyc, int iters) {
+    const int t = threadIdx.x;
+    double c[12][2], a[8], b[8];
+    for (int i = 0; i < 8; ++i) { a[i] = in[(t + i) & 63] + 1.0000001 + i; b[i] = in[(t + 7 + i) & 63] + 0.9999999 - i; }
+    for (int i = 0; i < 12; ++i) { c[i][0] = in[i] + i; c[i][1] = in[i + 8] - i; }
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int q = 0; q < ND; ++q) dmma(c[q % 12][0], c[q % 12][1], MODE == 0 ? a[q & 7] : a[(q / 3) & 7], b[q & 7]);
+    }
+    long long t1 = clock64();
+    double s = 0;
+    for (int i = 0; i < 12; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + t] = s;
+    if (t == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
+}
+template <int ND, int MODE> void rund(const char *what, int threads) {
+    double *out, *in; long long *cyc, h;
+    cudaMalloc(&out, 8 * 148 * 1024); cudaMalloc(&in, 8 * 2048); cudaMalloc(&cyc, 8);
+    cudaMemset(in, 0, 8 * 2048);
+    const int iters = 2000;
+    kd<ND, MODE><<<148, threads>>>(out, in, cyc, iters); cudaDeviceSynchronize();
+    kd<ND, MODE><<<148, threads>>>(out, in, cyc, iters); cudaDeviceSynchronize();
+    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("%-44s %7.2f SMSP-cycles per DMMA (%d warps per SMSP)\n", what, (double)h / iters / ND / (threads / 128.0), threads / 128);
+    cudaFree(out); cudaFree(in); cudaFree(cyc);
+}
+
 template <int ND, int NF, int NI>
 __global__ void k(double *out, const double *in, long long *cyc, int iters) {
     const int t = threadIdx.x;
@@ -60,5 +91,9 @@ int main() {
     run<8, 16, 32>("8 DMMA + 16 DFMA + 32 int");
     run<1, 0, 0>("1 DMMA (latency-bound chain per tile)");
     run<2, 16, 16>("2 DMMA + 16 DFMA + 16 int");
+    rund<24, 0>("24 DMMA, distinct A,B regs", 1024);
+    rund<24, 0>("24 DMMA, distinct A,B regs", 256);
+    rund<24, 1>("24 DMMA, A shared by 3, B distinct", 256);
+    rund<24, 0>("24 DMMA, distinct A,B regs", 128);
     return 0;
 }
