@@ -610,6 +610,21 @@ def main():
             ectx.set_y_csc(er, p, scp, sri, sx)
             ectx.set_m(ctx.get_rows(0, er))
             del cp, ri, x
+        # what the host side of this box can absorb: every rank copies 2 GiB device -> PINNED host memory at the same
+        # time (no library code involved); the e2e numbers below cannot exceed this x 1/8 B per entry
+        hb = torch.empty(1 << 28, dtype=torch.float64).pin_memory()
+        db = torch.zeros(1 << 28, dtype=torch.float64, device="cuda")
+        hb.copy_(db); torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            hb.copy_(db, non_blocking=True)
+        torch.cuda.synchronize()
+        tw = allmax(time.perf_counter() - t0)
+        out["host_d2h_ceiling"] = {"gb_per_s_per_gpu": 3 * 8 * (1 << 28) / tw / 1e9, "gb_per_s_all_gpus": world * 3 * 8 * (1 << 28) / tw / 1e9,
+                                   "entries_per_s_all_gpus": world * 3 * (1 << 28) / tw,
+                                   "how": "every rank: 3 x 2 GiB cudaMemcpyAsync device -> pinned host, concurrently; max over ranks"}
+        del hb, db
         # (b) ebpmf_log's loop: M is the previous step's output and stays resident (R/ebpmf_log.R:309); per step the
         #     factors and sigma2 go in (pageable NumPy arrays), M and v_sum come out.  The result matrix is a NEW
         #     matrix every call, allocated the way the .Call glue allocates it (allocVector3 with the library's
