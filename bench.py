@@ -20,12 +20,14 @@ partials in every step.  Inputs are generated ON THE DEVICE (ebpmf_ctx_sim_data_
              step whose history comes from DIFFERENT factors (the bench rewinds M between steps, so
              the plain history is a perfect predictor; the perturbed one is not)
   e2e        the same metric through the host-buffer C-ABI call the R .Call shim makes every outer
-             iteration, ebpmf_vga_step_resident_host, with PLAIN PAGEABLE host arrays (what R hands
-             the shim) and a FRESHLY ALLOCATED result matrix per call (what Rf_allocMatrix gives):
-             factors and sigma2 in, step, M and v_sum out; the full slab at N = 1.  Next to it:
-             e2e_reused_buffer (result buffer kept between calls), e2e_full_roundtrip (M in AND out),
-             e2e_batched (the batch_size < n branch), and m_products (N1: what flashier needs from M
-             computed on the device, so that M need not leave it at all)
+             iteration, ebpmf_vga_step_resident_host: factors and sigma2 in from PLAIN PAGEABLE host arrays
+             (what R hands the shim), step, M and v_sum out into a NEW result matrix per call, allocated
+             the way the glue allocates it (allocVector3 + the library's pool allocator: warm, page-locked
+             blocks that R's gc returns); the full slab at N = 1.  Next to it: e2e_pool_pageable (pool
+             blocks not page-locked), e2e_fresh_pages (plain Rf_allocMatrix: first-touch page faults every
+             call), e2e_full_roundtrip (M in AND out, pageable), e2e_batched (the batch_size < n branch),
+             host_d2h_ceiling (what the box's host side absorbs with every GPU copying at once), and
+             m_products (N1: what flashier needs from M computed on the device, so that M need not leave it)
   roofline   HBM line of the dominant kernel (first pass).  The FP64 pipe / issue port binds it
              (DESIGN.md section 4), so `fp64` (measured DFMA peak) and `issue_roofline` sit beside it; the
              instruction counts and DRAM traffic come from the committed ncu capture
@@ -647,7 +649,9 @@ def main():
             return w / steps, r["n_updates"]
 
         ks = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
         per, nu = timed_resident(pkg.host_matrix, 3, ks)
+        setup_s = time.perf_counter() - t0 - per * (3 + ks)
         cnt = ectx.counters()
         out["e2e"] = {"value": er * p * world / per, "unit": "entries/s",
                       "h2d_bytes_per_step": int(8 * (er + p) * (K + 2) + 8 * p),
@@ -655,37 +659,30 @@ def main():
                       "call": "ebpmf_vga_step_resident_host: the per-iteration call of ebpmf_log's outer loop -- factors and "
                               "sigma2 in from PAGEABLE host memory (plain NumPy arrays, as R's REAL() pointers are), M and "
                               "v_sum out; every call gets a NEW result matrix, allocated as the .Call glue allocates it "
-                              "(allocVector3 + the library's allocator ebpmf_host_alloc: pageable blocks of a warm pool, "
-                              "returned by R's gc); the step's input M is the previous step's output and is already on "
+                              "(allocVector3 + the library's allocator ebpmf_host_alloc: blocks of a warm pool, page-locked "
+                              "once, returned by R's gc); the step's input M is the previous step's output and is already on "
                               "the device (R feeds res$M back unchanged, R/ebpmf_log.R:309, R/ebpmf_log_flash_update.R:35)",
                       "sample": "rows [0,%d) of %d x %d cols per GPU per step%s" % (er, n, p, "" if er == n else " (bounded by host memory)"),
                       "steps": ks, "n_updates": nu, "ms_per_step": 1e3 * per,
                       "d2h_gb_per_s_per_gpu": 8.0 * er * p / per / 1e9,
+                      "one_time_pool_setup_s": setup_s,
                       "speculative_copy_bytes": cnt["spec_bytes"], "recopied_bytes": cnt["recopy_bytes"],
                       "host_pool": pkg.host_pool_stats()}
         pkg.host_pool_trim()
-        # (b0) diagnostic: ONE plain pageable result buffer reused by every call
-        Mr = pageable_f(er, p)
-        per, _ = timed_resident(lambda a, b: Mr, 2, ks)
-        out["e2e_reused_buffer"] = {"value": er * p * world / per, "unit": "entries/s", "ms_per_step": 1e3 * per,
+        # (b0) the pool with pageable blocks (EBPMF_B200_POOL_PIN=0): through the pinned ring + host memcpy threads
+        os.environ["EBPMF_B200_POOL_PIN"] = "0"
+        per, _ = timed_resident(pkg.host_matrix, 3, ks)
+        out["e2e_pool_pageable"] = {"value": er * p * world / per, "unit": "entries/s", "ms_per_step": 1e3 * per,
                                     "d2h_gb_per_s_per_gpu": 8.0 * er * p / per / 1e9,
-                                    "call": "as e2e, one np.empty result matrix allocated once and reused by every call"}
-        del Mr
-        # (b') the same with a plain Rf_allocMatrix-style result: fresh, never-touched pageable pages every call
+                                    "call": "as e2e with EBPMF_B200_POOL_PIN=0: warm but pageable result blocks"}
+        del os.environ["EBPMF_B200_POOL_PIN"]
+        pkg.host_pool_trim()
+        # (b') a plain Rf_allocMatrix-style result: fresh, never-touched pageable pages every call
         per, _ = timed_resident(pageable_f, 1, ks)
         out["e2e_fresh_pages"] = {"value": er * p * world / per, "unit": "entries/s", "ms_per_step": 1e3 * per,
                                   "d2h_gb_per_s_per_gpu": 8.0 * er * p / per / 1e9,
                                   "call": "as e2e, but the result is a freshly mmap'ed matrix every call (np.empty = what "
                                           "Rf_allocMatrix gives without the allocator): first-touch page faults included"}
-        # (b'') the pool with page-locked blocks (EBPMF_B200_POOL_PIN=1): the copy engine writes the result directly
-        os.environ["EBPMF_B200_POOL_PIN"] = "1"
-        t0 = time.perf_counter()
-        per, _ = timed_resident(pkg.host_matrix, 3, ks)
-        out["e2e_pool_pinned"] = {"value": er * p * world / per, "unit": "entries/s", "ms_per_step": 1e3 * per,
-                                  "d2h_gb_per_s_per_gpu": 8.0 * er * p / per / 1e9,
-                                  "one_time_setup_s": time.perf_counter() - t0 - per * ks,
-                                  "call": "as e2e with EBPMF_B200_POOL_PIN=1 (pool blocks are cudaHostRegister'ed once)"}
-        del os.environ["EBPMF_B200_POOL_PIN"]
         pkg.host_pool_trim()
         Mo = pageable_f(er, p)
         # (a) the stand-alone drop-in signature: M in AND out every step (pageable both ways)

@@ -350,8 +350,10 @@ class HostPipe {
 // rate (profiles/r02_probe_host_copy.txt: 17-29 GB/s into fresh pages against 53 GB/s into touched ones).
 // R lets a package supply the memory of a vector (allocVector3 with an R_allocator_t); the .Call glue hands
 // it blocks from this pool and the pool takes them back when R's garbage collector frees the matrix, so from
-// the second outer iteration on every result lands in pages that are already mapped (and, with
-// EBPMF_B200_POOL_PIN=1, page-locked: the copy engine then writes them directly, no staging memcpy).
+// the second outer iteration on every result lands in pages that are already mapped and page-locked (blocks of
+// 64 MB and more are cudaHostRegister'ed once, ~0.09 s per GiB; EBPMF_B200_POOL_PIN=0 keeps them pageable): the
+// copy engine then writes them directly, no staging memcpy -- which matters most when several GPUs share the
+// host's memory bandwidth (2 GPUs: 33.9 GB/s per GPU page-locked against 22.4 GB/s through the ring).
 class HostPool {
    public:
     static HostPool &instance() { static HostPool p; return p; }
@@ -380,8 +382,8 @@ class HostPool {
         (void)madvise(ptr, len, MADV_HUGEPAGE);
         Block b;
         b.ptr = ptr; b.bytes = len; b.pinned = false;
-        const char *pin = getenv("EBPMF_B200_POOL_PIN");
-        if (pin && atoi(pin) > 0 && len >= ((size_t)64 << 20)) {
+        const char *pin = getenv("EBPMF_B200_POOL_PIN");         // default on; "0" keeps the blocks pageable
+        if (!(pin && atoi(pin) == 0) && len >= ((size_t)64 << 20)) {
             populate(ptr, len);
             b.pinned = (cudaHostRegister(ptr, len, cudaHostRegisterPortable) == cudaSuccess);
             if (!b.pinned) (void)cudaGetLastError();

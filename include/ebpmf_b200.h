@@ -79,9 +79,9 @@ typedef struct ebpmf_solve_info {
  * millions of first-touch page faults per call, which halves the device->host rate.  The .Call glue instead
  * allocates result matrices with allocVector3() and an R_allocator_t whose mem_alloc / mem_free are these
  * two functions: blocks come from a process-wide pool and return to it when R's garbage collector frees the
- * matrix, so from the second outer iteration on a result lands in pages that are already mapped
- * (EBPMF_B200_POOL_PIN=1 also page-locks them: the copy engine then writes them directly;
- * EBPMF_B200_POOL_KEEP_GB, default 96, bounds what the pool keeps).  Any host pointer remains valid as an
+ * matrix, so from the second outer iteration on a result lands in pages that are already mapped and
+ * page-locked (blocks >= 64 MB are cudaHostRegister'ed once, so the copy engine writes them directly;
+ * EBPMF_B200_POOL_PIN=0 keeps them pageable; EBPMF_B200_POOL_KEEP_GB, default 96, bounds what the pool keeps).  Any host pointer remains valid as an
  * output argument of every entry point; the pool is an optimisation, not a requirement. */
 void *ebpmf_host_alloc(size_t bytes);          /* NULL when the system is out of memory */
 int   ebpmf_host_free(void *ptr);              /* EBPMF_ERR_ARG when ptr did not come from ebpmf_host_alloc */
