@@ -684,26 +684,33 @@ def main():
                                   "call": "as e2e, but the result is a freshly mmap'ed matrix every call (np.empty = what "
                                           "Rf_allocMatrix gives without the allocator): first-touch page faults included"}
         pkg.host_pool_trim()
-        Mo = pageable_f(er, p)
-        # (a) the stand-alone drop-in signature: M in AND out every step (pageable both ways)
-        Mi = ectx.get_m()                               # the resident M is the bench's M0 (every step above was rewound)
+        # (a) the stand-alone drop-in signature: M in AND out every step.  In ebpmf_log's loop the input M IS the previous
+        #     call's result (fit_flash$flash_fit$Y = res$M), i.e. a pool block, and the output is a new pool block
+        Mi = ectx.get_m(out=pkg.host_matrix(er, p))     # the resident M is the bench's M0 (every step above was rewound)
         kf = max(1, min(args.steps, 2))
-        ectx.vga_step_host(Mi, ELs, EF0, s2, "by_col", MAXITER_VGA, VGA_TOL, M_out=Mo)       # also touches Mo's pages
+        for _ in range(2):                              # both pool blocks warm
+            Mo = pkg.host_matrix(er, p)
+            ectx.vga_step_host(Mi, ELs, EF0, s2, "by_col", MAXITER_VGA, VGA_TOL, M_out=Mo)
+            del Mo
         barrier()
         t0 = time.perf_counter()
         for _ in range(kf):
+            Mo = pkg.host_matrix(er, p)
             ectx.vga_step_host(Mi, ELs, EF0, s2, "by_col", MAXITER_VGA, VGA_TOL, M_out=Mo)
+            del Mo
         torch.cuda.synchronize()
         w = allmax(time.perf_counter() - t0)
         out["e2e_full_roundtrip"] = {"value": er * p * world / (w / kf), "unit": "entries/s", "ms_per_step": 1e3 * w / kf,
                                      "h2d_bytes_per_step": int(8 * er * p + 8 * (er + p) * (K + 2) + 8 * p),
                                      "d2h_bytes_per_step": int(8 * er * p + 8 * p + 64),
-                                     "call": "ebpmf_vga_step_host: M in AND out every step, pageable (the stand-alone drop-in signature)"}
+                                     "call": "ebpmf_vga_step_host: M in AND out every step (the stand-alone drop-in signature); input and "
+                                             "result matrices are pool blocks, as in ebpmf_log's loop where the input is the previous result"}
         if er == n:
             ctx.rewind_m()                              # leave ctx with the bench's M0 again
         else:
             ectx.close()
-        del Mi, Mo
+        del Mi
+        pkg.host_pool_trim()
         # (c) ebpmf_log's batched branch (general_control$batch_size < n, R/ebpmf_log.R:254-300) on a bounded sample:
         #     one solve per row batch, stop test scoped to the batch, M in and out (pageable), 3 pipelined worker contexts
         import scipy.sparse as sp
@@ -711,8 +718,8 @@ def main():
         cp, ri, x = ctx.get_y_csc()
         scp, sri, sx = pkg.shard_csc(cp, ri, x, 0, br)
         del cp, ri, x
-        Mb = ctx.get_rows(0, br)
-        Mbo = pageable_f(br, p)
+        Mb = pkg.host_matrix(br, p); Mb[...] = ctx.get_rows(0, br)
+        Mbo = pkg.host_matrix(br, p)
         bs = max(256, br // 8)
         bh = pkg.VgaBatched(local_rank, 3)
         bh.set_y(sp.csc_matrix((sx, sri, scp), shape=(br, p)), batch_size=bs)
@@ -727,7 +734,7 @@ def main():
         b_wall = allmax(time.perf_counter() - t0)
         out["e2e_batched"] = {"value": br * p * world / (b_wall / ks), "unit": "entries/s",
                               "call": "ebpmf_batched_vga_step_host: ebpmf_log's batched branch (batch_size = %d rows, %d "
-                                      "batches, per-batch stop as in R/ebpmf_log.R:259-268), M in AND out (pageable), 3 pipelined "
+                                      "batches, per-batch stop as in R/ebpmf_log.R:259-268), M in AND out (pool blocks), 3 pipelined "
                                       "worker contexts; %d-row sample" % (bs, len(bh.batch_row0) - 1, br),
                               "n_updates_per_batch": rb_["n_updates"], "ms_per_step": 1e3 * b_wall / ks}
         bh.close()

@@ -224,8 +224,10 @@ class VgaContext:
     def rewind_m(self):
         self._ck(self._lib.ebpmf_ctx_rewind_m(self._h))
 
-    def get_m(self):
-        out = np.empty((self.n, self.p), order="F")
+    def get_m(self, out=None):
+        out = np.empty((self.n, self.p), order="F") if out is None else out
+        if out.shape != (self.n, self.p) or not out.flags.f_contiguous or out.dtype != np.float64:
+            raise ValueError("out must be an n x p column-major float64 array")
         self._ck(self._lib.ebpmf_ctx_get_m(self._h, _ptr(out)))
         return out
 
