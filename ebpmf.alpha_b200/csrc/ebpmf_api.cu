@@ -1422,21 +1422,24 @@ int ebpmf_vga_step_resident_host(ebpmf_ctx *ctx, int64_t n, int64_t p, int64_t K
 // ---- N1: products of the resident M with the factors, and the residual sums of squares -----------
 }  // extern "C"
 namespace {
+// warps (32-row groups) per CTA of the products kernel: one CTA per SM for KP >= 16 (159+ registers), so 12 warps
+// hide more latency than 8; KP = 8 fits two CTAs of 8 warps (measured on the bench slab: K = 22: 14.6 vs 16.2 ms
+// kernel time with 12 vs 8 warps, K = 8: 6.8 vs 7.3 ms with 8 vs 12)
 #ifndef EBPMF_PROD_NW
-#define EBPMF_PROD_NW 8       // warps (32-row groups) per CTA of the products kernel
+#define EBPMF_PROD_NW 12
 #endif
-constexpr int kProdRows = 32 * EBPMF_PROD_NW;
+inline int prod_rows_for(int KP) { return KP <= 8 ? 256 : 32 * EBPMF_PROD_NW; }
 
-template <int KP>
+template <int KP, int NW>
 int launch_products(ebpmf_ctx *ctx, const ProdArgs &a) {
-    const long long nRBp = (a.n + kProdRows - 1) / kProdRows;
-    const int smem = (int)sizeof(ProdSmem<KP, EBPMF_PROD_NW>);
+    const long long nRBp = (a.n + 32 * NW - 1) / (32 * NW);
+    const int smem = (int)sizeof(ProdSmem<KP, NW>);
     static bool configured[64] = {false};
     if (ctx->device < 64 ? !configured[ctx->device] : true) {
-        CU(cudaFuncSetAttribute(m_products_kernel<KP, EBPMF_PROD_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(m_products_kernel<KP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         if (ctx->device < 64) configured[ctx->device] = true;
     }
-    m_products_kernel<KP, EBPMF_PROD_NW><<<dim3((unsigned)a.nsplit, (unsigned)nRBp), 32 * EBPMF_PROD_NW, smem, ctx->stream>>>(a);
+    m_products_kernel<KP, NW><<<dim3((unsigned)a.nsplit, (unsigned)nRBp), 32 * NW, smem, ctx->stream>>>(a);
     CU(cudaGetLastError());
     ++ctx->launches;
     return EBPMF_OK;
@@ -1453,18 +1456,17 @@ int ebpmf_ctx_m_products(ebpmf_ctx *ctx, int64_t Kw, const double *EL_w, const d
     const long long n = ctx->n, p = ctx->p;
     const int K = (int)Kw;
     const int KPmax = ktp_for(std::min(K, 32));
-    const long long nRB = (n + kProdRows - 1) / kProdRows;
+    const long long nRB = (n + 255) / 256;          // the most row blocks any chunk's kernel uses (8 warps per CTA)
     // column spans: enough CTAs (one per SM at a time) for a dozen waves, few enough that the M %*% EF partials stay small
     const int nsplit = (int)std::max(1LL, std::min<long long>((p + kTileCols - 1) / kTileCols, (148LL * 12 + nRB - 1) / nRB));
     int cols_per_split = (int)((p + nsplit - 1) / nsplit);
     cols_per_split = ((cols_per_split + kTileCols - 1) / kTileCols) * kTileCols;
-    const long long nrange = nRB;                   // t(M) %*% EL: one partial per row block of the kernel
     // device scratch, carved out of one buffer
     size_t off = 0;
     auto carve = [&](size_t doubles) { const size_t o = off; off += (doubles + 1) & ~(size_t)1; return o; };
     const size_t oEL = carve((size_t)n * K), oEF = carve((size_t)p * K), oEFt = carve((size_t)p * (KPmax + 4));
     const size_t oMFp = carve((size_t)nsplit * KPmax * n), oRsq = carve((size_t)nsplit * n);
-    const size_t oMtLp = carve((size_t)nrange * p * KPmax), oCsq = carve((size_t)nrange * p);
+    const size_t oMtLp = carve((size_t)nRB * p * KPmax), oCsq = carve((size_t)nRB * p);
     const size_t oMF = carve((size_t)n * K), oMtL = carve((size_t)p * K), oGL = carve((size_t)K * K), oGF = carve((size_t)K * K);
     const size_t oSqR = carve((size_t)n), oSqC = carve((size_t)p), oR2r = carve((size_t)n), oR2c = carve((size_t)p);
     int rc = reserve(ctx, ctx->prod, sizeof(double) * off);
@@ -1485,21 +1487,23 @@ int ebpmf_ctx_m_products(ebpmf_ctx *ctx, int64_t Kw, const double *EL_w, const d
         a.MFpart = base + oMFp; a.rowsq = base + oRsq; a.MtLpart = base + oMtLp; a.colsq = base + oCsq;
         a.nsplit = nsplit; a.cols_per_split = cols_per_split;
         a.bulk = (n % 2 == 0 && !getenv("EBPMF_B200_NO_BULK")) ? 1 : 0;
+        const int prows = prod_rows_for(KP);
+        const int nrange = (int)((n + prows - 1) / prows);       // t(M) %*% EL: one partial per row block of this chunk's kernel
         CU(cudaEventRecord(ctx->ev_p1, ctx->stream));
         switch (KP) {
-            case 8: CHECK((launch_products<8>(ctx, a))); break;
-            case 16: CHECK((launch_products<16>(ctx, a))); break;
-            case 24: CHECK((launch_products<24>(ctx, a))); break;
-            default: CHECK((launch_products<32>(ctx, a))); break;
+            case 8: CHECK((launch_products<8, 8>(ctx, a))); break;
+            case 16: CHECK((launch_products<16, EBPMF_PROD_NW>(ctx, a))); break;
+            case 24: CHECK((launch_products<24, EBPMF_PROD_NW>(ctx, a))); break;
+            default: CHECK((launch_products<32, EBPMF_PROD_NW>(ctx, a))); break;
         }
         CU(cudaEventRecord(ctx->ev_p2, ctx->stream));
         sum_splits_kernel<<<(unsigned)(((long long)Kc * n + 255) / 256), 256, 0, ctx->stream>>>(base + oMFp, (long long)KP * n, (long long)Kc * n, nsplit,
                                                                                              base + oMF + (size_t)n * k0);
-        mtl_gather_kernel<<<(unsigned)((p * KP + 255) / 256), 256, 0, ctx->stream>>>(base + oMtLp, (int)nrange, p, KP, Kc, base + oMtL + (size_t)p * k0);
+        mtl_gather_kernel<<<(unsigned)((p * KP + 255) / 256), 256, 0, ctx->stream>>>(base + oMtLp, nrange, p, KP, Kc, base + oMtL + (size_t)p * k0);
         CU(cudaGetLastError());
         if (k0 == 0) {                               // sums of squares of M: any chunk's pass gives them
             sum_splits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(base + oRsq, n, n, nsplit, base + oSqR);
-            sum_splits_kernel<<<(unsigned)((p + 255) / 256), 256, 0, ctx->stream>>>(base + oCsq, p, p, (int)nrange, base + oSqC);
+            sum_splits_kernel<<<(unsigned)((p + 255) / 256), 256, 0, ctx->stream>>>(base + oCsq, p, p, nrange, base + oSqC);
             CU(cudaGetLastError());
         }
         CU(cudaEventRecord(ctx->ev_p3, ctx->stream));

@@ -60,11 +60,12 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 }
 
 template <int KP, int NW>
-__global__ void __launch_bounds__(32 * NW, NW <= 4 ? 3 : 1) m_products_kernel(const ProdArgs a)
+__global__ void __launch_bounds__(32 * NW, 1) m_products_kernel(const ProdArgs a)
 {
     constexpr int NT = KP / 8;                    // 8-wide tiles of factor columns
     constexpr int ROWS = 32 * NW, NTH = 32 * NW;
-    constexpr int TPC = NTH / kTileCols;          // threads per column for the column sums of squares
+    constexpr int TPC = 16;                       // threads per column for the column sums of squares (threads 0..255)
+    static_assert(NW >= 8, "the column sums of squares use 16 x 16 threads");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ProdSmem<KP, NW> &sm = *reinterpret_cast<ProdSmem<KP, NW> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(32 * NW, NW <= 4 ? 3 : 1) m_products_kernel(co
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) { accF[rt][nt][0] = 0.0; accF[rt][nt][1] = 0.0; }
     double rsq = 0.0;                              // sum over the span of M[r0 + tid, j]^2
-    const int sc = tid / TPC, sp = tid % TPC;      // column / row phase for the column sums of squares
+    const int sc = (tid >> 4) & 15, sp = tid & 15;   // column / row phase for the column sums of squares
 
     auto issue = [&](int buf, int j0) {            // bring the slab [j0, j0+16) and its EF rows into buffer `buf`
         const int ncv = min(kTileCols, jc1 - j0);
@@ -199,11 +200,13 @@ __global__ void __launch_bounds__(32 * NW, NW <= 4 ? 3 : 1) m_products_kernel(co
         double csq = 0.0;
 #pragma unroll
         for (int c = 0; c < kTileCols; ++c) { const double x = ms[c][tid]; rsq = fma(x, x, rsq); }
+        if (tid < 256) {
 #pragma unroll
-        for (int q = 0; q < ROWS / TPC; ++q) { const double x = ms[sc][sp + TPC * q]; csq = fma(x, x, csq); }
+            for (int q = 0; q < ROWS / TPC; ++q) { const double x = ms[sc][sp + TPC * q]; csq = fma(x, x, csq); }
+        }
 #pragma unroll
         for (int o = TPC / 2; o > 0; o >>= 1) csq += __shfl_xor_sync(0xffffffffu, csq, o);
-        if (sp == 0 && sc < ncv) a.colsq[(size_t)rb * p + j0 + sc] = csq;
+        if (tid < 256 && sp == 0 && sc < ncv) a.colsq[(size_t)rb * p + j0 + sc] = csq;
     }
     __syncthreads();
     flush(buf ^ 1, jc0 + ((jc1 - jc0 - 1) / kTileCols) * kTileCols);       // the last slab
