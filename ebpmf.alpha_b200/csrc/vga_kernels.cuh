@@ -794,6 +794,23 @@ __global__ void __launch_bounds__(kThreads, 2) vga_dense_kernel(const DenseArgs 
     int any_exhausted = 0, any_nan = 0, any_fail = 0;
     const long long ii = row_ok ? i : 0;
 
+    // raw operands of one unit (E columns of this thread's row); a padding column shadows column jb
+    struct Raw { double m[E], y[E], b[E], s2[E], s[E]; };
+    auto load_raw = [&](long long jb, Raw &q) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const long long jj = (jb + e < jc1) ? jb + e : jb;
+            q.m[e] = row_ok ? ld_stream(Msrc + i + a.n * jj) : 0.0;
+            q.y[e] = row_ok ? ld_stream(a.X + i + a.n * jj) : 0.0;
+            q.b[e] = row_ok ? a.Beta[ii * a.B_rs + jj * a.B_cs] : 0.0;
+            q.s2[e] = row_ok ? a.Sigma2[ii * a.V_rs + jj * a.V_cs] : 1.0;
+            q.s[e] = row_ok ? a.S[ii * a.S_rs + jj * a.S_cs] : 1.0;
+        }
+    };
+    // first pass: the NEXT unit's operands are requested before this unit iterates (the unit's ~7 evaluations hide
+    // the HBM latency); the top-up pass skips most units, so it loads on demand
+    Raw nxt;
+    if (MODE == MODE_FIRST && jc0 < jc1) load_raw(jc0, nxt);
 #pragma unroll 1
     for (long long jb = jc0; jb < jc1; jb += E) {
         const long long jg = jb / E;
@@ -803,21 +820,22 @@ __global__ void __launch_bounds__(kThreads, 2) vga_dense_kernel(const DenseArgs 
             k = a.kunit[jg * a.nRW + rw];
             if (k >= target) continue;
         }
+        Raw cur;
+        if (MODE == MODE_FIRST) {
+            cur = nxt;
+            if (jb + E < jc1) load_raw(jb + E, nxt);
+        } else {
+            load_raw(jb, cur);
+        }
         double m[E], c0[E], w[E], c1[E], c2[E], sc[E], s2[E], r[E], sexp[E], f[E];
         bool ok[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            const long long j = jb + e;
-            ok[e] = row_ok && (j < jc1);
-            const long long jj = (j < jc1) ? j : jb;                               // padding column shadows column jb
-            m[e] = row_ok ? ld_stream(Msrc + i + a.n * jj) : 0.0;
-            const double y = row_ok ? ld_stream(a.X + i + a.n * jj) : 0.0;
-            const double b = row_ok ? a.Beta[ii * a.B_rs + jj * a.B_cs] : 0.0;
-            s2[e] = row_ok ? a.Sigma2[ii * a.V_rs + jj * a.V_cs] : 1.0;
-            sc[e] = row_ok ? a.S[ii * a.S_rs + jj * a.S_cs] : 1.0;
+            ok[e] = row_ok && (jb + e < jc1);
+            m[e] = cur.m[e]; s2[e] = cur.s2[e]; sc[e] = cur.s[e];
             c1[e] = rcp_fast(s2[e]);                                               // :10
             c2[e] = __dmul_rn(s2[e], 0.5);                                         // :11
-            c0[e] = __dadd_rn(__fma_rn(s2[e], y, b), 1.0);                         // :9
+            c0[e] = __dadd_rn(__fma_rn(s2[e], cur.y[e], cur.b[e]), 1.0);           // :9
             const double c0m1 = __dadd_rn(c0[e], -1.0);
             w[e] = __dmul_rn(c0m1, c1[e]);                                         // x + const3
             if (MODE == MODE_FIRST) m[e] = (m[e] < c0m1) ? m[e] : c0m1;            // :16
