@@ -384,23 +384,18 @@ int ensure_common(ebpmf_ctx *ctx) {
     return EBPMF_OK;
 }
 
-// reductions of the per-tile partials into red = [sym, ssexp, slogv, sumV][v_sum...]
-// (the final M is in Malt at this point: sum(Y*M) runs over the CSC non-zeros only); also the column
+// reductions of the per-tile partials into red = [sym, ssexp, slogv, sumV][v_sum...]; also the column
 // span of the hardest tile, where the NEXT step's first pass will start
 int run_reductions(ebpmf_ctx *ctx) {
     const long long n = ctx->n, p = ctx->p;
     double *red = as<double>(ctx->red);
-    double *colsym = as<double>(ctx->colsums);
-    double *colv = (ctx->var_type == EBPMF_VAR_BY_COL) ? red + 4 : colsym + p;
+    double *colv = (ctx->var_type == EBPMF_VAR_BY_COL) ? red + 4 : as<double>(ctx->colsums);
     reduce_over_rows_kernel<1><<<(unsigned)((p + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(
         as<double>(ctx->colV), ctx->nRB, p, colv);
     CU(cudaGetLastError());
-    sym_nnz_kernel<<<(unsigned)((p * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-        as<int>(ctx->colptr), as<int>(ctx->rowidx), as<double>(ctx->yx), as<double>(ctx->Malt), n, p, colsym);
+    reduce_scalars_kernel<<<1, 1024, 0, ctx->stream>>>(colv, p, as<double>(ctx->tileS), ctx->cur_ntiles, red);
     CU(cudaGetLastError());
-    reduce_scalars_kernel<<<1, 1024, 0, ctx->stream>>>(colsym, colv, p, as<double>(ctx->tileS), ctx->cur_ntiles, red);
-    CU(cudaGetLastError());
-    ctx->launches += 3;
+    ctx->launches += 2;
     if (ctx->var_type == EBPMF_VAR_BY_ROW) {
         reduce_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(as<double>(ctx->rowpart), n, ctx->cur_nspans,
                                                                                  red + 4);
@@ -546,7 +541,7 @@ int reserve_shape_buffers(ebpmf_ctx *ctx, long long n, long long p) {
     CHECK(reserve(ctx, ctx->kunit, sizeof(unsigned short) * (size_t)nJG * (size_t)ctx->nRW));
     CHECK(reserve(ctx, ctx->status, sizeof(Status)));
     CHECK(reserve(ctx, ctx->colV, sizeof(double) * (size_t)ctx->nRB * (size_t)p));
-    CHECK(reserve(ctx, ctx->tileS, sizeof(double) * 2 * (size_t)ntiles));
+    CHECK(reserve(ctx, ctx->tileS, sizeof(double) * 3 * (size_t)ntiles));
     CHECK(reserve(ctx, ctx->tile_hard, sizeof(unsigned short) * (size_t)ntiles));
     CHECK(reserve(ctx, ctx->tile_kmin, sizeof(unsigned short) * (size_t)ntiles));
     CHECK(reserve(ctx, ctx->small_out, sizeof(int) * 16));

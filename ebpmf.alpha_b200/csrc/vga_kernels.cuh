@@ -93,7 +93,7 @@ struct FusedArgs {
     unsigned short *kunit;          // [nRW][nJG] updates each unit has received (kFrozen: delta-mode fixed point)
     long long nRW, nJG;             // ceil(n/32), ceil(p/E)
     double *colV;                   // [nRB][p]        sum over the row block's 256 rows of V
-    double *tileS;                  // [nRB*nspans][2] sum exp(M+V/2), sum(log(V)/2+c) of the tile
+    double *tileS;                  // [nRB*nspans][3] sum exp(M+V/2), sum(log(V)/2+c), sum(Y*M) of the tile
     double *rowpart;                // [nspans][n] sum over the tile's columns of V (by_row only), else null
     unsigned short *tile_hard;      // [nRB*nspans] max over the tile's units of the first converged count (pass 1)
     unsigned short *tile_kmin;      // [nRB*nspans] min over the tile's units of k_unit
@@ -405,9 +405,16 @@ struct FusedSmem {
     double c1s[kTileCols], c2s[kTileCols], f0s[kTileCols];
     double exptab[EBPMF_EXP_TABLE_SIZE];
     double2 logtab[EBPMF_LOG_TABLE_SIZE];
-    double wsum[2][kWarps];
+    double wsum[3][kWarps];
     int wk[2][kWarps];
     unsigned long long mbar;
+    // the slab's non-zeros (value, column << 8 | row) as the scatter met them: sum(Y * M) is taken against the FINAL
+    // M while it is still in shared memory, without a second walk of the CSC arrays.  Sized to keep 3 CTAs per SM;
+    // a slab with more non-zeros re-walks the CSC entries beyond the list.
+    static constexpr int kYList = (FORMULA == FORMULA_A1) ? (KTP == 32 ? 224 : 256) : 1;
+    double ylv[kYList];
+    int ybase[kTileCols + 1];
+    unsigned short ylp[kYList];
 };
 
 #ifndef EBPMF_MINB
@@ -476,6 +483,8 @@ __global__ void __launch_bounds__(kThreads, (FORMULA == FORMULA_A10) ? 2 : EBPMF
     int wkb = 0, wkmin = kFrozen;                    // this warp's max first-converged count / min k_unit
     int t0_next = (MODE == MODE_FIRST) ? *kstar_live : 0;
     double acc_exp = 0.0, acc_log = 0.0, acc_rowv = 0.0;     // this row's sums over the tile's columns
+    double acc_sym = 0.0;                                    // this thread's share of sum(Y * M) over the tile's non-zeros
+    constexpr int kYList = FusedSmem<KTP, FORMULA>::kYList;
     const double tol_lane = row_ok ? ((MODE == MODE_TOPUP) ? a.tol_verify : a.tol) : INFINITY;
     unsigned phase = 0;
 
@@ -516,14 +525,27 @@ __global__ void __launch_bounds__(kThreads, (FORMULA == FORMULA_A10) ? 2 : EBPMF
             sm.c2s[tid] = by_col ? a.sc2[j] : 0.5;
             sm.f0s[tid] = (FORMULA == FORMULA_A10) ? a.f0[j] : 1.0;
         }
+        if (FORMULA == FORMULA_A1 && warp == 1) {    // list offsets of the slab's columns: exclusive scan of their counts
+            const int *rp = a.rbptr + (size_t)rb * p + j0;
+            int cnt = (lane < ncv) ? rp[p + lane] - rp[lane] : 0, inc = cnt;
+#pragma unroll
+            for (int o = 1; o < kTileCols; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            if (lane < kTileCols) sm.ybase[lane] = inc - cnt;
+            if (lane == kTileCols - 1) sm.ybase[kTileCols] = inc;
+        }
         __syncthreads();
         // scatter the CSC non-zeros of rows [r0, r0+256) of each slab column
         {
             const int *rp0 = a.rbptr + (size_t)rb * p + j0, *rp1 = rp0 + p;
             for (int c = warp; c < ncv; c += kWarps) {
                 const int lo = rp0[c], hi = rp1[c];
-                for (int q = lo + lane; q < hi; q += 32)
-                    sm.cs[c][a.rowidx[q] - r0] = __ldg(a.yx + q);
+                const int base = (FORMULA == FORMULA_A1) ? sm.ybase[c] - lo : 0;
+                for (int q = lo + lane; q < hi; q += 32) {
+                    const int rr = a.rowidx[q] - r0;
+                    const double y = __ldg(a.yx + q);
+                    sm.cs[c][rr] = y;
+                    if (FORMULA == FORMULA_A1 && base + q < kYList) { sm.ylv[base + q] = y; sm.ylp[base + q] = (unsigned short)((c << 8) | rr); }
+                }
             }
         }
         __syncthreads();
@@ -661,6 +683,22 @@ __global__ void __launch_bounds__(kThreads, (FORMULA == FORMULA_A10) ? 2 : EBPMF
             for (int c = 0; c < ncv; ++c) st_stream(a.M_out + (size_t)i + ns * (size_t)(j0 + c), sm.ms[c][tid]);
         }
         if (FORMULA == FORMULA_A1) {
+            // a4: sum(Y * M) (R/ebpmf_log.R:316) over the slab's non-zeros against the final M in shared memory
+            const int total = sm.ybase[kTileCols];
+            for (int idx = tid; idx < min(total, kYList); idx += kThreads) {
+                const int pos = sm.ylp[idx];
+                acc_sym = fma(sm.ylv[idx], sm.ms[pos >> 8][pos & 255], acc_sym);
+            }
+            if (total > kYList) {                  // more non-zeros than the list holds: re-walk the rest
+                const int *rp0 = a.rbptr + (size_t)rb * p + j0, *rp1 = rp0 + p;
+                for (int c = warp; c < ncv; c += kWarps) {
+                    const int lo = rp0[c], hi = rp1[c], base = sm.ybase[c] - lo;
+                    for (int q = lo + lane; q < hi; q += 32)
+                        if (base + q >= kYList) acc_sym = fma(__ldg(a.yx + q), sm.ms[c][a.rowidx[q] - r0], acc_sym);
+                }
+            }
+        }
+        if (FORMULA == FORMULA_A1) {
             // 16 threads per column, each 16 rows (stride 16), then a fixed shuffle tree: deterministic
             const int col = tid >> 4, part = tid & 15;
             double s = 0.0;
@@ -686,15 +724,16 @@ __global__ void __launch_bounds__(kThreads, (FORMULA == FORMULA_A10) ? 2 : EBPMF
     for (int o = 16; o > 0; o >>= 1) {
         acc_exp += __shfl_xor_sync(0xffffffffu, acc_exp, o);
         acc_log += __shfl_xor_sync(0xffffffffu, acc_log, o);
+        acc_sym += __shfl_xor_sync(0xffffffffu, acc_sym, o);
     }
     __syncthreads();
-    if (lane == 0) { sm.wsum[0][warp] = acc_exp; sm.wsum[1][warp] = acc_log; sm.wk[0][warp] = wkb; sm.wk[1][warp] = wkmin; }
+    if (lane == 0) { sm.wsum[0][warp] = acc_exp; sm.wsum[1][warp] = acc_log; sm.wsum[2][warp] = acc_sym; sm.wk[0][warp] = wkb; sm.wk[1][warp] = wkmin; }
     __syncthreads();
     if (tid == 0) {
-        double s0 = 0.0, s1 = 0.0;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
         int hb = 0, km = kFrozen;
-        for (int q = 0; q < kWarps; ++q) { s0 += sm.wsum[0][q]; s1 += sm.wsum[1][q]; hb = max(hb, sm.wk[0][q]); km = min(km, sm.wk[1][q]); }
-        if (FORMULA == FORMULA_A1) { a.tileS[(size_t)tile * 2] = s0; a.tileS[(size_t)tile * 2 + 1] = s1; }
+        for (int q = 0; q < kWarps; ++q) { s0 += sm.wsum[0][q]; s1 += sm.wsum[1][q]; s2 += sm.wsum[2][q]; hb = max(hb, sm.wk[0][q]); km = min(km, sm.wk[1][q]); }
+        if (FORMULA == FORMULA_A1) { a.tileS[(size_t)tile * 3] = s0; a.tileS[(size_t)tile * 3 + 1] = s1; a.tileS[(size_t)tile * 3 + 2] = s2; }
         if (MODE == MODE_FIRST) a.tile_hard[tile] = (unsigned short)hb;
         a.tile_kmin[tile] = (unsigned short)km;
         if (MODE == MODE_TOPUP) {
@@ -727,21 +766,6 @@ __global__ void __launch_bounds__(1024) hardest_span_kernel(const unsigned short
         __syncthreads();
     }
     if (threadIdx.x == 0) out[0] = (best[0] < 0) ? 0 : (0x7FFF - (best[0] & 0x7FFF));
-}
-
-// sum(Y*M) over the non-zeros (R/ebpmf_log.R:316): one warp per column, colsym[j] = sum_q x_q M[i_q, j]
-__global__ void __launch_bounds__(256) sym_nnz_kernel(const int *colptr, const int *rowidx, const double *yx,
-                                                      const double *M, long long n, long long p, double *colsym)
-{
-    const long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (j >= p) return;
-    double acc = 0.0;
-    const double *Mc = M + n * j;
-    for (int q = colptr[j] + lane; q < colptr[j + 1]; q += 32) acc = fma(__ldg(yx + q), Mc[rowidx[q]], acc);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) colsym[j] = acc;
 }
 
 // 1/sigma2 and sigma2/2 (const1, const2 of R/vga_solver_mat.R:10-11) for every sigma2 element
@@ -953,14 +977,14 @@ __global__ void __launch_bounds__(256) reduce_over_rows_kernel(const double *src
     }
 }
 
-// one block: scalars[0] = sum colsym (sym), [1] = ssexp, [2] = slogv (from unit sums [nJG][2]), [3] = sum(V)
-__global__ void __launch_bounds__(1024) reduce_scalars_kernel(const double *colsym, const double *v_sum, long long p,
-                                                              const double *unitsum, long long nJG, double *scalars)
+// one block: scalars[0] = sym, [1] = ssexp, [2] = slogv (from the tile sums [ntiles][3]), [3] = sum(V)
+__global__ void __launch_bounds__(1024) reduce_scalars_kernel(const double *v_sum, long long p, const double *tilesum,
+                                                              long long ntiles, double *scalars)
 {
     __shared__ double sm[4][1024];
     double acc[4] = {0, 0, 0, 0};
-    for (long long j = threadIdx.x; j < p; j += 1024) { acc[0] += colsym[j]; acc[3] += v_sum[j]; }
-    for (long long g = threadIdx.x; g < nJG; g += 1024) { acc[1] += unitsum[g * 2]; acc[2] += unitsum[g * 2 + 1]; }
+    for (long long j = threadIdx.x; j < p; j += 1024) acc[3] += v_sum[j];
+    for (long long g = threadIdx.x; g < ntiles; g += 1024) { acc[1] += tilesum[g * 3]; acc[2] += tilesum[g * 3 + 1]; acc[0] += tilesum[g * 3 + 2]; }
     for (int q = 0; q < 4; ++q) sm[q][threadIdx.x] = acc[q];
     __syncthreads();
     for (int s = 512; s > 0; s >>= 1) {
