@@ -53,12 +53,6 @@ struct ProdSmem {
     unsigned long long mbar[2];
 };
 
-// D(8x8) += A(8x4) * B(4x8); lane holds A[lane/4][lane%4], B[lane%4][lane/4], D[lane/4][2*(lane%4) + {0,1}]
-__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
-
 template <int KP, int NW>
 __global__ void __launch_bounds__(32 * NW, 1) m_products_kernel(const ProdArgs a)
 {

@@ -385,13 +385,32 @@ __device__ __forceinline__ int newton_unit(double (&m)[E], const double (&c0)[E]
     return flags;
 }
 
-// stage EF rows [j0, j0+16) x factor columns [k0, k0+KTP) into efs[16][KTP]; a padding column
+// D(8x8) += A(8x4) * B(4x8) on the FP64 tensor path; lane holds A[lane/4][lane%4], B[lane%4][lane/4],
+// D[lane/4][2*(lane%4) + {0,1}]
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+#ifndef EBPMF_BETA_DMMA
+#define EBPMF_BETA_DMMA 1     // Beta = EL EF' of a slab on the FP64 tensor path (0: K_tot DFMAs per entry, thread = row)
+#endif
+
+// Layout of the slab's EF rows in shared memory, efs[c][k]: the B-fragment loads of the Beta DMMAs
+// (c = 8nt + lane/4, k = 4ks + lane%4) must hit 16 distinct bank pairs per half warp.  Row stride KTP + 4 does
+// that for KTP = 8, 16, 24; KTP = 32 keeps stride 32 (shared memory is full) and XOR-swizzles k by 4*(c & 3).
+template <int KTP> struct EfLayout {
+    static constexpr int kStride = (KTP == 32) ? 32 : KTP + 4;
+    __device__ __forceinline__ static int at(int c, int k) { return c * kStride + ((KTP == 32) ? (k ^ ((c & 3) << 2)) : k); }
+};
+
+// stage EF rows [j0, j0+16) x factor columns [k0, k0+KTP) into efs (EfLayout); a padding column
 // (j >= jc1) repeats the last real one
 template <int KTP>
 __device__ __forceinline__ void stage_ef_chunk(double *efs, const double *EFt, int ldk, int j0, int jc1, int k0, int tid) {
     for (int idx = tid; idx < kTileCols * KTP; idx += kThreads) {
         const int c = idx / KTP, k = idx - c * KTP;
-        efs[idx] = __ldg(EFt + (size_t)min(j0 + c, jc1 - 1) * ldk + k0 + k);
+        efs[EfLayout<KTP>::at(c, k)] = __ldg(EFt + (size_t)min(j0 + c, jc1 - 1) * ldk + k0 + k);
     }
 }
 
@@ -401,7 +420,7 @@ struct FusedSmem {
     double ms[kTileCols][kRowsPerCta];      // M slab: bulk-load target, final M in place, bulk-store source
     double cs[kTileCols][kRowsPerCta];      // Y image -> const0 image -> V image
     double bs[FORMULA == FORMULA_A10 ? kTileCols : 1][FORMULA == FORMULA_A10 ? kRowsPerCta : 2];   // Beta (A10 clamp, :78)
-    double efs[kTileCols][KTP];
+    double efs[kTileCols * EfLayout<KTP>::kStride];
     double c1s[kTileCols], c2s[kTileCols], f0s[kTileCols];
     double exptab[EBPMF_EXP_TABLE_SIZE];
     double2 logtab[EBPMF_LOG_TABLE_SIZE];
@@ -411,7 +430,7 @@ struct FusedSmem {
     // the slab's non-zeros (value, column << 8 | row) as the scatter met them: sum(Y * M) is taken against the FINAL
     // M while it is still in shared memory, without a second walk of the CSC arrays.  Sized to keep 3 CTAs per SM;
     // a slab with more non-zeros re-walks the CSC entries beyond the list.
-    static constexpr int kYList = (FORMULA == FORMULA_A1) ? (KTP == 32 ? 224 : 256) : 1;
+    static constexpr int kYList = (FORMULA == FORMULA_A1) ? (KTP == 32 ? 224 : 208) : 1;
     double ylv[kYList];
     int ybase[kTileCols + 1];
     unsigned short ylp[kYList];
@@ -518,7 +537,7 @@ __global__ void __launch_bounds__(kThreads, (FORMULA == FORMULA_A10) ? 2 : EBPMF
         // ---- stage the slab: zero Y image, EF rows, per-column constants --------------------
 #pragma unroll
         for (int c = 0; c < kTileCols; ++c) sm.cs[c][tid] = 0.0;
-        stage_ef_chunk<KTP>(&sm.efs[0][0], a.EFt, a.ldk, j0, jc1, 0, tid);
+        stage_ef_chunk<KTP>(sm.efs, a.EFt, a.ldk, j0, jc1, 0, tid);
         if (tid < kTileCols) {
             const int j = min(j0 + tid, jc1 - 1);
             sm.c1s[tid] = by_col ? a.sc1[j] : 1.0;
@@ -549,15 +568,75 @@ __global__ void __launch_bounds__(kThreads, (FORMULA == FORMULA_A10) ? 2 : EBPMF
             }
         }
         __syncthreads();
-        // a2: this row's Beta for the 16 slab columns, K_tot FMAs each (EL row lives in registers
-        // only here; EF rows are broadcast reads from shared memory), folded straight into
-        // const0 = (Sigma2*Y + Beta) + 1 (:9 | :81,:95) over this thread's own Y image.  K_tot > KTP
-        // (only possible with KTP = 32) walks the factor columns in chunks of KTP, restaging the EF rows.
+        // a2: Beta = EL EF' for this CTA's 256 rows x the 16 slab columns, folded straight into
+        // const0 = (Sigma2*Y + Beta) + 1 (:9 | :81,:95) over the Y image.  K_tot > KTP (only possible with
+        // KTP = 32) walks the factor columns in chunks of KTP, restaging the EF rows.
+#if EBPMF_BETA_DMMA
+        {
+            // FP64 tensor path: warp w owns rows [32w, 32w+32) = 4 row tiles x 2 column tiles of 8 x 8, K_tot/4 DMMAs
+            // each (an accumulating DFMA has three register sources and issues in 3 cycles; DMMA does not, and it
+            // leaves the issue port to the other warps).  A fragments = EL straight from global memory (L1/L2),
+            // B fragments = the staged EF rows.  Lane (l8 = lane/4, l4 = lane%4) ends up with Beta of rows
+            // 32w + 8rt + l8, columns 8nt + 2*l4 + {0,1}.
+            const int l4 = lane & 3, l8 = lane >> 2, wrow = 32 * warp;
+            double d[4][2][2];
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) { d[rt][nt][0] = 0.0; d[rt][nt][1] = 0.0; }
+            for (int k0 = 0; k0 < a.K; k0 += KTP) {
+                if (k0 != 0) {
+                    __syncthreads();
+                    stage_ef_chunk<KTP>(sm.efs, a.EFt, a.ldk, j0, jc1, k0, tid);
+                    __syncthreads();
+                }
+#pragma unroll
+                for (int ks = 0; ks < KTP / 4; ++ks) {
+                    if (k0 + 4 * ks >= a.K) break;               // factor columns past K_tot are zero padding (uniform)
+                    const int kk = k0 + 4 * ks + l4;
+                    const double bf0 = sm.efs[EfLayout<KTP>::at(l8, 4 * ks + l4)], bf1 = sm.efs[EfLayout<KTP>::at(8 + l8, 4 * ks + l4)];
+#pragma unroll
+                    for (int rt = 0; rt < 4; ++rt) {
+                        const int ir = r0 + wrow + 8 * rt + l8;
+                        const double af = (ir < n && kk < a.K) ? __ldg(a.EL + (size_t)ir + ns * (size_t)kk) : 0.0;
+                        dmma884(d[rt][0][0], d[rt][0][1], af, bf0);
+                        dmma884(d[rt][1][0], d[rt][1][1], af, bf1);
+                    }
+                }
+            }
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) {
+                const int row = wrow + 8 * rt + l8;
+                double c2r = c2_row;                     // by_row: sigma2/2 of THIS fragment row, not of row tid
+                if (a.var_type == 1) c2r = a.sc2[min(r0 + row, n - 1)];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int c = 8 * nt + 2 * l4 + e;
+                        const double c2c = by_col ? sm.c2s[c] : c2r;
+                        const double v = __dadd_rn(__fma_rn(__dadd_rn(c2c, c2c), sm.cs[c][row], d[rt][nt][e]), 1.0);
+                        if (c < ncv) {
+                            sm.cs[c][row] = v;
+                            if constexpr (FORMULA == FORMULA_A10) sm.bs[c][row] = d[rt][nt][e];
+                        }
+                    }
+            }
+            __syncwarp();
+            if (ncv < kTileCols) {                       // padding columns: copies of the last real one
+                for (int c = ncv; c < kTileCols; ++c) {
+                    sm.cs[c][tid] = sm.cs[ncv - 1][tid];
+                    if constexpr (FORMULA == FORMULA_A10) sm.bs[c][tid] = sm.bs[ncv - 1][tid];
+                }
+                __syncwarp();
+            }
+        }
+#else
         for (int k0 = 0; k0 < a.K; k0 += KTP) {
             const bool first = (k0 == 0), last = (k0 + KTP >= a.K);
             if (!first) {
                 __syncthreads();
-                stage_ef_chunk<KTP>(&sm.efs[0][0], a.EFt, a.ldk, j0, jc1, k0, tid);
+                stage_ef_chunk<KTP>(sm.efs, a.EFt, a.ldk, j0, jc1, k0, tid);
                 __syncthreads();
             }
             double el[KTP];
@@ -568,7 +647,7 @@ __global__ void __launch_bounds__(kThreads, (FORMULA == FORMULA_A10) ? 2 : EBPMF
             for (int c = 0; c < kTileCols; ++c) {
                 double b = 0.0;
 #pragma unroll
-                for (int k = 0; k < KTP; ++k) b = fma(el[k], sm.efs[c][k], b);
+                for (int k = 0; k < KTP; ++k) b = fma(el[k], sm.efs[EfLayout<KTP>::at(c, k)], b);
                 const double c2c = by_col ? sm.c2s[c] : c2_row;
                 double v = first ? __fma_rn(__dadd_rn(c2c, c2c), sm.cs[c][tid], b) : __dadd_rn(sm.cs[c][tid], b);
                 if (last) v = __dadd_rn(v, 1.0);
@@ -579,6 +658,7 @@ __global__ void __launch_bounds__(kThreads, (FORMULA == FORMULA_A10) ? 2 : EBPMF
                 }
             }
         }
+#endif
         if (bulk) mbar_wait(mbar_s, phase);          // the M slab has landed
         phase ^= 1u;
 
