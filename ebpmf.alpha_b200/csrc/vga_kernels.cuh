@@ -510,10 +510,12 @@ __global__ void __launch_bounds__(kThreads, (FORMULA == FORMULA_A10) ? 2 : EBPMF
     for (int j0 = jc0; j0 < jc1; j0 += kTileCols) {
         const int ncv = min(kTileCols, jc1 - j0);    // real columns of this slab
         __syncthreads();                             // previous slab fully consumed (and the mbarrier initialised)
-        // one thread per CTA peeks at one peer GPU's published count (round robin); the word is
-        // consumed after the slab's units, so the NVLink latency is never waited for
+        // one thread per CTA peeks at one peer GPU's published count, once per tile (round robin over the peers by
+        // tile; per slab it cost 3 % of the pass: the pointer fetch and the remote load are a dependent chain in
+        // front of warp 0's bulk copies); the word is consumed after the slab's units, so the NVLink latency is
+        // never waited for
         unsigned long long peer_word = 0ull;
-        if (MODE == MODE_FIRST && tid == 0) peer_word = peek_peer(a, (unsigned)(j0 / kTileCols) + (unsigned)tile);
+        if (MODE == MODE_FIRST && tid == 0 && j0 == jc0) peer_word = peek_peer(a, (unsigned)tile);
         // ---- the M slab: one bulk async copy per column (a padding column repeats the last real one)
         if (bulk) {
             if (warp == 0) {
