@@ -92,6 +92,8 @@ SIGNATURES = {
     "ebpmf_batched_sum_lfactorial": (_int, [_vp, C.POINTER(_dbl)]),
     "ebpmf_batched_vga_step_host": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _int, _vp, _int, _dbl, _vp, _vp, _vp, _PI, _vp,
                                            _vp]),
+    "ebpmf_calc_split_obj": (_int, [_vp, _i64, _i64, _vp, _vp, _int, _vp, _vp, _int, _i64, _vp, _i64, _vp, _dbl, _dbl,
+                                    C.POINTER(_dbl)]),
     "ebpmf_vga_newton": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _int, _vp, _int, _int,
                                 _dbl, _vp, _vp, _PI]),
     "ebpmf_vga_fixed_iter": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _int, _vp, _int, _vp, _int, _int, _vp, _vp]),

@@ -1381,6 +1381,83 @@ int ebpmf_calc_obj(ebpmf_ctx *ctx, int64_t n, int64_t p, double sym, double ssex
     return EBPMF_OK;
 }
 
+// calc_split_PMF_obj_flashier(Y,S,sigma2,M,V,fit_flash,KL_LF,const,var_type)  inst/code/Poisson_MF_splitting.R:373-391
+int ebpmf_calc_split_obj(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *Y, const double *S, int S_kind,
+                         const double *M, const double *V, int var_type, int64_t len_sigma2, const double *sigma2,
+                         int64_t len_r2, const double *R2, double KL_LF, double const_, double *obj) {
+    if (!ctx || !Y || !S || !M || !V || !sigma2 || !R2 || !obj || n < 1 || p < 1 || len_sigma2 < 1 || len_r2 < 1)
+        return fail(ctx, EBPMF_ERR_ARG, "calc_split_obj: bad arguments");
+    if (var_type < 0 || var_type > 2) return fail(ctx, EBPMF_ERR_VAR_TYPE, "Non-supported var type");
+    CHECK(ensure_common(ctx));
+    SplitObjArgs a;
+    memset(&a, 0, sizeof a);
+    if (stride_for(S_kind, n, &a.S_rs, &a.S_cs)) return fail(ctx, EBPMF_ERR_ARG, "calc_split_obj: bad operand kind");
+    const size_t NP = (size_t)n * (size_t)p, bytes = sizeof(double) * NP;
+    const long long nRB = (n + kRowsPerCta - 1) / kRowsPerCta;
+    const int cols = cols_per_cta_for(p, nRB);
+    const int nspans = (int)((p + cols - 1) / cols);
+    const size_t lS = operand_len(S_kind, n, p);
+    for (int b = 0; b < 3; ++b) CHECK(reserve(ctx, ctx->scratch[b], bytes));
+    const long long lsv = var_type == EBPMF_VAR_BY_COL ? p : var_type == EBPMF_VAR_BY_ROW ? n : 1;
+    // small scratch: S (when not a matrix), partials, sv, sigma2, R2, terms
+    const size_t small = (lS == NP ? 0 : lS) + (size_t)nRB * p + (size_t)nspans * n + (size_t)nRB * nspans + (size_t)std::max(n, p) + 8 +
+                         (size_t)len_sigma2 + (size_t)len_r2 + 64;
+    CHECK(reserve(ctx, ctx->scratch[4], sizeof(double) * small));
+    if (lS == NP) CHECK(reserve(ctx, ctx->scratch[3], bytes));
+    double *q = as<double>(ctx->scratch[4]);
+    double *dS = (lS == NP) ? as<double>(ctx->scratch[3]) : q; if (lS != NP) q += lS;
+    double *colV = q; q += (size_t)nRB * p;
+    double *rowpart = q; q += (size_t)nspans * n;
+    double *termpart = q; q += (size_t)nRB * nspans;
+    double *sv = q; q += (size_t)std::max(n, p);
+    double *sv_total = q; q += 8;
+    double *dsig = q; q += len_sigma2;
+    double *dR2 = q; q += len_r2;
+    double *terms = q;
+    {
+        void *dsts[4] = {ctx->scratch[0].ptr, ctx->scratch[1].ptr, ctx->scratch[2].ptr, dS};
+        const double *srcs[4] = {Y, M, V, lS == NP ? S : nullptr};
+        CHECK(matrices_in(ctx, dsts, srcs, 4, n, p));
+    }
+    if (lS != NP) CU(cudaMemcpyAsync(dS, S, sizeof(double) * lS, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dsig, sigma2, sizeof(double) * (size_t)len_sigma2, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dR2, R2, sizeof(double) * (size_t)len_r2, cudaMemcpyHostToDevice, ctx->stream));
+    a.n = n; a.p = p; a.Y = as<double>(ctx->scratch[0]); a.M = as<double>(ctx->scratch[1]); a.V = as<double>(ctx->scratch[2]);
+    a.S = dS; a.colV = colV; a.rowpart = rowpart; a.termpart = termpart; a.cols_per_cta = cols;
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    split_obj_kernel<<<dim3((unsigned)nspans, (unsigned)nRB), kThreads, 0, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    // sv (:377-388): column sums, row sums, or the total of V
+    double ss = 0.0;
+    if (var_type == EBPMF_VAR_BY_ROW) {
+        reduce_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(rowpart, n, nspans, sv);
+        ss = (double)p;
+    } else {
+        reduce_over_rows_kernel<1><<<(unsigned)((p + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(colV, nRB, p, sv);
+        ss = (double)n;
+        if (var_type == EBPMF_VAR_CONSTANT) {
+            sum_partials_kernel<<<1, 1024, 0, ctx->stream>>>(sv, (int)p, sv_total);
+            ss = (double)n * (double)p;
+        }
+    }
+    CU(cudaGetLastError());
+    // sum of the entry terms -> terms[8]; the sigma2 terms of :389 through obj_terms_kernel (a0 = -1, b0 = 0: its two prior terms vanish)
+    sum_partials_kernel<<<1, 1024, 0, ctx->stream>>>(termpart, (int)(nRB * nspans), terms + 8);
+    const double *svp = (var_type == EBPMF_VAR_CONSTANT) ? sv_total : sv;
+    obj_terms_kernel<<<1, 1024, 0, ctx->stream>>>(svp, lsv, dsig, len_sigma2, dR2, len_r2, ss, -1.0, 0.0, terms);
+    CU(cudaGetLastError());
+    ctx->launches += 4;
+    CU(cudaMemcpyAsync(ctx->h_small, terms, sizeof(double) * 9, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_kernel_ms = ms;
+    const double *tq = ctx->h_small;
+    *obj = tq[8] - tq[0] - tq[1] - tq[2] + const_ + KL_LF;      // :389, left to right
+    return EBPMF_OK;
+}
+
 }  // extern "C"
 namespace {
 // the host matrices of a *_step_host call must have the shape of the resident Y (R: "non-conformable arrays")

@@ -1315,6 +1315,72 @@ __global__ void __launch_bounds__(1024) obj_terms_kernel(const double *sv, long 
     if (threadIdx.x < 5) terms[threadIdx.x] = sm[threadIdx.x][0];
 }
 
+// ---------------------------------------------------------------------------------------
+// N4: calc_split_PMF_obj_flashier  inst/code/Poisson_MF_splitting.R:373-391 (archived driver): the un-fused ELBO
+// from dense Y, S, M, V.  One streaming pass (32 B per entry): thread = row, CTA = 256 rows x a column span;
+// per-thread sum of  Y*M - S*exp(M+V/2) + log(2*pi*V)/2 + 0.5  (:389), sums of V per (row block, column) and per
+// (span, row) for sv (:377-388).  Partials are combined by the fixed-order reduction kernels.
+// ---------------------------------------------------------------------------------------
+struct SplitObjArgs {
+    long long n, p;
+    const double *Y, *M, *V;
+    const double *S; long long S_rs, S_cs;
+    double *colV;        // [nRB][p]
+    double *rowpart;     // [nspans][n]
+    double *termpart;    // [nRB * nspans]
+    int cols_per_cta;
+};
+
+__global__ void __launch_bounds__(kThreads) split_obj_kernel(const SplitObjArgs a)
+{
+    __shared__ double red[kWarps];
+    __shared__ double vs[kTileCols][kRowsPerCta + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long rb = blockIdx.y, i = rb * kRowsPerCta + tid;
+    const bool row_ok = i < a.n;
+    const long long jc0 = (long long)blockIdx.x * a.cols_per_cta, jc1 = min(a.p, jc0 + (long long)a.cols_per_cta);
+    const double two_pi = 6.283185307179586;
+    double term = 0.0, rowv = 0.0;
+    for (long long j0 = jc0; j0 < jc1; j0 += kTileCols) {
+        const int ncv = (int)min((long long)kTileCols, jc1 - j0);
+        __syncthreads();
+#pragma unroll 4
+        for (int c = 0; c < kTileCols; ++c) {
+            double v = 0.0;
+            if (row_ok && c < ncv) {
+                const long long e = i + a.n * (j0 + c);
+                const double y = ld_stream(a.Y + e), m = ld_stream(a.M + e);
+                v = ld_stream(a.V + e);
+                const double s = a.S[i * a.S_rs + (j0 + c) * a.S_cs];
+                term += ((y * m - s * exp(m + v / 2)) + log(two_pi * v) / 2) + 0.5;
+                rowv += v;
+            }
+            vs[c][tid] = v;
+        }
+        __syncthreads();
+        const int col = tid >> 4, part = tid & 15;          // 16 threads per column, fixed shuffle tree
+        double sacc = 0.0;
+#pragma unroll
+        for (int q = 0; q < kRowsPerCta / 16; ++q) sacc += vs[col][part + 16 * q];
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 8);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+        if (part == 0 && col < ncv) a.colV[rb * a.p + j0 + col] = sacc;
+    }
+    if (row_ok) a.rowpart[(long long)blockIdx.x * a.n + i] = rowv;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = term;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int q = 0; q < kWarps; ++q) s += red[q];
+        a.termpart[rb * gridDim.x + blockIdx.x] = s;
+    }
+}
+
 // FP64 pipe probe: 8 independent DFMA chains per thread
 __global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, int iters, double seed)
 {

@@ -55,6 +55,13 @@ calc_ebpmf_log_obj = function(n,p,sym,ssexp,slogv,sv,sigma2,R2,KL_LF,const,ss,a0
         as.double(sigma2), as.double(R2), KL_LF, const, ss, a0, b0)
 }
 
+#'@title calc splitting PMF objective function.   (inst/code/Poisson_MF_splitting.R:373, archived driver)
+calc_split_PMF_obj_flashier = function(Y,S,sigma2,M,V,fit_flash,KL_LF,const,var_type){
+  Y = as.matrix(Y); storage.mode(Y) = 'double'; storage.mode(M) = 'double'; storage.mode(V) = 'double'
+  .Call(C_calc_split_PMF_obj_flashier, ebpmf_b200_ctx(), Y, as.double(S), as.double(sigma2), M, V,
+        as.double(fit_flash$flash.fit$R2), KL_LF, const, var_type)
+}
+
 #'@title update sigma2   (R/ebpmf_log.R:413)
 ebpmf_log_update_sigma2 = function(fit_flash,sigma2,v_sum,var_type,cap_var_mean_ratio,a0,b0,n,p){
   R2 = fit_flash$flash_fit$R2

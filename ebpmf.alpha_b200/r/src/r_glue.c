@@ -339,6 +339,23 @@ SEXP C_calc_ebpmf_log_obj(SEXP xp, SEXP n, SEXP p, SEXP sym, SEXP ssexp, SEXP sl
     return Rf_ScalarReal(obj);
 }
 
+/* ---- calc_split_PMF_obj_flashier(Y,S,sigma2,M,V,fit_flash,KL_LF,const,var_type)  inst/code/Poisson_MF_splitting.R:373
+ * (the archived driver's un-fused ELBO).  The R wrapper passes R2 = fit_flash$flash.fit$R2. */
+SEXP C_calc_split_PMF_obj_flashier(SEXP xp, SEXP Y, SEXP S, SEXP sigma2, SEXP M, SEXP V, SEXP R2, SEXP KL_LF, SEXP const_,
+                                   SEXP var_type)
+{
+    ebpmf_ctx *ctx = get_ctx(xp);
+    const int vt = var_type_code(var_type);
+    if (vt < 0) Rf_error("Non-supported var type");
+    const R_xlen_t n = Rf_nrows(M), p = Rf_ncols(M);
+    if (Rf_nrows(Y) != n || Rf_ncols(Y) != p || Rf_nrows(V) != n || Rf_ncols(V) != p) Rf_error("non-conformable arrays");
+    const int ks = operand_kind(S, n, p, "S");
+    double obj = 0.0;
+    check(ctx, ebpmf_calc_split_obj(ctx, (int64_t)n, (int64_t)p, REAL(Y), REAL(S), ks, REAL(M), REAL(V), vt, (int64_t)XLENGTH(sigma2),
+                                    REAL(sigma2), (int64_t)XLENGTH(R2), REAL(R2), Rf_asReal(KL_LF), Rf_asReal(const_), &obj));
+    return Rf_ScalarReal(obj);
+}
+
 /* ---- N1: what flashier needs from the RESIDENT M (R/ebpmf_log_flash_update.R:35,55-64) ---------
  * list(MF = M %*% EF_w, MtL = t(M) %*% EL_w, r2_col = colSums((M - EL_w EF_w')^2), r2_row = rowSums(...)) */
 SEXP C_ebpmf_m_products(SEXP xp, SEXP dims, SEXP EL_w, SEXP EF_w)
@@ -582,6 +599,7 @@ static const R_CallMethodDef call_methods[] = {
     {"C_vga_pois_solver_mat_newton_low_memory", (DL_FUNC)&C_vga_pois_solver_mat_newton_low_memory, 11},
     {"C_ebpmf_log_update_sigma2", (DL_FUNC)&C_ebpmf_log_update_sigma2, 12},
     {"C_calc_ebpmf_log_obj", (DL_FUNC)&C_calc_ebpmf_log_obj, 14},
+    {"C_calc_split_PMF_obj_flashier", (DL_FUNC)&C_calc_split_PMF_obj_flashier, 10},
     {"C_ebpmf_m_products", (DL_FUNC)&C_ebpmf_m_products, 4},
     {"C_ebpmf_sim_data_log", (DL_FUNC)&C_ebpmf_sim_data_log, 10},
     {"C_ebpmf_group_new", (DL_FUNC)&C_ebpmf_group_new, 1},

@@ -661,6 +661,24 @@ def calc_ebpmf_log_obj(n, p, sym, ssexp, slogv, sv, sigma2, R2, KL_LF, const, ss
     return out.value
 
 
+def calc_split_PMF_obj_flashier(Y, S, sigma2, M, V, fit_flash, KL_LF, const, var_type, ctx=None):
+    """inst/code/Poisson_MF_splitting.R:373-391 (the archived driver's un-fused ELBO).  ``fit_flash``: mapping with ``R2``."""
+    ctx = ctx or default_context()
+    if var_type not in VAR_TYPE:
+        raise EbpmfError(4, "Non-supported var type")
+    M = _f(M)
+    n, p = M.shape
+    Yd = _f(Y.toarray() if _is_sparse(Y) else Y); Vd = _f(V)
+    if Yd.shape != (n, p) or Vd.shape != (n, p):
+        raise ValueError("non-conformable arrays")
+    Sb, Sk = _operand(S, n, p, "S")
+    s2 = _vec(sigma2); R2 = _vec(fit_flash["R2"])
+    out = C.c_double()
+    ctx._ck(ctx._lib.ebpmf_calc_split_obj(ctx._h, n, p, _ptr(Yd), _ptr(Sb), Sk, _ptr(M), _ptr(Vd), VAR_TYPE[var_type], s2.size,
+                                          _ptr(s2), R2.size, _ptr(R2), float(KL_LF), float(const), C.byref(out)))
+    return out.value
+
+
 def sum_lfactorial_sparseMat(Y, ctx=None):
     """R/ebpmf_log.R:470-472: sum(lfactorial(Y@x)); a dense Y gives sum(lfactorial(Y)) (:175)."""
     ctx = ctx or default_context()

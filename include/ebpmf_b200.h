@@ -182,6 +182,13 @@ int  ebpmf_calc_obj(ebpmf_ctx *ctx, int64_t n, int64_t p, double sym, double sse
                     int64_t len_r2, const double *R2,
                     double KL_LF, double const_, double ss, double a0, double b0, double *obj);
 
+/* calc_split_PMF_obj_flashier(Y,S,sigma2,M,V,fit_flash,KL_LF,const,var_type), inst/code/Poisson_MF_splitting.R:373-391
+ * (the archived driver's un-fused ELBO): dense n x p Y, M, V; S by EBPMF_OP_* kind; R2 = fit_flash$flash.fit$R2.
+ * One streaming pass on the device (32 B per entry) + the sigma2 terms, every sum() at its own length. */
+int  ebpmf_calc_split_obj(ebpmf_ctx *ctx, int64_t n, int64_t p, const double *Y, const double *S, int S_kind,
+                          const double *M, const double *V, int var_type, int64_t len_sigma2, const double *sigma2,
+                          int64_t len_r2, const double *R2, double KL_LF, double const_, double *obj);
+
 /* The whole step with CALLER-OWNED HOST buffers in one call (what the .Call shim uses each outer iteration):
  * factors + sigma2 + M in, step, M [+ V] + v_sum out.  n, p are the dims of the host matrices and must equal
  * those of the resident Y (else EBPMF_ERR_ARG, R's "non-conformable arrays").  The host matrices may be
@@ -338,7 +345,8 @@ int  ebpmf_ctx_last_diag(ebpmf_ctx *ctx, uint64_t *topup_units, uint64_t *unit_e
 /* counters of the context / its last fused solve: out[0] units that needed second-pass work, [1] unit
  * evaluations, [2] tiles the second pass restaged, [3] kernels launched by this context so far, [4] bytes the
  * last host-buffer step copied out speculatively, [5] bytes it had to copy again, [6] tiles per pass,
- * [7] 1 if per-tile counts of a previous step are kept, [8] device ms of the last ebpmf_vga_fixed_iter kernel.
+ * [7] 1 if per-tile counts of a previous step are kept, [8] device ms of the last ebpmf_vga_fixed_iter /
+ * ebpmf_calc_split_obj kernel.
  * count <= 9. */
 int  ebpmf_ctx_counters(ebpmf_ctx *ctx, double *out, int count);
 

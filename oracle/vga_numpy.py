@@ -392,3 +392,25 @@ def ebpmf_log_vga_step(M, Y, EL, EF, sigma2, var_type, maxiter_vga=10, vga_tol=1
         v_sum = np.concatenate(v_rows)                                      # :292-293
     return dict(M=Mout, V=Vout, sym=sym, ssexp=ssexp, slogv=slogv, v_sum=v_sum,
                 n_updates=n_updates, converged=converged)
+
+
+# --------------------------------------------------------------------------
+# N4: calc_split_PMF_obj_flashier -- inst/code/Poisson_MF_splitting.R:373-391 (archived driver; un-fused ELBO)
+# --------------------------------------------------------------------------
+def calc_split_PMF_obj_flashier(Y, S, sigma2, M, V, R2, KL_LF, const, var_type):
+    """``R2`` is fit_flash$flash.fit$R2 (:374).  sv / ss per var_type (:377-388); the value (:389), every sum()
+    at its own length."""
+    Y = np.asarray(Y, dtype=np.float64); M = np.asarray(M, dtype=np.float64); V = np.asarray(V, dtype=np.float64)
+    S = np.asarray(S, dtype=np.float64)
+    sigma2 = np.asarray(sigma2, dtype=np.float64); R2 = np.asarray(R2, dtype=np.float64)
+    n, p = Y.shape
+    if var_type == "by_row":
+        sv, ss = V.sum(axis=1), p
+    elif var_type == "by_col":
+        sv, ss = V.sum(axis=0), n
+    elif var_type == "constant":
+        sv, ss = V.sum(), n * p
+    else:
+        raise ValueError("Non-supported var type")
+    return (_rsum(Y * M - S * np.exp(M + V / 2) + np.log(2 * np.pi * V) / 2 + 0.5) - _rsum(ss * np.log(2 * np.pi * sigma2) / 2)
+            - _rsum(sv / 2 / sigma2) - _rsum(R2 / 2 / sigma2) + const + KL_LF)

@@ -828,3 +828,22 @@ def test_step_input_stays_readable_after_the_step(gpu_ctx):
     assert np.array_equal(gpu_ctx.get_block(0, 700, 89, 1, "V"), gpu_ctx.get_v()[:, 89:90])
     gpu_ctx.rewind_m()
     assert np.array_equal(gpu_ctx.get_m(), st["M0"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("var_type", ["by_col", "by_row", "constant"])
+@pytest.mark.parametrize("s_kind", ["scalar", "matrix"])
+def test_calc_split_obj_unfused_elbo(gpu_ctx, pkg, var_type, s_kind):
+    """N4: calc_split_PMF_obj_flashier (inst/code/Poisson_MF_splitting.R:373-391) against the oracle's restatement, on
+    the output of a real VGA step (ragged shape: 700 x 90), scalar S and the matrix S = tcrossprod(l0, f0) of the
+    archived driver."""
+    sim, st = make_case(700, 90, 3, 0.15, var_type=var_type, seed=33)
+    n, p = sim["Y"].shape
+    ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], var_type, 10, 1e-5)
+    S = 1.0 if s_kind == "scalar" else np.asfortranarray(np.outer(np.exp(0.1 * np.arange(n) / n), np.exp(-0.1 * np.arange(p) / p)))
+    want = vga_numpy.calc_split_PMF_obj_flashier(sim["Y"], S, st["sigma2"], ref["M"], ref["V"], st["R2"], -12.5, -1234.5, var_type)
+    got = pkg.calc_split_PMF_obj_flashier(sim["Y"], S, st["sigma2"], ref["M"], ref["V"], dict(R2=st["R2"]), -12.5, -1234.5,
+                                          var_type, ctx=gpu_ctx)
+    assert abs(got - want) <= 1e-10 * abs(want), (got, want)
+    with pytest.raises(pkg.EbpmfError):
+        pkg.calc_split_PMF_obj_flashier(sim["Y"], S, st["sigma2"], ref["M"], ref["V"], dict(R2=st["R2"]), 0.0, 0.0, "by_both", ctx=gpu_ctx)

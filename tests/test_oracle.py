@@ -177,6 +177,9 @@ def test_vga_step_partials_and_elbo_recomposition(case, var_type):
                - np.sum(st["R2"] / 2 / S2) + const + KL - np.sum(np.log(S2)))     # (a0+1)*log with a0 = 0
     trunc = (0.5 * np.log(2 * np.pi) - vga_numpy.SLOGV_CONST) * n * p
     assert abs(fused - (unfused - trunc)) < 1e-9 * abs(unfused)
+    # the oracle's restatement of calc_split_PMF_obj_flashier (:373-391) is that formula without the prior term
+    split = vga_numpy.calc_split_PMF_obj_flashier(sim["Y"], 1.0, sig, M, V, st["R2"], KL, const, var_type)
+    assert abs(split - (unfused + np.sum(np.log(S2)))) < 1e-10 * abs(unfused)
 
 
 def test_sigma2_update_formulas():
