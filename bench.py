@@ -557,6 +557,15 @@ def main():
     # FP64 line: FP64-pipe warp-instructions per 32 entries from the ncu capture x the live launch time,
     # against the DFMA rate measured live (ebpmf_probe_fp64_tflops: one DFMA warp-instruction = 64 flop)
     fp64 = {"dfma_tflops_measured": fp64_tf}
+    # SURVEY.md section 8(d)'s ALGORITHMIC FP64 line: R performs u updates on every entry = (u+1) exp + (3u+2) divisions +
+    # 1 log + (13u+13+K_tot) add/mul, costed there at 25 / 10 / 30 FP64 instructions -> 70u + 110 + K_tot per entry
+    survey_instr = 70.0 * u + 110.0 + (K + 2)
+    survey_line = (fp64_tf * 1e12 / 2.0) / survey_instr
+    fp64["survey_8d_model"] = {"dp_instr_per_entry": survey_instr, "line_entries_per_s_per_gpu": survey_line,
+                               "frac": (value / world) / survey_line,
+                               "note": "the survey's attainable bound for a kernel that evaluates every entry u+1 times with "
+                                       "library-grade exp/div/log; > 1 here because exp costs 9, a reciprocal 2 and the "
+                                       "fast-forward skips the evaluations a converged unit would repeat"}
     issue = None
     if ncu:
         dfma_per_s = fp64_tf * 1e12 / 64.0                  # warp-level DFMA instructions per second, whole chip
