@@ -73,7 +73,7 @@ struct DevBuf {
 struct ebpmf_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_p1 = nullptr, ev_p2 = nullptr, ev_p3 = nullptr, ev_setup = nullptr, ev_topup = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_p1 = nullptr, ev_p2 = nullptr, ev_p3 = nullptr, ev_setup = nullptr;
     std::vector<cudaEvent_t> ev_chunk, ev_in;    // host-pipelined step: pass 1 of chunk c done / M_in of chunk c on the device
     std::string err;
 
@@ -900,7 +900,6 @@ int ebpmf_ctx_create(int device, ebpmf_ctx **out) {
     CREATE_STEP(cudaEventCreate(&ctx->ev_p2));
     CREATE_STEP(cudaEventCreate(&ctx->ev_p3));
     CREATE_STEP(cudaEventCreateWithFlags(&ctx->ev_setup, cudaEventDisableTiming));
-    CREATE_STEP(cudaEventCreateWithFlags(&ctx->ev_topup, cudaEventDisableTiming));
     CREATE_STEP(cudaMallocHost((void **)&ctx->h_status, sizeof(Status)));
     CREATE_STEP(cudaMallocHost((void **)&ctx->h_small, sizeof(double) * 64));
     CREATE_STEP(cudaMallocHost((void **)&ctx->h_ints, sizeof(int) * 4096));
@@ -946,7 +945,7 @@ int ebpmf_ctx_destroy(ebpmf_ctx *ctx) {
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
     if (ctx->h_ints) cudaFreeHost(ctx->h_ints);
-    cudaEvent_t evs[] = {ctx->ev0, ctx->ev1, ctx->ev_p1, ctx->ev_p2, ctx->ev_p3, ctx->ev_setup, ctx->ev_topup};
+    cudaEvent_t evs[] = {ctx->ev0, ctx->ev1, ctx->ev_p1, ctx->ev_p2, ctx->ev_p3, ctx->ev_setup};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_in) if (e) cudaEventDestroy(e);
