@@ -384,15 +384,43 @@ def run_variants(args, wl, pkg, torch, local_rank):
                                  "parity_max_rel_err_M_rows": rel(r["M"][:srows], ref["M"]),
                                  "parity_max_rel_err_V_rows": rel(r["V"][:srows], ref["V"])}
     variants["fixed_iter"] = fi
+    launches_slab = int(ctx.counters()["launches"])
+    ctx.close()
+    del Yd, Beta, S2, r
+    # --- K4 at config 5's STATED size, 200 000 x 20 000 (the fused path needs only M and the CSC Y; the dense signatures
+    #     would need 6 x 32 GB on the device): device time of the solve and a row-sample parity check -----------------
+    if mem_available_bytes() > 130e9:
+        nF = 200000
+        cF = pkg.VgaContext(local_rank)
+        nnzF = cF.sim_data_log(nF, p, K, row0=0, seed=SEED, log_offset=wl["log_offset"], warm_start=False)
+        cpF, riF, xF = cF.get_y_csc()
+        YF = sp.csc_matrix((xF, riF, cpF), shape=(nF, p))
+        ELF, EFF = cF.get_factors()
+        s2F = cF.get_sigma2()
+        M0F = cF.get_m()
+        l0F = np.exp(np.random.default_rng(6).normal(0, 0.1, nF))
+        infoF = {}
+        t0 = time.perf_counter()
+        MoF = pkg.vga_pois_solver_mat_newton_low_memory(M0F, YF, l0F, f0, ELF, EFF, s2F, "by_col", C5_MAXITER, C5_TOL, ctx=cF, info=infoF)
+        wallF = time.perf_counter() - t0
+        YsF = YF[:srows].toarray(order="F")
+        refF = c_oracle.vga_low_memory(M0F[:srows], YsF, l0F[:srows], f0, ELF[:srows], EFF, s2F, "by_col", infoF["n_updates"], 0.0)
+        variants["low_memory_full_size"] = {"rows": nF, "cols": p, "nnz": int(nnzF), "value": nF * p / (infoF["kernel_ms"] * 1e-3),
+                                            "kernel_ms": infoF["kernel_ms"], "n_updates": infoF["n_updates"],
+                                            "call_wall_s_incl_64GB_of_pageable_host_copies": wallF,
+                                            "parity_max_rel_err_M_rows": rel(MoF[:srows], refF["M"]),
+                                            "parity_how": "C oracle on rows [0,%d) with the global update count forced" % srows}
+        launches_slab += int(cF.counters()["launches"])
+        cF.close()
+        del MoF, M0F, YF
     out["variants"] = variants
     out["value"] = variants["dense_signature"]["value"]
     out["ms_per_step"] = variants["dense_signature"]["ms_per_step"]
     out["roofline"] = {"bound": "hbm", "kernel": "vga_dense_kernel<MODE_FIRST>", "achieved": 48.0 * n * p / (out["ms_per_step"] * 1e-3) / 1e9,
                        "peak": peak, "unit": "GB/s", "frac": variants["dense_signature"]["hbm_frac"], "traffic": None,
                        "peak_source": peak_src, "note": "whole solve (both passes) against 48 B/entry"}
-    out["gpu_launches"] = int(ctx.counters()["launches"])
+    out["gpu_launches"] = launches_slab
     emit(json.dumps(out))
-    ctx.close()
 
 
 def main():
