@@ -34,9 +34,14 @@ partials in every step.  Inputs are generated ON THE DEVICE (ebpmf_ctx_sim_data_
              profiles/r02_ncu_metrics.json (written by scripts/ncu_summary.py), the times are live
   cpu_baseline  the oracle's C transcription of the R code (OpenMP, all host cores) on a bounded
              row sample -- a restatement of the R code, NOT the R code (R is not installed)
+  parity     every run: rows [0, 2048) x all columns and ALL rows x 8 columns of the slab against the oracle
+             with the global update count forced (M, V, and v_sum of those columns); `--full-parity`: every
+             entry of the slab, the three ELBO sums, all of v_sum, and R's update count derived from the
+             oracle's global max|f| per iterate.  parity_multi: config 2 row-sharded over the N ranks
+             against the oracle on the whole matrix (M, V, all-reduced v_sum, the sums, u on every rank)
 
 `--workload c5` times the solver VARIANTS of BASELINE config 5 (dense drop-in signature, _fixed_iter,
-_low_memory) on a row slab of 200k x 20k.  `--impl reference` times the CPU restatement alone.
+_low_memory) on a row slab of 200k x 20k, and _low_memory at the full 200k x 20k.  `--impl reference` times the CPU restatement alone.
 """
 from __future__ import annotations
 
