@@ -416,6 +416,13 @@ class RList:
         return len(self.vals)
 
 
+class REnvObj:
+    """An environment as a value (`new.env()`): `$` reads, `$<-` writes IN PLACE (reference semantics)."""
+
+    def __init__(self):
+        self.vars = {}
+
+
 class RDiag:
     """Matrix::Diagonal(n, x): only ever an operand of %*% here (exact column / row scaling, no summation)."""
 
@@ -509,7 +516,7 @@ def dense(v):
     if isinstance(v, RSparse):
         return v.dense
     if isinstance(v, np.ndarray):
-        return v
+        return v if type(v) is np.ndarray else v.view(np.ndarray)     # a flagged subclass (integer storage) is plain data
     if isinstance(v, (int, float, bool, np.floating, np.integer, np.bool_)):
         return np.atleast_1d(np.asarray(v))
     raise RError("non-numeric argument (%s)" % type(v).__name__)
@@ -993,6 +1000,8 @@ class Interp:
             obj = self.eval(e[1], env)
             if obj is None:
                 return None
+            if isinstance(obj, REnvObj):
+                return obj.vars.get(e[2])
             if not isinstance(obj, RList):
                 raise RError("$ operator is invalid for atomic vectors")
             return obj.get(e[2], partial=True)
@@ -1082,6 +1091,9 @@ class Interp:
             if inner is None:
                 raise RError("invalid assignment target")
             cur = self.current(inner, env)
+            if k == "dollar" and isinstance(cur, REnvObj):
+                cur.vars[target[2]] = value
+                return
             if k == "dollar":
                 new = RList() if cur is None else cur
                 if not isinstance(new, RList):
@@ -1200,8 +1212,8 @@ class Interp:
 
 def to_r(v):
     """Python / NumPy value -> interpreter value."""
-    if v is None or isinstance(v, (RList, RDiag, RSparse, Closure, Builtin)):
-        return v
+    if v is None or isinstance(v, (RList, RDiag, RSparse, Closure, Builtin, REnvObj)) or hasattr(v, "sexp"):
+        return v                                           # (an object with .sexp: an external pointer of tests/r_mock.py)
     if isinstance(v, str):
         return strs(v)
     if hasattr(v, "toarray"):                          # scipy.sparse -> the dgCMatrix stand-in
