@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(kThreads, (FORMULA == FORMULA_A10) ? 2 : EBPMF
                 if (MODE == MODE_FIRST) {
                     double cap = c0m1;                                             // :16
                     if constexpr (FORMULA == FORMULA_A10) cap = sm.bs[c][tid];     // :78
-                    m[e] = (m[e] < cap) ? m[e] : cap;
+                    m[e] = (cap < m[e]) ? cap : m[e];                              // Rfast::Pmin = std::min(M, cap): a NaN in M stays
                 }
             }
             int k = 0, kb, kk = 0;
@@ -944,7 +944,7 @@ __global__ void __launch_bounds__(kThreads, 2) vga_dense_kernel(const DenseArgs 
             c0[e] = __dadd_rn(__fma_rn(s2[e], cur.y[e], cur.b[e]), 1.0);           // :9
             const double c0m1 = __dadd_rn(c0[e], -1.0);
             w[e] = __dmul_rn(c0m1, c1[e]);                                         // x + const3
-            if (MODE == MODE_FIRST) m[e] = (m[e] < c0m1) ? m[e] : c0m1;            // :16
+            if (MODE == MODE_FIRST) m[e] = (c0m1 < m[e]) ? c0m1 : m[e];            // :16  std::min(M, const0-1): a NaN in M stays
         }
         int kb;
         unsigned evals = 0;

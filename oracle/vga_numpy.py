@@ -112,7 +112,7 @@ def vga_pois_solver_mat_newton(M, X, S, Beta, Sigma2, maxiter=1000, tol=1e-8,
     const1 = 1 / Sigma2                          # :10
     const2 = Sigma2 / 2                          # :11
     const3 = Beta / Sigma2                       # :12
-    M = np.minimum(M, const0 - 1)                # :16  Rfast::Pmin
+    M = np.where(const0 - 1 < M, const0 - 1, M)  # :16  Rfast::Pmin = std::min(M, const0-1): (y < x) ? y : x, a NaN in M stays
     n_updates = 0
     converged = False
     trace = []
@@ -177,7 +177,7 @@ def vga_pois_solver_mat_newton_low_memory(M, Y, l0, f0, EL, EF, sigma2, var_type
     EL = np.asarray(EL, dtype=np.float64).reshape(n, -1)
     EF = np.asarray(EF, dtype=np.float64).reshape(p, -1)
     Beta = EL @ EF.T                             # :77 tcrossprod
-    M = np.minimum(M, Beta)                      # :78
+    M = np.where(Beta < M, Beta, M)              # :78  std::min(M, Beta)
     n_updates = 0
     converged = False
     franges = []

@@ -81,7 +81,7 @@ int oracle_vga_newton(i64 n, i64 p, const double *M0, const double *X,
             const double s2 = Sigma2[i * V_rs + j * V_cs], be = Beta[i * B_rs + j * B_cs];
             const double const0 = (s2 * X[e] + be + 1);          /* :9  */
             const double c0m1 = const0 - 1;
-            A[e] = (M0[e] < c0m1) ? M0[e] : c0m1;                /* :16 Pmin */
+            A[e] = (c0m1 < M0[e]) ? c0m1 : M0[e];                /* :16 Rfast::Pmin = std::min(M, const0-1): a NaN in M stays a NaN */
         }
 
     double *cur = A, *nxt = B;
@@ -250,7 +250,7 @@ int oracle_vga_low_memory(i64 n, i64 p, i64 K, const double *M0, const double *Y
             double b = 0.0;
             for (i64 k = 0; k < K; ++k) b += EL[i + n * k] * EF[j + p * k];          /* :77 tcrossprod */
             Beta[i + n * j] = b;
-            A[i + n * j] = (M0[i + n * j] < b) ? M0[i + n * j] : b;                   /* :78 */
+            A[i + n * j] = (b < M0[i + n * j]) ? b : M0[i + n * j];                   /* :78 std::min(M, Beta) */
         }
     double *cur = A, *nxt = B;
     int u = 0, conv = 0, nan_seen = 0;

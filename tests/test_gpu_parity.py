@@ -158,6 +158,22 @@ def test_nan_raises_like_r(gpu_ctx, pkg):
     assert ei.value.code == 3
     with pytest.raises(vga_numpy.RError):
         vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], EL, st["EF"], st["sigma2"], "by_col", 10, 1e-5)
+    # a NaN in the START matrix survives the clamp M = Pmin(M, const0-1) (Rfast: std::min(M, cap) = (cap < M) ? cap : M),
+    # reaches f and stops R the same way -- on the fused path, the dense signature and _low_memory alike
+    with pytest.raises(pkg.EbpmfError) as ei:
+        gpu_ctx.vga_step_host(M0, st["EL"], st["EF"], st["sigma2"], "by_col", 10, 1e-5)
+    assert ei.value.code == 3
+    with pytest.raises(pkg.EbpmfError) as ei:
+        pkg.vga_pois_solver_mat_newton(M0, sim["Y"], 1, st["EL"] @ st["EF"].T, 0.5, maxiter=10, tol=1e-5, ctx=gpu_ctx)
+    assert ei.value.code == 3
+    with pytest.raises(pkg.EbpmfError) as ei:
+        pkg.vga_pois_solver_mat_newton_low_memory(M0, sim["Y"], sim["L0"], sim["F0"], st["EL"][:, 2:], st["EF"][:, 2:], st["sigma2"], "by_col",
+                                                  10, 1e-5, ctx=gpu_ctx)
+    assert ei.value.code == 3
+    with pytest.raises(vga_numpy.RError):
+        vga_numpy.ebpmf_log_vga_step(M0, sim["Y"], st["EL"], st["EF"], st["sigma2"], "by_col", 10, 1e-5)
+    with pytest.raises(c_oracle.OracleNaN):
+        c_oracle.vga_step(M0, sim["Y"], st["EL"], st["EF"], st["sigma2"], "by_col", 10, 1e-5)
 
 
 def test_bad_var_type_and_call_order(pkg):
