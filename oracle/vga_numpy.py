@@ -5,13 +5,16 @@ THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
 reference`` legs may import it, and only as the checker.  The product path
 (``ebpmf.alpha_b200``) never imports anything under ``oracle/``.
 
-PARITY UNPINNED: the reference (DongyueXie/ebpmf.alpha, 100 % R) ships no golden
-vectors, no assertions and no known-answer tests for this path, and R is not
-installed here or on the GPU box, so the reference itself cannot be executed.
-What pins this file instead: (i) it follows the R source operator by operator
-(citations below, all relative to /root/reference), (ii) an independent C
-transcription (``oracle/vga_oracle.c``) must agree with it to <= 1e-13, (iii)
-mathematical invariants and an mpmath high-precision root (tests/).
+PARITY: the reference (DongyueXie/ebpmf.alpha, 100 % R) ships no golden vectors, no
+assertions and no known-answer tests for this path, and GNU R is not installed here or
+on the GPU box.  What pins this file: (i) the reference's own source, executed statement
+by statement by the restricted R evaluator oracle/mini_r.py (tests/golden/
+minir_reference.npz, tests/test_minir_reference.py) -- this transcription reproduces it
+bit for bit; (ii) it follows the R source operator by operator (citations below, all
+relative to /root/reference); (iii) an independent C transcription
+(``oracle/vga_oracle.c``) must agree with it to <= 1e-13; (iv) mathematical invariants
+and an mpmath high-precision root (tests/).  NOT pinned against GNU R output: that needs
+tests/golden/make_golden.R to be run by someone who has R ("parity unpinned" in that sense).
 
 R evaluation rules that are reproduced on purpose:
   * matrices are column-major; a length-n vector recycles DOWN each column;

@@ -5,9 +5,11 @@
  * and bench.py's cpu_baseline / --impl reference legs may load it, and only as the
  * checker or the timed CPU baseline.  Nothing under ebpmf.alpha_b200/ links or calls it.
  *
- * PARITY UNPINNED: the reference (DongyueXie/ebpmf.alpha) is 100 % R, ships no golden
- * vectors or assertions for this path, and R is not installed here, so the reference
- * cannot be executed.  This file is a second, independent transcription of the R source
+ * PARITY: the reference (DongyueXie/ebpmf.alpha) is 100 % R, ships no golden vectors or
+ * assertions for this path, and GNU R is not installed here ("parity unpinned" against GNU R
+ * output).  What this file is held to instead: the outputs of the reference's own R source
+ * as executed by the restricted R evaluator oracle/mini_r.py (tests/golden/minir_reference.npz,
+ * tests/test_minir_reference.py).  It is a second, independent transcription of the R source
  * (the first is oracle/vga_numpy.py); tests require the two to agree to <= 1e-13.
  *
  * Citations are relative to /root/reference.  All matrices are column-major (R layout):
