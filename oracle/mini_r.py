@@ -746,6 +746,8 @@ def take(vec, pos):
 def index_get(obj, idx, drop=True):
     if obj is None:
         return None
+    if hasattr(obj, "r_index_get"):                    # an object that brings its own `[` (oracle/minir_io.py's data frame)
+        return obj.r_index_get(idx, drop)
     if isinstance(obj, RList):
         pos = resolve_index(idx[0], len(obj), obj.names)
         return RList([obj.vals[i] if i < len(obj) else None for i in pos], [obj.names[i] if i < len(obj) else None for i in pos],
@@ -790,6 +792,8 @@ def index_get2(obj, i):
 
 def index_set(obj, idx, value):
     """`obj[idx] <- value` as a pure function of obj."""
+    if hasattr(obj, "r_index_set"):
+        return obj.r_index_set(idx, value)
     if isinstance(obj, RList):
         new = obj.copy()
         pos = resolve_index(idx[0], len(new), new.names, extend=True)
@@ -1002,6 +1006,8 @@ class Interp:
                 return None
             if isinstance(obj, REnvObj):
                 return obj.vars.get(e[2])
+            if hasattr(obj, "r_dollar"):
+                return obj.r_dollar(e[2])
             if not isinstance(obj, RList):
                 raise RError("$ operator is invalid for atomic vectors")
             return obj.get(e[2], partial=True)
@@ -1520,6 +1526,8 @@ def _which(it, x, **kw):
 
 
 def _dim(it, x):
+    if hasattr(x, "r_dim"):
+        return x.r_dim()
     if isinstance(x, (np.ndarray, RSparse)) and dense(x).ndim == 2:
         return np.array(dense(x).shape, dtype=np.float64)
     return None
@@ -1698,6 +1706,10 @@ def _install_builtins(it):
     d("modifyList", _modify_list)
     d("names", lambda it_, x: strs(*[nm or "" for nm in x.names]) if isinstance(x, RList) and any(x.names) else None)
     d("names<-", _names_set)
+    d("storage.mode<-", lambda it_, x, value=None: np.array(dense(x), dtype=np.float64, order="F"))      # only ever 'double' here
+    d("character", lambda it_, length=0: strs(*[""] * int(scalar(length)) if not isinstance(length, int) else [""] * length))
+    d("integer", lambda it_, length=0: np.zeros(int(scalar(length)) if not isinstance(length, int) else length))
+    d("source", lambda it_, file, **kw: it_.source(r_string(file)))
     d("class<-", _class_set)
     d("class", lambda it_, x: x.cls if isinstance(x, RList) and x.cls is not None else strs("list" if isinstance(x, RList) else "numeric"))
     d("paste", _paste(" "))

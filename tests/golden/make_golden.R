@@ -12,6 +12,10 @@
 # the directory the test is skipped and says why.  Nothing here is a re-implementation: every number comes out
 # of the reference's functions, except sym/ssexp/slogv/v_sum, which the reference computes inline in ebpmf_log
 # (R/ebpmf_log.R:316-327) and which are restated here line by line with the citation.
+#
+# Nobody here has GNU R, but the script is not untested: tests/test_golden_r.py runs it, unmodified, under the restricted
+# R evaluator oracle/mini_r.py (base R's file I/O stood in for by oracle/minir_io.py) against the reference checkout and
+# feeds what it writes to the same loader.
 args = commandArgs(trailingOnly = TRUE)
 if (length(args) < 1) stop("usage: Rscript tests/golden/make_golden.R /path/to/ebpmf.alpha")
 ref = args[1]

@@ -53,7 +53,10 @@ def test_exported_inputs_are_the_fixture_inputs():
 @pytest.mark.parametrize("vt", ["by_col", "by_row", "constant"])
 @pytest.mark.parametrize("tag", sorted(CASES))
 def test_oracle_matches_the_reference_outputs(vt, tag):
-    R = read_dir(REF)
+    check_oracle_steps(read_dir(REF), vt, tag)
+
+
+def check_oracle_steps(R, vt, tag):
     mi, tol = CASES[tag]
     k = "%s_%s_" % (vt, tag)
     for res, u in ((lambda r: (r, r["n_updates"][0]))(vn.ebpmf_log_vga_step(G[vt + "_M0"], G["Y"], G[vt + "_EL"], G[vt + "_EF"],
@@ -78,7 +81,10 @@ def test_oracle_matches_the_reference_outputs(vt, tag):
 
 @needs_r
 def test_oracle_other_solvers_match_the_reference_outputs():
-    R = read_dir(REF)
+    check_oracle_other_solvers(read_dir(REF))
+
+
+def check_oracle_other_solvers(R):
     EL, EF, s2 = G["by_col_EL"], G["by_col_EF"], G["by_col_sigma2"]
     S2 = vn.adjust_var_shape(s2, "by_col", *G["Y"].shape)
     fi = c_oracle.vga_fixed_iter(G["by_col_M0"], None, G["Y"], 1, EL @ EF.T, S2, 1)
@@ -112,3 +118,30 @@ def test_cuda_matches_the_reference_outputs(gpu_ctx, pkg, vt, tag):
         obj = pkg.calc_ebpmf_log_obj(n, p, res["sym"], res["ssexp"], res["slogv"], res["v_sum"], s2, G[vt + "_R2"], -123.4, -5.5,
                                      ss, 1, 1, ctx=gpu_ctx)
         assert abs(obj - R[k + "obj"].ravel()[0]) <= 1e-8 * abs(R[k + "obj"].ravel()[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# make_golden.R itself, run by the restricted R evaluator (oracle/mini_r.py) instead of GNU R
+# ---------------------------------------------------------------------------------------------------------------
+REFROOT = os.environ.get("EBPMF_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFROOT, "R", "vga_solver_mat.R")),
+                    reason="the reference checkout is not present (it never is on the GPU box)")
+def test_make_golden_r_runs_under_the_evaluator_and_writes_what_the_loader_expects(tmp_path):
+    """The script a maintainer is asked to run has never seen GNU R here.  Executed by oracle/mini_r.py -- base R's
+    file I/O (readBin, writeBin, read.delim, data.frame rows, write.table) stood in for by oracle/minir_io.py -- it
+    sources the reference's files, runs to the end and leaves a directory that the loader above reads and that both
+    transcriptions of the oracle match.  (Its outputs are NOT committed as tests/golden/r_reference/: that name is
+    reserved for files written by GNU R.)"""
+    from oracle import minir_io
+    out = minir_io.run_make_golden(os.path.join(HERE, "golden", "make_golden.R"), REFROOT, str(tmp_path / "r_reference"))
+    R = read_dir(str(tmp_path / "r_reference"))
+    assert len(R) == 46 and "wrote 46 arrays" in out
+    for vt in ("by_col", "by_row", "constant"):
+        for tag in sorted(CASES):
+            check_oracle_steps(R, vt, tag)
+    check_oracle_other_solvers(R)
+    MR = np.load(os.path.join(HERE, "golden", "minir_reference.npz"))              # same evaluator, other driver: identical numbers
+    for k in ("by_col_def_M", "by_row_tight_V", "constant_exh_scal", "fixed1_V", "lowmem_M", "lfact"):
+        assert np.array_equal(R[k].ravel(), MR["fn/" + k].ravel()), k
