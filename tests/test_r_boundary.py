@@ -291,3 +291,36 @@ def test_r_group_wrappers_on_one_device(rs):
     check_step_list(rs.call("ebpmf_b200_group_vga_step", M0, N, P, EL, EF, s2, "by_col", 10, 1e-5, True), "fn/by_col_def_")
     rs.call("ebpmf_b200_group_set_m", M0)
     check_step_list(rs.call("ebpmf_b200_group_vga_step", None, N, P, EL, EF, s2, "by_col", 10, 1e-5, True), "fn/by_col_def_")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("vt", ["by_col", "by_row"])
+def test_r_group_wrappers_on_two_devices(pkg, vt):
+    """EBPMF_B200_NGPU = 2 from one R session: rows sharded over two GPUs inside the library (NCCL for the update count
+    and the column sums), full host matrices in and out through the R wrappers; against the C oracle on the whole
+    matrix.  Skipped on single-GPU boxes (profiles/r02_r_boundary_group_n2.log is a 2-GPU run)."""
+    import ctypes
+    from oracle import c_oracle, simdata
+    cnt = ctypes.c_int()
+    pkg.load().ebpmf_device_count(ctypes.byref(cnt))
+    if cnt.value < 2:
+        pytest.skip("needs 2 GPUs")
+    sim = simdata.sim_data_log(1500, 211, K=4, seed=12345, log_offset=simdata.offset_for_density(0.10, K=4))
+    st = simdata.solver_state(sim, start="cold", var_type=vt, seed=12346)
+    ref = c_oracle.vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], vt, 10, 1e-5)
+    s = r_mock.RSession()
+    try:
+        s.call("ebpmf_b200_group", r_mock.as_int([0, 1]))
+        s.call("ebpmf_b200_group_set_y", R.RSparse(sim["Y"]))
+        assert abs(s.call("ebpmf_b200_group_sum_lfactorial")[0] - c_oracle.sum_lfactorial(sim["Y"])) < 1e-8 * c_oracle.sum_lfactorial(sim["Y"])
+        s.call("ebpmf_b200_group_set_m", st["M0"])
+        for M in (st["M0"], None):                     # M in and out; then the shards' resident M (rewound by set_m above)
+            if M is None:
+                s.call("ebpmf_b200_group_set_m", st["M0"])
+            res = s.call("ebpmf_b200_group_vga_step", M, 1500, 211, st["EL"], st["EF"], st["sigma2"], vt, 10, 1e-5, True)
+            assert int(res.get("n_updates")[0]) == ref["n_updates"]
+            assert relM(res.get("M"), ref["M"]) < RTOL and rel(res.get("V"), ref["V"]) < RTOL and rel(res.get("v_sum"), ref["v_sum"]) < RTOL
+            for name in ("sym", "ssexp", "slogv"):
+                assert abs(res.get(name)[0] - ref[name]) <= RTOL * max(1.0, abs(ref[name]))
+    finally:
+        s.close()
