@@ -38,13 +38,15 @@ def standin_flash(M, l0, f0, K, var_type, shrink=0.9):
     return dict(EL=np.asfortranarray(EL), EF=np.asfortranarray(EF), R2=R2, KL1=KL1, KL2=KL2)
 
 
-def outer_loop(Y, l0, f0, M_init, sigma2_init, var_type, K, outer_iters, step, update_sigma2, calc_obj, const, a0=1.0, b0=1.0,
-               cap_var_mean_ratio=0.0):
+def outer_loop(Y, l0, f0, M_init, sigma2_init, var_type, K, outer_iters, step=None, update_sigma2=None, calc_obj=None, const=0.0,
+               a0=1.0, b0=1.0, block=None):
     """`ebpmf_log`'s outer loop (R/ebpmf_log.R:228-352) around a backend's VGA step, with `standin_flash` where the
     reference calls flashier -- the product-side / oracle-side counterpart of minir_reference.run_driver.
 
     step(M, EL, EF, sigma2) -> dict(M, V, v_sum, sym, ssexp, slogv); update_sigma2(fit, sigma2, v_sum) -> sigma2;
     calc_obj(n, p, sym, ssexp, slogv, v_sum, sigma2, R2, KL_LF, const, ss, a0, b0) -> float.
+    Instead of step + update_sigma2, `block(M, fit, sigma2)` may do both and return the new sigma2 in its dict (the
+    shape of ebpmf_b200_vga_block, ebpmf.alpha_b200/r/R/ebpmf_log_vga_block.R).
     Returns dict(elbo_trace, sigma2, M, V)."""
     Y = np.asarray(Y, dtype=np.float64)
     n, p = Y.shape
@@ -55,9 +57,13 @@ def outer_loop(Y, l0, f0, M_init, sigma2_init, var_type, K, outer_iters, step, u
     obj = [-np.inf]
     res = None
     for _ in range(outer_iters):
-        res = step(M, fit["EL"], fit["EF"], sigma2)                         # :254-334
-        M = res["M"]
-        sigma2 = update_sigma2(dict(R2=fit["R2"], EL=fit["EL"], EF=fit["EF"]), sigma2, res["v_sum"])
+        if block is not None:
+            res = block(M, fit, sigma2)                                     # :254-334 in one call
+            M, sigma2 = res["M"], res["sigma2"]
+        else:
+            res = step(M, fit["EL"], fit["EF"], sigma2)                     # :254-327
+            M = res["M"]
+            sigma2 = update_sigma2(dict(R2=fit["R2"], EL=fit["EL"], EF=fit["EF"]), sigma2, res["v_sum"])     # :329-332
         fit = standin_flash(M, l0, f0, K, var_type)                         # ebpmf_log_flash_update, :343-349
         KL_LF = float(np.sum(fit["KL1"])) + float(np.sum(fit["KL2"]))       # :352
         obj.append(float(calc_obj(n, p, res["sym"], res["ssexp"], res["slogv"], res["v_sum"], sigma2, fit["R2"], KL_LF, const, ss, a0, b0)))

@@ -3,7 +3,7 @@
 * `ebpmf.alpha_b200/r/src/r_glue.c` (the `.Call` shim, unmodified) is compiled together with
   tests/r_api_stub/mock_r.c, a functional mock of the R C-API subset the glue uses, and linked to the shipped
   libebpmf_b200.so: tests/_build/libr_glue_mock.so.
-* `ebpmf.alpha_b200/r/R/vga_cuda.R` (the R wrappers, unmodified) is executed by oracle/mini_r.py; its `.Call(C_xxx,
+* `ebpmf.alpha_b200/r/R/vga_cuda.R` and `ebpmf_log_vga_block.R` (the R side, unmodified) are executed by oracle/mini_r.py; its `.Call(C_xxx,
   ...)` goes through `RSession.dot_call`: interpreter values -> SEXPs -> the glue's registered routine (arity
   checked against the glue's own R_registerRoutines table, Rf_error caught, PROTECT balance checked) -> SEXPs ->
   interpreter values.
@@ -23,6 +23,7 @@ from oracle import mini_r as R
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GLUE = os.path.join(ROOT, "ebpmf.alpha_b200", "r", "src", "r_glue.c")
 RWRAP = os.path.join(ROOT, "ebpmf.alpha_b200", "r", "R", "vga_cuda.R")
+RBLOCK = os.path.join(ROOT, "ebpmf.alpha_b200", "r", "R", "ebpmf_log_vga_block.R")
 STUB = os.path.join(ROOT, "tests", "r_api_stub")
 LIBDIR = os.path.join(ROOT, "ebpmf.alpha_b200", "lib")
 BUILD = os.path.join(ROOT, "tests", "_build")
@@ -217,6 +218,7 @@ class RSession:
         it.def_builtin("attr", lambda it_, x, which: getattr(x, "attrs", {}).get(R.r_string(which)))
         it.def_builtin("attr<-", self._attr_set)
         it.source(RWRAP)
+        it.source(RBLOCK)
 
     @staticmethod
     def _as(it_, obj, cls):

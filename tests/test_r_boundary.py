@@ -324,3 +324,98 @@ def test_r_group_wrappers_on_two_devices(pkg, vt):
                 assert abs(res.get(name)[0] - ref[name]) <= RTOL * max(1.0, abs(ref[name]))
     finally:
         s.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ebpmf_b200_vga_block: the ONE statement of ebpmf_log's loop that changes
+# ---------------------------------------------------------------------------------------------------------------
+PATCH_INIT = """
+blk = ebpmf_b200_vga_block_init(Y_as_given, fit_flash$flash_fit$Y, if(n_batch>1) batches else NULL)
+const = - blk$sum_lfactorial
+"""
+PATCH_BLOCK = """
+{
+  out = ebpmf_b200_vga_block(blk, fit_flash, sigma2, var_type, vga_control, sigma2_control, general_control$save_latent_M)
+  fit_flash$flash_fit$Y = out$M
+  if(general_control$save_latent_M){ V = out$V }
+  sym = out$sym ; ssexp = out$ssexp ; slogv = out$slogv ; v_sum = out$v_sum ; sigma2 = out$sigma2
+}
+"""
+
+
+def install_drop_in(it):
+    """Splices the statements of INTEGRATION.md section 2 into the parsed body of the reference's ebpmf_log():
+    `Y_as_given = Y` before the data is split, the init after the flash initialisation, the block in place of the
+    `if(n_batch >1){...}else{...}` statement of the loop.  Nothing else of the function is touched."""
+    from oracle import minir_reference as mr
+    fn = it.get("ebpmf_log")
+    body = fn.body[1]
+    nb_stmt, split_if, vga_if = mr.loop_statements(it)
+    body.insert(body.index(nb_stmt), R.parse("Y_as_given = Y")[0])
+    i_init = mr._find(body, lambda s: s[0] == "assign" and s[1] == ("name", "fit_flash") and s[2][0] == "call"
+                      and s[2][1] == ("name", "ebpmf_log_flash_init"))
+    body[i_init + 1:i_init + 1] = R.parse(PATCH_INIT)
+    loop = body[mr._find(body, lambda s: s[0] == "for" and s[1] == "iter")]
+    lbody = loop[3][1]
+    lbody[lbody.index(vga_if)] = R.parse(PATCH_BLOCK)[0]
+
+
+@pytest.mark.skipif(os.path.exists("/root/reference/R/ebpmf_log.R") is False, reason="the reference checkout is not present")
+@pytest.mark.parametrize("vt", VTS)
+@pytest.mark.parametrize("bs", ["inf", "25"])
+def test_reference_ebpmf_log_with_the_drop_in_spliced_in(vt, bs):
+    """The reference's own ebpmf_log(), its VGA block replaced by ebpmf_b200_vga_block as INTEGRATION.md says, run by
+    the evaluator with `.Call` answered by a test double (the CPU oracle; there is no GPU where the checkout is):
+    the R-level plumbing -- which values travel, in which storage mode, in which order, what comes back under which
+    name -- reproduces the traces of the untouched ebpmf_log()."""
+    import r_fake_calls
+    from oracle import minir_reference as mr
+    s = r_mock.RSession(reference_root="/root/reference")
+    fake = r_fake_calls.OracleBackedCalls(s)
+    s.dot_call = fake
+    install_drop_in(s.it)
+    l0 = np.log(Y.mean(axis=1) + 0.1)
+    f0 = np.log((Y.sum(axis=0) + 0.1) / np.exp(l0).sum())
+    s2 = {"by_col": np.full(P, 0.5), "by_row": np.full(N, 0.5), "constant": np.array([0.5])}[vt]
+    out = mr.run_driver(s.it, Y, l0, f0, np.asfortranarray(np.log(Y + 0.5)), s2, vt, K=3, outer_iters=4,
+                        batch_size=np.inf if bs == "inf" else 25, sparse=bs != "inf")
+    k = "drv/%s/%s/" % (vt, bs)
+    assert rel(out["elbo_trace"][1:], MR[k + "elbo_trace"][1:]) < 1e-12 and rel(out["sigma2"], MR[k + "sigma2"]) < 1e-12
+    if bs == "inf":
+        assert relM(out["M"], MR[k + "M"]) < 1e-12 and rel(out["V"], MR[k + "V"]) < 1e-12
+    step = "C_ebpmf_vga_step_resident" if bs == "inf" else "C_ebpmf_batched_vga_step"
+    assert fake.log.count(step) == 4 and fake.log.count("C_ebpmf_log_update_sigma2") == 4 and fake.log.count("C_calc_ebpmf_log_obj") == 4
+    assert "C_vga_pois_solver_mat_newton" not in fake.log          # the per-call dense signature is no longer on the loop's path
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("vt", VTS)
+@pytest.mark.parametrize("bs", ["inf", "25"])
+def test_r_block_through_the_whole_driver(rs, vt, bs):
+    """ebpmf_b200_vga_block over the compiled glue and the GPU, four outer iterations, against ebpmf_log() itself."""
+    l0 = np.log(Y.mean(axis=1) + 0.1)
+    f0 = np.log((Y.sum(axis=0) + 0.1) / np.exp(l0).sum())
+    M_init = np.asfortranarray(np.log(Y + 0.5))
+    s2 = {"by_col": np.full(P, 0.5), "by_row": np.full(N, 0.5), "constant": np.array([0.5])}[vt]
+    batches = None if bs == "inf" else rs.it.run("split(1:%d, cut(seq_along(1:%d), 4, labels = FALSE))" % (N, N))
+    blk = rs.call("ebpmf_b200_vga_block_init", Y if bs == "inf" else R.RSparse(Y), M_init, batches)
+    assert R.r_string(blk.get("route")) == ("resident" if bs == "inf" else "batched")
+    vga_control = dict(maxiter_vga=10, vga_tol=1e-5)
+    sigma2_control = dict(est_sigma2=True, a0=1, b0=1, cap_var_mean_ratio=0)
+
+    def block(M, fit, sig):
+        ff = dict(flash_fit=dict(Y=np.asfortranarray(M), R2=fit["R2"], EF=[fit["EL"], fit["EF"]]))
+        o = rs.call("ebpmf_b200_vga_block", blk, ff, sig, vt, vga_control, sigma2_control, bs == "inf")
+        return dict(M=o.get("M"), V=o.get("V"), v_sum=o.get("v_sum"), sym=o.get("sym")[0], ssexp=o.get("ssexp")[0], slogv=o.get("slogv")[0],
+                    sigma2=o.get("sigma2"))
+
+    try:
+        out = standin_flash.outer_loop(Y, l0, f0, M_init, s2, vt, 3, 4, block=block, calc_obj=lambda *a: rs.call("calc_ebpmf_log_obj", *a)[0],
+                                       const=-blk.get("sum_lfactorial")[0])
+    finally:
+        if blk.get("handle") is not None:
+            r_mock.lib().mockr_free(blk.get("handle").sexp)
+    k = "drv/%s/%s/" % (vt, bs)
+    assert rel(out["elbo_trace"][1:], MR[k + "elbo_trace"][1:]) < RTOL and rel(out["sigma2"], MR[k + "sigma2"]) < RTOL
+    if bs == "inf":
+        assert relM(out["M"], MR[k + "M"]) < RTOL and rel(out["V"], MR[k + "V"]) < RTOL
