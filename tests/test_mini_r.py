@@ -159,3 +159,14 @@ def test_rerunning_the_reference_reproduces_the_committed_fixture():
     import json
     prov = json.load(open(os.path.join(HERE, "golden", "minir_reference.provenance.json")))
     assert prov["reference_files_sha256"] == mr.provenance(REF)
+
+
+def test_r_snippets_of_integration_md_are_valid_r():
+    """The ```r blocks of INTEGRATION.md (loop excerpts: braces left open are closed here) parse as R."""
+    import re
+    text = open(os.path.join(os.path.dirname(HERE), "INTEGRATION.md")).read()
+    blocks = re.findall(r"```r\n(.*?)```", text, flags=re.S)
+    assert len(blocks) >= 4
+    for b in blocks:
+        code = "\n".join(line.split("#")[0] for line in b.splitlines())
+        R.parse(code + "\n" + "}" * (code.count("{") - code.count("}")))
