@@ -104,23 +104,22 @@ def run_functions(it, G):
             res = it.call("vga_pois_solver_mat_newton", M0, Y, 1, Beta, S2, maxiter=maxiter, tol=tol, return_V=True)
             M, V = res.get("M"), res.get("V")
             u = update_count(it, M0, Y, Beta, S2, maxiter, tol, M)
-            env = R.Env(it.globalenv)                                               # the inline sums, :316-327, verbatim
-            for k, v in (("Y", Y), ("res", res), ("var_type", R.strs(vt))):
-                env.set(k, v)
-            it.run("sym = sum(Y*res$M); ssexp = sum(exp(res$M+res$V/2)); slogv = sum(log(res$V)/2+0.9189385)", env)
-            it.run("if(var_type=='constant'){ v_sum =sum(res$V) }else if(var_type=='by_col'){ v_sum =colSums(res$V) }"
-                   "else if(var_type=='by_row'){ v_sum =rowSums(res$V) }", env)
+            # the inline sums of the loop body (R/ebpmf_log.R:316-327) are not a function: they are taken from the
+            # parsed body of ebpmf_log and executed in place (run_loop_blocks), on the same call
+            blk = run_loop_blocks(it, Y, M0, EL, EF, sigma2, R2, vt, maxiter_vga=maxiter, vga_tol=tol, est_sigma2=False)
+            assert np.array_equal(blk["M"], M) and np.array_equal(blk["V"], V)
+            sums = {k: np.atleast_1d(np.asarray(blk[k], dtype=np.float64)) for k in ("sym", "ssexp", "slogv", "v_sum")}
             k0 = "%s_%s_" % (vt, tag)
-            out[k0 + "M"], out[k0 + "V"], out[k0 + "v_sum"] = M, V, env.vars["v_sum"]
-            out[k0 + "scal"] = np.array([env.vars["sym"][0], env.vars["ssexp"][0], env.vars["slogv"][0], float(u)])
+            out[k0 + "M"], out[k0 + "V"], out[k0 + "v_sum"] = M, V, sums["v_sum"]
+            out[k0 + "scal"] = np.array([sums["sym"][0], sums["ssexp"][0], sums["slogv"][0], float(u)])
             if tag == "def":
-                s2new = it.call("ebpmf_log_update_sigma2", _fit_flash(M, EL, EF, R2), sigma2, env.vars["v_sum"], vt, 0, 1, 1, n, p)
+                s2new = it.call("ebpmf_log_update_sigma2", _fit_flash(M, EL, EF, R2), sigma2, sums["v_sum"], vt, 0, 1, 1, n, p)
                 ss = {"by_col": n, "by_row": p, "constant": n * p}[vt]              # var_offset_for_obj, :178-192
-                obj = it.call("calc_ebpmf_log_obj", n, p, env.vars["sym"], env.vars["ssexp"], env.vars["slogv"], env.vars["v_sum"],
+                obj = it.call("calc_ebpmf_log_obj", n, p, sums["sym"], sums["ssexp"], sums["slogv"], sums["v_sum"],
                               s2new, R2, -123.4, -5.5, ss, 1, 1)
                 out[k0 + "sigma2_new"], out[k0 + "obj"] = s2new, obj
                 # the cap gate of ebpmf_log_update_sigma2 (cap_var_mean_ratio > 0), R/ebpmf_log.R:415-419,424-429,435-440
-                out[k0 + "sigma2_new_cap"] = it.call("ebpmf_log_update_sigma2", _fit_flash(M, EL, EF, R2), sigma2, env.vars["v_sum"],
+                out[k0 + "sigma2_new_cap"] = it.call("ebpmf_log_update_sigma2", _fit_flash(M, EL, EF, R2), sigma2, sums["v_sum"],
                                                      vt, 2.0, 1, 1, n, p)
     M0, EL, EF, sigma2 = (np.asarray(G["by_col_" + k], dtype=np.float64) for k in ("M0", "EL", "EF", "sigma2"))
     Beta = it.call("tcrossprod", EL, EF)
