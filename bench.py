@@ -27,7 +27,8 @@ partials in every step.  Inputs are generated ON THE DEVICE (ebpmf_ctx_sim_data_
              blocks not page-locked), e2e_fresh_pages (plain Rf_allocMatrix: first-touch page faults every
              call), e2e_full_roundtrip (M in AND out, pageable), e2e_batched (the batch_size < n branch),
              host_d2h_ceiling (what the box's host side absorbs with every GPU copying at once), and
-             m_products (N1: what flashier needs from M computed on the device, so that M need not leave it)
+             m_products (N1: what flashier needs from M computed on the device, so that M need not leave it) and
+             e2e_m_resident (the outer iteration end to end when only those products cross PCIe)
   roofline   HBM line of the dominant kernel (first pass).  The FP64 pipe / issue port binds it
              (DESIGN.md section 4), so `fp64` (measured DFMA peak) and `issue_roofline` sit beside it; the
              instruction counts and DRAM traffic come from the committed ncu capture
@@ -574,6 +575,35 @@ def main():
                   "what": "ebpmf_ctx_m_products: M %*% EF, t(M) %*% EL, column/row sums of (M - EL EF')^2 (flashier's R2) from the "
                           "resident M (R/ebpmf_log_flash_update.R:35,55-64); ONE streaming kernel reads M once"}
 
+    # ---- N1 end to end: one outer iteration of ebpmf_log when M NEVER leaves the device -------------------
+    # factors and sigma2 in from pageable host arrays; out: v_sum, the three ELBO sums, and what flashier takes from M
+    # (M %*% EF, t(M) %*% EL, R2) instead of M itself.  Wall clock around the public calls, max over ranks.
+    e2e_n1 = None
+    try:
+        s20 = ctx.get_sigma2()
+        t0 = 0.0
+        for it in range(1 + args.steps):
+            if it == 1:
+                barrier()
+                t0 = time.perf_counter()
+            ctx.set_factors(EL0, EF0)
+            ctx.set_sigma2(s20, "by_col")
+            ninf = ctx.vga_step(MAXITER_VGA, VGA_TOL)
+            nvs = ctx.get_v_sum()
+            nmp = ctx.m_products(EL0, EF0)              # of the step's result, still on the device
+            ctx.rewind_m()
+        barrier()
+        per = allmax(time.perf_counter() - t0) / args.steps
+        e2e_n1 = {"value": entries / per, "unit": "entries/s", "ms_per_step": 1e3 * per, "n_updates": ninf.n_updates,
+                  "h2d_bytes_per_step": int(EL0.nbytes + EF0.nbytes + s20.nbytes),
+                  "d2h_bytes_per_step": int(nvs.nbytes + nmp["MF"].nbytes + nmp["MtL"].nbytes + nmp["r2_col"].nbytes + nmp["r2_row"].nbytes + 24),
+                  "call": "set_factors + set_sigma2 + vga_step + get_v_sum + m_products through the C ABI with pageable host arrays: "
+                          "the per-iteration traffic of a flashier backend built on ebpmf_b200_m_products (INTEGRATION.md, N1); "
+                          "NOT the reference's loop as it stands -- that needs M on the host and is `e2e`"}
+        ctx.vga_step(MAXITER_VGA, VGA_TOL); ctx.rewind_m()
+    except Exception as e:                                  # a diagnostic leg must never cost the bench line
+        e2e_n1 = {"error": repr(e)}
+
     # ---- roofline (HBM line of the dominant kernel = first pass) --------------------------------
     ncu = read_ncu_metrics() if args.workload == "c4slab" else None
     alg_bytes_per_entry = 16.0 + 12.0 * density            # read M 8 + write M 8 + CSC (x 8 + i 4) * density
@@ -631,7 +661,7 @@ def main():
         "first_step": first_step, "perturbed_history": perturbed,
         "peer_kstar_sharing": {"peers_mapped": ctx.peer_count() if world > 1 else 0,
                                "how": "pass-1 kernels read the other GPUs' published update count over NVLink peer memory"},
-        "roofline": roofline, "fp64": fp64, "issue_roofline": issue, "delta_mode": delta_mode, "m_products": m_products,
+        "roofline": roofline, "fp64": fp64, "issue_roofline": issue, "delta_mode": delta_mode, "m_products": m_products, "e2e_m_resident": e2e_n1,
         "gpu_launches": launches, "gpu_launches_how": "kernel launches counted by the library inside the timed region",
         "clocks": clk.summary(),
     }
