@@ -580,6 +580,8 @@ def main():
     # (M %*% EF, t(M) %*% EL, R2) instead of M itself.  Wall clock around the public calls, max over ranks.
     e2e_n1 = None
     try:
+        if world > 1:
+            raise RuntimeError("measured at N = 1 only (a diagnostic leg adds no collectives to the scaling runs)")
         s20 = ctx.get_sigma2()
         t0 = 0.0
         for it in range(1 + args.steps):
