@@ -1559,21 +1559,38 @@ def _t(it, x):
     return np.asfortranarray(a.T) if a.ndim == 2 else a[None, :]
 
 
-def _tcrossprod(it, x, y=None):
+def _as_matprod_operands(x, y, op):
+    """The shapes R's do_matprod (array.c) gives vector operands of crossprod (op 1) / tcrossprod (op 2)."""
     a = dense(x).astype(np.float64)
     b = a if y is None else dense(y).astype(np.float64)
-    a = a if a.ndim == 2 else a[:, None]
-    b = b if b.ndim == 2 else b[:, None]
+    if a.ndim != 2 and b.ndim != 2:                      # both vectors: column vectors
+        return a[:, None], b[:, None]
+    if a.ndim != 2:                                      # x a vector, y a matrix
+        nry, ncy = b.shape
+        if op == 1:
+            a = a[:, None] if a.size == nry else None    # crossprod: x is a column vector
+        else:
+            a = a[None, :] if a.size == ncy else (a[:, None] if ncy == 1 else None)      # tcrossprod: a ROW vector if it fits
+    elif b.ndim != 2:                                    # y a vector, x a matrix
+        nrx, ncx = a.shape
+        if op == 1:
+            b = b[:, None] if b.size == nrx else (b[None, :] if nrx == 1 else None)
+        else:
+            b = b[None, :] if b.size == ncx else (b[:, None] if ncx == 1 else None)
+    if a is None or b is None:
+        raise RError("non-conformable arguments")
+    return a, b
+
+
+def _tcrossprod(it, x, y=None):
+    a, b = _as_matprod_operands(x, y, 2)
     if a.shape[1] != b.shape[1]:
         raise RError("non-conformable arguments")
     return np.asfortranarray(a @ b.T)
 
 
 def _crossprod(it, x, y=None):
-    a = dense(x).astype(np.float64)
-    b = a if y is None else dense(y).astype(np.float64)
-    a = a if a.ndim == 2 else a[:, None]
-    b = b if b.ndim == 2 else b[:, None]
+    a, b = _as_matprod_operands(x, y, 1)
     if a.shape[0] != b.shape[0]:
         raise RError("non-conformable arguments")
     return np.asfortranarray(a.T @ b)

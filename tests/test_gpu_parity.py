@@ -743,6 +743,25 @@ def test_batched_step_vs_oracle_batched_branch(pkg, var_type, nslots):
         h.close()
 
 
+def test_batched_with_a_one_row_batch(pkg):
+    """n = 5 in 3 batches is cut 2/1/2.  The reference itself stops there with "non-conformable arrays" (a one-row
+    batch drops to a vector, tests/test_minir_reference.py); the CUDA path solves it like any other batch, as the
+    oracle does."""
+    sim = simdata.sim_data_log(5, 7, K=2, seed=5, log_offset=-1.0)
+    st = simdata.solver_state(sim, start="cold", var_type="by_col", seed=6)
+    batches = vga_numpy.r_cut_batches(5, 3)
+    h = pkg.VgaBatched(0, 2)
+    try:
+        h.set_y(sp.csc_matrix(sim["Y"]), batch_size=2)
+        assert list(h.batch_row0) == [0, 2, 3, 5]
+        res = h.vga_step_host(st["M0"], st["EL"], st["EF"], st["sigma2"], "by_col", 10, 1e-5, return_V=True)
+    finally:
+        h.close()
+    ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], "by_col", 10, 1e-5, batches=batches)
+    assert res["n_updates"] == list(ref["n_updates"])
+    assert relM(res["M"], ref["M"]) < RTOL and rel(res["V"], ref["V"]) < RTOL and rel(res["v_sum"], ref["v_sum"]) < RTOL
+
+
 def test_batched_equals_one_context_per_batch(pkg):
     """The batched handle against the plain context run batch by batch on row slices (bit-identical), M_out
     aliasing M_in, an uneven last batch, and a batch count that is not a multiple of the slot count."""

@@ -92,6 +92,12 @@ def test_matrices_are_column_major_and_vectors_recycle_down_columns():
     assert ev("m = matrix(0, 3, 2); m[c(1, 3), ] = matrix(1:4, 2, 2); m").tolist() == [[1, 3], [0, 0], [2, 4]]
     assert ev("colSums(matrix(1:6, 2, 3))").tolist() == [3, 7, 11] and ev("rowSums(matrix(1:6, 2, 3))").tolist() == [9, 12]
     assert ev("tcrossprod(matrix(1:4, 2, 2), matrix(1:6, 3, 2))").tolist() == [[13, 17, 21], [18, 24, 30]]
+    # do_matprod's rules for vector operands: tcrossprod(EL[b,], EF) with a one-row batch takes the vector as a ROW
+    assert ev("tcrossprod(c(1, 2), matrix(1:6, 3, 2))").tolist() == [[9, 12, 15]]
+    assert ev("tcrossprod(c(1, 2, 3), c(1, 10))").tolist() == [[1, 10], [2, 20], [3, 30]]       # two vectors: outer product
+    assert ev("crossprod(c(1, 2, 3), matrix(1:6, 3, 2))").tolist() == [[14, 32]]
+    with pytest.raises(R.RError, match="non-conformable"):
+        ev("tcrossprod(c(1, 2, 3), matrix(1:6, 3, 2))")
     with pytest.raises(R.RError, match="non-conformable"):
         ev("matrix(1, 2, 3) + matrix(1, 3, 2)")
 
