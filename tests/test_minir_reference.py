@@ -331,3 +331,59 @@ def test_reference_breaks_on_a_one_row_batch_and_the_oracle_does_not():
         mr.run_loop_blocks(it, sim["Y"], st["M0"], st["EL"], st["EF"], st["sigma2"], st["R2"], "by_col", batch_size=2)
     o = vn.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], "by_col", 10, 1e-5, batches=batches)
     assert np.isfinite(o["M"]).all() and len(o["n_updates"]) == 3
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFROOT, "R", "vga_solver_mat.R")),
+                    reason="the reference checkout is not present (it never is on the GPU box)")
+def test_oracle_equals_the_executed_reference_operand_kinds_and_elbo():
+    """The stand-alone signatures with every operand shape R would recycle (scalar / length-n vector / matrix for S,
+    Beta and Sigma2; V given or NULL; dense or dgCMatrix counts), the ELBO with operands of unequal length (each sum()
+    at its own length, R/ebpmf_log.R:407), the constant-variance sigma2 update with a vector R2, and the archived
+    driver's un-fused ELBO (inst/code/Poisson_MF_splitting.R:373-391) -- oracle vs the reference's source."""
+    from oracle import mini_r, minir_reference as mr, simdata
+    it = mr.load_reference(REFROOT)
+    it.source(os.path.join(REFROOT, "inst", "code", "Poisson_MF_splitting.R"))     # archived driver: calc_split_PMF_obj_flashier
+    for f in mr.FILES:                                                             # ... whose adjust_var_shape etc. must not shadow the package's
+        it.source(os.path.join(REFROOT, f))
+    rng = np.random.default_rng(7)
+    TOL = 1e-12
+    for case in range(24):
+        n, p = int(rng.integers(2, 40)), int(rng.integers(2, 30))
+        sim = simdata.sim_data_log(n, p, K=2, seed=300 + case, log_offset=float(rng.uniform(-2.0, 0.5)))
+        st = simdata.solver_state(sim, start="cold", var_type="by_col", seed=400 + case)
+        Yc, M0 = sim["Y"], st["M0"]
+        kinds = {"scalar": lambda lo, hi: float(rng.uniform(lo, hi)), "rowvec": lambda lo, hi: rng.uniform(lo, hi, size=n),
+                 "matrix": lambda lo, hi: np.asfortranarray(rng.uniform(lo, hi, size=(n, p)))}
+        ks, kb, kv = (list(kinds)[int(rng.integers(0, 3))] for _ in range(3))
+        S, Beta, Sigma2 = kinds[ks](0.5, 1.5), kinds[kb](-1.0, 1.0), kinds[kv](0.1, 1.2)
+        mi, tol = int(rng.integers(1, 30)), float(10.0 ** rng.uniform(-9, -4))
+        X = mini_r.RSparse(Yc) if case % 2 else Yc
+        ref = it.call("vga_pois_solver_mat_newton", M0, X, S, Beta, Sigma2, maxiter=mi, tol=tol)
+        o = vn.vga_pois_solver_mat_newton(M0, Yc, S, Beta, Sigma2, mi, tol)
+        what = (case, n, p, ks, kb, kv, mi, tol)
+        assert relM(o["M"], ref.get("M")) < TOL and rel(o["V"], ref.get("V")) < TOL, what
+        c = c_oracle.vga_newton(M0, Yc, S, Beta, Sigma2, mi, tol)
+        assert relM(c["M"], ref.get("M")) < TOL and rel(c["V"], ref.get("V")) < TOL, what
+        V0 = None if case % 3 == 0 else np.asfortranarray(rng.uniform(0.05, 0.4, size=(n, p)))
+        ref = it.call("vga_pois_solver_mat_newton_fixed_iter", M0, V0, Yc, S, Beta, Sigma2, maxiter=int(rng.integers(1, 6)) if V0 is None else 3)
+        with np.errstate(all="ignore"):                     # exp() overflows on the way for some draws, in R as here
+            o = vn.vga_pois_solver_mat_newton_fixed_iter(M0, V0, Yc, S, Beta, Sigma2, 3) if V0 is not None else None
+        if o is not None:
+            assert relM(o["M"], ref.get("M")) < TOL and rel(o["V"], ref.get("V")) < TOL, what
+        # ELBO with operands of unequal length, sigma2 update 'constant' with a vector R2, un-fused ELBO
+        r = vn.ebpmf_log_vga_step(M0, Yc, st["EL"], st["EF"], st["sigma2"], "by_col", 10, 1e-5)
+        lens = [(p, p, p), (1, 1, p), (p, 1, n), (1, p, 1)][case % 4]                          # len(sv), len(sigma2), len(R2)
+        sv, sg, R2 = rng.uniform(1, 5, lens[0]), rng.uniform(0.2, 1.5, lens[1]), rng.uniform(0.5, 9, lens[2])
+        a = (n, p, r["sym"], r["ssexp"], r["slogv"], sv, sg, R2, -12.5, -3.25, float(n), 1.0, 1.0)
+        assert abs(vn.calc_ebpmf_log_obj(*a) - it.call("calc_ebpmf_log_obj", *a)[0]) <= TOL * abs(vn.calc_ebpmf_log_obj(*a)), what
+        R2v = rng.uniform(0.5, 9, p)
+        s_ref = it.call("ebpmf_log_update_sigma2", {"flash_fit": {"R2": R2v}}, 0.7, 33.0, "constant", 0, 1, 1, n, p)
+        s_o = vn.ebpmf_log_update_sigma2(dict(R2=R2v), np.array([0.7]), 33.0, "constant", 0, 1, 1, n, p)
+        assert rel(np.atleast_1d(s_o), s_ref) < TOL, what
+        for vt in VTS:
+            sg = {"by_col": rng.uniform(0.2, 1.5, p), "by_row": rng.uniform(0.2, 1.5, n), "constant": rng.uniform(0.2, 1.5, 1)}[vt]
+            R2s = rng.uniform(0.5, 9, sg.size)
+            ref_v = it.call("calc_split_PMF_obj_flashier", Yc, S if ks != "rowvec" else 1.0, sg, r["M"], r["V"], {"flash.fit": {"R2": R2s}}, -2.5, -77.0, vt)
+            o_v = vn.calc_split_PMF_obj_flashier(Yc, S if ks != "rowvec" else 1.0, sg, r["M"], r["V"], R2s, -2.5, -77.0, vt)
+            assert abs(o_v - ref_v[0]) <= TOL * abs(o_v), (what, vt)
+    assert abs(vn.sum_lfactorial_sparseMat(sp.csc_matrix(Yc)) - it.call("sum_lfactorial_sparseMat", mini_r.RSparse(Yc))[0]) <= TOL * 1e3
