@@ -67,6 +67,26 @@ class OracleBackedCalls:
             out = _step_list(r, bool(wv[0]))
             out.attrs = {"n_updates_per_batch": r_mock.as_int(r["n_updates"])}
             return out
+        if name == "C_ebpmf_group_new":
+            assert is_int(0) and a[0].size >= 1
+            self.group_devices = [int(v) for v in a[0]]
+            return r_mock.RExt(None)
+        if name == "C_ebpmf_group_set_y":
+            assert isinstance(a[1], R.RSparse)            # the group wants the dgCMatrix (rows are dealt by 256-row blocks)
+            self.Y = a[1].dense
+            return None
+        if name == "C_ebpmf_group_set_m":
+            assert is_real(1) and a[1].ndim == 2
+            self.M = a[1]
+            return None
+        if name == "C_ebpmf_group_sum_lfactorial":
+            return np.array([vn.sum_lfactorial_sparseMat(self.Y)])
+        if name == "C_ebpmf_group_vga_step":
+            M, dims, EL, EF, s2, v, mi, tol, wv = a[1:]
+            assert is_int(2) and is_int(7) and wv.dtype == bool and list(dims) == list(self.Y.shape)
+            r = vn.ebpmf_log_vga_step(self.M if M is None else M, self.Y, EL, EF, s2, vt(v), int(mi[0]), f(tol))
+            self.M = r["M"]
+            return _step_list(r, bool(wv[0]))
         if name == "C_vga_pois_solver_mat_newton":
             M, X, S, Beta, S2, mi, tol, rv = a[1:]
             n, p = M.shape

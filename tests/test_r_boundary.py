@@ -388,6 +388,26 @@ def test_reference_ebpmf_log_with_the_drop_in_spliced_in(vt, bs):
     assert "C_vga_pois_solver_mat_newton" not in fake.log          # the per-call dense signature is no longer on the loop's path
 
 
+@pytest.mark.skipif(os.path.exists("/root/reference/R/ebpmf_log.R") is False, reason="the reference checkout is not present")
+def test_reference_ebpmf_log_with_the_drop_in_on_the_group_route(monkeypatch):
+    """EBPMF_B200_NGPU = 2: the block takes the one-process multi-GPU route (ebpmf_b200_group_*).  Same spliced
+    ebpmf_log(), `.Call` answered by the test double: the R-level plumbing of that route (the 2-GPU run of the group
+    wrappers themselves is tests/test_r_boundary.py::test_r_group_wrappers_on_two_devices)."""
+    import r_fake_calls
+    from oracle import minir_reference as mr
+    monkeypatch.setenv("EBPMF_B200_NGPU", "2")
+    s = r_mock.RSession(reference_root="/root/reference")
+    fake = r_fake_calls.OracleBackedCalls(s)
+    s.dot_call = fake
+    install_drop_in(s.it)
+    l0 = np.log(Y.mean(axis=1) + 0.1)
+    f0 = np.log((Y.sum(axis=0) + 0.1) / np.exp(l0).sum())
+    out = mr.run_driver(s.it, Y, l0, f0, np.asfortranarray(np.log(Y + 0.5)), np.full(P, 0.5), "by_col", K=3, outer_iters=4, sparse=True)
+    k = "drv/by_col/inf/"
+    assert rel(out["elbo_trace"][1:], MR[k + "elbo_trace"][1:]) < 1e-12 and relM(out["M"], MR[k + "M"]) < 1e-12
+    assert fake.group_devices == [0, 1] and fake.log.count("C_ebpmf_group_vga_step") == 4 and "C_ebpmf_vga_step_resident" not in fake.log
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("vt", VTS)
 @pytest.mark.parametrize("bs", ["inf", "25"])
