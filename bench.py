@@ -604,7 +604,7 @@ def main():
                           "NOT the reference's loop as it stands -- that needs M on the host and is `e2e`"}
         ctx.vga_step(MAXITER_VGA, VGA_TOL); ctx.rewind_m()
     except Exception as e:                                  # a diagnostic leg must never cost the bench line
-        e2e_n1 = {"error": repr(e)}
+        e2e_n1 = {"skipped" if world > 1 else "error": str(e)}
 
     # ---- roofline (HBM line of the dominant kernel = first pass) --------------------------------
     ncu = read_ncu_metrics() if args.workload == "c4slab" else None
