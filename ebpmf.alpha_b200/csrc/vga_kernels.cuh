@@ -1254,18 +1254,23 @@ __global__ void __launch_bounds__(256) fitted_colmax_kernel(const double *EL, co
     if (threadIdx.x == 0) out[j] = sm[0];
 }
 
+// R/ebpmf_log.R:425 gates the by_row update on `rowMaxs(fitted(fit_flash))`, and the package imports rowMaxs from
+// Rfast (NAMESPACE: importFrom(Rfast,rowMaxs); colMaxs comes from matrixStats).  Rfast::rowMaxs(x, value = FALSE)
+// returns the POSITION of each row's maximum (1-based, first one on ties), not its value -- so what the reference
+// compares with the threshold is a column index.  Reproduced as is.
 __global__ void __launch_bounds__(256) fitted_rowmax_kernel(const double *EL, const double *EF, long long n,
                                                             long long p, int K, double *out)
 {
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     double mx = -INFINITY;
+    long long jbest = 0;
     for (long long j = 0; j < p; ++j) {
         double b = 0.0;
         for (int k = 0; k < K; ++k) b = fma(EL[i + n * k], EF[j + p * k], b);
-        mx = fmax(mx, b);
+        if (b > mx) { mx = b; jbest = j; }
     }
-    out[i] = mx;
+    out[i] = (double)(jbest + 1);
 }
 
 __global__ void __launch_bounds__(1024) max_reduce_kernel(const double *in, long long len, double *out)

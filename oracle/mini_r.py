@@ -1665,8 +1665,10 @@ def _install_builtins(it):
     d("rowSums", lambda it_, x, **kw: np.asarray(np.sum(dense(x).astype(LD), axis=1), dtype=np.float64))
     d("colMeans", lambda it_, x, **kw: np.asarray(np.sum(dense(x).astype(LD), axis=0) / dense(x).shape[0], dtype=np.float64))
     d("rowMeans", lambda it_, x, **kw: np.asarray(np.sum(dense(x).astype(LD), axis=1) / dense(x).shape[1], dtype=np.float64))
-    d("rowMaxs", lambda it_, x, value=True, **kw: np.max(dense(x), axis=1))          # Rfast/matrixStats
-    d("colMaxs", lambda it_, x, value=True, **kw: np.max(dense(x), axis=0))
+    # the package takes rowMaxs from Rfast and colMaxs from matrixStats (NAMESPACE).  Rfast::rowMaxs(x, value = FALSE)
+    # returns the POSITIONS of the row maxima (1-based, first on ties) unless value = TRUE; matrixStats::colMaxs the values.
+    d("rowMaxs", lambda it_, x, value=False, **kw: np.max(dense(x), axis=1) if as_logical_scalar(value) else np.argmax(dense(x), axis=1) + 1.0)
+    d("colMaxs", lambda it_, x, **kw: np.max(dense(x), axis=0))
     d("cumsum", lambda it_, x: np.cumsum(flat(dense(x)).astype(np.float64)))
     d("diff", lambda it_, x, **kw: np.diff(flat(dense(x)).astype(np.float64)))
     d("all", lambda it_, *a, **kw: np.array([all(bool(np.all(dense(x))) for x in a)]))

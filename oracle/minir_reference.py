@@ -121,6 +121,10 @@ def run_functions(it, G):
                 # the cap gate of ebpmf_log_update_sigma2 (cap_var_mean_ratio > 0), R/ebpmf_log.R:415-419,424-429,435-440
                 out[k0 + "sigma2_new_cap"] = it.call("ebpmf_log_update_sigma2", _fit_flash(M, EL, EF, R2), sigma2, sums["v_sum"],
                                                      vt, 2.0, 1, 1, n, p)
+                # ... and with a ratio so large (threshold ~ 20) that the gate SELECTS: for by_row what it compares with the
+                # threshold is Rfast::rowMaxs' column position, for by_col matrixStats::colMaxs' value
+                out[k0 + "sigma2_new_cap_big"] = it.call("ebpmf_log_update_sigma2", _fit_flash(M, EL, EF, R2), sigma2, sums["v_sum"],
+                                                         vt, 1e9, 1, 1, n, p)
     M0, EL, EF, sigma2 = (np.asarray(G["by_col_" + k], dtype=np.float64) for k in ("M0", "EL", "EF", "sigma2"))
     Beta = it.call("tcrossprod", EL, EF)
     S2 = it.call("adjust_var_shape", sigma2, "by_col", n, p)

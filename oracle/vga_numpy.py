@@ -275,7 +275,10 @@ def ebpmf_log_update_sigma2(fit_flash, sigma2, v_sum, var_type, cap_var_mean_rat
     elif var_type == "by_row":
         new = ((v_sum + R2) / 2 + b0) / (p / 2 + a0 + 1)                     # :428,431
         if cap > 0:
-            idx = gate(np.max(fitted(), axis=1))                             # :425 rowMaxs
+            # :425 rowMaxs is Rfast's (NAMESPACE: importFrom(Rfast,rowMaxs)) and Rfast::rowMaxs(x, value = FALSE)
+            # returns the POSITION of each row's maximum (1-based, first on ties), not the value: the reference
+            # compares a column index with the threshold.  Kept as is.
+            idx = gate(np.argmax(fitted(), axis=1) + 1.0)
             sigma2[idx] = new[idx]
         else:
             sigma2 = new

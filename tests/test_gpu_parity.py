@@ -141,10 +141,14 @@ def test_update_sigma2_other_var_types(gpu_ctx, pkg, var_type):
     n, p = sim["Y"].shape
     ref = vga_numpy.ebpmf_log_vga_step(st["M0"], sim["Y"], st["EL"], st["EF"], st["sigma2"], var_type, 10, 1e-5)
     fit = dict(R2=st["R2"], EL=st["EL"], EF=st["EF"])
-    for cap in (0.0, 3.0):
+    changed = []
+    for cap in (0.0, 3.0, 1e9):        # 1e9: a threshold near 20, so the gate selects (by_row: against Rfast::rowMaxs' POSITIONS)
         s_ref = vga_numpy.ebpmf_log_update_sigma2(fit, st["sigma2"], ref["v_sum"], var_type, cap, 1.0, 1.0, n, p)
         s_gpu = pkg.ebpmf_log_update_sigma2(fit, st["sigma2"], ref["v_sum"], var_type, cap, 1.0, 1.0, n, p, ctx=gpu_ctx)
         assert rel(s_gpu, s_ref) < RTOL
+        changed.append(int(np.sum(np.atleast_1d(s_ref) != np.atleast_1d(st["sigma2"]))))
+    if var_type == "by_row":
+        assert 0 < changed[2] < changed[1] == n
 
 
 def test_nan_raises_like_r(gpu_ctx, pkg):

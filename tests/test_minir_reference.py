@@ -68,7 +68,7 @@ def check_driver(out, vt, bs):
 # CPU: both transcriptions of the oracle
 # ---------------------------------------------------------------------------------------------------------------
 def test_fixture_is_what_the_generator_says():
-    assert len(MR.files) == 131
+    assert len(MR.files) == 134
     import json
     prov = json.load(open(os.path.join(HERE, "golden", "minir_reference.provenance.json")))
     assert "NOT GNU R" in prov["evaluator"] and set(prov["reference_files_sha256"]) == {"R/vga_solver_mat.R", "R/ebpmf_log.R",
@@ -86,7 +86,7 @@ def test_oracle_functions(vt, tag):
     c = c_oracle.vga_step(M0, Y, EL, EF, s2, vt, mi, tol)
     check_step(c, c["n_updates"], k)
     if tag == "def":
-        for cap, key in ((0.0, "sigma2_new"), (2.0, "sigma2_new_cap")):
+        for cap, key in ((0.0, "sigma2_new"), (2.0, "sigma2_new_cap"), (1e9, "sigma2_new_cap_big")):
             s = vn.ebpmf_log_update_sigma2(dict(R2=R2, EL=EL, EF=EF), s2, r["v_sum"], vt, cap, 1, 1, N, P)
             assert rel(np.atleast_1d(s), MR[k + key]) < RTOL
         s = vn.ebpmf_log_update_sigma2(dict(R2=R2), s2, r["v_sum"], vt, 0, 1, 1, N, P)
@@ -171,7 +171,7 @@ def test_cuda_functions(gpu_ctx, pkg, vt, tag):
         ss = {"by_col": N, "by_row": P, "constant": N * P}[vt]
         obj = pkg.calc_ebpmf_log_obj(N, P, res["sym"], res["ssexp"], res["slogv"], res["v_sum"], s, R2, -123.4, -5.5, ss, 1, 1, ctx=gpu_ctx)
         assert abs(obj - MR[k + "obj"][0]) <= RTOL * abs(MR[k + "obj"][0])
-        for cap, key in ((0.0, "sigma2_new"), (2.0, "sigma2_new_cap")):     # host signature, with the cap gate
+        for cap, key in ((0.0, "sigma2_new"), (2.0, "sigma2_new_cap"), (1e9, "sigma2_new_cap_big")):     # host signature, with the cap gate
             s = pkg.ebpmf_log_update_sigma2(dict(R2=R2, EL=EL, EF=EF), s2, res["v_sum"], vt, cap, 1, 1, N, P, ctx=gpu_ctx)
             assert rel(np.atleast_1d(s), MR[k + key]) < RTOL
     # the drop-in dense signature on the same inputs (R/vga_solver_mat.R:6-41 called directly)
@@ -273,7 +273,7 @@ def test_oracle_equals_the_executed_reference_on_random_cases():
         sim = simdata.sim_data_log(n, p, K=K, seed=1000 + case, log_offset=float(rng.uniform(-2.5, 0.5)))
         st = simdata.solver_state(sim, start="warm" if case % 4 == 0 else "cold", var_type=vt, seed=2000 + case)
         mi, tol = int(rng.integers(1, 41)), float(10.0 ** rng.uniform(-10, -3))
-        cap = float(rng.choice([0.0, 0.5, 3.0]))
+        cap = float(rng.choice([0.0, 0.5, 3.0, 1e9]))
         bs = np.inf if case % 2 == 0 or n < 4 else int(rng.integers(2, max(3, n // 2 + 1)))
         Yc, M0, EL, EF, s2, R2 = sim["Y"], st["M0"], st["EL"], st["EF"], st["sigma2"], st["R2"]
         n_batch = 0 if np.isinf(bs) else int(np.ceil(n / bs))

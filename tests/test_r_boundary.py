@@ -170,7 +170,7 @@ def test_r_solver_and_step_wrappers(rs, vt, tag):
     res = rs.call("ebpmf_b200_vga_step_resident", N, P, EL, EF, s2, vt, mi, tol, want_V=True)
     check_step_list(res, k)
     if tag == "def":
-        for cap, key in ((0.0, "sigma2_new"), (2.0, "sigma2_new_cap")):
+        for cap, key in ((0.0, "sigma2_new"), (2.0, "sigma2_new_cap"), (1e9, "sigma2_new_cap_big")):
             s = rs.call("ebpmf_log_update_sigma2", fit_flash(R2, EL, EF), s2, res.get("v_sum"), vt, cap, 1, 1, N, P)
             assert rel(s, MR[k + key]) < RTOL
         s = rs.call("ebpmf_log_update_sigma2", fit_flash(R2, EL, EF), s2, res.get("v_sum"), vt, 0, 1, 1, N, P)
