@@ -20,10 +20,13 @@ args = commandArgs(trailingOnly = TRUE)
 if (length(args) < 1) stop("usage: Rscript tests/golden/make_golden.R /path/to/ebpmf.alpha")
 ref = args[1]
 here = dirname(normalizePath(sub("--file=", "", grep("--file=", commandArgs(FALSE), value = TRUE)[1])))
-suppressPackageStartupMessages({ library(Matrix); library(Rfast) })
+suppressPackageStartupMessages({ library(Matrix); library(Rfast); library(matrixStats) })
 source(file.path(ref, "R", "vga_solver_mat.R"))
 source(file.path(ref, "R", "ebpmf_log.R"))
 
+fitted.standin = function(object, ...) tcrossprod(object$L_pm, object$F_pm)     # see the cap gate below
+colMaxs = matrixStats::colMaxs                                                  # as the package's NAMESPACE resolves them:
+rowMaxs = Rfast::rowMaxs                                                        # importFrom(matrixStats,colMaxs), importFrom(Rfast,rowMaxs)
 inp = file.path(here, "r_inputs"); outd = file.path(here, "r_reference")
 dir.create(outd, showWarnings = FALSE)
 man = read.delim(file.path(inp, "manifest.tsv"), stringsAsFactors = FALSE)
@@ -70,6 +73,12 @@ for (vt in c("by_col", "by_row", "constant")) {
       ss = if (vt == "by_col") n else if (vt == "by_row") p else n * p                                     # var_offset_for_obj, :178-192
       obj = calc_ebpmf_log_obj(n, p, sym, ssexp, slogv, v_sum, s2new, R2, -123.4, -5.5, ss, 1, 1)          # :355, :406-410
       wr(paste0(k0, "sigma2_new"), s2new); wr(paste0(k0, "obj"), obj)
+      # the cap gate (:415-419, :424-429, :435-440) calls fitted(fit_flash): give the stand-in list a class with a fitted()
+      # method = what fitted.flash returns, L_pm %*% t(F_pm).  by_row goes through Rfast::rowMaxs (positions!), by_col
+      # through matrixStats::colMaxs (values); 1e9 puts the threshold near 20 so that the by_row gate selects rows.
+      fit_cap = list(flash_fit = list(R2 = R2), L_pm = EL, F_pm = EF); class(fit_cap) = "standin"
+      wr(paste0(k0, "sigma2_new_cap"), ebpmf_log_update_sigma2(fit_cap, sigma2, v_sum, vt, 2, 1, 1, n, p))
+      wr(paste0(k0, "sigma2_new_cap_big"), ebpmf_log_update_sigma2(fit_cap, sigma2, v_sum, vt, 1e9, 1, 1, n, p))
     }
   }
 }

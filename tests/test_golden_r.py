@@ -72,6 +72,10 @@ def check_oracle_steps(R, vt, tag):
         if tag == "def":
             s2 = vn.ebpmf_log_update_sigma2(dict(R2=G[vt + "_R2"]), G[vt + "_sigma2"], res["v_sum"], vt, 0, 1, 1, *G["Y"].shape)
             assert rel(np.atleast_1d(s2), R[k + "sigma2_new"].ravel()) < 1e-8
+            for cap, key in ((2.0, "sigma2_new_cap"), (1e9, "sigma2_new_cap_big")):      # the cap gate; by_row: Rfast::rowMaxs' positions
+                sc2 = vn.ebpmf_log_update_sigma2(dict(R2=G[vt + "_R2"], EL=G[vt + "_EL"], EF=G[vt + "_EF"]), G[vt + "_sigma2"], res["v_sum"], vt,
+                                                 cap, 1, 1, *G["Y"].shape)
+                assert rel(np.atleast_1d(sc2), R[k + key].ravel()) < 1e-8
             n, p = G["Y"].shape
             ss = {"by_col": n, "by_row": p, "constant": n * p}[vt]
             obj = vn.calc_ebpmf_log_obj(n, p, res["sym"], res["ssexp"], res["slogv"], res["v_sum"], s2, G[vt + "_R2"], -123.4, -5.5,
@@ -113,6 +117,10 @@ def test_cuda_matches_the_reference_outputs(gpu_ctx, pkg, vt, tag):
     if tag == "def":
         s2 = gpu_ctx.update_sigma2(G[vt + "_R2"], 1.0, 1.0, 0.0)
         assert rel(np.atleast_1d(s2), R[k + "sigma2_new"].ravel()) < 1e-8
+        for cap, key in ((2.0, "sigma2_new_cap"), (1e9, "sigma2_new_cap_big")):
+            sc2 = pkg.ebpmf_log_update_sigma2(dict(R2=G[vt + "_R2"], EL=G[vt + "_EL"], EF=G[vt + "_EF"]), G[vt + "_sigma2"], res["v_sum"], vt,
+                                              cap, 1, 1, *G["Y"].shape, ctx=gpu_ctx)
+            assert rel(np.atleast_1d(sc2), R[k + key].ravel()) < 1e-8
         n, p = G["Y"].shape
         ss = {"by_col": n, "by_row": p, "constant": n * p}[vt]
         obj = pkg.calc_ebpmf_log_obj(n, p, res["sym"], res["ssexp"], res["slogv"], res["v_sum"], s2, G[vt + "_R2"], -123.4, -5.5,
@@ -137,11 +145,12 @@ def test_make_golden_r_runs_under_the_evaluator_and_writes_what_the_loader_expec
     from oracle import minir_io
     out = minir_io.run_make_golden(os.path.join(HERE, "golden", "make_golden.R"), REFROOT, str(tmp_path / "r_reference"))
     R = read_dir(str(tmp_path / "r_reference"))
-    assert len(R) == 46 and "wrote 46 arrays" in out
+    assert len(R) == 52 and "wrote 52 arrays" in out
     for vt in ("by_col", "by_row", "constant"):
         for tag in sorted(CASES):
             check_oracle_steps(R, vt, tag)
     check_oracle_other_solvers(R)
     MR = np.load(os.path.join(HERE, "golden", "minir_reference.npz"))              # same evaluator, other driver: identical numbers
-    for k in ("by_col_def_M", "by_row_tight_V", "constant_exh_scal", "fixed1_V", "lowmem_M", "lfact"):
+    for k in ("by_col_def_M", "by_row_tight_V", "constant_exh_scal", "fixed1_V", "lowmem_M", "lfact", "by_row_def_sigma2_new_cap_big",
+              "by_col_def_sigma2_new_cap"):
         assert np.array_equal(R[k].ravel(), MR["fn/" + k].ravel()), k
