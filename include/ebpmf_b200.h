@@ -158,8 +158,11 @@ int  ebpmf_ctx_get_block(ebpmf_ctx *ctx, int which, int64_t row0, int64_t nrows,
 /* ebpmf_log_update_sigma2, R/ebpmf_log.R:413-447, on the device from the v_sum of the last step.
  * R2 = fit_flash$flash_fit$R2 (length 1|n|p; for 'constant' the caller passes sum(R2)).
  * n_total / p_total are the FULL matrix dims (n of all ranks).  cap_var_mean_ratio > 0 enables
- * the gate of :416,:425,:435 (col/row/global max of fitted(fit_flash), recomputed on device from
- * EL, EF).  The new sigma2 becomes the resident one and is copied to sigma2_out. */
+ * the gate of :416,:425,:435 on fitted(fit_flash), recomputed on device from EL, EF: the global max
+ * ('constant'), matrixStats::colMaxs = the column maxima ('by_col'), and for 'by_row' what the reference
+ * really compares -- Rfast::rowMaxs(x), whose default value = FALSE returns the 1-based POSITION of each
+ * row's maximum, not the maximum (NAMESPACE: importFrom(Rfast,rowMaxs)).  The new sigma2 becomes the
+ * resident one and is copied to sigma2_out. */
 int  ebpmf_ctx_update_sigma2(ebpmf_ctx *ctx, const double *R2, double a0, double b0,
                              double cap_var_mean_ratio, int64_t n_total, int64_t p_total,
                              double *sigma2_out);
